@@ -1,0 +1,178 @@
+/*
+ * kinisi_b200.h -- C ABI of the B200-native displacement-statistics path.
+ *
+ * The reference (bjmorgan/kinisi 1.1.1) is pure Python/numpy and has no FFI layer; its boundary is
+ * the Python API of kinisi/parser.py and kinisi/diffusion.py.  This header declares the entry points
+ * a ctypes binding for that path calls (see INTEGRATION.md for the reference-side stub).  Each entry
+ * point cites the reference code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - Every pointer is a DEVICE pointer owned by the caller unless the name ends in _host.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls only enqueue work on that stream; none of
+ *     them synchronises, allocates or keeps state between calls (re-entrant per stream).
+ *   - Return value: 0 on success, non-zero on error; kb2_last_error() returns a thread-local
+ *     message for the last non-zero return on the calling thread.
+ *   - Trajectory arrays: cumulative unwrapped displacements `dc` are float64, component-major
+ *     ("SoA"): dc[(atom*3 + component)*pitch + frame], pitch >= n_frames, pitch % 2 == 0, the
+ *     pad [n_frames, pitch) is zero.
+ */
+#ifndef KINISI_B200_H
+#define KINISI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB2_ABI_VERSION 1
+
+/* coordinate element types */
+#define KB2_F32 0
+#define KB2_F64 1
+
+/* input meaning for the stage-1 kernels */
+#define KB2_MODE_FRACTIONAL 0 /* fractional coordinates + lattices: unwrap, then cumulative sum     */
+#define KB2_MODE_DISPLACEMENT 1 /* already-unwrapped cumulative displacement (Parser(disp, ...))      */
+
+/* dimension mask bits (kinisi/diffusion.py:23-38 DIMENSIONALITY) */
+#define KB2_DIM_X 1
+#define KB2_DIM_Y 2
+#define KB2_DIM_Z 4
+
+int kb2_abi_version(void);
+const char* kb2_last_error(void);
+
+/* Device properties the host side sizes its launches with (SM count, max opt-in smem). */
+int kb2_device_info(int* sm_count, int* max_smem_optin, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 1 -- displacement construction.  Replaces Parser.get_disp (kinisi/parser.py:101-129),
+ * Parser.correct_drift (:131-148) and the layout change feeding Parser.get_disps (:170-222).
+ *
+ * coords: [n_atoms_total][n_frames_in][3] (atom-major, as np.concatenate(coords, axis=1) yields at
+ *         parser.py:120), element type `dtype`.  In KB2_MODE_FRACTIONAL n_frames_in includes the
+ *         duplicated first frame (parser.py:323-324) and the result has n_frames_in-1 frames; in
+ *         KB2_MODE_DISPLACEMENT the result has n_frames_in frames.
+ * latt / latt_inv: [n_frames_in][3][3] float64 row-vector convention (cart = frac @ latt),
+ *         `latt_stride` = 9 for per-frame lattices or 0 when every frame shares latt[0].
+ * ------------------------------------------------------------------------------------------- */
+
+/* inv[f] = latt[f]^-1 for f < n (np.linalg.inv at parser.py:121). */
+int kb2_invert_lattice(const double* latt, double* latt_inv, int n, void* stream);
+
+/* frame_sums[c*pitch + t] = sum_{i < n_idx} w[i] * u[idx[i]][t][c], where u is the per-frame
+ * unwrapped displacement (MODE_FRACTIONAL; its cumulative sum over t is the summed displacement)
+ * or the displacement itself (MODE_DISPLACEMENT).  w == NULL means unit weights.  The buffer
+ * [3][pitch] is zeroed by the call.  Used for the framework drift (parser.py:143-145) and for the
+ * collective / charge-weighted sums of MSTD / MSCD (diffusion.py:659, 751). */
+int kb2_frame_sums(const void* coords, int dtype, int mode, int n_atoms_total, int n_frames_in, const double* latt,
+                   const double* latt_inv, int latt_stride, const int32_t* idx, const double* w, int n_idx,
+                   double* frame_sums, int64_t pitch, void* stream);
+
+/* In place on buf[3][pitch] (n_frames valid entries per row):
+ *   cumulative != 0:  buf <- cumsum_t(buf)
+ *   then              buf <- buf / divide - sub_scale * sub      (sub may be NULL)
+ * Turns frame sums into the framework mean displacement (divide = n_framework) or into the
+ * drift-corrected collective sum (divide = 1, sub = framework mean, sub_scale = sum of weights). */
+int kb2_scan_frames(double* buf, int n_frames, int64_t pitch, int cumulative, double divide, const double* sub,
+                    double sub_scale, void* stream);
+
+/* dc_out[(i*3 + c)*pitch + t] = cumulative unwrapped displacement of atom idx[i] minus drift[c][t]
+ * (drift == NULL: no correction).  dc[:, 0] == 0 in MODE_FRACTIONAL exactly as in the reference. */
+int kb2_unwrap_cumsum(const void* coords, int dtype, int mode, int n_atoms_total, int n_frames_in, const double* latt,
+                      const double* latt_inv, int latt_stride, const int32_t* idx, int n_idx, const double* drift,
+                      double* dc_out, int64_t pitch, void* stream);
+
+/* out[c*pitch + t] = sum_{a < n_atoms} w[a] * dc[(a*3 + c)*pitch + t]  (w == NULL: unit weights).
+ * The collective displacement of MSTD (np.sum(disp_slice, axis=0), kinisi/diffusion.py:659) and the
+ * charge-weighted one of MSCD (:751), formed once per trajectory instead of once per dt.  The buffer
+ * [3][pitch] is zeroed by the call. */
+int kb2_atom_sum(const double* dc, int n_atoms, int64_t pitch, const double* w, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 2 -- moment reductions, fused with Parser.get_disps so the O(N*T*n_dt) displacement list
+ * (parser.py:208-216) is never materialised.  Replaces the default branch of
+ * MSDBootstrap.__init__ (kinisi/diffusion.py:571-602) and the per-atom part of MSTD/MSCD.
+ *
+ * For every lag k = lags[i] (ascending, 1 <= k <= n_frames):
+ *   sums[2i]   = sum over atoms a and observations of d^2
+ *   sums[2i+1] = sum of d^4
+ * where the observations of atom a are dc[a][k-1] (the extra first observation, parser.py:209) and
+ * dc[a][j+k] - dc[a][j] for 0 <= j < n_frames-k, and d^2 sums the components in dim_mask.
+ * Calling it with n_atoms = 1 on a collective sum [3][pitch] yields the MSTD/MSCD sums
+ * (diffusion.py:659, 683-684, 751, 775-776).
+ *
+ * variant: 0 = direct kernel (L1-cached partner loads), 1 = TMA-staged ring-buffer kernel.
+ * workspace: kb2_self_moments_workspace_bytes(n_lags) bytes, contents irrelevant on entry.
+ * ------------------------------------------------------------------------------------------- */
+size_t kb2_self_moments_workspace_bytes(int n_lags);
+int kb2_self_moments(const double* dc, int n_atoms, int n_frames, int64_t pitch, const int32_t* lags, int n_lags,
+                     int dim_mask, int variant, void* workspace, double* sums, void* stream);
+
+/* The same sums from ONE materialised displacement array disp[n_atoms][n_obs][3] (float64, the
+ * reference seam: an entry of disp_3d as passed to the *Bootstrap constructors,
+ * diffusion.py:552-564).  out[0..1] = sum d^2, sum d^4 over atoms x observations (dim_mask);
+ * out[2..3] = sum_j c_j, sum_j c_j^2 with c_j = |sum_a w_a disp[a][j]|^2 over coll_mask components
+ * (w == NULL: unit weights; coll_mask == 0: skip).  out[4] is zeroed by the call. */
+int kb2_disp_moments(const double* disp, int n_atoms, int n_obs, int dim_mask, const double* w, int coll_mask,
+                     double* out, void* stream);
+
+/* n, v, s, ngp from raw sums (diffusion.py:597-600, 683-686, 291-303):
+ *   n   = m1/cnt,  var = (m2 - m1^2/cnt)/(cnt-1),  v = var/divisor,  s = sqrt(v)
+ *   ngp = 3 (g2/gcnt) / (5 (g1/gcnt)^2) - 1
+ * main_sums / ngp_sums are [n][2] (they may alias for MSD); cnt, divisor, gcnt are [n] float64. */
+int kb2_moment_stats(const double* main_sums, const double* cnt, const double* divisor, const double* ngp_sums,
+                     const double* gcnt, int n, double* out_n, double* out_v, double* out_s, double* out_ngp,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 3 -- covariance and Bayesian regression.
+ * ------------------------------------------------------------------------------------------- */
+
+/* cov[i][j] = cov[j][i] = (n_o[i] / n_o[j]) * v[i] for i <= j
+ * (_populate_covariance_matrix, kinisi/diffusion.py:838-854). */
+int kb2_cov_build(const double* v, const double* n_o, int n, double* cov, void* stream);
+
+/* Turns the symmetric eigendecomposition (evals[n] ascending, evecs[n][n] row-major with
+ * eigenvectors in columns) of the reconditioned covariance into the truncated whitening factor that
+ * scipy.linalg.pinvh implies (diffusion.py:352: directions with |lambda| <= n*eps*max|lambda| are
+ * dropped), applied to the straight-line model of diffusion.py:362-364:
+ *   proj[0][r] = s_r V_r.x     proj[1][r] = s_r V_r.1     proj[2][r] = s_r V_r.y
+ *   proj[3][r] = sign(lambda_r) or 0 if dropped,          s_r = |lambda_r|^-1/2
+ * so that diff^T pinvh(C) diff = sum_r proj[3][r] (g proj[0][r] + c proj[1][r] - proj[2][r])^2.
+ * theta_ml[0..1] receives the generalised-least-squares optimum (slope clamped at >= 1e-20 like
+ * diffusion.py:370-371), the start point the reference finds with scipy.optimize.minimize (:380-383). */
+int kb2_gls_prepare(const double* evals, const double* evecs, const double* x, const double* y, int n,
+                    int fit_intercept, double* proj, double* theta_ml, void* stream);
+
+/* out[w] = log_likelihood(theta[w]) of diffusion.py:354-365 for n_walkers parameter vectors
+ * theta[n_walkers][ndim] (ndim = 1 or 2); -inf where theta[w][0] < 0.
+ * logdet_term is a device scalar holding slogdet(C) + n ln(2 pi) (diffusion.py:350-351). */
+int kb2_mvn_loglike(const double* theta, int n_walkers, int ndim, const double* proj, int n,
+                    const double* logdet_term, double* out, void* stream);
+
+/* The whole ensemble MCMC of diffusion.py:384-390 in one launch: walkers start at
+ * theta_ml + theta_ml * 1e-3 * N(0,1) (:384), then n_steps affine-invariant stretch moves (a = 2,
+ * red/blue split with a random balanced partition per step) are run.
+ * chain[n_steps][n_walkers][ndim], logp[n_steps][n_walkers].
+ * workspace: kb2_sampler_workspace_bytes(n_steps, n_walkers) bytes. */
+size_t kb2_sampler_workspace_bytes(int n_steps, int n_walkers);
+int kb2_ensemble_sample(const double* theta_ml, int ndim, int n_walkers, int n_steps, const double* proj, int n,
+                        const double* logdet_term, uint64_t seed, void* workspace, double* chain, double* logp,
+                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Measurement helpers (bench.py): a dependent-free DFMA loop and a streaming copy, to measure the
+ * FP64-pipe and HBM rooflines on the device the bench runs on.
+ * ------------------------------------------------------------------------------------------- */
+/* Launches grid x 256 threads, each doing iters * 16 DFMAs (counted: grid*256*iters*16). */
+int kb2_fp64_peak(int grid, int iters, double* sink, void* stream);
+int kb2_stream_copy(const double* src, double* dst, size_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KINISI_B200_H */

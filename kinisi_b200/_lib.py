@@ -1,0 +1,70 @@
+"""ctypes binding of include/kinisi_b200.h.  There is no CPU fallback: if the shared library is missing
+the import fails loudly."""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_uint64, c_void_p, POINTER
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libkinisi_b200.so')
+
+F32, F64 = 0, 1
+MODE_FRACTIONAL, MODE_DISPLACEMENT = 0, 1
+ABI_VERSION = 1
+
+# name -> (restype, argtypes); mirrors include/kinisi_b200.h one to one
+SIGNATURES = {
+    'kb2_abi_version': (c_int, []),
+    'kb2_last_error': (c_char_p, []),
+    'kb2_device_info': (c_int, [POINTER(c_int)] * 4),
+    'kb2_invert_lattice': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    'kb2_frame_sums': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                               c_void_p, c_int64, c_void_p]),
+    'kb2_scan_frames': (c_int, [c_void_p, c_int, c_int64, c_int, c_double, c_void_p, c_double, c_void_p]),
+    'kb2_unwrap_cumsum': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
+                                  c_void_p, c_void_p, c_int64, c_void_p]),
+    'kb2_atom_sum': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    'kb2_self_moments_workspace_bytes': (c_size_t, [c_int]),
+    'kb2_self_moments': (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p]),
+    'kb2_disp_moments': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    'kb2_moment_stats': (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 4 + [c_void_p]),
+    'kb2_cov_build': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    'kb2_gls_prepare': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'kb2_mvn_loglike': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    'kb2_sampler_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'kb2_ensemble_sample': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_uint64, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
+    'kb2_fp64_peak': (c_int, [c_int, c_int, c_void_p, c_void_p]),
+    'kb2_stream_copy': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+_lib = None
+
+
+class KinisiB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load libkinisi_b200.so (built by kinisi_b200._build.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f'{LIB_PATH} is missing: build the CUDA extension first '
+                          '(python -m kinisi_b200._build). kinisi_b200 has no CPU fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means the library is stale
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.kb2_abi_version() != ABI_VERSION:
+        raise ImportError(f'{LIB_PATH}: ABI version {lib.kb2_abi_version()} != {ABI_VERSION}; rebuild it')
+    _lib = lib
+    return lib
+
+
+def check(rc, fn):
+    if rc != 0:
+        msg = load().kb2_last_error().decode('utf-8', 'replace')
+        raise KinisiB200Error(f'{fn} failed ({rc}): {msg}')

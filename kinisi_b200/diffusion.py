@@ -1,0 +1,557 @@
+"""
+Host-side mirror of kinisi/diffusion.py for the displacement-statistics path: `Bootstrap`,
+`MSDBootstrap`, `MSTDBootstrap`, `MSCDBootstrap` with the reference's constructor signatures,
+attributes (`dt n s v ngp n_o covariance_matrix gradient intercept flatchain D D_J sigma`) and error
+behaviour; the arithmetic runs in the sm_100a kernels behind include/kinisi_b200.h.
+
+`disp_3d` may be the lazy sequence a :py:class:`kinisi_b200.parser.Parser` produces (fused path: the
+displacement list is never materialised) or a plain list of `[atom, observation, axis]` arrays (the
+reference's seam, kinisi/diffusion.py:552-564; each entry is reduced by one kernel).
+
+Not provided (off the default path): `bootstrap=True` resampling (diffusion.py:258-289,
+783-835), `block=True` (pyblock) and `model=True` variance smoothing (:406-420).
+"""
+from typing import List, Union
+
+import numpy as np
+import scipy.constants as const
+import torch
+
+from . import dist, engine
+from .distribution import Distribution
+from .parser import LazyDisplacements, SingleOriginDisplacements
+
+DIMENSIONALITY = {
+    'x': np.s_[0],
+    'y': np.s_[1],
+    'z': np.s_[2],
+    'xy': np.s_[:2],
+    'xz': np.s_[::2],
+    'yz': np.s_[1:],
+    'xyz': np.s_[:],
+    b'x': np.s_[0],
+    b'y': np.s_[1],
+    b'z': np.s_[2],
+    b'xy': np.s_[:2],
+    b'xz': np.s_[::2],
+    b'yz': np.s_[1:],
+    b'xyz': np.s_[:]
+}
+
+
+class _LazyEuclidian:
+    """`euclidian_displacements` (kinisi/diffusion.py:577): sqrt(d^2) of every observation at each dt,
+    as Distributions built on demand (O(N*T) values per dt: never on the hot path)."""
+
+    def __init__(self, disps, used, mask_slice, dims):
+        self._disps, self._used, self._slice, self._dims = disps, list(used), mask_slice, dims
+
+    def __len__(self):
+        return len(self._used)
+
+    def __getitem__(self, i):
+        d = np.asarray(self._disps[self._used[i]])
+        sl = d[:, :, self._slice].reshape(d.shape[0], d.shape[1], self._dims)
+        return Distribution(np.sqrt(np.sum(sl**2, axis=-1).flatten()))
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class Bootstrap:
+    """
+    The top-level class for the moment statistics and the Bayesian regression (kinisi/diffusion.py:41-521).
+
+    :param delta_t: An array of the time interval values.
+    :param disp_3d: The displacements: a lazy sequence from the parser or a list of arrays
+        `[atom, displacement observation, dimension]`, one per delta_t.
+    :param n_o: Number of statistically independent observations at each time interval.
+    :param sub_sample_dt: The frequency in observations to be sampled. Optional, default is 1.
+    :param dimension: Subset of 'xyz'. Optional, defaults to 'xyz'.
+    """
+
+    def __init__(self, delta_t, disp_3d, n_o, sub_sample_dt: int = 1, dimension: str = 'xyz'):
+        engine.require_cuda()
+        self._displacements = disp_3d[::sub_sample_dt]
+        self._delta_t = np.array(delta_t[::sub_sample_dt])
+        self._lazy = isinstance(self._displacements, LazyDisplacements)
+        self._max_obs = self._shape_of(0)[1]
+        self._distributions = []
+        self._n_o = n_o
+        self._sub_sample_dt = sub_sample_dt
+        self._dimension = dimension
+        self._euclidian_displacements = []
+        self._diffusion_coefficient = None
+        self._jump_diffusion_coefficient = None
+        self._sigma = None
+        self._intercept = None
+        self.gradient = None
+        self.flatchain = None
+        self._covariance_matrix_dev = None
+        self._npd_covariance_matrix_dev = None
+        self._slice = DIMENSIONALITY[dimension.lower()]
+        self._mask = engine.dim_mask(dimension)
+        self._start_dt = None
+        self.dims = len(dimension.lower())
+        self._model = None
+        self._cond_max = None
+        self._n_bootstrap = np.array([])
+        self._s_bootstrap = np.array([])
+        self._v_bootstrap = np.array([])
+        self._stats_dev = None  # [4, n] = n, v, s, ngp on the device
+        self._stats_host = None
+        self._dt = np.array([])
+        self._device = self._displacements.dc.device if self._lazy else torch.device('cuda',
+                                                                                     torch.cuda.current_device())
+
+    # ---- helpers -----------------------------------------------------------------------------
+    def _shape_of(self, i):
+        if self._lazy:
+            return self._displacements.shape_of(i)
+        return tuple(self._displacements[i].shape)
+
+    def _n_atoms(self):
+        """disp.shape[0] in the reference: the (global) number of atoms of entry 0."""
+        return self._displacements.n_atoms_global if self._lazy else self._shape_of(0)[0]
+
+    def _reject_unsupported(self, bootstrap, block):
+        if bootstrap:
+            raise NotImplementedError('bootstrap=True (kinisi/diffusion.py:258-289) is not on the default '
+                                      'displacement-statistics path built here')
+        if block:
+            raise NotImplementedError('block=True needs pyblock (kinisi/diffusion.py:584-595); not built here')
+
+    def _dev(self, a):
+        return torch.as_tensor(np.asarray(a, dtype=np.float64)).to(self._device)
+
+    def _self_sums(self, used, mask):
+        """[len(used), 2] sums of d^2, d^4 over atoms x observations for the entries in `used`."""
+        d = self._displacements
+        if self._lazy and not isinstance(d, SingleOriginDisplacements):
+            lags = d.lags[used]
+            order = np.argsort(lags, kind='stable')
+            lags_dev = torch.as_tensor(lags[order].astype(np.int32)).to(self._device)
+            if d.dc.shape[0] > 0:
+                sums = engine.self_moments(d.dc, d.n_frames, lags_dev, mask)
+            else:
+                sums = torch.zeros((len(used), 2), dtype=torch.float64, device=self._device)
+            if dist.active():
+                dist.allreduce_sum_(sums)
+            if not np.array_equal(order, np.arange(len(order))):
+                inv = np.empty_like(order)
+                inv[order] = np.arange(len(order))
+                sums = sums[torch.as_tensor(inv).to(self._device)]
+            return sums
+        rows = []
+        for i in used:
+            arr = d.device_entry(i) if isinstance(d, SingleOriginDisplacements) else engine.to_device(
+                d[i], self._device, torch.float64)
+            rows.append(engine.disp_moments(arr, mask)[:2])
+        sums = torch.stack(rows)
+        if self._lazy and dist.active():
+            dist.allreduce_sum_(sums)
+        return sums
+
+    def _collective_sums(self, used, weights, coll_mask):
+        """[len(used), 2] sums of c, c^2 with c_j = |sum_a w_a disp_a(j)|^2 over observations."""
+        d = self._displacements
+        if self._lazy and not isinstance(d, SingleOriginDisplacements):
+            w = None if weights is None else self._dev(weights)
+            if d.dc.shape[0] > 0:
+                S = engine.atom_sum(d.dc, w)
+            else:
+                S = torch.zeros((3, d.dc.shape[2]), dtype=torch.float64, device=self._device)
+            if dist.active():
+                dist.allreduce_sum_(S)
+            lags_dev = torch.as_tensor(d.lags[used].astype(np.int32)).to(self._device)
+            return engine.self_moments(S.unsqueeze(0), d.n_frames, lags_dev, coll_mask)
+        w = None if weights is None else self._dev(weights)
+        rows = []
+        for i in used:
+            arr = d.device_entry(i) if isinstance(d, SingleOriginDisplacements) else engine.to_device(
+                d[i], self._device, torch.float64)
+            rows.append(engine.disp_moments(arr, self._mask, w, coll_mask)[2:])
+        return torch.stack(rows)
+
+    def _finish(self, used, main_sums, cnt, divisor, ngp_sums, gcnt):
+        used = list(used)
+        if len(used) == 0:
+            self._stats_dev = torch.zeros((4, 0), dtype=torch.float64, device=self._device)
+        else:
+            self._stats_dev = engine.moment_stats(main_sums, self._dev(cnt), self._dev(divisor), ngp_sums,
+                                                  self._dev(gcnt))
+        self._dt = np.array([self._delta_t[i] for i in used], dtype=float)
+        self._n_o = self._n_o[:len(used)]  # diffusion.py:602
+        self._euclidian_displacements = _LazyEuclidian(self._displacements, used, self._slice, self.dims)
+
+    def _host_stats(self):
+        if self._stats_host is None:
+            self._stats_host = self._stats_dev.cpu().numpy()
+        return self._stats_host
+
+    # ---- the reference's attribute surface ---------------------------------------------------
+    @property
+    def _n(self):
+        return self._host_stats()[0]
+
+    @property
+    def _v(self):
+        return self._host_stats()[1]
+
+    @property
+    def _s(self):
+        return self._host_stats()[2]
+
+    @property
+    def _ngp(self):
+        return self._host_stats()[3]
+
+    @property
+    def dt(self) -> np.ndarray:
+        """:return: Timestep values that were sampled."""
+        return self._dt
+
+    @property
+    def n(self) -> np.ndarray:
+        """:return: The mean MSD/MSTD/MSCD, in units Å^2."""
+        return self._n
+
+    @property
+    def s(self) -> np.ndarray:
+        """:return: The MSD/MSTD/MSCD standard deviation, in units Å^2."""
+        return self._s
+
+    @property
+    def v(self) -> np.ndarray:
+        """:return: The MSD/MSTD/MSCD variance, in units Å^4."""
+        return self._v
+
+    @property
+    def euclidian_displacements(self):
+        """:return: Displacements between particles at each dt."""
+        return self._euclidian_displacements
+
+    @property
+    def ngp(self) -> np.ndarray:
+        """:return: Non-Gaussian parameter as a function of dt."""
+        return self._ngp
+
+    @property
+    def intercept(self) -> Union[Distribution, None]:
+        """:return: The estimated intercept (None if fit_intercept was False)."""
+        return self._intercept
+
+    @property
+    def covariance_matrix(self) -> np.ndarray:
+        """:return: The covariance matrix for the trajectories."""
+        return None if self._covariance_matrix_dev is None else self._covariance_matrix_dev.cpu().numpy()
+
+    @property
+    def _covariance_matrix(self):
+        return self.covariance_matrix
+
+    @property
+    def _npd_covariance_matrix(self):
+        return None if self._npd_covariance_matrix_dev is None else self._npd_covariance_matrix_dev.cpu().numpy()
+
+    @staticmethod
+    def ngp_calculation(d_squared: np.ndarray) -> float:
+        """
+        Non-Gaussian parameter (kinisi/diffusion.py:291-303) of an array of squared displacements, through
+        the same moment kernels: 3 <d^4> / (5 <d^2>^2) - 1.
+        """
+        d = np.sqrt(np.asarray(d_squared, dtype=np.float64).reshape(-1, 1, 1))
+        dev = torch.device('cuda', torch.cuda.current_device())
+        arr = engine.to_device(np.concatenate([d, np.zeros_like(d), np.zeros_like(d)], axis=2), dev)
+        sums = engine.disp_moments(arr, 7)[:2].reshape(1, 2)
+        cnt = torch.full((1, ), float(d.shape[0]), dtype=torch.float64, device=dev)
+        one = torch.ones(1, dtype=torch.float64, device=dev)
+        return float(engine.moment_stats(sums, cnt + 1.0, one, sums, cnt)[3, 0].item())
+
+    # ---- stage 3 -----------------------------------------------------------------------------
+    def generate_covariance_matrix(self, diff_regime: int):
+        """
+        The model covariance, reconditioned and repaired (kinisi/diffusion.py:397-425), on the device:
+        `_populate_covariance_matrix` (:838-854) -> `minimum_eigenvalue_method` (:870-888) ->
+        `cov_nearest` (statsmodels, clipped-correlation repair).
+        """
+        if self._model:
+            raise NotImplementedError('model=True variance smoothing (kinisi/diffusion.py:406-420) is not built here')
+        v = self._stats_dev[1, diff_regime:].contiguous()
+        n_o = self._dev(self._n_o[diff_regime:])
+        cov = engine.cov_build(v, n_o)
+        self._npd_covariance_matrix_dev = cov
+        # minimum eigenvalue method: clip the spectrum at lambda_max / cond_max and rebuild
+        lam, vec = torch.linalg.eigh(cov)
+        floor = lam.max() / self._cond_max
+        cov = (vec * torch.clamp(lam, min=floor)) @ vec.T
+        # cov_nearest(method='clipped', threshold=1e-15)
+        std = torch.sqrt(torch.diagonal(cov))
+        corr = cov / torch.outer(std, std)
+        ev, evec = torch.linalg.eigh(corr)
+        repaired = (evec * torch.clamp(ev, min=1e-15)) @ evec.T
+        rstd = torch.sqrt(torch.diagonal(repaired))
+        repaired = repaired / rstd / rstd[:, None]
+        corr = torch.where((ev < 1e-15).any(), repaired, corr)
+        return corr * torch.outer(std, std)
+
+    def bootstrap_GLS(self,
+                      start_dt: float,
+                      cond_max: float = 1e16,
+                      model: bool = False,
+                      fit_intercept: bool = True,
+                      n_samples: int = 1000,
+                      n_walkers: int = 32,
+                      n_burn: int = 500,
+                      thin: int = 10,
+                      progress: bool = True,
+                      random_state: np.random.mtrand.RandomState = None):
+        """
+        Generalised-least-squares estimate of gradient and intercept under the model covariance, sampled
+        with an affine-invariant ensemble sampler (kinisi/diffusion.py:305-395).  Same parameters and
+        defaults as the reference.  Everything from the covariance build to the last MCMC step is
+        enqueued on the device without a host synchronisation; the flat chain is copied back at the end.
+        """
+        if random_state is not None:
+            np.random.seed(random_state.get_state()[1][1])
+        if n_walkers % 2 or n_walkers < 2:
+            raise ValueError('n_walkers must be an even number >= 2')
+
+        self._start_dt = start_dt
+        self._model = model
+        self._cond_max = cond_max
+
+        diff_regime = np.argwhere(self._dt >= self._start_dt)[0][0]
+
+        cov = self.generate_covariance_matrix(diff_regime)
+        self._covariance_matrix_dev = cov
+        n_dt = cov.shape[0]
+
+        _, logdet = torch.linalg.slogdet(cov)
+        logdet_term = (logdet + float(np.log(2 * np.pi) * n_dt)).reshape(1)
+        lam, vec = torch.linalg.eigh(cov)  # pinvh is an eigendecomposition with a relative cut-off
+
+        x = self._dev(self._dt[diff_regime:])
+        y = self._stats_dev[0, diff_regime:].contiguous()
+        proj, theta_ml = engine.gls_prepare(lam, vec, x, y, fit_intercept)
+        self._proj, self._logdet_term, self._theta_ml = proj, logdet_term, theta_ml
+
+        ndim = 2 if fit_intercept else 1
+        seed = int(np.random.randint(0, 2**31 - 1)) * 2654435761 + 12345
+        chain, logp = engine.ensemble_sample(theta_ml, ndim, n_walkers, n_samples + n_burn, proj, logdet_term, seed)
+        self._chain_dev, self._logp_dev = chain, logp
+        # emcee get_chain(flat=True, thin=thin, discard=n_burn)
+        self.flatchain = chain[n_burn + thin - 1::thin].reshape(-1, ndim).cpu().numpy()
+        self.gradient = Distribution(self.flatchain[:, 0])
+        self._intercept = None
+        if fit_intercept:
+            self._intercept = Distribution(self.flatchain[:, 1])
+
+    def log_likelihood(self, theta) -> np.ndarray:
+        """Batched log-likelihood (kinisi/diffusion.py:354-365) of parameter vectors `[n, ndim]`."""
+        theta = np.atleast_2d(np.asarray(theta, dtype=np.float64))
+        return engine.mvn_loglike(self._dev(theta), self._proj, self._logdet_term).cpu().numpy()
+
+    def diffusion(self, start_dt: float, **kwargs):
+        """Diffusion coefficient in cm^2/s (kinisi/diffusion.py:427-436)."""
+        self.bootstrap_GLS(start_dt, **kwargs)
+        self._diffusion_coefficient = Distribution(self.gradient.samples / (2e4 * self.dims))
+
+    @property
+    def D(self) -> Union[Distribution, None]:
+        """:return: Diffusion coefficient, with units of cm^2 s^-1."""
+        return self._diffusion_coefficient
+
+    def jump_diffusion(self, start_dt: float, **kwargs):
+        """Jump diffusion coefficient in cm^2/s (kinisi/diffusion.py:447-457)."""
+        self.bootstrap_GLS(start_dt, **kwargs)
+        self._jump_diffusion_coefficient = Distribution(self.gradient.samples / (2e4 * self.dims * self._n_atoms()))
+
+    @property
+    def D_J(self) -> Union[Distribution, None]:
+        """:return: Jump diffusion coefficient, with units of cm^2 s^-1."""
+        return self._jump_diffusion_coefficient
+
+    def conductivity(self, start_dt: float, temperature: float, volume: float, **kwargs):
+        """Ionic conductivity in mS/cm (kinisi/diffusion.py:468-482)."""
+        self.bootstrap_GLS(start_dt, **kwargs)
+        volume = volume * 1e-24  # cm^3
+        D = self.gradient.samples / (2e4 * self.dims)  # cm^2s^-1
+        conversion = 1000 / (volume * const.N_A) * (const.N_A * const.e)**2 / (const.R * temperature)
+        self._sigma = Distribution(D * conversion)
+
+    @property
+    def sigma(self) -> Union[Distribution, None]:
+        """:return: The estimated conductivity, with units mS cm^-1."""
+        return self._sigma
+
+    def posterior_predictive(self, n_posterior_samples: int = None, n_predictive_samples: int = 256,
+                             progress: bool = True) -> np.ndarray:
+        """
+        Sample the posterior predictive distribution (kinisi/diffusion.py:492-521); the result has the shape
+        `(n_posterior_samples * n_predictive_samples, n_dt)`.  One eigen-factor of the covariance serves every
+        posterior draw (the reference rebuilds a frozen multivariate normal per draw).
+        """
+        if n_posterior_samples is None:
+            n_posterior_samples = self.gradient.size
+        diff_regime = np.argwhere(self._dt >= self._start_dt)[0][0]
+        x = self._dev(self._dt[diff_regime:])
+        lam, vec = torch.linalg.eigh(self._covariance_matrix_dev)
+        factor = vec * torch.sqrt(torch.clamp(lam, min=0.0))  # cov = factor @ factor.T (allow_singular)
+        draw = np.random.randint(0, self.gradient.size, size=n_posterior_samples)
+        g = self._dev(self.gradient.samples[draw])
+        c = self._dev(self.intercept.samples[draw])
+        mu = g[:, None] * x[None, :] + c[:, None]
+        gen = torch.Generator(device=self._device)
+        gen.manual_seed(int(np.random.randint(0, 2**31 - 1)))
+        z = torch.randn((n_posterior_samples, n_predictive_samples, x.numel()), dtype=torch.float64,
+                        device=self._device, generator=gen)
+        ppd = mu[:, None, :] + z @ factor.T
+        return ppd.reshape(-1, x.numel()).cpu().numpy()
+
+    def to_dict(self) -> dict:
+        """:return: Dictionary description of the statistics (arrays only; the displacements stay on the device)."""
+        return {
+            'delta_t': self._delta_t,
+            'n_o': np.asarray(self._n_o),
+            'max_obs': self._max_obs,
+            'dt': self._dt,
+            'n': self._n,
+            's': self._s,
+            'v': self._v,
+            'sub_sample_dt': self._sub_sample_dt,
+            'dimension': self._dimension,
+            'ngp': self._ngp,
+            'covariance_matrix': self.covariance_matrix,
+            'flatchain': self.flatchain,
+            'start_dt': self._start_dt,
+            'model': self._model,
+            'cond_max': self._cond_max
+        }
+
+
+class MSDBootstrap(Bootstrap):
+    """
+    Mean and uncertainty of the mean squared displacements (kinisi/diffusion.py:524-602).
+
+    :param delta_t: An array of the time interval values, units of ps.
+    :param disp_3d: The displacements (see :py:class:`Bootstrap`).
+    :param n_o: Number of statistically independent observations of the MSD at each time interval.
+    :param sub_sample_dt, dimension, progress: as in the reference.
+    :param bootstrap, block, n_resamples, max_resamples, alpha, random_state: accepted for signature
+        compatibility; `bootstrap=True` / `block=True` raise NotImplementedError.
+    """
+
+    def __init__(self,
+                 delta_t: np.ndarray,
+                 disp_3d,
+                 n_o: np.ndarray,
+                 sub_sample_dt: int = 1,
+                 bootstrap: bool = False,
+                 block: bool = False,
+                 n_resamples: int = 1000,
+                 max_resamples: int = 10000,
+                 dimension: str = 'xyz',
+                 alpha: float = 1e-3,
+                 random_state: np.random.mtrand.RandomState = None,
+                 progress: bool = True):
+        super().__init__(delta_t, disp_3d, n_o, sub_sample_dt, dimension)
+        self._reject_unsupported(bootstrap, block)
+        n_atoms = self._n_atoms()
+        used, cnt, div = [], [], []
+        for i in range(len(self._displacements)):
+            shp = self._shape_of(i)
+            n_local = shp[0] if not self._lazy else n_atoms
+            size = n_local * shp[1]
+            if size <= 1:  # diffusion.py:575
+                continue
+            used.append(i)
+            cnt.append(float(size))
+            div.append(float(n_o[i]))  # diffusion.py:598: n_o is NOT strided by sub_sample_dt
+        if used:
+            sums = self._self_sums(np.array(used), self._mask)
+            self._finish(used, sums, cnt, div, sums, cnt)
+        else:
+            self._finish(used, None, cnt, div, None, cnt)
+
+
+class _CollectiveBootstrap(Bootstrap):
+    """Shared body of MSTDBootstrap (kinisi/diffusion.py:636-688) and MSCDBootstrap (:723-780)."""
+
+    def _run(self, n_o, weights, coll_mask):
+        n_atoms = self._n_atoms()
+        used, m, div, gcnt = [], [], [], []
+        for i in range(int(len(self._displacements) / 2)):  # diffusion.py:650, 738: first half of the grid
+            shp = self._shape_of(i)
+            if shp[1] <= 1:  # coll_motion.size <= 1
+                continue
+            n_local = shp[0] if not self._lazy else n_atoms
+            used.append(i)
+            m.append(float(shp[1]))
+            div.append(float(n_o[i]) / n_local)  # diffusion.py:684, 776
+            gcnt.append(float(n_local * shp[1]))
+        if used:
+            u = np.array(used)
+            self_sums = self._self_sums(u, self._mask)
+            coll = self._collective_sums(u, weights, coll_mask)
+            self._finish(used, coll, m, div, self_sums, gcnt)
+        else:
+            self._finish(used, None, m, div, None, gcnt)
+
+
+class MSTDBootstrap(_CollectiveBootstrap):
+    """
+    Mean and uncertainty of the total (collective) mean squared displacements
+    (kinisi/diffusion.py:605-688).  Only the first half of the time intervals is used (:650).
+    """
+
+    def __init__(self,
+                 delta_t: np.ndarray,
+                 disp_3d,
+                 n_o: np.ndarray,
+                 sub_sample_dt: int = 1,
+                 bootstrap: bool = False,
+                 block: bool = False,
+                 n_resamples: int = 1000,
+                 max_resamples: int = 10000,
+                 dimension: str = 'xyz',
+                 alpha: float = 1e-3,
+                 random_state: np.random.mtrand.RandomState = None,
+                 progress: bool = True):
+        super().__init__(delta_t, disp_3d, n_o, sub_sample_dt, dimension)
+        self._reject_unsupported(bootstrap, block)
+        self._run(n_o, None, self._mask)
+
+
+class MSCDBootstrap(_CollectiveBootstrap):
+    """
+    Mean and uncertainty of the mean squared charge displacements (kinisi/diffusion.py:691-780).
+
+    :param ionic_charge: The charge on the mobile ions, either an array with a value for each ion or a
+        scalar if all values are the same.
+    The charged sum uses all three components whatever `dimension` says, as the reference does (:751).
+    """
+
+    def __init__(self,
+                 delta_t: np.ndarray,
+                 disp_3d,
+                 ionic_charge: Union[np.ndarray, int],
+                 n_o: np.ndarray,
+                 sub_sample_dt: int = 1,
+                 bootstrap: bool = False,
+                 block: bool = False,
+                 n_resamples: int = 1000,
+                 max_resamples: int = 10000,
+                 dimension: str = 'xyz',
+                 alpha: float = 1e-3,
+                 random_state: np.random.mtrand.RandomState = None,
+                 progress: bool = True):
+        super().__init__(delta_t, disp_3d, n_o, sub_sample_dt, dimension)
+        self._reject_unsupported(bootstrap, block)
+        try:
+            _ = len(ionic_charge)
+            ionic_charge = np.asarray(ionic_charge, dtype=np.float64)
+        except TypeError:
+            n_local = self._displacements.dc.shape[0] if self._lazy else self._shape_of(0)[0]
+            ionic_charge = np.ones(n_local) * ionic_charge
+        self._run(n_o, ionic_charge, 7)

@@ -1,0 +1,228 @@
+"""
+Thin wrappers that call the C ABI (include/kinisi_b200.h) on PyTorch CUDA tensors.  PyTorch is only the
+carrier of device memory and streams here; every function below enqueues hand-written sm_100a kernels
+on torch's current stream and returns without synchronising.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F32, F64, MODE_DISPLACEMENT, MODE_FRACTIONAL, check
+
+DIM_MASK = {'x': 1, 'y': 2, 'z': 4, 'xy': 3, 'xz': 5, 'yz': 6, 'xyz': 7}
+
+# self-moment kernel variants (kb2_self_moments `variant`)
+VARIANT_DIRECT = 0
+VARIANT_TMA = 1
+DEFAULT_VARIANT = VARIANT_TMA
+
+# count of kernel launches issued through this module (bench.py reports it as gpu_launches)
+LAUNCHES = {'n': 0}
+
+
+def _count(n=1):
+    LAUNCHES['n'] += n
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError('kinisi_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.')
+    return _lib.load()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def dim_mask(dimension):
+    if isinstance(dimension, bytes):
+        dimension = dimension.decode()
+    return DIM_MASK[dimension.lower()]
+
+
+def pitch_for(n_frames):
+    """Row pitch (in float64 elements) of the component-major displacement array: a multiple of 16."""
+    return (int(n_frames) + 15) // 16 * 16
+
+
+def coords_dtype_code(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise TypeError(f'coordinates must be float32 or float64, got {t.dtype}')
+
+
+def invert_lattice(latt):
+    lib = require_cuda()
+    latt = latt.contiguous()
+    inv = torch.empty_like(latt)
+    check(lib.kb2_invert_lattice(latt.data_ptr(), inv.data_ptr(), latt.shape[0], _stream()), 'kb2_invert_lattice')
+    _count()
+    return inv
+
+
+def frame_sums(coords, mode, latt, latt_inv, latt_stride, idx, weights, pitch):
+    """[3, pitch] per-frame (weighted) sums over the atoms in idx; see kb2_frame_sums."""
+    lib = require_cuda()
+    out = torch.empty((3, pitch), dtype=torch.float64, device=coords.device)
+    check(
+        lib.kb2_frame_sums(coords.data_ptr(), coords_dtype_code(coords), mode, coords.shape[0], coords.shape[1],
+                           _ptr(latt), _ptr(latt_inv), latt_stride, idx.data_ptr(), _ptr(weights), idx.numel(),
+                           out.data_ptr(), pitch, _stream()), 'kb2_frame_sums')
+    _count(2)
+    return out
+
+
+def scan_frames(buf, n_frames, cumulative, divide, sub=None, sub_scale=0.0):
+    lib = require_cuda()
+    check(
+        lib.kb2_scan_frames(buf.data_ptr(), n_frames, buf.shape[1], int(bool(cumulative)), float(divide), _ptr(sub),
+                            float(sub_scale), _stream()), 'kb2_scan_frames')
+    _count()
+    return buf
+
+
+def unwrap_cumsum(coords, mode, latt, latt_inv, latt_stride, idx, drift, pitch):
+    """dc [n_idx, 3, pitch] float64 component-major, drift-corrected; see kb2_unwrap_cumsum."""
+    lib = require_cuda()
+    out = torch.empty((idx.numel(), 3, pitch), dtype=torch.float64, device=coords.device)
+    check(
+        lib.kb2_unwrap_cumsum(coords.data_ptr(), coords_dtype_code(coords), mode, coords.shape[0], coords.shape[1],
+                              _ptr(latt), _ptr(latt_inv), latt_stride, idx.data_ptr(), idx.numel(), _ptr(drift),
+                              out.data_ptr(), pitch, _stream()), 'kb2_unwrap_cumsum')
+    _count()
+    return out
+
+
+def atom_sum(dc, weights=None):
+    """[3, pitch] (weighted) sum over atoms of a component-major displacement array; see kb2_atom_sum."""
+    lib = require_cuda()
+    out = torch.empty((3, dc.shape[2]), dtype=torch.float64, device=dc.device)
+    check(lib.kb2_atom_sum(dc.data_ptr(), dc.shape[0], dc.shape[2], _ptr(weights), out.data_ptr(), _stream()),
+          'kb2_atom_sum')
+    _count(2)
+    return out
+
+
+def self_moments(dc, n_frames, lags, mask=7, variant=None):
+    """sums [K, 2] = (sum d^2, sum d^4) per lag over atoms x observations; see kb2_self_moments.
+
+    dc: [n_atoms, 3, pitch] float64; lags: int32 device tensor, ascending."""
+    lib = require_cuda()
+    if variant is None:
+        variant = DEFAULT_VARIANT
+    K = lags.numel()
+    ws = torch.empty(lib.kb2_self_moments_workspace_bytes(K), dtype=torch.uint8, device=dc.device)
+    sums = torch.empty((K, 2), dtype=torch.float64, device=dc.device)
+    check(
+        lib.kb2_self_moments(dc.data_ptr(), dc.shape[0], n_frames, dc.shape[2], lags.data_ptr(), K, mask, variant,
+                             ws.data_ptr(), sums.data_ptr(), _stream()), 'kb2_self_moments')
+    _count(3 * ((K + 767) // 768))
+    return sums
+
+
+def disp_moments(disp, mask=7, weights=None, coll_mask=0):
+    """[4] = sum d^2, sum d^4, sum c, sum c^2 of one materialised displacement array [N, M, 3]."""
+    lib = require_cuda()
+    out = torch.empty(4, dtype=torch.float64, device=disp.device)
+    check(
+        lib.kb2_disp_moments(disp.data_ptr(), disp.shape[0], disp.shape[1], mask, _ptr(weights), coll_mask,
+                             out.data_ptr(), _stream()), 'kb2_disp_moments')
+    _count(3 if coll_mask else 2)
+    return out
+
+
+def moment_stats(main_sums, cnt, divisor, ngp_sums, gcnt):
+    lib = require_cuda()
+    n = cnt.numel()
+    out = torch.empty((4, n), dtype=torch.float64, device=cnt.device)
+    check(
+        lib.kb2_moment_stats(main_sums.data_ptr(), cnt.data_ptr(), divisor.data_ptr(), ngp_sums.data_ptr(),
+                             gcnt.data_ptr(), n, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                             out[3].data_ptr(), _stream()), 'kb2_moment_stats')
+    _count()
+    return out
+
+
+def cov_build(v, n_o):
+    lib = require_cuda()
+    n = v.numel()
+    cov = torch.empty((n, n), dtype=torch.float64, device=v.device)
+    check(lib.kb2_cov_build(v.data_ptr(), n_o.data_ptr(), n, cov.data_ptr(), _stream()), 'kb2_cov_build')
+    _count()
+    return cov
+
+
+def gls_prepare(evals, evecs, x, y, fit_intercept=True):
+    lib = require_cuda()
+    n = evals.numel()
+    evecs = evecs.contiguous()
+    proj = torch.empty((4, n), dtype=torch.float64, device=evals.device)
+    theta = torch.empty(2, dtype=torch.float64, device=evals.device)
+    check(
+        lib.kb2_gls_prepare(evals.data_ptr(), evecs.data_ptr(), x.data_ptr(), y.data_ptr(), n, int(bool(fit_intercept)),
+                            proj.data_ptr(), theta.data_ptr(), _stream()), 'kb2_gls_prepare')
+    _count(2)
+    return proj, theta
+
+
+def mvn_loglike(theta, proj, logdet_term):
+    lib = require_cuda()
+    theta = theta.contiguous()
+    W, ndim = theta.shape
+    out = torch.empty(W, dtype=torch.float64, device=theta.device)
+    check(
+        lib.kb2_mvn_loglike(theta.data_ptr(), W, ndim, proj.data_ptr(), proj.shape[1], logdet_term.data_ptr(),
+                            out.data_ptr(), _stream()), 'kb2_mvn_loglike')
+    _count()
+    return out
+
+
+def ensemble_sample(theta_ml, ndim, n_walkers, n_steps, proj, logdet_term, seed):
+    lib = require_cuda()
+    dev = proj.device
+    ws = torch.empty(lib.kb2_sampler_workspace_bytes(n_steps, n_walkers), dtype=torch.uint8, device=dev)
+    chain = torch.empty((n_steps, n_walkers, ndim), dtype=torch.float64, device=dev)
+    logp = torch.empty((n_steps, n_walkers), dtype=torch.float64, device=dev)
+    check(
+        lib.kb2_ensemble_sample(theta_ml.data_ptr(), ndim, n_walkers, n_steps, proj.data_ptr(), proj.shape[1],
+                                logdet_term.data_ptr(), int(seed) & 0xFFFFFFFFFFFFFFFF, ws.data_ptr(),
+                                chain.data_ptr(), logp.data_ptr(), _stream()), 'kb2_ensemble_sample')
+    _count(3)
+    return chain, logp
+
+
+def fp64_peak(grid, iters, sink):
+    lib = require_cuda()
+    check(lib.kb2_fp64_peak(grid, iters, sink.data_ptr(), _stream()), 'kb2_fp64_peak')
+    _count()
+
+
+def stream_copy(src, dst):
+    lib = require_cuda()
+    check(lib.kb2_stream_copy(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), 'kb2_stream_copy')
+    _count()
+
+
+def device_info():
+    lib = require_cuda()
+    import ctypes
+    vals = [ctypes.c_int(0) for _ in range(4)]
+    check(lib.kb2_device_info(*[ctypes.byref(v) for v in vals]), 'kb2_device_info')
+    return {'sm_count': vals[0].value, 'max_smem_optin': vals[1].value, 'cc': (vals[2].value, vals[3].value)}
+
+
+def to_device(a, device, dtype=None):
+    """numpy / torch -> contiguous CUDA tensor (float32 stays float32 unless dtype is given)."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(device, non_blocking=True).contiguous()

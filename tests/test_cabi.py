@@ -1,0 +1,84 @@
+"""The C-ABI shared library builds for sm_100a without a GPU, loads, and exports every symbol that
+include/kinisi_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib_path():
+    from kinisi_b200 import _build
+    return _build.build(force=False)
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'kinisi_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(kb2_\w+)\s*\(', text)))
+
+
+def test_header_symbols_are_exported(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    names = declared_symbols()
+    assert len(names) >= 19
+    for name in names:
+        assert hasattr(lib, name), f'{name} is declared in include/kinisi_b200.h but not exported'
+
+
+def test_bindings_cover_the_header(lib_path):
+    from kinisi_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    lib = _lib.load()
+    assert lib.kb2_abi_version() == _lib.ABI_VERSION
+    assert lib.kb2_self_moments_workspace_bytes(100) > 0
+    assert lib.kb2_sampler_workspace_bytes(1500, 32) > 1500 * 32 * 28
+
+
+def test_argument_errors_are_reported_without_a_gpu(lib_path):
+    """Argument validation happens before any CUDA call, with a message through kb2_last_error()."""
+    from kinisi_b200 import _lib
+    lib = _lib.load()
+    rc = lib.kb2_cov_build(None, None, 0, None, None)
+    assert rc != 0 and b'kb2_cov_build' in lib.kb2_last_error()
+    rc = lib.kb2_self_moments(None, 1, 1, 2, None, 1, 7, 0, None, None, None)
+    assert rc != 0 and b'null pointer' in lib.kb2_last_error()
+
+
+def test_sass_has_tma_and_fp64(lib_path):
+    """The TMA variant really uses the bulk-copy engine (UBLKCP) and the moment kernels are FP64."""
+    cuobjdump = '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run([cuobjdump, '-sass', lib_path], capture_output=True, text=True).stdout
+    assert 'sm_100a' in sass
+    assert 'UBLKCP' in sass and 'SYNCS' in sass
+    assert 'DFMA' in sass
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'kinisi_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert 'oracle' not in src.replace('kinisi_oracle', 'oracle') or 'import' not in [
+                line for line in src.splitlines() if 'oracle' in line and 'import' in line
+            ], fn
+            for line in src.splitlines():
+                assert not (('import' in line) and ('oracle' in line)), f'{fn}: {line}'
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('only meaningful on a box without a GPU')
+    import numpy as np
+    from kinisi_b200 import diffusion, parser
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        parser.Parser(np.zeros((4, 10, 3)), [0, 1], [], 1, 1, progress=False)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        diffusion.MSDBootstrap([1.0], [np.zeros((2, 2, 3))], [1.0])

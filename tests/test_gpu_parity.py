@@ -1,0 +1,394 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs,
+against the golden vectors the unmodified reference produced, and against the reference's own KATs.
+
+Tolerances (BASELINE.json north_star): MSD and variance <= 1e-9 relative, covariance <= 1e-6 relative,
+posterior within Monte-Carlo error."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+
+from duck_atoms import trajectory_from_arrays
+from oracle import kinisi_oracle as ko
+from synth_inputs import (ASE_CASES, CHARGES12, REGRESS_CASES, ase_case_inputs, list_bootstrap_inputs,
+                          parser_random_disp, regress_case_inputs)
+
+RTOL_MOMENT = 1e-9
+
+
+@pytest.fixture(scope='module')
+def kb():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    from kinisi_b200 import analyze, diffusion, engine, parser
+    engine.require_cuda()
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.analyze, ns.diffusion, ns.engine, ns.parser = analyze, diffusion, engine, parser
+    return ns
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + '.npz'))
+
+
+def check_boot(b, g, prefix, rtol=RTOL_MOMENT):
+    np.testing.assert_allclose(b.dt, g[prefix + 'dt'], rtol=1e-14, err_msg=prefix + 'dt')
+    np.testing.assert_allclose(b.n, g[prefix + 'n'], rtol=rtol, err_msg=prefix + 'n')
+    np.testing.assert_allclose(b.v, g[prefix + 'v'], rtol=rtol, err_msg=prefix + 'v')
+    np.testing.assert_allclose(b.s, g[prefix + 's'], rtol=rtol, err_msg=prefix + 's')
+    np.testing.assert_allclose(b.ngp, g[prefix + 'ngp'], rtol=1e-8, atol=1e-10, err_msg=prefix + 'ngp')
+    np.testing.assert_allclose(np.asarray(b._n_o), g[prefix + 'n_o'], rtol=1e-15, err_msg=prefix + 'n_o')
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 1 + 2 against the reference's golden vectors
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('name', list(ASE_CASES))
+def test_ase_parser_and_bootstraps(kb, golden_dir, name, variant):
+    kb.engine.DEFAULT_VARIANT = variant
+    g = load(golden_dir, name)
+    symbols, frac, latt, pp = ase_case_inputs(name)
+    traj = trajectory_from_arrays(symbols, frac, latt)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        p = kb.parser.ASEParser(traj, **pp)
+    np.testing.assert_allclose(p.dc, g['dc'], rtol=1e-11, atol=1e-12)
+    np.testing.assert_array_equal(p.time_intervals, g['time_intervals'])
+    np.testing.assert_allclose(p.delta_t, g['delta_t'], rtol=1e-15)
+    np.testing.assert_allclose(p._n_o, g['n_o'], rtol=1e-15)
+    assert p.volume == pytest.approx(float(g['volume']), rel=1e-12)
+    np.testing.assert_array_equal(np.array(p.disp_3d.shapes), g['disp_shapes'])
+    np.testing.assert_allclose(p.disp_3d[0], g['disp_first'], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(p.disp_3d[len(p.disp_3d) // 2], g['disp_mid'], rtol=1e-10, atol=1e-12)
+    for dim in ('xyz', 'xy', 'z', 'xz'):
+        b = kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, dimension=dim, progress=False)
+        check_boot(b, g, f'msd_{dim}_')
+        b = kb.diffusion.MSTDBootstrap(p.delta_t, p.disp_3d, p._n_o, dimension=dim, progress=False)
+        check_boot(b, g, f'mstd_{dim}_')
+        b = kb.diffusion.MSCDBootstrap(p.delta_t, p.disp_3d, CHARGES12, p._n_o, dimension=dim, progress=False)
+        check_boot(b, g, f'mscd_{dim}_')
+    b = kb.diffusion.MSCDBootstrap(p.delta_t, p.disp_3d, 2, p._n_o, progress=False)
+    check_boot(b, g, 'mscd_scalar2_')
+    b = kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, sub_sample_dt=3, progress=False)
+    np.testing.assert_allclose(b.n, g['msd_sub3_n'], rtol=RTOL_MOMENT)
+    np.testing.assert_allclose(b.v, g['msd_sub3_v'], rtol=RTOL_MOMENT)
+
+
+def test_parser_on_displacement_array(kb, golden_dir):
+    """Mirrors kinisi/tests/test_parser.py:31-67 (Parser fed with a numpy displacement array)."""
+    g = load(golden_dir, 'parser_random')
+    disp = parser_random_disp()
+    p = kb.parser.Parser(disp, np.arange(100), [], 1, 1, progress=False)
+    assert p.delta_t.size == 100
+    assert p.disp_3d.shape_of(0) == (100, 100, 3)
+    np.testing.assert_allclose(p.delta_t, g['lin_delta_t'])
+    np.testing.assert_allclose(p._n_o, g['lin_n_o'])
+    check_boot(kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False), g, 'lin_msd_')
+    p = kb.parser.Parser(disp, np.arange(0, 100, 2), np.arange(1, 100, 2), 0.5, 4, min_dt=10., max_dt=150., n_steps=30,
+                         spacing='logarithmic', progress=False)
+    np.testing.assert_array_equal(p.time_intervals, g['log_intervals'])
+    np.testing.assert_allclose(p.dc, g['log_dc'], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(p._n_o, g['log_n_o'])
+    check_boot(kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False), g, 'log_msd_')
+    # a single atom: the parser drops the tail of the grid (kinisi/parser.py:214-215)
+    p = kb.parser.Parser(disp[:1], np.arange(1), [], 1, 1, n_steps=20, progress=False)
+    np.testing.assert_allclose(p.delta_t, g['one_delta_t'])
+    np.testing.assert_allclose(p._n_o, g['one_n_o'])
+    assert len(p.disp_3d) == g['one_shapes'].shape[0]
+    check_boot(kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False), g, 'one_msd_')
+    np.testing.assert_allclose(kb.parser.Parser.correct_drift(np.arange(1, 100, 2), disp),
+                               ko.correct_drift(np.arange(1, 100, 2), disp), rtol=1e-13, atol=1e-15)
+
+
+def test_list_seam(kb, golden_dir):
+    """The *Bootstrap constructors on materialised lists, as kinisi/tests/test_diffusion.py feeds them."""
+    g = load(golden_dir, 'list_bootstrap')
+    dt, disp_3d, n_o, disp_skip = list_bootstrap_inputs()
+    b = kb.diffusion.MSDBootstrap(dt, disp_3d, n_o, progress=False)
+    assert b.n.shape == (10, ) and b.dt.shape == (10, )
+    check_boot(b, g, 'msd_')
+    np.testing.assert_allclose(b.v, b.s**2, rtol=1e-14)  # test_diffusion.py:147
+    b = kb.diffusion.MSTDBootstrap(dt, disp_3d, n_o, progress=False)
+    assert b.n.shape == (5, )  # half-grid rule, test_diffusion.py:402
+    check_boot(b, g, 'mstd_')
+    b = kb.diffusion.MSCDBootstrap(dt, disp_3d, 1, n_o, progress=False)
+    assert b.n.shape == (5, )
+    check_boot(b, g, 'mscd_')
+    b = kb.diffusion.MSDBootstrap(np.linspace(100, 400, 4), disp_skip, np.ones(4), progress=False)
+    assert b.n.shape == g['skip_msd_n'].shape  # skip rule, test_diffusion.py:228-243
+    check_boot(b, g, 'skip_msd_')
+    assert len(b.euclidian_displacements) == b.n.size
+    assert b.euclidian_displacements[0].size == disp_skip[0].shape[0] * disp_skip[0].shape[1]
+
+
+def test_reference_kats(kb, golden_dir):
+    g = load(golden_dir, 'reference_kats')
+    assert kb.diffusion.Bootstrap.ngp_calculation(np.array([1, 2, 3])) == pytest.approx(-0.3, abs=1e-14)
+    symbols = list(g['drift_symbols'])
+    traj = trajectory_from_arrays(symbols, g['drift_frac'], g['drift_latt'])
+    p = kb.parser.ASEParser(traj, specie='H', time_step=1, step_skip=1, progress=False)
+    np.testing.assert_allclose(p.dc[0], [[0, 0, 0], [0.2, 0.2, 0.2], [0.4, 0.4, 0.4], [1, 1, 1]], atol=1e-12)
+    p = kb.parser.ASEParser(traj, specie='H', time_step=1, step_skip=1, progress=False, framework_indices=[])
+    np.testing.assert_allclose(p.dc[0], g['nodrift_dc0'], atol=1e-12)
+    b = kb.diffusion.MSDBootstrap(np.array([1.0]), [g['docs_disp']], np.array([384.0]), progress=False)
+    assert b.n[0] == pytest.approx(5.1108279, rel=1e-7)
+    assert b.v[0] == pytest.approx(0.0911415, rel=1e-6)
+    assert b.ngp[0] == pytest.approx(0.4038798, rel=1e-6)
+    assert b.n[0] == pytest.approx(float(g['docs_msd']), rel=1e-12)
+    # the real Li6PS5Cl-like XDATCAR of kinisi/tests/test_analyze.py:92-98, float32 coordinates
+    symbols = list(g['lips_symbols'])
+    latt = np.tile(g['lips_latt'], (140, 1, 1))
+    traj = trajectory_from_arrays(symbols, g['lips_frac'].astype(np.float64), latt)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        an = kb.analyze.DiffusionAnalyzer.from_ase(traj, parser_params=dict(specie='Li', time_step=2.0, step_skip=50,
+                                                                            progress=False))
+    assert an._disp_3d.shape_of(0) == (192, 140, 3) and an._disp_3d.shape_of(len(an._disp_3d) - 1) == (192, 1, 3)
+    assert an._delta_t.max() == 14000.0
+    check_boot(an._diff, g, 'lips_msd_')
+
+
+# ---------------------------------------------------------------------------------------------
+# the moment kernels against the oracle's raw sums: tiles, partial tiles, both variants, f32 input
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('variant', [0, 0 | (16 << 8), 1])
+@pytest.mark.parametrize('dimension', ['xyz', 'xz', 'y'])
+def test_self_moment_kernels_raw_sums(kb, variant, dimension):
+    n_atoms, n_frames = 5, 9300  # > 2 tiles of 4096 and > 4 tiles of 2048, last tile partial
+    frac, latt = ko.synthetic_walk(n_atoms, n_frames, box=11.0, sigma=0.12, seed=21)
+    dc = ko.get_disp(frac, latt)
+    lags = np.unique(np.concatenate([[1, 2, 3, 17, 255, 256, 257, 511, 512, 513, 2047, 2048, 2049, 4095, 4096, 4097],
+                                     np.linspace(1, n_frames, 57, dtype=int),
+                                     [n_frames - 4096, n_frames - 2, n_frames - 1, n_frames]]))
+    S1, S2, _, _ = ko.raw_sums_streaming(dc, lags, dimension)
+    dev = torch.device('cuda')
+    pitch = kb.engine.pitch_for(n_frames)
+    dct = torch.zeros((n_atoms, 3, pitch), dtype=torch.float64, device=dev)
+    dct[:, :, :n_frames] = torch.from_numpy(dc).permute(0, 2, 1).to(dev)
+    sums = kb.engine.self_moments(dct, n_frames, torch.as_tensor(lags.astype(np.int32)).to(dev),
+                                  kb.engine.dim_mask(dimension), variant).cpu().numpy()
+    np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
+    np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
+
+
+@pytest.mark.parametrize('variant', [0, 1])
+def test_long_lag_grid_is_chunked(kb, variant):
+    """More lags than one launch holds in shared memory (every lag of a 1500-frame trajectory)."""
+    n_atoms, n_frames = 3, 1500
+    frac, latt = ko.synthetic_walk(n_atoms, n_frames, box=9.0, sigma=0.2, seed=5)
+    dc = ko.get_disp(frac, latt)
+    lags = np.arange(1, n_frames + 1)
+    S1, S2, _, _ = ko.raw_sums_streaming(dc, lags)
+    dev = torch.device('cuda')
+    pitch = kb.engine.pitch_for(n_frames)
+    dct = torch.zeros((n_atoms, 3, pitch), dtype=torch.float64, device=dev)
+    dct[:, :, :n_frames] = torch.from_numpy(dc).permute(0, 2, 1).to(dev)
+    sums = kb.engine.self_moments(dct, n_frames, torch.as_tensor(lags.astype(np.int32)).to(dev), 7, variant).cpu().numpy()
+    np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
+    np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
+
+
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_stage1_dtypes_and_collective(kb, dtype):
+    """float32 / float64 wrapped coordinates, framework drift, collective and charge-weighted sums."""
+    n_mobile, n_fw, n_frames = 40, 24, 3000
+    frac, latt = ko.synthetic_walk(n_mobile, n_frames, box=14.0, sigma=0.1, seed=33, n_framework=n_fw, dtype=dtype)
+    idx, fw = list(range(n_mobile)), list(range(n_mobile, n_mobile + n_fw))
+    parsed = ko.parse(ko.get_disp(frac.astype(np.float64), latt), idx, fw, 0.002, 2, n_steps=64)
+    traj = kb.parser.Parser.get_disp(frac, latt)
+    p = kb.parser.Parser(traj, idx, fw, 0.002, 2, n_steps=64, progress=False)
+    np.testing.assert_allclose(p.dc, parsed['dc'], rtol=1e-11, atol=1e-11)
+    q = np.where(np.arange(n_mobile) % 3 == 0, -2.0, 1.0)
+    for kind, cls, args in (('msd', kb.diffusion.MSDBootstrap, ()), ('mstd', kb.diffusion.MSTDBootstrap, ()),
+                            ('mscd', kb.diffusion.MSCDBootstrap, (q, ))):
+        b = cls(p.delta_t, p.disp_3d, *args, p._n_o, progress=False)
+        ref = ko.bootstrap_streaming(parsed, kind, q if kind == 'mscd' else None)
+        for key in ('dt', 'n', 'v', 's'):
+            np.testing.assert_allclose(getattr(b, key), ref[key], rtol=RTOL_MOMENT, err_msg=f'{kind} {key}')
+        np.testing.assert_allclose(b.ngp, ref['ngp'], rtol=1e-8, atol=1e-10)
+
+
+def test_identical_trajectories_stack(kb):
+    """dtype='identical' (kinisi/analyzer.py:111-116, 274-290): more atoms, n_o summed."""
+    symbols = ['Li'] * 6 + ['O'] * 3
+    trajs, parsed = [], []
+    for seed in (1, 2):
+        frac, latt = ko.synthetic_walk(6, 400, box=8.0, sigma=0.15, seed=seed, n_framework=3)
+        trajs.append(trajectory_from_arrays(symbols, frac[:, 1:], latt[1:]))
+        parsed.append(ko.parse(ko.get_disp(frac, latt), list(range(6)), [6, 7, 8], 0.001, 1, n_steps=30))
+    pp = dict(specie='Li', time_step=0.001, step_skip=1, n_steps=30, progress=False)
+    an = kb.analyze.DiffusionAnalyzer.from_ase(trajs, parser_params=pp, dtype='identical')
+    joint = dict(parsed[0])
+    joint['dc_sel'] = np.concatenate([parsed[0]['dc_sel'], parsed[1]['dc_sel']], axis=0)
+    joint['n_o'] = parsed[0]['n_o'] + parsed[1]['n_o']
+    ref = ko.bootstrap_streaming(joint, 'msd')
+    assert an._disp_3d.shape_of(0)[0] == 12
+    np.testing.assert_allclose(an.msd, ref['n'], rtol=RTOL_MOMENT)
+    np.testing.assert_allclose(an._diff.v, ref['v'], rtol=RTOL_MOMENT)
+    an2 = kb.analyze.DiffusionAnalyzer.from_ase(trajs, parser_params=pp, dtype='consecutive')
+    assert an2._disp_3d.n_frames == 800
+    with pytest.raises(ValueError):
+        kb.analyze.DiffusionAnalyzer.from_ase(trajs, parser_params=pp, dtype='nonsense')
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 3
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', list(REGRESS_CASES))
+def test_covariance_likelihood_and_posterior(kb, golden_dir, name):
+    g = load(golden_dir, name)
+    symbols, frac, latt, pp, start_idx, kind = regress_case_inputs(name)
+    traj = trajectory_from_arrays(symbols, frac, latt)
+    cls = {'msd': kb.analyze.DiffusionAnalyzer, 'mstd': kb.analyze.JumpDiffusionAnalyzer,
+           'mscd': kb.analyze.ConductivityAnalyzer}[kind]
+    an = cls.from_ase(traj, parser_params=pp, uncertainty_params={'progress': False})
+    check_boot(an._diff, g, '')
+    start_dt = float(g['start_dt'])
+    kw = {'progress': False, 'random_state': np.random.RandomState(3)}
+    if kind == 'msd':
+        an.diffusion(start_dt, kw)
+        coeff = an.D
+    elif kind == 'mstd':
+        an.jump_diffusion(start_dt, kw)
+        coeff = an.D_J
+    else:
+        an.conductivity(start_dt, 500.0, kw)
+        coeff = an.sigma
+    b = an._diff
+    # covariance: <= 1e-6 relative (entries are all of the order of the variances)
+    scale = np.abs(g['covariance_matrix']).max()
+    np.testing.assert_allclose(b._npd_covariance_matrix, g['npd_covariance_matrix'], rtol=1e-9)
+    np.testing.assert_allclose(b.covariance_matrix, g['covariance_matrix'], rtol=1e-6, atol=1e-9 * scale)
+    assert b.covariance_matrix.shape == g['covariance_matrix'].shape
+    # log-likelihood: the reference's logdet of a matrix pinned at condition number 1e16 is not
+    # reproducible across LAPACK builds, so values are compared up to that additive constant
+    ll = b.log_likelihood(g['thetas'])
+    assert ll[-1] == -np.inf and g['loglike'][-1] == -np.inf
+    d_mine = ll[1:-1] - ll[0]
+    d_ref = g['loglike'][1:-1] - g['loglike'][0]
+    np.testing.assert_allclose(d_mine, d_ref, rtol=1e-5, atol=1e-5)
+    # flat chain layout (kinisi/tests/test_diffusion.py:280) and the posterior against the closed form
+    assert an.flatchain.shape == (3200, 2)
+    dr = int(np.argwhere(b.dt >= start_dt)[0][0])
+    _, _, inv = ko.make_log_likelihood(b.dt[dr:], b.n[dr:], g['covariance_matrix'])
+    mean, cov_theta = ko.gls_posterior(b.dt[dr:], b.n[dr:], inv)
+    sd = np.sqrt(np.diag(cov_theta))
+    grad, icpt = b.gradient.samples, b.intercept.samples
+    # Monte-Carlo error of the mean of ~3200 correlated draws: allow 0.25 sigma; widths within 15 %
+    assert abs(grad.mean() - mean[0]) < 0.25 * sd[0]
+    assert abs(icpt.mean() - mean[1]) < 0.25 * sd[1]
+    assert grad.std() == pytest.approx(sd[0], rel=0.15)
+    assert icpt.std() == pytest.approx(sd[1], rel=0.15)
+    # ... and against the reference's own draws (emcee stand-in, 640 samples)
+    ref_grad = g['gradient_samples']
+    assert abs(np.median(grad) - np.median(ref_grad)) < 0.35 * sd[0]
+    lo, hi = np.percentile(grad, [2.5, 97.5])
+    rlo, rhi = np.percentile(ref_grad, [2.5, 97.5])
+    assert abs(lo - rlo) < 0.6 * sd[0] and abs(hi - rhi) < 0.6 * sd[0]
+    # unit conversions (kinisi/diffusion.py:436, 456-457, 479-482)
+    if kind == 'msd':
+        np.testing.assert_allclose(coeff.samples, ko.diffusion_coefficient(grad, 3), rtol=1e-14)
+    elif kind == 'mstd':
+        np.testing.assert_allclose(coeff.samples, ko.jump_diffusion_coefficient(grad, 3, 32), rtol=1e-14)
+    else:
+        np.testing.assert_allclose(coeff.samples, ko.conductivity(grad, 3, an.volume, 500.0), rtol=1e-14)
+    assert an.distribution.shape == (b.dt.size, 3200)
+    ppd = an.posterior_predictive({'n_posterior_samples': 16, 'n_predictive_samples': 8, 'progress': False})
+    assert ppd.shape == (128, b.dt.size - dr)
+
+
+def test_sampler_sizes_and_options(kb):
+    """Output sizes as pinned by kinisi/tests/test_diffusion.py:280, 318, 331, 357."""
+    dt, disp_3d, n_o, _ = list_bootstrap_inputs()
+    b = kb.diffusion.MSDBootstrap(dt, disp_3d, n_o, progress=False)
+    b.diffusion(0, progress=False)
+    assert b.covariance_matrix.shape == (10, 10) and b.gradient.size == 3200 and b.intercept.size == 3200
+    assert b.D.size == 3200
+    b.diffusion(0, thin=1, progress=False)
+    assert b.gradient.size == 32000
+    b.diffusion(0, n_samples=100, fit_intercept=False, progress=False)
+    assert b.gradient.size == 320 and b.intercept is None
+    b.diffusion(0, n_walkers=16, progress=False)
+    assert b.gradient.size == 1600
+    b.diffusion(400, progress=False)
+    assert b.covariance_matrix.shape == (7, 7)  # start_dt, test_diffusion.py:290
+    with pytest.raises(IndexError):
+        b.diffusion(1e9, progress=False)
+    assert np.all(b.gradient.samples >= 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# error behaviour of the boundary
+# ---------------------------------------------------------------------------------------------
+def test_errors(kb):
+    disp = parser_random_disp()
+    with pytest.raises(ValueError):
+        kb.parser.Parser(disp, np.arange(100), [], 1, 1, min_dt=100, progress=False)
+    with pytest.raises(ValueError):
+        kb.parser.Parser(disp, np.arange(100), [], 1, 1, spacing='cubic', progress=False)
+    with pytest.raises(ValueError):
+        kb.parser.Parser(disp, np.arange(100), [], 1, 1, sampling='all-origins', progress=False)
+    with pytest.raises(MemoryError):
+        kb.parser.Parser(disp, np.arange(100), [], 1, 1, memory_limit=1e-9, progress=False)
+    symbols, frac, latt, pp = ase_case_inputs('ase_nvt')
+    traj = trajectory_from_arrays(symbols, frac, latt)
+    with pytest.raises(ValueError):
+        kb.parser.ASEParser(traj, specie='Na', time_step=1, step_skip=1, progress=False)
+    with pytest.raises(TypeError):
+        kb.parser.ASEParser(traj, specie=None, time_step=1, step_skip=1, progress=False)
+    with pytest.warns(UserWarning):
+        s2, f2, l2, pp2 = ase_case_inputs('ase_npt_triclinic')
+        kb.parser.ASEParser(trajectory_from_arrays(s2, f2, l2), **pp2)
+    p = kb.parser.Parser(disp, np.arange(100), [], 1, 1, sampling='single-origin', progress=False)
+    b = kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False)
+    ref = np.array([np.mean(np.sum(disp[:, i]**2, axis=-1)) for i in range(b.n.size)])
+    np.testing.assert_allclose(b.n, ref, rtol=1e-12)  # single-origin takes frame i (kinisi/parser.py:203)
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[1]): no oracle at this size, so size-independent checks
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties(kb):
+    n_atoms, n_frames = 448, 20000
+    dev = torch.device('cuda')
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1002)
+    steps = torch.randn((n_atoms, 3, n_frames), dtype=torch.float64, device=dev, generator=gen) * 0.1
+    steps[:, :, 0] = 0
+    pitch = kb.engine.pitch_for(n_frames)
+    dc = torch.zeros((n_atoms, 3, pitch), dtype=torch.float64, device=dev)
+    dc[:, :, :n_frames] = torch.cumsum(steps, dim=2)
+    lags = np.linspace(1, n_frames, 100, dtype=int)
+    lt = torch.as_tensor(lags.astype(np.int32)).to(dev)
+    a = kb.engine.self_moments(dc, n_frames, lt, 7, 0).cpu().numpy()
+    b = kb.engine.self_moments(dc, n_frames, lt, 7, 1).cpu().numpy()
+    np.testing.assert_allclose(a, b, rtol=1e-12)  # the two kernel variants agree
+    # scaling: positions x 2 -> sums x 4 and x 16 (exact in binary floating point)
+    c = kb.engine.self_moments(dc * 2.0, n_frames, lt, 7, 1).cpu().numpy()
+    # (exact per term; the reduction order differs from launch to launch, hence a tolerance)
+    np.testing.assert_allclose(c[:, 0], 4.0 * b[:, 0], rtol=1e-13)
+    np.testing.assert_allclose(c[:, 1], 16.0 * b[:, 1], rtol=1e-13)
+    # components add up: sum d^2 over xyz = x + y + z
+    parts = sum(kb.engine.self_moments(dc, n_frames, lt, m, 1).cpu().numpy()[:, 0] for m in (1, 2, 4))
+    np.testing.assert_allclose(parts, b[:, 0], rtol=1e-12)
+    # atoms are independent: halves add up
+    h1 = kb.engine.self_moments(dc[:224].contiguous(), n_frames, lt, 7, 1).cpu().numpy()
+    h2 = kb.engine.self_moments(dc[224:].contiguous(), n_frames, lt, 7, 1).cpu().numpy()
+    np.testing.assert_allclose(h1 + h2, b, rtol=1e-12)
+    # a Gaussian walk: MSD slope 3 sigma^2 per frame, NGP -> 0 at short lags
+    cnt = n_atoms * (n_frames - lags + 1.0)
+    msd = b[:, 0] / cnt
+    short = lags < 2500
+    slope = np.polyfit(lags[short], msd[short], 1)[0]
+    assert slope == pytest.approx(3 * 0.1**2, rel=0.05)
+    ngp = 3 * (b[:, 1] / cnt) / (5 * msd**2) - 1
+    assert np.all(np.abs(ngp[short][1:]) < 0.05)
