@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""
+bench.py -- one JSON line for the displacement-statistics hot path.
+
+A "step" is one pass of the hot path over one synthetic trajectory: stage 1 (unwrap + cumulative sum +
+framework drift), stage 2 (MSD moments over atoms x time origins x dt) and stage 3 (covariance build,
+reconditioning, log-likelihood factor, 1500-step x 32-walker ensemble MCMC -> D).
+
+Workload at N=1: BASELINE.json configs[1] -- LLZO-like cell, 1,536 atoms (448 Li) x 20,000 steps,
+100 time intervals, MSD + covariance + D.  With N>1 every rank gets a cell of that size (atoms are
+sharded, weak scaling); the per-frame framework sums and the per-dt moment sums are all-reduced.
+
+  python bench.py --gpus N --steps K --warmup W            (own arm; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  (the reference's CPU algorithm, oracle port)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG = dict(n_mobile=448, n_framework=1088, n_frames=20000, box=26.0, sigma=0.1, n_steps=100, time_step=0.001,
+           step_skip=1, start_idx=10, seed=1002)
+METRIC = 'displacement terms/s (atom*origin*dt), MSD+cov+D per trajectory'
+UNIT = 'terms/s'
+WORKLOAD = 'configs[1]: LLZO-like 1536 atoms (448 Li) x 20000 steps, 100 dt, MSD+covariance+emcee D'
+
+
+def lag_grid(n_frames, n_steps):
+    return np.linspace(1, n_frames, n_steps, dtype=int)
+
+
+def n_terms(n_atoms, n_frames, lags):
+    """terms = N_sel * sum_k (T - k + 1), the first-observation term included."""
+    return int(n_atoms * np.sum(n_frames - lags + 1))
+
+
+def make_inputs(seed, n_mobile, n_framework, n_frames, box, sigma, dtype=np.float32):
+    """Seeded 3-D Gaussian random walk stored WRAPPED as fractional coordinates [N_all, T+1, 3]
+    (frame 0 duplicated as the reference's front-ends do, kinisi/parser.py:323-324) in a cubic cell;
+    framework atoms jitter about fixed sites and share a slow common drift."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n_all = n_mobile + n_framework
+    frac = np.empty((n_all, n_frames + 1, 3), dtype=dtype)
+    start = rng.uniform(0, box, size=(n_all, 1, 3))
+    chunk = 64
+    for a0 in range(0, n_mobile, chunk):
+        a1 = min(n_mobile, a0 + chunk)
+        steps = rng.normal(0.0, sigma, size=(a1 - a0, n_frames, 3))
+        steps[:, 0] = 0.0
+        pos = start[a0:a1] + np.cumsum(steps, axis=1)
+        frac[a0:a1, 1:] = (pos / box) % 1.0
+    drift = 0.01 * sigma * np.arange(n_frames)[None, :, None]
+    for a0 in range(n_mobile, n_all, chunk):
+        a1 = min(n_all, a0 + chunk)
+        pos = start[a0:a1] + rng.normal(0.0, 0.05, size=(a1 - a0, n_frames, 3)) + drift
+        frac[a0:a1, 1:] = (pos / box) % 1.0
+    frac[:, 0] = frac[:, 1]
+    latt = (np.eye(3) * box)[None]
+    return frac, latt
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline: the oracle port (the reference is pure Python; it cannot travel)
+# ------------------------------------------------------------------------------------------------
+def _cpu_shard_sums(args):
+    from oracle import kinisi_oracle as ko
+    dc_sel, lags = args
+    S1, S2, _, _ = ko.raw_sums_streaming(dc_sel, lags)
+    return S1, S2
+
+
+def cpu_pass(frac, latt, n_mobile, n_framework, lags_cfg, pool=None, n_shards=1):
+    """One pass of the reference's algorithm (oracle port) on the host.  Returns (terms, seconds)."""
+    from oracle import kinisi_oracle as ko
+    t0 = time.perf_counter()
+    latt_full = np.broadcast_to(latt, (frac.shape[1], 3, 3))
+    dc = ko.get_disp(frac.astype(np.float64), latt_full)
+    idx = list(range(n_mobile))
+    fw = list(range(n_mobile, n_mobile + n_framework))
+    parsed = ko.parse(dc, idx, fw, CFG['time_step'], CFG['step_skip'], n_steps=lags_cfg)
+    if pool is None:
+        stats = ko.bootstrap_streaming(parsed, 'msd')
+    else:
+        bounds = np.linspace(0, n_mobile, n_shards + 1).astype(int)
+        parts = pool.map(_cpu_shard_sums, [(parsed['dc_sel'][bounds[i]:bounds[i + 1]], parsed['lags'])
+                                           for i in range(n_shards) if bounds[i + 1] > bounds[i]])
+        S1 = sum(p[0] for p in parts)
+        S2 = sum(p[1] for p in parts)
+        cnt = n_mobile * (dc.shape[1] - parsed['lags'] + 1.0)
+        n = S1 / cnt
+        v = (S2 - S1 * n) / (cnt - 1) / parsed['n_o']
+        stats = {'dt': parsed['delta_t'][:len(parsed['lags'])], 'n': n, 'v': v, 'n_o': parsed['n_o']}
+    res = ko.bootstrap_gls(stats, stats['dt'][CFG['start_idx']], random_state=np.random.RandomState(1))
+    dt = time.perf_counter() - t0
+    assert np.isfinite(res['gradient']).all()
+    return n_terms(n_mobile, dc.shape[1], parsed['lags']), dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm on all host cores, bounded sample per step."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    n_mob = min(CFG['n_mobile'], 16 * cores)
+    n_fw = 64
+    frac, latt = make_inputs(CFG['seed'], n_mob, n_fw, CFG['n_frames'], CFG['box'], CFG['sigma'])
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_pass(frac, latt, n_mob, n_fw, CFG['n_steps'], pool, cores)
+        t0 = time.perf_counter()
+        terms = 0
+        for _ in range(args.steps):
+            t, _dt = cpu_pass(frac, latt, n_mob, n_fw, CFG['n_steps'], pool, cores)
+            terms += t
+        total = time.perf_counter() - t0
+    value = terms / total
+    sample = (f'{n_mob} of {CFG["n_mobile"]} mobile atoms + {n_fw} framework atoms x {CFG["n_frames"]} frames, '
+              f'{CFG["n_steps"]} dt, full covariance + 1500-step x 32-walker sampler; numpy oracle port of '
+              'kinisi/parser.py + kinisi/diffusion.py, moment sums atom-sharded over a fork pool')
+    line = {
+        'impl': 'reference',
+        'metric': METRIC,
+        'value': value,
+        'unit': UNIT,
+        'n_gpus': args.gpus,
+        'steps': args.steps,
+        'warmup': args.warmup,
+        'ms_per_step': 1e3 * total / args.steps,
+        'higher_is_better': True,
+        'scaling': 'weak',
+        'vs_baseline': None,
+        'dtype': 'f64',
+        'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'l2': 'n/a (host)'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.proc, self.path = None, None
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={self.FIELDS}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(',')]
+                if len(f) < 7:
+                    continue
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                for name, val in zip(names, f[3:7]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if not sm:
+            return None
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def run_own(args):
+    import torch
+    import torch.distributed as td
+    from kinisi_b200 import diffusion, dist, engine
+    from kinisi_b200.parser import Parser
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device; there is no CPU fallback'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        td.init_process_group('nccl', device_id=dev)
+    engine.require_cuda()
+    if args.variant is not None:
+        engine.DEFAULT_VARIANT = args.variant
+
+    n_mob, n_fw, T = CFG['n_mobile'], CFG['n_framework'], CFG['n_frames']
+    frac, latt = make_inputs(CFG['seed'] + rank, n_mob, n_fw, T, CFG['box'], CFG['sigma'])
+    lags = lag_grid(T, CFG['n_steps'])
+    terms_rank = n_terms(n_mob, T, lags)
+    start_dt = float(lags[CFG['start_idx']] * CFG['time_step'] * CFG['step_skip'])
+    idx = np.arange(n_mob)
+    fw = np.arange(n_mob, n_mob + n_fw)
+    host = torch.from_numpy(frac).pin_memory()
+    resident = host.to(dev)
+    pkw = dict(n_steps=CFG['n_steps'], memory_limit=64., progress=False, distributed=world > 1)
+    gkw = dict(progress=False)
+
+    k2_events = []
+    raw_self_moments = engine.self_moments
+
+    def timed_self_moments(dc, n_frames, lg, mask=7, variant=None):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = raw_self_moments(dc, n_frames, lg, mask, variant)
+        e1.record()
+        k2_events.append((e0, e1, dc.shape[0]))
+        return out
+
+    engine.self_moments = timed_self_moments
+
+    def step(coords):
+        traj = Parser.get_disp(coords, latt, progress=False, device=dev)
+        p = Parser(traj, idx, fw, CFG['time_step'], CFG['step_skip'], **pkw)
+        b = diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False)
+        b.diffusion(start_dt, **gkw)  # ends with the device->host read of the flat chain
+        return b
+
+    def timed(coords, steps):
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            b = step(coords)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        if world > 1:
+            td.barrier()
+        ms = e0.elapsed_time(e1)  # device time is the clock; the wall time is reported beside it
+        t = torch.tensor([ms, 1e3 * wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), b
+
+    # warm-up (untimed), both paths
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    step(host)
+    torch.cuda.synchronize()
+
+    # FP64-pipe peak of this device, measured live (16 independent DFMA chains per thread)
+    sink = torch.zeros(1, dtype=torch.float64, device=dev)
+    info = engine.device_info()
+    grid, iters = info['sm_count'] * 8, 4096
+    engine.fp64_peak(grid, 64, sink)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    engine.fp64_peak(grid, iters, sink)
+    e1.record()
+    torch.cuda.synchronize()
+    fp64_peak_tflops = 2.0 * grid * 256 * iters * 16 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+    launches0 = engine.LAUNCHES['n']
+    k2_events.clear()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_total, wall_total, b = timed(resident, args.steps)
+    launches = engine.LAUNCHES['n'] - launches0
+    k2_ms = [a.elapsed_time(z) for a, z, n in k2_events if n == n_mob]
+    e2e_ms, _, b2 = timed(host, args.steps)
+    clocks = sampler.stop() if sampler is not None else None
+
+    value = world * terms_rank * args.steps / (ms_total * 1e-3)
+    e2e_value = world * terms_rank * args.steps / (e2e_ms * 1e-3)
+    h2d = host.numel() * host.element_size() + latt.nbytes + 4 * (n_mob + n_fw) + 8 * (2 * CFG['n_steps'])
+    d2h = b2.flatchain.nbytes
+
+    if rank == 0:
+        k2 = float(np.mean(k2_ms)) if k2_ms else float('nan')
+        achieved = 16.0 * terms_rank / (k2 * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            n_c, n_cf = 96, 64
+            fc, lc = make_inputs(CFG['seed'], n_c, n_cf, T, CFG['box'], CFG['sigma'])
+            t_c, s_c = cpu_pass(fc, lc, n_c, n_cf, CFG['n_steps'])
+            cpu = {'value': t_c / s_c, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                   'sample': f'{n_c} of {n_mob} mobile + {n_cf} framework atoms x {T} frames, {CFG["n_steps"]} dt, '
+                             f'full covariance + sampler; numpy oracle port, {s_c:.1f} s'}
+        line = {
+            'metric': METRIC,
+            'value': value,
+            'unit': UNIT,
+            'n_gpus': world,
+            'steps': args.steps,
+            'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_total / args.steps,
+            'higher_is_better': True,
+            'scaling': 'weak',
+            'vs_baseline': None,
+            'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {
+                'workload': WORKLOAD,
+                'per_gpu': f'{n_mob + n_fw} atoms ({n_mob} mobile) x {T} frames, f32 wrapped fractional coordinates',
+                'sharding': 'atoms' if world > 1 else 'none',
+                'l2': f'inputs ({host.numel() * 4 / 1e6:.0f} MB f32 + {n_mob * 3 * T * 8 / 1e6:.0f} MB f64 per step) '
+                      'exceed the 126 MB L2; no flush needed',
+                'self_moment_variant': 'tma' if engine.DEFAULT_VARIANT == 1 else 'direct',
+                'wall_ms_per_step': wall_total / args.steps,
+            },
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                    'ms_per_step': e2e_ms / args.steps},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+            'roofline': {
+                'kernel': 'self_moments (stage 2)',
+                'bound': 'fp64',
+                'achieved': achieved,
+                'peak': fp64_peak_tflops,
+                'unit': 'TFLOP/s',
+                'frac': achieved / fp64_peak_tflops,
+                'traffic': None,
+                'note': '8 FP64 instructions per term counted as 2 flop each; peak = DFMA micro-benchmark measured '
+                        'in this run (MEASURED_PEAKS.json has no FP64 figure); kernel time = CUDA events on the '
+                        'launching stream inside the timed steps',
+                'kernel_ms': k2,
+                'hbm_gbs_algorithmic': n_mob * 3 * T * 8 / (k2 * 1e-3) / 1e9,
+                'hbm_peak_gbs': peaks.get('hbm_gbs', 6650.0),
+                'hbm_peak_source': 'measured' if 'hbm_gbs' in peaks else 'fallback',
+            },
+            'cpu_baseline': cpu,
+            'result': {'D_median_cm2_s': b.D.n, 'D_ci95': [float(x) for x in b.D.con_int()],
+                       'D_true': 3 * CFG['sigma']**2 / CFG['time_step'] / (2e4 * 3)},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='own', choices=['own', 'reference'])
+    ap.add_argument('--variant', type=int, default=None, help='self-moment kernel: 0 direct, 1 TMA ring')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == '__main__':
+    main()
