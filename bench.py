@@ -46,19 +46,20 @@ def n_terms(n_atoms, n_frames, lags):
 def make_inputs(seed, n_mobile, n_framework, n_frames, box, sigma, dtype=np.float32):
     """Seeded 3-D Gaussian random walk stored WRAPPED as fractional coordinates [N_all, T+1, 3]
     (frame 0 duplicated as the reference's front-ends do, kinisi/parser.py:323-324) in a cubic cell;
-    framework atoms jitter about fixed sites and share a slow common drift."""
+    framework atoms jitter about fixed sites; every atom shares a slow common drift
+    that the framework correction removes."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n_all = n_mobile + n_framework
     frac = np.empty((n_all, n_frames + 1, 3), dtype=dtype)
     start = rng.uniform(0, box, size=(n_all, 1, 3))
     chunk = 64
+    drift = 0.01 * sigma * np.arange(n_frames)[None, :, None]  # whole-cell drift, shared by every atom
     for a0 in range(0, n_mobile, chunk):
         a1 = min(n_mobile, a0 + chunk)
         steps = rng.normal(0.0, sigma, size=(a1 - a0, n_frames, 3))
         steps[:, 0] = 0.0
-        pos = start[a0:a1] + np.cumsum(steps, axis=1)
+        pos = start[a0:a1] + np.cumsum(steps, axis=1) + drift
         frac[a0:a1, 1:] = (pos / box) % 1.0
-    drift = 0.01 * sigma * np.arange(n_frames)[None, :, None]
     for a0 in range(n_mobile, n_all, chunk):
         a1 = min(n_all, a0 + chunk)
         pos = start[a0:a1] + rng.normal(0.0, 0.05, size=(a1 - a0, n_frames, 3)) + drift

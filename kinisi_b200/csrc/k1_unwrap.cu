@@ -20,8 +20,8 @@ __device__ __forceinline__ void load9(const double* __restrict__ p, double (&m)[
 
 // Unwrapped displacement between input frames f-1 and f of one atom (parser.py:122-127):
 //   diff = frac_f @ L_f - frac_{f-1} @ L_{f-1};  u = diff - floor(diff @ L_f^-1 + 1/2) @ L_f
-template <typename T>
-__device__ __forceinline__ void unwrapped_step(const T* __restrict__ cur, const T* __restrict__ prev,
+template <typename T, typename P>
+__device__ __forceinline__ void unwrapped_step(const P& cur, const P& prev,
                                                const double (&Lc)[9], const double (&Lp)[9], const double (&Ic)[9],
                                                double (&u)[3]) {
     const double c0 = (double)cur[0], c1 = (double)cur[1], c2 = (double)cur[2];
@@ -37,6 +37,22 @@ __device__ __forceinline__ void unwrapped_step(const T* __restrict__ cur, const 
     for (int l = 0; l < 3; ++l) img[l] = floor(d[0] * Ic[l] + d[1] * Ic[3 + l] + d[2] * Ic[6 + l] + 0.5);
 #pragma unroll
     for (int l = 0; l < 3; ++l) u[l] = d[l] - (img[0] * Lc[l] + img[1] * Lc[3 + l] + img[2] * Lc[6 + l]);
+}
+
+// The same step when every frame shares one lattice L: diff @ L^-1 is the fractional difference itself,
+// so u = (w - floor(w + 1/2)) @ L with w = frac_f - frac_{f-1} (21 FP64 operations instead of 48, and
+// no lattice traffic).  Differs from the general formula by rounding only.
+template <typename T>
+__device__ __forceinline__ void unwrapped_step_const(const T (&cur)[3], const T (&prev)[3], const double (&L)[9],
+                                                     double (&u)[3]) {
+    double w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double d = (double)cur[k] - (double)prev[k];
+        w[k] = d - floor(d + 0.5);
+    }
+#pragma unroll
+    for (int l = 0; l < 3; ++l) u[l] = w[0] * L[l] + w[1] * L[3 + l] + w[2] * L[6 + l];
 }
 
 __global__ void invert_lattice_kernel(const double* __restrict__ latt, double* __restrict__ inv, int n) {
@@ -62,7 +78,7 @@ __global__ void invert_lattice_kernel(const double* __restrict__ latt, double* _
 // One thread per output frame, looping over a chunk of atoms: per-frame weighted sums of the
 // unwrapped displacement.  The sum over atoms commutes with the cumulative sum over time, so the
 // framework drift and the collective (MSTD/MSCD) sums need no per-atom scan and no per-atom atomics.
-template <typename T, int MODE>
+template <typename T, int MODE, bool CONSTL>
 __global__ void __launch_bounds__(256) frame_sums_kernel(const T* __restrict__ coords, int F,
                                                          const double* __restrict__ latt,
                                                          const double* __restrict__ inv, int lstride,
@@ -77,13 +93,20 @@ __global__ void __launch_bounds__(256) frame_sums_kernel(const T* __restrict__ c
     if (MODE == KB2_MODE_FRACTIONAL) {
         double Lc[9], Lp[9], Ic[9];
         load9(latt + (size_t)(t + 1) * lstride, Lc);
-        load9(latt + (size_t)t * lstride, Lp);
-        load9(inv + (size_t)(t + 1) * lstride, Ic);
+        if (!CONSTL) {
+            load9(latt + (size_t)t * lstride, Lp);
+            load9(inv + (size_t)(t + 1) * lstride, Ic);
+        }
 #pragma unroll 4
         for (int i = i0; i < i1; ++i) {
             const T* base = coords + ((size_t)idx[i] * F + t) * 3;
             double u[3];
-            unwrapped_step<T>(base + 3, base, Lc, Lp, Ic, u);
+            if (CONSTL) {
+                const T cur[3] = {base[3], base[4], base[5]}, prev[3] = {base[0], base[1], base[2]};
+                unwrapped_step_const<T>(cur, prev, Lc, u);
+            } else {
+                unwrapped_step<T>(base + 3, base, Lc, Lp, Ic, u);
+            }
             const double wi = w ? w[i] : 1.0;
             acc[0] += wi * u[0];
             acc[1] += wi * u[1];
@@ -138,14 +161,16 @@ __global__ void __launch_bounds__(1024) scan_frames_kernel(double* __restrict__ 
 }
 
 // A atoms per CTA, one thread per frame of a 256-frame tile, tiles walked in time order with a
-// running carry (no cross-CTA dependency).  The per-frame lattice loads are shared by the A atoms.
-template <typename T, int MODE, int A>
+// running carry (no cross-CTA dependency).  The raw coordinates of the next tile are fetched before
+// the current tile is scanned, so the only serial chain per tile is the scan itself.
+template <typename T, int MODE, int A, bool CONSTL>
 __global__ void __launch_bounds__(256) unwrap_cumsum_kernel(const T* __restrict__ coords, int F,
                                                             const double* __restrict__ latt,
                                                             const double* __restrict__ inv, int lstride,
                                                             const int32_t* __restrict__ idx, int n_idx,
                                                             const double* __restrict__ drift, double* __restrict__ out,
                                                             int64_t pitch, int Tn) {
+    constexpr int NV = (MODE == KB2_MODE_FRACTIONAL) ? 6 : 3;  // raw values per atom and frame
     __shared__ double s_tot[A][3][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g0 = blockIdx.x * A;
@@ -159,15 +184,32 @@ __global__ void __launch_bounds__(256) unwrap_cumsum_kernel(const T* __restrict_
     double carry[A][3];
 #pragma unroll
     for (int a = 0; a < A; ++a) carry[a][0] = carry[a][1] = carry[a][2] = 0.0;
+    double Lconst[9];
+    if (MODE == KB2_MODE_FRACTIONAL && CONSTL) load9(latt, Lconst);
+
+    T raw[A][NV], nxt[A][NV];
+    auto fetch = [&](int64_t t0, T (&dst)[A][NV]) {
+        const int64_t t = t0 + tid;
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                // fractional mode: [0..2] = frame t+1 (current), [3..5] = frame t (previous)
+                const int64_t e = (MODE == KB2_MODE_FRACTIONAL) ? (k < 3 ? (t + 1) * 3 + k : t * 3 + (k - 3)) : t * 3 + k;
+                dst[a][k] = (t < Tn && have[a]) ? base[a][e] : (T)0;
+            }
+    };
+    fetch(0, raw);
 
     for (int64_t t0 = 0; t0 < pitch; t0 += 256) {
         const int64_t t = t0 + tid;
         const bool valid = t < Tn;
+        if (t0 + 256 < Tn) fetch(t0 + 256, nxt);
         double val[A][3];
         if (MODE == KB2_MODE_FRACTIONAL) {
             if (t0 < Tn) {  // block-uniform: tiles that lie entirely in the pad skip the scan
                 double Lc[9], Lp[9], Ic[9];
-                if (valid) {
+                if (!CONSTL && valid) {
                     load9(latt + (size_t)(t + 1) * lstride, Lc);
                     load9(latt + (size_t)t * lstride, Lp);
                     load9(inv + (size_t)(t + 1) * lstride, Ic);
@@ -175,7 +217,12 @@ __global__ void __launch_bounds__(256) unwrap_cumsum_kernel(const T* __restrict_
 #pragma unroll
                 for (int a = 0; a < A; ++a) {
                     if (valid && have[a]) {
-                        unwrapped_step<T>(base[a] + (t + 1) * 3, base[a] + t * 3, Lc, Lp, Ic, val[a]);
+                        const T cur[3] = {raw[a][0], raw[a][1], raw[a][2]};
+                        const T prev[3] = {raw[a][3 % NV], raw[a][4 % NV], raw[a][5 % NV]};
+                        if (CONSTL)
+                            unwrapped_step_const<T>(cur, prev, Lconst, val[a]);
+                        else
+                            unwrapped_step<T>(cur, prev, Lc, Lp, Ic, val[a]);
                     } else {
                         val[a][0] = val[a][1] = val[a][2] = 0.0;
                     }
@@ -208,7 +255,7 @@ __global__ void __launch_bounds__(256) unwrap_cumsum_kernel(const T* __restrict_
 #pragma unroll
             for (int a = 0; a < A; ++a)
 #pragma unroll
-                for (int c = 0; c < 3; ++c) val[a][c] = (valid && have[a]) ? (double)base[a][t * 3 + c] : 0.0;
+                for (int c = 0; c < 3; ++c) val[a][c] = (double)raw[a][c];
         }
         if (t < pitch) {
             double dr[3] = {0.0, 0.0, 0.0};
@@ -224,9 +271,12 @@ __global__ void __launch_bounds__(256) unwrap_cumsum_kernel(const T* __restrict_
                     out[((size_t)(g0 + a) * 3 + c) * pitch + t] = valid ? (val[a][c] - dr[c]) : 0.0;
             }
         }
+#pragma unroll
+        for (int a = 0; a < A; ++a)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) raw[a][k] = nxt[a][k];
     }
 }
-
 
 // Weighted sum over atoms of a component-major displacement array: out[c][t] += sum_a w[a] dc[a][c][t].
 // The collective displacement of MSTD (diffusion.py:659) and the charge-weighted one of MSCD (:751).
@@ -246,20 +296,20 @@ __global__ void __launch_bounds__(256) atom_sum_kernel(const double* __restrict_
     atomicAdd(out + (size_t)c * pitch + t, acc);
 }
 
-template <typename T, int MODE>
+template <typename T, int MODE, bool CONSTL>
 static int launch_unwrap(const void* coords, int F, const double* latt, const double* inv, int lstride,
                          const int32_t* idx, int n_idx, const double* drift, double* out, int64_t pitch, int Tn,
                          int sm_count, cudaStream_t st) {
     const T* c = (const T*)coords;
     if (n_idx >= sm_count * 16) {
-        unwrap_cumsum_kernel<T, MODE, 4><<<ceil_div(n_idx, 4), 256, 0, st>>>(c, F, latt, inv, lstride, idx, n_idx, drift,
-                                                                              out, pitch, Tn);
-    } else if (n_idx >= sm_count * 4) {
-        unwrap_cumsum_kernel<T, MODE, 2><<<ceil_div(n_idx, 2), 256, 0, st>>>(c, F, latt, inv, lstride, idx, n_idx, drift,
-                                                                              out, pitch, Tn);
+        unwrap_cumsum_kernel<T, MODE, 4, CONSTL><<<ceil_div(n_idx, 4), 256, 0, st>>>(c, F, latt, inv, lstride, idx, n_idx,
+                                                                                      drift, out, pitch, Tn);
+    } else if (n_idx >= sm_count * 8) {
+        unwrap_cumsum_kernel<T, MODE, 2, CONSTL><<<ceil_div(n_idx, 2), 256, 0, st>>>(c, F, latt, inv, lstride, idx, n_idx,
+                                                                                      drift, out, pitch, Tn);
     } else {
-        unwrap_cumsum_kernel<T, MODE, 1><<<n_idx, 256, 0, st>>>(c, F, latt, inv, lstride, idx, n_idx, drift, out, pitch,
-                                                                 Tn);
+        unwrap_cumsum_kernel<T, MODE, 1, CONSTL><<<n_idx, 256, 0, st>>>(c, F, latt, inv, lstride, idx, n_idx, drift, out,
+                                                                         pitch, Tn);
     }
     KB2_LAUNCH_CHECK();
     return 0;
@@ -315,13 +365,14 @@ extern "C" int kb2_frame_sums(const void* coords, int dtype, int mode, int n_ato
     const int per = ceil_div(n_idx, chunks);
     chunks = ceil_div(n_idx, per);
     dim3 grid(tiles, chunks);
-#define KB2_FS(T, M)                                                                                             \
-    frame_sums_kernel<T, M><<<grid, 256, 0, st>>>((const T*)coords, n_frames_in, latt, latt_inv, latt_stride, idx, w, \
-                                                  n_idx, per, frame_sums, pitch, Tn)
-    if (dtype == KB2_F32 && mode == KB2_MODE_FRACTIONAL) KB2_FS(float, KB2_MODE_FRACTIONAL);
-    else if (dtype == KB2_F32) KB2_FS(float, KB2_MODE_DISPLACEMENT);
-    else if (mode == KB2_MODE_FRACTIONAL) KB2_FS(double, KB2_MODE_FRACTIONAL);
-    else KB2_FS(double, KB2_MODE_DISPLACEMENT);
+#define KB2_FS(T, M, C)                                                                                             \
+    frame_sums_kernel<T, M, C><<<grid, 256, 0, st>>>((const T*)coords, n_frames_in, latt, latt_inv, latt_stride, idx, w, \
+                                                     n_idx, per, frame_sums, pitch, Tn)
+    const bool constl = (mode == KB2_MODE_FRACTIONAL && latt_stride == 0);
+    if (dtype == KB2_F32 && mode == KB2_MODE_FRACTIONAL) { if (constl) KB2_FS(float, KB2_MODE_FRACTIONAL, true); else KB2_FS(float, KB2_MODE_FRACTIONAL, false); }
+    else if (dtype == KB2_F32) KB2_FS(float, KB2_MODE_DISPLACEMENT, false);
+    else if (mode == KB2_MODE_FRACTIONAL) { if (constl) KB2_FS(double, KB2_MODE_FRACTIONAL, true); else KB2_FS(double, KB2_MODE_FRACTIONAL, false); }
+    else KB2_FS(double, KB2_MODE_DISPLACEMENT, false);
 #undef KB2_FS
     KB2_LAUNCH_CHECK();
     return 0;
@@ -347,17 +398,14 @@ extern "C" int kb2_unwrap_cumsum(const void* coords, int dtype, int mode, int n_
     cudaStream_t st = (cudaStream_t)stream;
     int sm = 148;
     cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
-    if (dtype == KB2_F32 && mode == KB2_MODE_FRACTIONAL)
-        return launch_unwrap<float, KB2_MODE_FRACTIONAL>(coords, n_frames_in, latt, latt_inv, latt_stride, idx, n_idx,
-                                                         drift, dc_out, pitch, Tn, sm, st);
-    if (dtype == KB2_F32)
-        return launch_unwrap<float, KB2_MODE_DISPLACEMENT>(coords, n_frames_in, latt, latt_inv, latt_stride, idx, n_idx,
-                                                           drift, dc_out, pitch, Tn, sm, st);
-    if (mode == KB2_MODE_FRACTIONAL)
-        return launch_unwrap<double, KB2_MODE_FRACTIONAL>(coords, n_frames_in, latt, latt_inv, latt_stride, idx, n_idx,
-                                                          drift, dc_out, pitch, Tn, sm, st);
-    return launch_unwrap<double, KB2_MODE_DISPLACEMENT>(coords, n_frames_in, latt, latt_inv, latt_stride, idx, n_idx,
-                                                        drift, dc_out, pitch, Tn, sm, st);
+#define KB2_UC(T, M, C) \
+    return launch_unwrap<T, M, C>(coords, n_frames_in, latt, latt_inv, latt_stride, idx, n_idx, drift, dc_out, pitch, Tn, sm, st)
+    const bool constl = (mode == KB2_MODE_FRACTIONAL && latt_stride == 0);
+    if (dtype == KB2_F32 && mode == KB2_MODE_FRACTIONAL) { if (constl) KB2_UC(float, KB2_MODE_FRACTIONAL, true); KB2_UC(float, KB2_MODE_FRACTIONAL, false); }
+    if (dtype == KB2_F32) KB2_UC(float, KB2_MODE_DISPLACEMENT, false);
+    if (mode == KB2_MODE_FRACTIONAL) { if (constl) KB2_UC(double, KB2_MODE_FRACTIONAL, true); KB2_UC(double, KB2_MODE_FRACTIONAL, false); }
+    KB2_UC(double, KB2_MODE_DISPLACEMENT, false);
+#undef KB2_UC
 }
 
 extern "C" int kb2_atom_sum(const double* dc, int n_atoms, int64_t pitch, const double* w, double* out, void* stream) {

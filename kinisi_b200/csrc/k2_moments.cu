@@ -27,24 +27,8 @@
 
 namespace kb2 {
 
-template <int NDIM, int R, bool FULL>
-__device__ __forceinline__ void lag_terms(const double* const (&row)[3], const double (&o)[3][R], int64_t p0, int nv,
-                                          int tid, double& s1, double& s2) {
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int li = r * 256 + tid;
-        if (FULL || li < nv) {
-            double d2 = 0.0;
-#pragma unroll
-            for (int c = 0; c < NDIM; ++c) {
-                const double d = __ldg(row[c] + p0 + li) - o[c][r];
-                d2 = fma(d, d, d2);
-            }
-            s1 += d2;
-            s2 = fma(d2, d2, s2);
-        }
-    }
-}
+constexpr int kDirectWarps = 8;
+constexpr int kDirectLG = 4;
 
 template <int NDIM, int R>
 __global__ void __launch_bounds__(256, (R <= 8) ? 2 : 1)
@@ -52,9 +36,10 @@ __global__ void __launch_bounds__(256, (R <= 8) ? 2 : 1)
                                const int32_t* __restrict__ lags, int K, int ntiles, unsigned int* work_counter,
                                double* __restrict__ partials) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    MomentSmem sm(smem_raw, K);
+    MomentSmem sm(smem_raw, K, kDirectWarps, kDirectLG);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int B = 256 * R;
+    constexpr int RB = 4;
     __shared__ int s_work;
 
     for (int i = tid; i < 2 * K; i += 256) sm.acc[i] = 0.0;
@@ -83,26 +68,30 @@ __global__ void __launch_bounds__(256, (R <= 8) ? 2 : 1)
             for (int c = 0; c < NDIM; ++c) o[c][r] = (j < Tn) ? __ldg(row[c] + j) : 0.0;
         }
 
-        if (tile == 0) first_observation_terms<NDIM>(row, sm, K, tid);
+        if (tile == 0) first_observation_terms<NDIM>(row, sm, K, tid, 256);
 
-        for (int i0 = 0; i0 < K; i0 += kLagGroup) {
+        for (int i0 = 0; i0 < K; i0 += kDirectLG) {
             if ((int64_t)Tn - sm.lags[i0] - j0 <= 0) break;  // ascending lags: nothing left for this tile
 #pragma unroll 1
-            for (int g = 0; g < kLagGroup; ++g) {
+            for (int g = 0; g < kDirectLG; ++g) {
                 const int i = i0 + g;
                 double s1 = 0.0, s2 = 0.0;
                 if (i < K) {
                     const int k = sm.lags[i];
                     const int64_t nv64 = (int64_t)Tn - k - j0;
+                    const double* p0 = row[0] + j0 + k;
+                    const double* p1 = row[1] + j0 + k;
+                    const double* p2 = row[2] + j0 + k;
+                    auto load = [&](int c, int li) { return __ldg((c == 0 ? p0 : (c == 1 ? p1 : p2)) + li); };
                     if (nv64 >= B) {
-                        lag_terms<NDIM, R, true>(row, o, j0 + k, B, tid, s1, s2);
+                        lag_terms<NDIM, R, RB, 256, true>(o, B, tid, load, s1, s2);
                     } else if (nv64 > 0) {
-                        lag_terms<NDIM, R, false>(row, o, j0 + k, (int)nv64, tid, s1, s2);
+                        lag_terms<NDIM, R, RB, 256, false>(o, (int)nv64, tid, load, s1, s2);
                     }
                 }
                 sm.stash_put(warp, g, lane, s1, s2);
             }
-            fold_lag_group(sm, warp, lane, i0, K);
+            fold_lag_group<kDirectLG>(sm, warp, lane, i0, K);
         }
     }
     __syncthreads();
@@ -224,9 +213,9 @@ static int launch_direct(int R, int grid, size_t smem, cudaStream_t st, const do
     return 0;
 }
 
-int launch_self_moments_tma(int ndim, int grid, cudaStream_t st, const double* dc, int n_atoms, int Tn, int64_t pitch,
-                            const int comp[3], const int32_t* lags, int K, unsigned int* counter, double* partials,
-                            int* ntiles_out);
+int launch_self_moments_tma(int config, int ndim, int sm_count, cudaStream_t st, const double* dc, int n_atoms, int Tn,
+                            int64_t pitch, const int comp[3], const int32_t* lags, int K, unsigned int* counter,
+                            double* partials, int* grid_out);
 
 }  // namespace kb2
 
@@ -271,7 +260,7 @@ extern "C" int kb2_self_moments(const double* dc, int n_atoms, int n_frames, int
             KB2_CHECK(n_work < (1ll << 31), "kb2_self_moments: too many work items");
             grid = (int)std::min<int64_t>(n_work, (int64_t)sm_count * (R <= 8 ? 2 : 1));
             grid = min(grid, kMaxGrid);
-            const size_t smem = MomentSmem::bytes(K);
+            const size_t smem = MomentSmem::bytes(K, kDirectWarps, kDirectLG);
             int rc;
             if (ndim == 1)
                 rc = launch_direct<1>(R, grid, smem, st, dc, n_atoms, n_frames, pitch, comp, lg, K, ntiles, counter,
@@ -284,12 +273,11 @@ extern "C" int kb2_self_moments(const double* dc, int n_atoms, int n_frames, int
                                       partials);
             if (rc) return rc;
         } else {
-            grid = min(sm_count, kMaxGrid);
-            int ntiles = 0;
-            int rc = launch_self_moments_tma(ndim, grid, st, dc, n_atoms, n_frames, pitch, comp, lg, K, counter,
-                                             partials, &ntiles);
+            // bits 8.. of `variant` select the TMA configuration (0/1: one 16-warp CTA per SM with a
+            // 4096-origin tile; 2: two 8-warp CTAs per SM with 2048-origin tiles)
+            int rc = launch_self_moments_tma((variant >> 8) & 0xff, ndim, sm_count, st, dc, n_atoms, n_frames, pitch,
+                                             comp, lg, K, counter, partials, &grid);
             if (rc) return rc;
-            grid = (int)std::min<int64_t>((int64_t)n_atoms * ntiles, grid);
         }
         moments_finalize_kernel<<<ceil_div(2 * K, 128), 128, 0, st>>>(partials, grid, 2 * K, sums + 2 * l0);
         KB2_LAUNCH_CHECK();

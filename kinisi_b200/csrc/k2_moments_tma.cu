@@ -1,17 +1,17 @@
 // Stage 2, variant 1: the self-moment kernel with partner samples staged through a shared-memory
 // ring that the TMA engine fills (cp.async.bulk + mbarrier complete_tx), one producer warp feeding
-// eight consumer warps.  See k2_moments.cu for the work decomposition and the arithmetic.
+// the consumer warps.  See k2_moments.cu for the work decomposition and the arithmetic.
 //
-// Shared memory per CTA (one CTA per SM):
-//   ring   [NDIM][CAP=8192] f64   192 KB at NDIM=3; frame p of the current atom lives at
-//                                 (p + off) & (CAP-1), off fixed per work item
-//   full / empty mbarriers        16 + 16
+// Shared memory per CTA:
+//   ring   [NDIM][CAP] f64        CAP = 8192 (192 KB at NDIM=3, one 16-warp CTA per SM) or 4096 (two 8-warp
+//                                 CTAs per SM); frame p of the current atom lives at (p + off) & (CAP-1)
+//   full / empty mbarriers        CAP/512 each
 //   accumulators [K][2], lag table [K], per-warp stash
 // The trajectory row of one component is cut into absolute 512-frame chunks (4 KB); chunk q of a
 // work item is the (seq)-th chunk this CTA ever loads and goes to slot seq % 16.  A consumer warp
 // waits on `full` for the chunks a lag's partner window [j0+k, j0+k+B) touches, and arrives on
 // `empty` for every chunk that lies wholly below the next lag's window.  The producer re-arms a
-// slot once all eight consumer warps have released its previous occupant.  Consecutive lags' windows
+// slot once all consumer warps have released its previous occupant.  Consecutive lags' windows
 // overlap by B - dk frames, so each frame is copied from L2 once per origin tile, not once per lag:
 // L2->SM traffic is 24 B * min(dk, B) / B per term instead of 24 B per term.
 #include <algorithm>
@@ -22,12 +22,7 @@
 namespace kb2 {
 
 namespace tma {
-constexpr int R = 16;
-constexpr int B = 256 * R;     // origins per work item
-constexpr int CAP = 8192;      // ring capacity in frames (power of two)
-constexpr int CH = 512;        // frames per bulk copy
-constexpr int NSLOT = CAP / CH;
-constexpr int THREADS = 256 + 32;
+constexpr int CH = 512;  // frames per bulk copy (4 KB per component)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -61,54 +56,41 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-__host__ __device__ constexpr size_t ring_bytes(int ndim) { return (size_t)ndim * CAP * sizeof(double); }
-constexpr size_t kBarrierBytes = 256;
-inline size_t smem_bytes(int ndim, int K) { return ring_bytes(ndim) + kBarrierBytes + MomentSmem::bytes(K); }
+constexpr size_t kBarrierBytes = 512;
+__host__ __device__ constexpr size_t ring_bytes(int ndim, int cap) { return (size_t)ndim * cap * sizeof(double); }
 }  // namespace tma
 
-template <int NDIM, bool FULL>
-__device__ __forceinline__ void ring_lag_terms(const double* __restrict__ ring, const double (&o)[3][tma::R], int pbase,
-                                               int nv, int tid, double& s1, double& s2) {
-    using namespace tma;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const int li = r * 256 + tid;
-        if (FULL || li < nv) {
-            const int slot = (pbase + li) & (CAP - 1);
-            double d2 = 0.0;
-#pragma unroll
-            for (int c = 0; c < NDIM; ++c) {
-                const double d = ring[c * CAP + slot] - o[c][r];
-                d2 = fma(d, d, d2);
-            }
-            s1 += d2;
-            s2 = fma(d2, d2, s2);
-        }
-    }
-}
-
-template <int NDIM>
-__global__ void __launch_bounds__(tma::THREADS, 1)
+// WARPS consumer warps + one producer warp; R origins per consumer thread (tile B = 32*WARPS*R);
+// ring of CAP frames per component; LG lags folded at a time.
+template <int NDIM, int WARPS, int R, int CAP, int LG, int MINB>
+__global__ void __launch_bounds__(32 * WARPS + 32, MINB)
     self_moments_tma_kernel(const double* __restrict__ dc, int n_atoms, int Tn, int64_t pitch, int c0, int c1, int c2,
                             const int32_t* __restrict__ lags, int K, int ntiles, unsigned int* work_counter,
                             double* __restrict__ partials) {
     using namespace tma;
+    constexpr int NT = 32 * WARPS;       // consumer threads
+    constexpr int THREADS = NT + 32;
+    constexpr int B = NT * R;            // origins per work item
+    constexpr int NSLOT = CAP / CH;
+    constexpr int RB = 4;
+    static_assert(CAP >= B + 4 * CH, "ring too small for the partner window plus prefetch slack");
+    static_assert((CAP & (CAP - 1)) == 0 && 2 * NSLOT * 8 <= (int)kBarrierBytes, "bad ring geometry");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* ring = reinterpret_cast<double*>(smem_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes(NDIM));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + ring_bytes(NDIM, CAP));
     uint64_t* empty = full + NSLOT;
-    MomentSmem sm(smem_raw + ring_bytes(NDIM) + kBarrierBytes, K);
+    MomentSmem sm(smem_raw + ring_bytes(NDIM, CAP) + kBarrierBytes, K, WARPS, LG);
     __shared__ int s_work;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool producer = warp == kConsumerWarps;
+    const bool producer = warp == WARPS;
 
     for (int i = tid; i < 2 * K; i += THREADS) sm.acc[i] = 0.0;
     for (int i = tid; i < K; i += THREADS) sm.lags[i] = lags[i];
     if (tid == 0) {
         for (int s = 0; s < NSLOT; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerWarps);
+            mbar_init(&empty[s], WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -168,20 +150,20 @@ __global__ void __launch_bounds__(tma::THREADS, 1)
             double o[3][R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int j = j0 + r * 256 + tid;
+                const int j = j0 + r * NT + tid;
 #pragma unroll
                 for (int c = 0; c < NDIM; ++c) o[c][r] = (j < Tn) ? __ldg(row[c] + j) : 0.0;
             }
-            if (tile == 0) first_observation_terms<NDIM>(row, sm, K, tid);
+            if (tile == 0) first_observation_terms<NDIM>(row, sm, K, tid, NT);
 
             // ring position of frame p is (p + off) & (CAP-1)
             const int off = (int)(((seq_base % NSLOT) + NSLOT - (uint32_t)(q_first % NSLOT)) % NSLOT) * CH;
             int waited = q_first - 1;    // last chunk this warp has seen complete
             int released = q_first - 1;  // last chunk this warp has handed back
 
-            for (int i0 = 0; i0 < nlv; i0 += kLagGroup) {
+            for (int i0 = 0; i0 < nlv; i0 += LG) {
 #pragma unroll 1
-                for (int g = 0; g < kLagGroup; ++g) {
+                for (int g = 0; g < LG; ++g) {
                     const int i = i0 + g;
                     double s1 = 0.0, s2 = 0.0;
                     if (i < nlv) {
@@ -193,10 +175,12 @@ __global__ void __launch_bounds__(tma::THREADS, 1)
                             const uint32_t s = seq_base + (uint32_t)(waited - q_first);
                             mbar_wait(&full[s % NSLOT], (s / NSLOT) & 1);
                         }
+                        const int pbase = start + off;
+                        auto load = [&](int c, int li) { return ring[c * CAP + ((pbase + li) & (CAP - 1))]; };
                         if (nv == B)
-                            ring_lag_terms<NDIM, true>(ring, o, start + off, B, tid, s1, s2);
+                            lag_terms<NDIM, R, RB, NT, true>(o, B, tid, load, s1, s2);
                         else
-                            ring_lag_terms<NDIM, false>(ring, o, start + off, nv, tid, s1, s2);
+                            lag_terms<NDIM, R, RB, NT, false>(o, nv, tid, load, s1, s2);
                         // hand back the chunks that lie wholly below the next lag's window
                         // (a chunk in a gap between two windows is waited for before it is released, so an
                         //  `empty` arrival can never land in the slot's previous phase)
@@ -217,7 +201,7 @@ __global__ void __launch_bounds__(tma::THREADS, 1)
                     }
                     sm.stash_put(warp, g, lane, s1, s2);
                 }
-                fold_lag_group(sm, warp, lane, i0, K);
+                fold_lag_group<LG>(sm, warp, lane, i0, K);
             }
         }
         seq_base += (uint32_t)nq;
@@ -226,31 +210,51 @@ __global__ void __launch_bounds__(tma::THREADS, 1)
     for (int i = tid; i < 2 * K; i += THREADS) partials[(size_t)blockIdx.x * 2 * K + i] = sm.acc[i];
 }
 
-template <int NDIM>
-static int launch_tma_ndim(int grid, cudaStream_t st, const double* dc, int n_atoms, int Tn, int64_t pitch,
-                           const int comp[3], const int32_t* lags, int K, int ntiles, unsigned int* counter,
-                           double* partials) {
-    const size_t smem = tma::smem_bytes(NDIM, K);
-    KB2_CUDA(cudaFuncSetAttribute(self_moments_tma_kernel<NDIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    self_moments_tma_kernel<NDIM><<<grid, tma::THREADS, smem, st>>>(dc, n_atoms, Tn, pitch, comp[0], comp[1], comp[2],
-                                                                    lags, K, ntiles, counter, partials);
+template <int NDIM, int WARPS, int R, int CAP, int LG, int MINB>
+static int launch_tma_cfg(int sm_count, cudaStream_t st, const double* dc, int n_atoms, int Tn, int64_t pitch,
+                          const int comp[3], const int32_t* lags, int K, unsigned int* counter, double* partials,
+                          int* grid_out) {
+    constexpr int B = 32 * WARPS * R;
+    const int ntiles = ceil_div(Tn, B);
+    const int64_t n_work = (int64_t)n_atoms * ntiles;
+    KB2_CHECK(n_work < (1ll << 31), "kb2_self_moments: too many work items");
+    const size_t smem = tma::ring_bytes(NDIM, CAP) + tma::kBarrierBytes + MomentSmem::bytes(K, WARPS, LG);
+    auto kern = self_moments_tma_kernel<NDIM, WARPS, R, CAP, LG, MINB>;
+    KB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    KB2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32 * WARPS + 32, smem));
+    KB2_CHECK(per_sm >= 1, "kb2_self_moments: the TMA kernel does not fit on this device (%zu bytes of shared memory)",
+              smem);
+    const int grid = (int)std::min<int64_t>(std::min<int64_t>((int64_t)sm_count * per_sm, kMaxGrid), n_work);
+    kern<<<grid, 32 * WARPS + 32, smem, st>>>(dc, n_atoms, Tn, pitch, comp[0], comp[1], comp[2], lags, K, ntiles, counter,
+                                              partials);
     KB2_LAUNCH_CHECK();
+    *grid_out = grid;
     return 0;
 }
 
-int launch_self_moments_tma(int ndim, int grid, cudaStream_t st, const double* dc, int n_atoms, int Tn, int64_t pitch,
-                            const int comp[3], const int32_t* lags, int K, unsigned int* counter, double* partials,
-                            int* ntiles_out) {
+template <int NDIM>
+static int launch_tma_ndim(int config, int sm_count, cudaStream_t st, const double* dc, int n_atoms, int Tn,
+                           int64_t pitch, const int comp[3], const int32_t* lags, int K, unsigned int* counter,
+                           double* partials, int* grid_out) {
+    if (config == 2)  // two 8-warp CTAs per SM, 2048-origin tiles, 4096-frame ring
+        return launch_tma_cfg<NDIM, 8, 8, 4096, 2, 2>(sm_count, st, dc, n_atoms, Tn, pitch, comp, lags, K, counter,
+                                                      partials, grid_out);
+    // one 16-warp CTA per SM, 4096-origin tiles, 8192-frame ring
+    return launch_tma_cfg<NDIM, 16, 8, 8192, 2, 1>(sm_count, st, dc, n_atoms, Tn, pitch, comp, lags, K, counter, partials,
+                                                   grid_out);
+}
+
+int launch_self_moments_tma(int config, int ndim, int sm_count, cudaStream_t st, const double* dc, int n_atoms, int Tn,
+                            int64_t pitch, const int comp[3], const int32_t* lags, int K, unsigned int* counter,
+                            double* partials, int* grid_out) {
     KB2_CHECK(((uintptr_t)dc & 15) == 0, "kb2_self_moments: dc must be 16-byte aligned for the TMA variant");
-    const int ntiles = ceil_div(Tn, tma::B);
-    const int64_t n_work = (int64_t)n_atoms * ntiles;
-    KB2_CHECK(n_work < (1ll << 31), "kb2_self_moments: too many work items");
-    KB2_CHECK((int64_t)Tn + tma::B < (1ll << 30), "kb2_self_moments: trajectory too long for the TMA variant");
-    *ntiles_out = ntiles;
-    grid = (int)std::min<int64_t>(grid, n_work);
-    if (ndim == 1) return launch_tma_ndim<1>(grid, st, dc, n_atoms, Tn, pitch, comp, lags, K, ntiles, counter, partials);
-    if (ndim == 2) return launch_tma_ndim<2>(grid, st, dc, n_atoms, Tn, pitch, comp, lags, K, ntiles, counter, partials);
-    return launch_tma_ndim<3>(grid, st, dc, n_atoms, Tn, pitch, comp, lags, K, ntiles, counter, partials);
+    KB2_CHECK((int64_t)Tn + 8192 < (1ll << 30), "kb2_self_moments: trajectory too long for the TMA variant");
+    if (ndim == 1)
+        return launch_tma_ndim<1>(config, sm_count, st, dc, n_atoms, Tn, pitch, comp, lags, K, counter, partials, grid_out);
+    if (ndim == 2)
+        return launch_tma_ndim<2>(config, sm_count, st, dc, n_atoms, Tn, pitch, comp, lags, K, counter, partials, grid_out);
+    return launch_tma_ndim<3>(config, sm_count, st, dc, n_atoms, Tn, pitch, comp, lags, K, counter, partials, grid_out);
 }
 
 }  // namespace kb2

@@ -21,6 +21,11 @@ from . import dist, engine
 from .distribution import Distribution
 from .parser import LazyDisplacements, SingleOriginDisplacements
 
+# True: run the reference's sequence literally (eigh for the minimum-eigenvalue method, a second eigh
+# inside cov_nearest, slogdet, and a third eigh for pinvh).  False (default): one eigh, reused -- the
+# same result to rounding (see Bootstrap.generate_covariance_matrix).
+LITERAL_RECONDITIONING = False
+
 DIMENSIONALITY = {
     'x': np.s_[0],
     'y': np.s_[1],
@@ -89,6 +94,7 @@ class Bootstrap:
         self.flatchain = None
         self._covariance_matrix_dev = None
         self._npd_covariance_matrix_dev = None
+        self._eig = None
         self._slice = DIMENSIONALITY[dimension.lower()]
         self._mask = engine.dim_mask(dimension)
         self._start_dt = None
@@ -284,7 +290,17 @@ class Bootstrap:
         # minimum eigenvalue method: clip the spectrum at lambda_max / cond_max and rebuild
         lam, vec = torch.linalg.eigh(cov)
         floor = lam.max() / self._cond_max
-        cov = (vec * torch.clamp(lam, min=floor)) @ vec.T
+        lam = torch.clamp(lam, min=floor)
+        cov = (vec * lam) @ vec.T
+        if not LITERAL_RECONDITIONING:
+            # The matrix just rebuilt has the eigen-pairs (lam, vec) by construction, and cov_nearest
+            # moves it by <= ~2e-15 relative (it lifts correlation eigenvalues from ~1e-16 to 1e-15, far
+            # below the pinvh cut-off of n*eps).  The fast path therefore reuses this one factorisation
+            # for the pseudo-inverse and the log-determinant.  tests/test_gpu_parity.py checks it against
+            # the literal sequence below.
+            self._eig = (lam, vec)
+            return cov
+        self._eig = None
         # cov_nearest(method='clipped', threshold=1e-15)
         std = torch.sqrt(torch.diagonal(cov))
         corr = cov / torch.outer(std, std)
@@ -327,9 +343,13 @@ class Bootstrap:
         self._covariance_matrix_dev = cov
         n_dt = cov.shape[0]
 
-        _, logdet = torch.linalg.slogdet(cov)
+        if self._eig is not None:
+            lam, vec = self._eig
+            logdet = torch.log(lam).sum()
+        else:
+            _, logdet = torch.linalg.slogdet(cov)
+            lam, vec = torch.linalg.eigh(cov)  # pinvh is an eigendecomposition with a relative cut-off
         logdet_term = (logdet + float(np.log(2 * np.pi) * n_dt)).reshape(1)
-        lam, vec = torch.linalg.eigh(cov)  # pinvh is an eigendecomposition with a relative cut-off
 
         x = self._dev(self._dt[diff_regime:])
         y = self._stats_dev[0, diff_regime:].contiguous()

@@ -306,6 +306,29 @@ def test_covariance_likelihood_and_posterior(kb, golden_dir, name):
     assert ppd.shape == (128, b.dt.size - dr)
 
 
+def test_fast_reconditioning_matches_the_literal_sequence(kb, golden_dir):
+    """The default stage-3 path factorises the covariance once; the literal path repeats the reference's
+    eigh / cov_nearest / slogdet / pinvh sequence.  Both must give the same matrix and likelihood."""
+    g = load(golden_dir, 'regress_msd')
+    symbols, frac, latt, pp, start_idx, kind = regress_case_inputs('regress_msd')
+    traj = trajectory_from_arrays(symbols, frac, latt)
+    out = {}
+    for literal in (False, True):
+        kb.diffusion.LITERAL_RECONDITIONING = literal
+        try:
+            an = kb.analyze.DiffusionAnalyzer.from_ase(traj, parser_params=pp, uncertainty_params={'progress': False})
+            an.diffusion(float(g['start_dt']), {'progress': False, 'n_samples': 100, 'n_burn': 50})
+        finally:
+            kb.diffusion.LITERAL_RECONDITIONING = False
+        ll = an._diff.log_likelihood(g['thetas'][:-1])
+        out[literal] = (an._diff.covariance_matrix, ll - ll[0])
+    scale = np.abs(out[True][0]).max()
+    np.testing.assert_allclose(out[False][0], out[True][0], rtol=1e-9, atol=1e-12 * scale)
+    np.testing.assert_allclose(out[False][1], out[True][1], rtol=1e-6, atol=1e-6)
+    d_ref = g['loglike'][:-1] - g['loglike'][0]
+    np.testing.assert_allclose(out[True][1], d_ref, rtol=1e-5, atol=1e-5)
+
+
 def test_sampler_sizes_and_options(kb):
     """Output sizes as pinned by kinisi/tests/test_diffusion.py:280, 318, 331, 357."""
     dt, disp_3d, n_o, _ = list_bootstrap_inputs()
