@@ -143,10 +143,12 @@ int kb2_cov_build(const double* v, const double* n_o, int n, double* cov, void* 
  *   proj[0][r] = s_r V_r.x     proj[1][r] = s_r V_r.1     proj[2][r] = s_r V_r.y
  *   proj[3][r] = sign(lambda_r) or 0 if dropped,          s_r = |lambda_r|^-1/2
  * so that diff^T pinvh(C) diff = sum_r proj[3][r] (g proj[0][r] + c proj[1][r] - proj[2][r])^2.
- * theta_ml[0..1] receives the generalised-least-squares optimum (slope clamped at >= 1e-20 like
- * diffusion.py:370-371), the start point the reference finds with scipy.optimize.minimize (:380-383). */
+ * gls[8] receives {g0, c0, AA, AB, BB, RA, RB, Q0}: the generalised-least-squares optimum (slope clamped
+ * at >= 1e-20 like diffusion.py:370-371; the start point the reference finds with scipy.optimize.minimize,
+ * :380-383) and the exact expansion of the quadratic form about it,
+ *   Q(g0+dg, c0+dc) = Q0 + 2 (dg RA + dc RB) + dg^2 AA + 2 dg dc AB + dc^2 BB. */
 int kb2_gls_prepare(const double* evals, const double* evecs, const double* x, const double* y, int n,
-                    int fit_intercept, double* proj, double* theta_ml, void* stream);
+                    int fit_intercept, double* proj, double* gls, void* stream);
 
 /* out[w] = log_likelihood(theta[w]) of diffusion.py:354-365 for n_walkers parameter vectors
  * theta[n_walkers][ndim] (ndim = 1 or 2); -inf where theta[w][0] < 0.
@@ -156,13 +158,13 @@ int kb2_mvn_loglike(const double* theta, int n_walkers, int ndim, const double* 
 
 /* The whole ensemble MCMC of diffusion.py:384-390 in one launch: walkers start at
  * theta_ml + theta_ml * 1e-3 * N(0,1) (:384), then n_steps affine-invariant stretch moves (a = 2,
- * red/blue split with a random balanced partition per step) are run.
+ * red/blue split with a random balanced partition per step) are run on the log-likelihood
+ * -0.5 (logdet_term + Q(theta)), -inf for a negative slope, Q given by gls[8] from kb2_gls_prepare.
  * chain[n_steps][n_walkers][ndim], logp[n_steps][n_walkers].
  * workspace: kb2_sampler_workspace_bytes(n_steps, n_walkers) bytes. */
 size_t kb2_sampler_workspace_bytes(int n_steps, int n_walkers);
-int kb2_ensemble_sample(const double* theta_ml, int ndim, int n_walkers, int n_steps, const double* proj, int n,
-                        const double* logdet_term, uint64_t seed, void* workspace, double* chain, double* logp,
-                        void* stream);
+int kb2_ensemble_sample(const double* gls, int ndim, int n_walkers, int n_steps, const double* logdet_term,
+                        uint64_t seed, void* workspace, double* chain, double* logp, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): a dependent-free DFMA loop and a streaming copy, to measure the

@@ -32,8 +32,8 @@ SIGNATURES = {
     'kb2_gls_prepare': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'kb2_mvn_loglike': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     'kb2_sampler_workspace_bytes': (c_size_t, [c_int, c_int]),
-    'kb2_ensemble_sample': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_uint64, c_void_p,
-                                    c_void_p, c_void_p, c_void_p]),
+    'kb2_ensemble_sample': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
     'kb2_fp64_peak': (c_int, [c_int, c_int, c_void_p, c_void_p]),
     'kb2_stream_copy': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
 }

@@ -128,7 +128,7 @@ class Bootstrap:
             raise NotImplementedError('block=True needs pyblock (kinisi/diffusion.py:584-595); not built here')
 
     def _dev(self, a):
-        return torch.as_tensor(np.asarray(a, dtype=np.float64)).to(self._device)
+        return engine.small_to_device(a, self._device, np.float64)
 
     def _self_sums(self, used, mask):
         """[len(used), 2] sums of d^2, d^4 over atoms x observations for the entries in `used`."""
@@ -136,7 +136,7 @@ class Bootstrap:
         if self._lazy and not isinstance(d, SingleOriginDisplacements):
             lags = d.lags[used]
             order = np.argsort(lags, kind='stable')
-            lags_dev = torch.as_tensor(lags[order].astype(np.int32)).to(self._device)
+            lags_dev = engine.small_to_device(lags[order], self._device, np.int32)
             if d.dc.shape[0] > 0:
                 sums = engine.self_moments(d.dc, d.n_frames, lags_dev, mask)
             else:
@@ -146,7 +146,7 @@ class Bootstrap:
             if not np.array_equal(order, np.arange(len(order))):
                 inv = np.empty_like(order)
                 inv[order] = np.arange(len(order))
-                sums = sums[torch.as_tensor(inv).to(self._device)]
+                sums = sums[engine.small_to_device(inv, self._device, np.int64)]
             return sums
         rows = []
         for i in used:
@@ -169,7 +169,7 @@ class Bootstrap:
                 S = torch.zeros((3, d.dc.shape[2]), dtype=torch.float64, device=self._device)
             if dist.active():
                 dist.allreduce_sum_(S)
-            lags_dev = torch.as_tensor(d.lags[used].astype(np.int32)).to(self._device)
+            lags_dev = engine.small_to_device(d.lags[used], self._device, np.int32)
             return engine.self_moments(S.unsqueeze(0), d.n_frames, lags_dev, coll_mask)
         w = None if weights is None else self._dev(weights)
         rows = []
@@ -358,7 +358,7 @@ class Bootstrap:
 
         ndim = 2 if fit_intercept else 1
         seed = int(np.random.randint(0, 2**31 - 1)) * 2654435761 + 12345
-        chain, logp = engine.ensemble_sample(theta_ml, ndim, n_walkers, n_samples + n_burn, proj, logdet_term, seed)
+        chain, logp = engine.ensemble_sample(theta_ml, ndim, n_walkers, n_samples + n_burn, logdet_term, seed)
         self._chain_dev, self._logp_dev = chain, logp
         # emcee get_chain(flat=True, thin=thin, discard=n_burn)
         self.flatchain = chain[n_burn + thin - 1::thin].reshape(-1, ndim).cpu().numpy()

@@ -163,7 +163,7 @@ def gls_prepare(evals, evecs, x, y, fit_intercept=True):
     n = evals.numel()
     evecs = evecs.contiguous()
     proj = torch.empty((4, n), dtype=torch.float64, device=evals.device)
-    theta = torch.empty(2, dtype=torch.float64, device=evals.device)
+    theta = torch.empty(8, dtype=torch.float64, device=evals.device)  # g0, c0, AA, AB, BB, RA, RB, Q0
     check(
         lib.kb2_gls_prepare(evals.data_ptr(), evecs.data_ptr(), x.data_ptr(), y.data_ptr(), n, int(bool(fit_intercept)),
                             proj.data_ptr(), theta.data_ptr(), _stream()), 'kb2_gls_prepare')
@@ -183,15 +183,15 @@ def mvn_loglike(theta, proj, logdet_term):
     return out
 
 
-def ensemble_sample(theta_ml, ndim, n_walkers, n_steps, proj, logdet_term, seed):
+def ensemble_sample(gls, ndim, n_walkers, n_steps, logdet_term, seed):
     lib = require_cuda()
-    dev = proj.device
+    dev = gls.device
     ws = torch.empty(lib.kb2_sampler_workspace_bytes(n_steps, n_walkers), dtype=torch.uint8, device=dev)
     chain = torch.empty((n_steps, n_walkers, ndim), dtype=torch.float64, device=dev)
     logp = torch.empty((n_steps, n_walkers), dtype=torch.float64, device=dev)
     check(
-        lib.kb2_ensemble_sample(theta_ml.data_ptr(), ndim, n_walkers, n_steps, proj.data_ptr(), proj.shape[1],
-                                logdet_term.data_ptr(), int(seed) & 0xFFFFFFFFFFFFFFFF, ws.data_ptr(),
+        lib.kb2_ensemble_sample(gls.data_ptr(), ndim, n_walkers, n_steps, logdet_term.data_ptr(),
+                                int(seed) & 0xFFFFFFFFFFFFFFFF, ws.data_ptr(),
                                 chain.data_ptr(), logp.data_ptr(), _stream()), 'kb2_ensemble_sample')
     _count(3)
     return chain, logp
@@ -215,6 +215,12 @@ def device_info():
     vals = [ctypes.c_int(0) for _ in range(4)]
     check(lib.kb2_device_info(*[ctypes.byref(v) for v in vals]), 'kb2_device_info')
     return {'sm_count': vals[0].value, 'max_smem_optin': vals[1].value, 'cc': (vals[2].value, vals[3].value)}
+
+
+def small_to_device(a, device, np_dtype=np.float64):
+    """Small host array -> CUDA tensor without a stream synchronisation (the driver stages small
+    pageable copies, so the call returns as soon as the copy is enqueued)."""
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np_dtype))).to(device, non_blocking=True)
 
 
 def to_device(a, device, dtype=None):

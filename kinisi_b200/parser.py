@@ -198,7 +198,7 @@ class Parser:
         dev = traj.device
         n_frames = traj.n_frames
 
-        idx = torch.as_tensor(np.asarray(indices, dtype=np.int64), dtype=torch.int32).to(dev)
+        idx = engine.small_to_device(indices, dev, np.int32)
         n_sel_local = idx.numel()
         n_sel = int(round(dist.allreduce_sum_scalar(n_sel_local, dev))) if self._distributed else n_sel_local
         self._n_atoms_global = n_sel
@@ -238,7 +238,7 @@ class Parser:
         if n_fw == 0:
             return None
         if n_fw_local > 0:
-            fw = torch.as_tensor(np.asarray(drift_indices, dtype=np.int64), dtype=torch.int32).to(traj.device)
+            fw = engine.small_to_device(drift_indices, traj.device, np.int32)
             sums = traj.frame_sums(fw)
         else:
             sums = torch.zeros((3, engine.pitch_for(traj.n_frames)), dtype=torch.float64, device=traj.device)
@@ -289,7 +289,7 @@ class Parser:
         traj = disp if isinstance(disp, Trajectory) else Trajectory(disp, mode=MODE_DISPLACEMENT)
         if len(drift_indices) == 0:
             return traj.numpy()
-        fw = torch.as_tensor(np.asarray(drift_indices, dtype=np.int64), dtype=torch.int32).to(traj.device)
+        fw = engine.small_to_device(drift_indices, traj.device, np.int32)
         drift = engine.scan_frames(traj.frame_sums(fw), traj.n_frames, traj.mode == MODE_FRACTIONAL,
                                    float(len(drift_indices)))
         return traj.numpy(drift=drift)

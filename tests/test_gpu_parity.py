@@ -276,6 +276,10 @@ def test_covariance_likelihood_and_posterior(kb, golden_dir, name):
     d_mine = ll[1:-1] - ll[0]
     d_ref = g['loglike'][1:-1] - g['loglike'][0]
     np.testing.assert_allclose(d_mine, d_ref, rtol=1e-5, atol=1e-5)
+    # the sampler's O(1) expansion of the quadratic form agrees with the O(n) whitened form
+    chain = b._chain_dev[::97].reshape(-1, 2).cpu().numpy()
+    logp = b._logp_dev[::97].reshape(-1).cpu().numpy()
+    np.testing.assert_allclose(b.log_likelihood(chain), logp, rtol=1e-10, atol=1e-8)
     # flat chain layout (kinisi/tests/test_diffusion.py:280) and the posterior against the closed form
     assert an.flatchain.shape == (3200, 2)
     dr = int(np.argwhere(b.dt >= start_dt)[0][0])
