@@ -150,6 +150,20 @@ int kb2_cov_build(const double* v, const double* n_o, int n, double* cov, void* 
 int kb2_gls_prepare(const double* evals, const double* evecs, const double* x, const double* y, int n,
                     int fit_intercept, double* proj, double* gls, void* stream);
 
+/* The spectral step of the regression in one call, for n <= kb2_spectral_prepare_max_n(): a cyclic Jacobi
+ * eigen-iteration of the model covariance cov[n][n] in shared memory that yields, without forming eigenvectors,
+ *   evals[n]       the raw spectrum (unsorted),
+ *   proj[4][n]     the whitened model of kb2_gls_prepare for the spectrum clipped at lambda_max / cond_max
+ *                  (minimum_eigenvalue_method, kinisi/diffusion.py:870-888) and cut at n*eps (pinvh, :352),
+ *   gls[8]         as kb2_gls_prepare,
+ *   logdet_term    sum_r log(clipped lambda_r) + n ln(2 pi)  (diffusion.py:350-351),
+ *   info[0]        (optional) the number of Jacobi sweeps.
+ * Equivalent, to rounding, to eigh + clip + rebuild + cov_nearest + slogdet + pinvh of the reference. */
+int kb2_spectral_prepare_max_n(void);
+int kb2_spectral_prepare(const double* cov, const double* x, const double* y, int n, double cond_max,
+                         int fit_intercept, double* evals, double* proj, double* gls, double* logdet_term, int* info,
+                         void* stream);
+
 /* out[w] = log_likelihood(theta[w]) of diffusion.py:354-365 for n_walkers parameter vectors
  * theta[n_walkers][ndim] (ndim = 1 or 2); -inf where theta[w][0] < 0.
  * logdet_term is a device scalar holding slogdet(C) + n ln(2 pi) (diffusion.py:350-351). */

@@ -30,6 +30,9 @@ SIGNATURES = {
     'kb2_moment_stats': (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 4 + [c_void_p]),
     'kb2_cov_build': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     'kb2_gls_prepare': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'kb2_spectral_prepare_max_n': (c_int, []),
+    'kb2_spectral_prepare': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_double, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
     'kb2_mvn_loglike': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     'kb2_sampler_workspace_bytes': (c_size_t, [c_int, c_int]),
     'kb2_ensemble_sample': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p,

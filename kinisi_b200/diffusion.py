@@ -21,9 +21,10 @@ from . import dist, engine
 from .distribution import Distribution
 from .parser import LazyDisplacements, SingleOriginDisplacements
 
-# True: run the reference's sequence literally (eigh for the minimum-eigenvalue method, a second eigh
-# inside cov_nearest, slogdet, and a third eigh for pinvh).  False (default): one eigh, reused -- the
-# same result to rounding (see Bootstrap.generate_covariance_matrix).
+# True: run the reference's sequence literally with library eigensolvers (eigh for the minimum-eigenvalue
+# method, a second eigh inside cov_nearest, slogdet, and a third eigh for pinvh).  False (default): one
+# spectral decomposition (a Jacobi kernel for n <= 128, csrc/k4_eigen.cu), reused for all of them -- the same
+# result to rounding (see Bootstrap.generate_covariance_matrix and bootstrap_GLS).
 LITERAL_RECONDITIONING = False
 
 DIMENSIONALITY = {
@@ -95,6 +96,7 @@ class Bootstrap:
         self._covariance_matrix_dev = None
         self._npd_covariance_matrix_dev = None
         self._eig = None
+        self._cov_regime = None
         self._slice = DIMENSIONALITY[dimension.lower()]
         self._mask = engine.dim_mask(dimension)
         self._start_dt = None
@@ -247,10 +249,18 @@ class Bootstrap:
         """:return: The estimated intercept (None if fit_intercept was False)."""
         return self._intercept
 
+    def _covariance_device(self):
+        """The reconditioned covariance on the device; on the default path the sampler does not need the
+        matrix itself (only its spectrum), so it is rebuilt here on first use."""
+        if self._covariance_matrix_dev is None and self._cov_regime is not None:
+            self._covariance_matrix_dev = self.generate_covariance_matrix(self._cov_regime)
+        return self._covariance_matrix_dev
+
     @property
     def covariance_matrix(self) -> np.ndarray:
         """:return: The covariance matrix for the trajectories."""
-        return None if self._covariance_matrix_dev is None else self._covariance_matrix_dev.cpu().numpy()
+        cov = self._covariance_device()
+        return None if cov is None else cov.cpu().numpy()
 
     @property
     def _covariance_matrix(self):
@@ -339,21 +349,31 @@ class Bootstrap:
 
         diff_regime = np.argwhere(self._dt >= self._start_dt)[0][0]
 
-        cov = self.generate_covariance_matrix(diff_regime)
-        self._covariance_matrix_dev = cov
-        n_dt = cov.shape[0]
-
-        if self._eig is not None:
-            lam, vec = self._eig
-            logdet = torch.log(lam).sum()
-        else:
-            _, logdet = torch.linalg.slogdet(cov)
-            lam, vec = torch.linalg.eigh(cov)  # pinvh is an eigendecomposition with a relative cut-off
-        logdet_term = (logdet + float(np.log(2 * np.pi) * n_dt)).reshape(1)
-
         x = self._dev(self._dt[diff_regime:])
         y = self._stats_dev[0, diff_regime:].contiguous()
-        proj, theta_ml = engine.gls_prepare(lam, vec, x, y, fit_intercept)
+        n_dt = x.numel()
+        self._cov_regime = diff_regime
+        self._covariance_matrix_dev = None
+        if not LITERAL_RECONDITIONING and not model and n_dt <= engine.spectral_prepare_max_n():
+            # One kernel: Jacobi spectrum of the model covariance -> clipped spectrum, pinvh cut-off, whitened
+            # model, log-determinant and the GLS expansion (csrc/k4_eigen.cu).  The reconditioned matrix itself
+            # is only materialised if `covariance_matrix` is read.
+            v = self._stats_dev[1, diff_regime:].contiguous()
+            cov0 = engine.cov_build(v, self._dev(self._n_o[diff_regime:]))
+            self._npd_covariance_matrix_dev = cov0
+            self._evals, proj, theta_ml, logdet_term, self._sweeps = engine.spectral_prepare(
+                cov0, x, y, cond_max, fit_intercept)
+        else:
+            cov = self.generate_covariance_matrix(diff_regime)
+            self._covariance_matrix_dev = cov
+            if self._eig is not None:
+                lam, vec = self._eig
+                logdet = torch.log(lam).sum()
+            else:
+                _, logdet = torch.linalg.slogdet(cov)
+                lam, vec = torch.linalg.eigh(cov)  # pinvh is an eigendecomposition with a relative cut-off
+            logdet_term = (logdet + float(np.log(2 * np.pi) * n_dt)).reshape(1)
+            proj, theta_ml = engine.gls_prepare(lam, vec, x, y, fit_intercept)
         self._proj, self._logdet_term, self._theta_ml = proj, logdet_term, theta_ml
 
         ndim = 2 if fit_intercept else 1
@@ -416,7 +436,7 @@ class Bootstrap:
             n_posterior_samples = self.gradient.size
         diff_regime = np.argwhere(self._dt >= self._start_dt)[0][0]
         x = self._dev(self._dt[diff_regime:])
-        lam, vec = torch.linalg.eigh(self._covariance_matrix_dev)
+        lam, vec = torch.linalg.eigh(self._covariance_device())
         factor = vec * torch.sqrt(torch.clamp(lam, min=0.0))  # cov = factor @ factor.T (allow_singular)
         draw = np.random.randint(0, self.gradient.size, size=n_posterior_samples)
         g = self._dev(self.gradient.samples[draw])

@@ -171,6 +171,28 @@ def gls_prepare(evals, evecs, x, y, fit_intercept=True):
     return proj, theta
 
 
+def spectral_prepare_max_n():
+    return require_cuda().kb2_spectral_prepare_max_n()
+
+
+def spectral_prepare(cov, x, y, cond_max, fit_intercept=True):
+    """One-kernel spectral step (Jacobi) -> evals [n], proj [4, n], gls [8], logdet_term [1], sweeps [1]."""
+    lib = require_cuda()
+    n = cov.shape[0]
+    dev = cov.device
+    evals = torch.empty(n, dtype=torch.float64, device=dev)
+    proj = torch.empty((4, n), dtype=torch.float64, device=dev)
+    gls = torch.empty(8, dtype=torch.float64, device=dev)
+    logdet_term = torch.empty(1, dtype=torch.float64, device=dev)
+    info = torch.empty(1, dtype=torch.int32, device=dev)
+    check(
+        lib.kb2_spectral_prepare(cov.data_ptr(), x.data_ptr(), y.data_ptr(), n, float(cond_max),
+                                 int(bool(fit_intercept)), evals.data_ptr(), proj.data_ptr(), gls.data_ptr(),
+                                 logdet_term.data_ptr(), info.data_ptr(), _stream()), 'kb2_spectral_prepare')
+    _count(2)
+    return evals, proj, gls, logdet_term, info
+
+
 def mvn_loglike(theta, proj, logdet_term):
     lib = require_cuda()
     theta = theta.contiguous()

@@ -333,6 +333,43 @@ def test_fast_reconditioning_matches_the_literal_sequence(kb, golden_dir):
     np.testing.assert_allclose(out[True][1], d_ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize('n', [1, 2, 3, 17, 54, 90, 127, 128])
+def test_jacobi_spectral_kernel(kb, n):
+    """kb2_spectral_prepare against numpy: spectrum, log-determinant, and the quadratic form of pinvh."""
+    from scipy.linalg import pinvh
+    rng = np.random.RandomState(n)
+    # a model-covariance-like matrix (kinisi/diffusion.py:838-854): not positive definite in general
+    v = rng.uniform(0.5, 2.0, n) * np.linspace(1, 30, n)**2
+    n_o = 1000.0 / np.arange(1, n + 1)
+    cov = ko.populate_covariance_matrix(v, n_o)
+    x = np.linspace(0.1, 9.0, n)
+    y = 3.0 * x + 0.2 + rng.randn(n) * np.sqrt(v)
+    dev = torch.device('cuda')
+    evals, proj, gls, logdet_term, info = kb.engine.spectral_prepare(torch.from_numpy(cov).to(dev),
+                                                                     torch.from_numpy(x).to(dev),
+                                                                     torch.from_numpy(y).to(dev), 1e16, True)
+    w = np.linalg.eigvalsh(cov)
+    np.testing.assert_allclose(np.sort(evals.cpu().numpy()), w, rtol=0, atol=1e-13 * np.abs(w).max())
+    assert 0 <= int(info.item()) <= 20
+    # reference route: recondition, then pinvh (the oracle restates diffusion.py:397-425, 350-365)
+    cov2 = ko.generate_covariance_matrix(v, n_o, 0)
+    inv = pinvh(cov2)
+    thetas = np.array([[3.0, 0.2], [2.5, 0.5], [3.4, -0.3], [0.1, 4.0]])
+    ll = kb.engine.mvn_loglike(torch.from_numpy(thetas).to(dev), proj, logdet_term).cpu().numpy()
+    q_ref = np.array([(t[0] * x + t[1] - y) @ inv @ (t[0] * x + t[1] - y) for t in thetas])
+    q_mine = -2.0 * ll - float(logdet_term.item())
+    np.testing.assert_allclose(q_mine - q_mine[0], q_ref - q_ref[0], rtol=1e-6, atol=1e-6 * np.abs(q_ref).max())
+    # the GLS optimum and the O(1) expansion about it
+    g = gls.cpu().numpy()
+    q_exp = g[7] + 2 * ((thetas[:, 0] - g[0]) * g[5] + (thetas[:, 1] - g[1]) * g[6]) + (thetas[:, 0] - g[0])**2 * g[2] \
+        + 2 * (thetas[:, 0] - g[0]) * (thetas[:, 1] - g[1]) * g[3] + (thetas[:, 1] - g[1])**2 * g[4]
+    np.testing.assert_allclose(q_exp, q_mine, rtol=1e-9, atol=1e-9 * np.abs(q_mine).max())
+    if n > 2:
+        mean, _ = ko.gls_posterior(x, y, inv)
+        if mean[0] > 0:
+            np.testing.assert_allclose(g[:2], mean, rtol=1e-5, atol=1e-7)
+
+
 def test_sampler_sizes_and_options(kb):
     """Output sizes as pinned by kinisi/tests/test_diffusion.py:280, 318, 331, 357."""
     dt, disp_3d, n_o, _ = list_bootstrap_inputs()
