@@ -49,6 +49,28 @@ __device__ __forceinline__ void tournament_pair(int k, int r, int m, int& p, int
     q = max(a, b);
 }
 
+// Rotation angle for the pivot block [[app, apq], [apq, aqq]].  The tangent is evaluated in single
+// precision on operands rescaled by an exact power of two (FP64 division and square root are long
+// software sequences and sit on the critical path of every round); c and s are then formed in double
+// precision from that tangent, so the rotation is orthogonal to FP64 rounding and merely leaves a
+// residual of ~1e-7 |apq| in the pivot instead of zero.  Jacobi converges with inexact angles: the
+// off-diagonal norm still shrinks by >= 1e-7 per sweep on top of the quadratic term.
+__device__ __forceinline__ void jacobi_angle(double app, double aqq, double apq, double& c, double& s) {
+    const double d = aqq - app, h = 2.0 * apq;
+    const double mx = fmax(fabs(d), fabs(h));
+    // 2^-e with e the unbiased exponent of mx (exact rescale into [1, 2))
+    const long long bits = __double_as_longlong(mx);
+    const long long expo = (bits >> 52) & 0x7ff;
+    const double scale = __longlong_as_double((long long)(2046 - expo) << 52);
+    const float df = (float)(d * scale), hf = (float)(h * scale);
+    // t = h / (d + sign(d) sqrt(d^2 + h^2)): the smaller root, |t| <= 1
+    const float rf = sqrtf(fmaf(df, df, hf * hf));
+    const float tf = hf / (df + copysignf(rf, df));
+    const double t = (double)tf;
+    c = rsqrt(fma(t, t, 1.0));
+    s = t * c;
+}
+
 __global__ void __launch_bounds__(kJacobiThreads)
     jacobi_project_kernel(const double* __restrict__ cov, int n, const double* __restrict__ x,
                           const double* __restrict__ y, double cond_max, double* __restrict__ evals,
@@ -60,6 +82,7 @@ __global__ void __launch_bounds__(kJacobiThreads)
     double* A = smj;             // [m][ld]; element (i, j) lives at A[min(i,j)][max(i,j)]
     double* u = A + (size_t)m * ld;  // [3][m]: dt, 1, msd -> rotated into the eigenbasis
     double* cs = u + 3 * m;          // [m/2][2] rotation (c, s) of each pair of the current round
+    int* prs = reinterpret_cast<int*>(cs + m);  // [m/2][2] the pairs (p, q) of the current round
     const int tid = threadIdx.x;
     const int half = m / 2;
 
@@ -72,14 +95,35 @@ __global__ void __launch_bounds__(kJacobiThreads)
         u[m + i] = i < n ? 1.0 : 0.0;
         u[2 * m + i] = i < n ? y[i] : 0.0;
     }
+    // The off-diagonal 2x2 blocks (ka < kb) are the same index set every round: each thread owns up to
+    // kMaxOwn of them for the whole run.
+    constexpr int kMaxOwn = (kJacobiMaxN / 2) * (kJacobiMaxN / 2 - 1) / 2 / kJacobiThreads + 1;
+    const int n_blocks = half * (half - 1) / 2;
+    int own_ka[kMaxOwn], own_kb[kMaxOwn];
+#pragma unroll
+    for (int o = 0; o < kMaxOwn; ++o) {
+        int e = tid + o * kJacobiThreads;
+        own_ka[o] = -1;
+        own_kb[o] = 0;
+        if (e < n_blocks) {  // decode the e-th pair (ka < kb) of the upper triangle, row by row
+            int ka = 0, row = half - 1;
+            while (e >= row) {
+                e -= row;
+                --row;
+                ++ka;
+            }
+            own_ka[o] = ka;
+            own_kb[o] = ka + 1 + e;
+        }
+    }
     __syncthreads();
 
     int sweeps = 0;
     bool polishing = false;
     for (; sweeps < kJacobiMaxSweeps; ++sweeps) {
-        // Converged when the off-diagonal norm is <= 1e-13 of the matrix norm; convergence is quadratic, so
-        // ONE more sweep after that takes it to rounding level (its floor is ~sqrt(n) eps, so a tighter test
-        // could never fire).
+        // Converged when the off-diagonal norm is <= 1e-13 of the matrix norm; ONE more sweep after that
+        // takes it to rounding level (the floor of the off-diagonal norm is ~sqrt(n) eps, so a much
+        // tighter test could never fire).
         double off = 0.0, dg = 0.0;
         for (int e = tid; e < m * m; e += kJacobiThreads) {
             const int i = e / m, j = e - i * m;
@@ -100,16 +144,17 @@ __global__ void __launch_bounds__(kJacobiThreads)
             if (tid < half) {
                 int p, q;
                 tournament_pair(tid, r, m, p, q);
+                prs[2 * tid] = p;
+                prs[2 * tid + 1] = q;
                 const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
                 double c = 1.0, s = 0.0;
                 if (apq != 0.0) {
-                    const double tau = (aqq - app) / (2.0 * apq);
-                    const double t = (fabs(tau) > 1e150) ? 0.5 / tau : copysign(1.0, tau) / (fabs(tau) + sqrt(fma(tau, tau, 1.0)));
-                    c = 1.0 / sqrt(fma(t, t, 1.0));
-                    s = t * c;
-                    A[p * ld + p] = app - t * apq;
-                    A[q * ld + q] = aqq + t * apq;
-                    A[p * ld + q] = 0.0;
+                    jacobi_angle(app, aqq, apq, c, s);
+                    // J^T [[app, apq], [apq, aqq]] J with J = [[c, s], [-s, c]]
+                    const double cc = c * c, ss = s * s, sc = s * c;
+                    A[p * ld + p] = fma(cc, app, fma(ss, aqq, -2.0 * sc * apq));
+                    A[q * ld + q] = fma(ss, app, fma(cc, aqq, 2.0 * sc * apq));
+                    A[p * ld + q] = fma(sc, app - aqq, (cc - ss) * apq);
 #pragma unroll
                     for (int v = 0; v < 3; ++v) {
                         const double up = u[v * m + p], uq = u[v * m + q];
@@ -122,12 +167,11 @@ __global__ void __launch_bounds__(kJacobiThreads)
             }
             __syncthreads();
             // off-diagonal 2x2 blocks (pair ka rows) x (pair kb columns), ka < kb:  M <- J_ka^T M J_kb
-            for (int e = tid; e < half * half; e += kJacobiThreads) {
-                const int ka = e / half, kb = e - ka * half;
-                if (ka >= kb) continue;
-                int p1, q1, p2, q2;
-                tournament_pair(ka, r, m, p1, q1);
-                tournament_pair(kb, r, m, p2, q2);
+#pragma unroll
+            for (int o = 0; o < kMaxOwn; ++o) {
+                const int ka = own_ka[o], kb = own_kb[o];
+                if (ka < 0) continue;
+                const int p1 = prs[2 * ka], q1 = prs[2 * ka + 1], p2 = prs[2 * kb], q2 = prs[2 * kb + 1];
                 const double c1 = cs[2 * ka], s1 = cs[2 * ka + 1], c2 = cs[2 * kb], s2 = cs[2 * kb + 1];
                 double* e00 = A + min(p1, p2) * ld + max(p1, p2);
                 double* e01 = A + min(p1, q2) * ld + max(p1, q2);
@@ -197,7 +241,7 @@ extern "C" int kb2_spectral_prepare(const double* cov, const double* x, const do
     KB2_CHECK(cond_max > 0.0, "kb2_spectral_prepare: cond_max must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     const int m = (n + 1) & ~1, ld = m | 1;
-    const size_t smem = sizeof(double) * ((size_t)m * ld + 3 * (size_t)m + (size_t)m);
+    const size_t smem = sizeof(double) * ((size_t)m * ld + 3 * (size_t)m + (size_t)m) + sizeof(int) * (size_t)m;
     KB2_CUDA(cudaFuncSetAttribute(jacobi_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     jacobi_project_kernel<<<1, kJacobiThreads, smem, st>>>(cov, n, x, y, cond_max, evals, proj, logdet_term, info);
     KB2_LAUNCH_CHECK();
