@@ -141,32 +141,38 @@ __global__ void __launch_bounds__(kJacobiThreads)
         if (off <= 1e-26 * (dg + 2.0 * off)) polishing = true;
 
         for (int r = 0; r < m - 1; ++r) {
+            // phase 1: the rotation of every pair (the only serial arithmetic of the round)
             if (tid < half) {
                 int p, q;
                 tournament_pair(tid, r, m, p, q);
                 prs[2 * tid] = p;
                 prs[2 * tid + 1] = q;
-                const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
+                const double apq = A[p * ld + q];
                 double c = 1.0, s = 0.0;
-                if (apq != 0.0) {
-                    jacobi_angle(app, aqq, apq, c, s);
-                    // J^T [[app, apq], [apq, aqq]] J with J = [[c, s], [-s, c]]
-                    const double cc = c * c, ss = s * s, sc = s * c;
-                    A[p * ld + p] = fma(cc, app, fma(ss, aqq, -2.0 * sc * apq));
-                    A[q * ld + q] = fma(ss, app, fma(cc, aqq, 2.0 * sc * apq));
-                    A[p * ld + q] = fma(sc, app - aqq, (cc - ss) * apq);
-#pragma unroll
-                    for (int v = 0; v < 3; ++v) {
-                        const double up = u[v * m + p], uq = u[v * m + q];
-                        u[v * m + p] = c * up - s * uq;
-                        u[v * m + q] = s * up + c * uq;
-                    }
-                }
+                if (apq != 0.0) jacobi_angle(A[p * ld + p], A[q * ld + q], apq, c, s);
                 cs[2 * tid] = c;
                 cs[2 * tid + 1] = s;
             }
             __syncthreads();
-            // off-diagonal 2x2 blocks (pair ka rows) x (pair kb columns), ka < kb:  M <- J_ka^T M J_kb
+            // phase 2, all independent given (c, s): pivot blocks and the three vectors (threads < 4*half) ...
+            if (tid < half) {
+                const int p = prs[2 * tid], q = prs[2 * tid + 1];
+                const double c = cs[2 * tid], s = cs[2 * tid + 1];
+                const double app = A[p * ld + p], aqq = A[q * ld + q], apq = A[p * ld + q];
+                // J^T [[app, apq], [apq, aqq]] J with J = [[c, s], [-s, c]]
+                const double cc = c * c, ss = s * s, sc = s * c;
+                A[p * ld + p] = fma(cc, app, fma(ss, aqq, -2.0 * sc * apq));
+                A[q * ld + q] = fma(ss, app, fma(cc, aqq, 2.0 * sc * apq));
+                A[p * ld + q] = fma(sc, app - aqq, (cc - ss) * apq);
+            } else if (tid < 4 * half) {
+                const int v = tid / half - 1, k = tid - (v + 1) * half;
+                const int p = prs[2 * k], q = prs[2 * k + 1];
+                const double c = cs[2 * k], s = cs[2 * k + 1];
+                const double up = u[v * m + p], uq = u[v * m + q];
+                u[v * m + p] = c * up - s * uq;
+                u[v * m + q] = s * up + c * uq;
+            }
+            // ... and the off-diagonal 2x2 blocks (pair ka rows) x (pair kb columns), ka < kb:  M <- J_ka^T M J_kb
 #pragma unroll
             for (int o = 0; o < kMaxOwn; ++o) {
                 const int ka = own_ka[o], kb = own_kb[o];
