@@ -105,12 +105,28 @@ int kb2_atom_sum(const double* dc, int n_atoms, int64_t pitch, const double* w, 
  * Calling it with n_atoms = 1 on a collective sum [3][pitch] yields the MSTD/MSCD sums
  * (diffusion.py:659, 683-684, 751, 775-776).
  *
- * variant: 0 = direct kernel (L1-cached partner loads), 1 = TMA-staged ring-buffer kernel.
+ * variant: 0 = direct kernel (L1-cached partner loads), 1 = TMA-staged ring-buffer kernel
+ *          (the arithmetic-run kernel, variant 2, needs the lags on the host: kb2_self_moments_runs).
  * workspace: kb2_self_moments_workspace_bytes(n_lags) bytes, contents irrelevant on entry.
  * ------------------------------------------------------------------------------------------- */
 size_t kb2_self_moments_workspace_bytes(int n_lags);
 int kb2_self_moments(const double* dc, int n_atoms, int n_frames, int64_t pitch, const int32_t* lags, int n_lags,
                      int dim_mask, int variant, void* workspace, double* sums, void* stream);
+
+/* The same sums through the arithmetic-run kernel (variant 2).  `lags_host` is the lag grid in HOST memory
+ * (ascending): the call splits it into arithmetic progressions k0 + i*delta (kinisi's default grid,
+ * np.linspace(min_dt, max_dt, n_steps, dtype=int) at kinisi/parser.py:150-168, is one up to integer
+ * truncation), runs the register-window kernel on every progression of >= 3 lags (one partner sample per step
+ * serves up to 8 terms) and the direct kernel on the lags left over, and enqueues the small plan copies on
+ * `stream`.  workspace: kb2_self_moments_runs_workspace_bytes(n_lags, n_frames) bytes. */
+size_t kb2_self_moments_runs_workspace_bytes(int n_lags, int n_frames);
+int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames, int64_t pitch, const int32_t* lags_host,
+                          int n_lags, int dim_mask, void* workspace, double* sums, void* stream);
+/* The plan kb2_self_moments_runs makes for (the first 768 lags of) a grid, for tests and diagnostics: returns the
+ * number of runs, fills up to max_runs entries of run_k0 / run_delta / run_len (host arrays, may be NULL) and
+ * stores the number of lags left to the direct kernel in *n_rest. */
+int kb2_self_moments_plan(const int32_t* lags_host, int n_lags, int n_frames, int32_t* run_k0, int32_t* run_delta,
+                          int32_t* run_len, int max_runs, int* n_rest);
 
 /* The same sums from ONE materialised displacement array disp[n_atoms][n_obs][3] (float64, the
  * reference seam: an entry of disp_3d as passed to the *Bootstrap constructors,

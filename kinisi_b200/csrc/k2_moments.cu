@@ -217,6 +217,25 @@ int launch_self_moments_tma(int config, int ndim, int sm_count, cudaStream_t st,
                             int64_t pitch, const int comp[3], const int32_t* lags, int K, unsigned int* counter,
                             double* partials, int* grid_out);
 
+// Launches the direct kernel on `K` <= kMaxLags lags; partials [grid][K][2], counter zeroed by the caller.
+int launch_self_moments_direct(int R, int ndim, int sm_count, cudaStream_t st, const double* dc, int n_atoms, int Tn,
+                               int64_t pitch, const int comp[3], const int32_t* lags, int K, unsigned int* counter,
+                               double* partials, int* grid_out) {
+    if (R != 8 && R != 16) R = 8;
+    const int B = 256 * R;
+    const int ntiles = ceil_div(Tn, B);
+    const int64_t n_work = (int64_t)n_atoms * ntiles;
+    KB2_CHECK(n_work < (1ll << 31), "kb2_self_moments: too many work items");
+    int grid = (int)std::min<int64_t>(n_work, (int64_t)sm_count * (R <= 8 ? 2 : 1));
+    grid = min(grid, kMaxGrid);
+    *grid_out = grid;
+    const size_t smem = MomentSmem::bytes(K, kDirectWarps, kDirectLG);
+    if (ndim == 1) return launch_direct<1>(R, grid, smem, st, dc, n_atoms, Tn, pitch, comp, lags, K, ntiles, counter, partials);
+    if (ndim == 2) return launch_direct<2>(R, grid, smem, st, dc, n_atoms, Tn, pitch, comp, lags, K, ntiles, counter, partials);
+    return launch_direct<3>(R, grid, smem, st, dc, n_atoms, Tn, pitch, comp, lags, K, ntiles, counter, partials);
+}
+
+
 }  // namespace kb2
 
 using namespace kb2;
@@ -252,26 +271,9 @@ extern "C" int kb2_self_moments(const double* dc, int n_atoms, int n_frames, int
         int grid = 0;
         if ((variant & 0xff) == 0) {
             // bits 8.. of `variant` optionally force R (8 or 16); default 8 (two CTAs per SM)
-            int R = (variant >> 8) & 0xff;
-            if (R != 8 && R != 16) R = 8;
-            const int B = 256 * R;
-            const int ntiles = ceil_div(n_frames, B);
-            const int64_t n_work = (int64_t)n_atoms * ntiles;
-            KB2_CHECK(n_work < (1ll << 31), "kb2_self_moments: too many work items");
-            grid = (int)std::min<int64_t>(n_work, (int64_t)sm_count * (R <= 8 ? 2 : 1));
-            grid = min(grid, kMaxGrid);
-            const size_t smem = MomentSmem::bytes(K, kDirectWarps, kDirectLG);
-            int rc;
-            if (ndim == 1)
-                rc = launch_direct<1>(R, grid, smem, st, dc, n_atoms, n_frames, pitch, comp, lg, K, ntiles, counter,
-                                      partials);
-            else if (ndim == 2)
-                rc = launch_direct<2>(R, grid, smem, st, dc, n_atoms, n_frames, pitch, comp, lg, K, ntiles, counter,
-                                      partials);
-            else
-                rc = launch_direct<3>(R, grid, smem, st, dc, n_atoms, n_frames, pitch, comp, lg, K, ntiles, counter,
-                                      partials);
-            if (rc) return rc;
+            if (int rc = launch_self_moments_direct((variant >> 8) & 0xff, ndim, sm_count, st, dc, n_atoms, n_frames, pitch,
+                                                    comp, lg, K, counter, partials, &grid))
+                return rc;
         } else {
             // bits 8.. of `variant` select the TMA configuration (0/1: one 16-warp CTA per SM with a
             // 4096-origin tile; 2: two 8-warp CTAs per SM with 2048-origin tiles)

@@ -138,9 +138,8 @@ class Bootstrap:
         if self._lazy and not isinstance(d, SingleOriginDisplacements):
             lags = d.lags[used]
             order = np.argsort(lags, kind='stable')
-            lags_dev = engine.small_to_device(lags[order], self._device, np.int32)
             if d.dc.shape[0] > 0:
-                sums = engine.self_moments(d.dc, d.n_frames, lags_dev, mask)
+                sums = engine.self_moments(d.dc, d.n_frames, lags[order], mask)
             else:
                 sums = torch.zeros((len(used), 2), dtype=torch.float64, device=self._device)
             if dist.active():
@@ -171,8 +170,7 @@ class Bootstrap:
                 S = torch.zeros((3, d.dc.shape[2]), dtype=torch.float64, device=self._device)
             if dist.active():
                 dist.allreduce_sum_(S)
-            lags_dev = engine.small_to_device(d.lags[used], self._device, np.int32)
-            return engine.self_moments(S.unsqueeze(0), d.n_frames, lags_dev, coll_mask)
+            return engine.self_moments(S.unsqueeze(0), d.n_frames, d.lags[used], coll_mask)
         w = None if weights is None else self._dev(weights)
         rows = []
         for i in used:

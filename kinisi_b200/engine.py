@@ -14,7 +14,8 @@ DIM_MASK = {'x': 1, 'y': 2, 'z': 4, 'xy': 3, 'xz': 5, 'yz': 6, 'xyz': 7}
 # self-moment kernel variants (kb2_self_moments `variant`)
 VARIANT_DIRECT = 0
 VARIANT_TMA = 1
-DEFAULT_VARIANT = VARIANT_TMA
+VARIANT_RUNS = 2  # arithmetic-run kernel (register window); plans on the host, needs the lags there
+DEFAULT_VARIANT = VARIANT_RUNS
 
 # count of kernel launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = {'n': 0}
@@ -110,20 +111,47 @@ def atom_sum(dc, weights=None):
 
 
 def self_moments(dc, n_frames, lags, mask=7, variant=None):
-    """sums [K, 2] = (sum d^2, sum d^4) per lag over atoms x observations; see kb2_self_moments.
+    """sums [K, 2] = (sum d^2, sum d^4) per lag over atoms x observations; see kb2_self_moments /
+    kb2_self_moments_runs.
 
-    dc: [n_atoms, 3, pitch] float64; lags: int32 device tensor, ascending."""
+    dc: [n_atoms, 3, pitch] float64; lags: ascending, a host array (numpy / list) or an int32 device tensor.
+    The arithmetic-run variant plans on the host: with device-resident lags it costs a device->host copy."""
     lib = require_cuda()
     if variant is None:
         variant = DEFAULT_VARIANT
-    K = lags.numel()
-    ws = torch.empty(lib.kb2_self_moments_workspace_bytes(K), dtype=torch.uint8, device=dc.device)
+    K = len(lags) if not isinstance(lags, torch.Tensor) else lags.numel()
     sums = torch.empty((K, 2), dtype=torch.float64, device=dc.device)
+    if (variant & 0xff) == VARIANT_RUNS:
+        lags_host = np.ascontiguousarray(lags.cpu().numpy() if isinstance(lags, torch.Tensor) else lags, dtype=np.int32)
+        ws = torch.empty(lib.kb2_self_moments_runs_workspace_bytes(K, n_frames), dtype=torch.uint8, device=dc.device)
+        check(
+            lib.kb2_self_moments_runs(dc.data_ptr(), dc.shape[0], n_frames, dc.shape[2], lags_host.ctypes.data, K, mask,
+                                      ws.data_ptr(), sums.data_ptr(), _stream()), 'kb2_self_moments_runs')
+        _count(4 * ((K + 767) // 768))
+        return sums
+    if not isinstance(lags, torch.Tensor):
+        lags = small_to_device(lags, dc.device, np.int32)
+    ws = torch.empty(lib.kb2_self_moments_workspace_bytes(K), dtype=torch.uint8, device=dc.device)
     check(
         lib.kb2_self_moments(dc.data_ptr(), dc.shape[0], n_frames, dc.shape[2], lags.data_ptr(), K, mask, variant,
                              ws.data_ptr(), sums.data_ptr(), _stream()), 'kb2_self_moments')
     _count(3 * ((K + 767) // 768))
     return sums
+
+
+def self_moments_plan(lags, n_frames):
+    """The arithmetic runs kb2_self_moments_runs would use: ([(k0, delta, len), ...], n_leftover_lags)."""
+    lib = _lib.load()
+    import ctypes
+    lags_host = np.ascontiguousarray(lags, dtype=np.int32)
+    cap = max(1, len(lags_host))
+    k0 = np.zeros(cap, dtype=np.int32)
+    dl = np.zeros(cap, dtype=np.int32)
+    ln = np.zeros(cap, dtype=np.int32)
+    rest = ctypes.c_int(0)
+    n = lib.kb2_self_moments_plan(lags_host.ctypes.data, len(lags_host), int(n_frames), k0.ctypes.data, dl.ctypes.data,
+                                  ln.ctypes.data, cap, ctypes.byref(rest))
+    return [(int(k0[i]), int(dl[i]), int(ln[i])) for i in range(n)], rest.value
 
 
 def disp_moments(disp, mask=7, weights=None, coll_mask=0):

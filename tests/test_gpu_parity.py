@@ -160,7 +160,7 @@ def test_reference_kats(kb, golden_dir):
 # ---------------------------------------------------------------------------------------------
 # the moment kernels against the oracle's raw sums: tiles, partial tiles, both variants, f32 input
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('variant', [0, 0 | (16 << 8), 1])
+@pytest.mark.parametrize('variant', [0, 0 | (16 << 8), 1, 2])
 @pytest.mark.parametrize('dimension', ['xyz', 'xz', 'y'])
 def test_self_moment_kernels_raw_sums(kb, variant, dimension):
     n_atoms, n_frames = 5, 9300  # > 2 tiles of 4096 and > 4 tiles of 2048, last tile partial
@@ -180,7 +180,7 @@ def test_self_moment_kernels_raw_sums(kb, variant, dimension):
     np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
 
 
-@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('variant', [0, 1, 2])
 def test_long_lag_grid_is_chunked(kb, variant):
     """More lags than one launch holds in shared memory (every lag of a 1500-frame trajectory)."""
     n_atoms, n_frames = 3, 1500
@@ -195,6 +195,71 @@ def test_long_lag_grid_is_chunked(kb, variant):
     sums = kb.engine.self_moments(dct, n_frames, torch.as_tensor(lags.astype(np.int32)).to(dev), 7, variant).cpu().numpy()
     np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
     np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
+
+
+
+def _device_dc(kb, dc):
+    dev = torch.device('cuda')
+    n_atoms, n_frames = dc.shape[0], dc.shape[1]
+    dct = torch.zeros((n_atoms, 3, kb.engine.pitch_for(n_frames)), dtype=torch.float64, device=dev)
+    dct[:, :, :n_frames] = torch.from_numpy(dc).permute(0, 2, 1).to(dev)
+    return dct
+
+
+RUN_GRIDS = {
+    # kinisi's default grids (parser.py:150-168) at several truncation patterns, plus adversarial ones
+    'linspace_100': lambda T: np.linspace(1, T, 100, dtype=int),
+    'linspace_alternating': lambda T: np.linspace(1, T, int(T / 50.4949), dtype=int),
+    'linspace_min_dt': lambda T: np.linspace(37, T - 11, 64, dtype=int),
+    'geomspace': lambda T: np.unique(np.geomspace(1, T, 100, dtype=int)),
+    'dense_1_to_300': lambda T: np.arange(1, 301),
+    'stride_2': lambda T: np.arange(2, T + 1, 2),
+    'stride_33_short': lambda T: np.arange(5, 5 + 33 * 11, 33),
+    'stride_half': lambda T: np.array([3, 3 + T // 2 - 2, 3 + 2 * (T // 2 - 2)]),
+    'two_interleaved': lambda T: np.unique(np.concatenate([np.arange(1, T, 97), np.arange(13, T, 211)])),
+    'primes': lambda T: np.array([2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53, 59, 61, 67, 71]),
+    'single': lambda T: np.array([T // 3]),
+    'last_two': lambda T: np.array([T - 1, T]),
+    'all': lambda T: np.arange(1, T + 1),
+}
+
+
+@pytest.mark.parametrize('grid', sorted(RUN_GRIDS))
+@pytest.mark.parametrize('n_frames', [700, 5431])
+def test_arithmetic_run_kernel_on_structured_and_irregular_grids(kb, grid, n_frames):
+    """kb2_self_moments_runs (register-window kernel + direct kernel for the leftover lags) against the
+    oracle's raw sums on every kind of lag grid: bit-for-bit the same terms, reduction order aside."""
+    n_atoms = 3
+    frac, latt = ko.synthetic_walk(n_atoms, n_frames, box=10.0, sigma=0.15, seed=77)
+    dc = ko.get_disp(frac, latt)
+    lags = RUN_GRIDS[grid](n_frames)
+    lags = lags[(lags >= 1) & (lags <= n_frames)]
+    if grid == 'all' and n_frames > 2000:
+        lags = lags[:1700]  # three chunks of the 768-lag launch limit
+    S1, S2, _, _ = ko.raw_sums_streaming(dc, lags)
+    sums = kb.engine.self_moments(_device_dc(kb, dc), n_frames, lags, 7, kb.engine.VARIANT_RUNS).cpu().numpy()
+    np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
+    np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
+    runs, rest = kb.engine.self_moments_plan(lags[:768], n_frames)
+    assert sum(r[2] for r in runs) + rest == min(len(lags), 768)
+
+
+def test_arithmetic_run_kernel_many_atoms_and_tiles(kb):
+    """Enough atoms and frames that every persistent CTA takes several work items, with a short trajectory
+    tail (partial tiles, warps that straddle two origin tiles, inactive lanes)."""
+    n_atoms, n_frames = 37, 12347
+    rng = np.random.default_rng(5)
+    dc = np.cumsum(rng.normal(0, 0.1, size=(n_atoms, n_frames, 3)), axis=1)
+    dc[:, 0] = 0.0
+    lags = np.linspace(1, n_frames, 100, dtype=int)
+    S1, S2, _, _ = ko.raw_sums_streaming(dc, lags)
+    dct = _device_dc(kb, dc)
+    for mask, dim in ((7, 'xyz'), (5, 'xz'), (2, 'y')):
+        if dim != 'xyz':
+            S1, S2, _, _ = ko.raw_sums_streaming(dc, lags, dim)
+        sums = kb.engine.self_moments(dct, n_frames, lags, mask, kb.engine.VARIANT_RUNS).cpu().numpy()
+        np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
+        np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
 
 
 @pytest.mark.parametrize('dtype', [np.float32, np.float64])
@@ -435,7 +500,9 @@ def test_full_size_properties(kb):
     lt = torch.as_tensor(lags.astype(np.int32)).to(dev)
     a = kb.engine.self_moments(dc, n_frames, lt, 7, 0).cpu().numpy()
     b = kb.engine.self_moments(dc, n_frames, lt, 7, 1).cpu().numpy()
-    np.testing.assert_allclose(a, b, rtol=1e-12)  # the two kernel variants agree
+    np.testing.assert_allclose(a, b, rtol=1e-12)  # the kernel variants agree
+    r = kb.engine.self_moments(dc, n_frames, lags, 7, kb.engine.VARIANT_RUNS).cpu().numpy()
+    np.testing.assert_allclose(r, a, rtol=1e-12)
     # scaling: positions x 2 -> sums x 4 and x 16 (exact in binary floating point)
     c = kb.engine.self_moments(dc * 2.0, n_frames, lt, 7, 1).cpu().numpy()
     # (exact per term; the reduction order differs from launch to launch, hence a tolerance)

@@ -73,3 +73,35 @@ def test_lazy_displacements_materialise_like_the_reference():
     for i, k in enumerate([1, 7, 30]):
         np.testing.assert_array_equal(lazy[i], ko.displacements_for_lag(dc, k))
     assert len(lazy[::2]) == 2 and lazy[::2].lags.tolist() == [1, 30]
+
+
+def test_lag_grid_is_split_into_arithmetic_runs():
+    """The host-side planner of kb2_self_moments_runs (no GPU needed): every lag lands in exactly one run or in
+    the leftover set, and kinisi's default linspace grids come out as a handful of long runs."""
+    import numpy as np
+    from kinisi_b200 import engine
+
+    def check(lags, n_frames):
+        lags = np.asarray(lags)
+        runs, rest = engine.self_moments_plan(lags, n_frames)
+        covered = []
+        for k0, d, n in runs:
+            assert n >= 3 and d >= 1
+            covered += [k0 + i * d for i in range(n)]
+        assert len(covered) + rest == len(lags)
+        assert len(set(covered)) == len(covered)
+        assert set(covered) <= set(int(x) for x in lags)
+        return runs, rest
+
+    runs, rest = check(np.linspace(1, 20000, 100, dtype=int), 20000)  # BASELINE configs[1]
+    assert rest <= 1 and max(r[2] for r in runs) >= 99
+    runs, rest = check(np.linspace(1, 5000, 100, dtype=int), 5000)  # configs[0]: alternating 50/51 spacing
+    assert rest <= 2 and len(runs) <= 4
+    runs, rest = check(np.linspace(1, 20000, 2000, dtype=int)[:768], 20000)  # 2000-point grid, one 768-lag launch
+    assert rest == 0 and len(runs) <= 8
+    runs, rest = check(np.unique(np.geomspace(1, 20000, 100, dtype=int)), 20000)
+    assert runs[0][1] == 1  # the dense start 1, 2, 3, ...
+    runs, rest = check([5], 100)
+    assert runs == [] and rest == 1
+    runs, rest = check([2, 3, 5, 7, 11, 13, 17, 19, 23], 100)
+    assert rest + sum(r[2] for r in runs) == 9
