@@ -309,7 +309,7 @@ def run_own(args):
     # the stage-2 kernel timed back to back on the last step's displacement array (215 MB > L2, so every
     # launch streams it from HBM again); free of the host launch gaps the in-step interval can contain
     pz = b._bench_parser
-    lg = engine.small_to_device(pz.disp_3d.lags, dev, np.int32)
+    lg = np.asarray(pz.disp_3d.lags, dtype=np.int32)
     for _ in range(2):
         raw_self_moments(pz._dc_sel, T, lg, 7, None)
     torch.cuda.synchronize()
@@ -364,7 +364,7 @@ def run_own(args):
                 'sharding': 'atoms' if world > 1 else 'none',
                 'l2': f'inputs ({host.numel() * 4 / 1e6:.0f} MB f32 + {n_mob * 3 * T * 8 / 1e6:.0f} MB f64 per step) '
                       'exceed the 126 MB L2; no flush needed',
-                'self_moment_variant': 'tma' if engine.DEFAULT_VARIANT == 1 else 'direct',
+                'self_moment_variant': {0: 'direct', 1: 'tma-ring', 2: 'arithmetic-runs'}[engine.DEFAULT_VARIANT & 0xff],
                 'wall_ms_per_step': wall_total / args.steps,
             },
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
@@ -405,7 +405,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
-    ap.add_argument('--variant', type=int, default=None, help='self-moment kernel: 0 direct, 1 TMA ring')
+    ap.add_argument('--variant', type=int, default=None, help='self-moment kernel: 0 direct, 1 TMA ring, 2 arithmetic runs (default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

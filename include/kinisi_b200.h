@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KB2_ABI_VERSION 1
+#define KB2_ABI_VERSION 2
 
 /* coordinate element types */
 #define KB2_F32 0
@@ -80,11 +80,15 @@ int kb2_frame_sums(const void* coords, int dtype, int mode, int n_atoms_total, i
 int kb2_scan_frames(double* buf, int n_frames, int64_t pitch, int cumulative, double divide, const double* sub,
                     double sub_scale, void* stream);
 
-/* dc_out[(i*3 + c)*pitch + t] = cumulative unwrapped displacement of atom idx[i] minus drift[c][t]
- * (drift == NULL: no correction).  dc[:, 0] == 0 in MODE_FRACTIONAL exactly as in the reference. */
+/* dc_out[(i*3 + c)*pitch + t] = cumulative unwrapped displacement of atom idx[i], drift-corrected: the
+ * per-frame quantity (unwrapped step in MODE_FRACTIONAL, displacement in MODE_DISPLACEMENT) minus
+ * step_scale * step_sums[c*pitch + t], summed over time in MODE_FRACTIONAL.  With step_sums = kb2_frame_sums of the
+ * framework atoms and step_scale = 1/n_framework this is dc - mean(dc[framework]) of parser.py:143-145 (the sum over
+ * atoms commutes with the sum over time); step_sums == NULL: no correction.  dc[:, 0] == 0 in MODE_FRACTIONAL
+ * exactly as in the reference. */
 int kb2_unwrap_cumsum(const void* coords, int dtype, int mode, int n_atoms_total, int n_frames_in, const double* latt,
-                      const double* latt_inv, int latt_stride, const int32_t* idx, int n_idx, const double* drift,
-                      double* dc_out, int64_t pitch, void* stream);
+                      const double* latt_inv, int latt_stride, const int32_t* idx, int n_idx, const double* step_sums,
+                      double step_scale, double* dc_out, int64_t pitch, void* stream);
 
 /* out[c*pitch + t] = sum_{a < n_atoms} w[a] * dc[(a*3 + c)*pitch + t]  (w == NULL: unit weights).
  * The collective displacement of MSTD (np.sum(disp_slice, axis=0), kinisi/diffusion.py:659) and the

@@ -160,121 +160,155 @@ __global__ void __launch_bounds__(1024) scan_frames_kernel(double* __restrict__ 
     }
 }
 
-// A atoms per CTA, one thread per frame of a 256-frame tile, tiles walked in time order with a
-// running carry (no cross-CTA dependency).  The raw coordinates of the next tile are fetched before
-// the current tile is scanned, so the only serial chain per tile is the scan itself.
-template <typename T, int MODE, int A, bool CONSTL>
-__global__ void __launch_bounds__(256) unwrap_cumsum_kernel(const T* __restrict__ coords, int F,
-                                                            const double* __restrict__ latt,
-                                                            const double* __restrict__ inv, int lstride,
-                                                            const int32_t* __restrict__ idx, int n_idx,
-                                                            const double* __restrict__ drift, double* __restrict__ out,
-                                                            int64_t pitch, int Tn) {
-    constexpr int NV = (MODE == KB2_MODE_FRACTIONAL) ? 6 : 3;  // raw values per atom and frame
-    __shared__ double s_tot[A][3][8];
+// One CTA per selected atom, walking the trajectory in tiles of kUwTile = 256 * kUwE frames with a running carry.
+//   raw tile   -> shared memory with cp.async (coalesced 4- or 8-byte copies, the next tile in flight while the
+//                 current one is scanned; the atom-major [F][3] rows are only element-aligned, so no bulk copy)
+//   thread     -> kUwE consecutive frames: unwrapped steps, minus step_scale * step_sums (the per-frame framework
+//                 mean, subtracted BEFORE the cumulative sum: the sum over atoms commutes with the sum over time),
+//                 sequential prefix, then one warp scan + one block scan of the thread totals per tile
+//   result     -> staged through shared memory and written as full rows of the component-major dc
+// Shared-memory strides are padded by one element per kUwE frames so that the per-thread walks are conflict free.
+constexpr int kUwE = 8;
+constexpr int kUwTile = 256 * kUwE;
+
+__host__ __device__ constexpr int uw_raw_elems() { return (kUwTile + 1) * 3 + (kUwTile + 1) / kUwE + 4; }
+__host__ __device__ constexpr int uw_out_elems() { return kUwTile + kUwTile / kUwE; }
+template <typename T>
+__host__ __device__ constexpr size_t uw_smem_bytes() {
+    return ((2 * uw_raw_elems() * sizeof(T) + 15) & ~(size_t)15) + 3 * uw_out_elems() * sizeof(double);
+}
+
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "n"(sizeof(T))
+                 : "memory");
+}
+
+template <typename T, int MODE, bool CONSTL>
+__global__ void __launch_bounds__(256, 2) unwrap_cumsum_kernel(const T* __restrict__ coords, int F,
+                                                               const double* __restrict__ latt,
+                                                               const double* __restrict__ inv, int lstride,
+                                                               const int32_t* __restrict__ idx, int n_idx,
+                                                               const double* __restrict__ step_sums, double step_scale,
+                                                               double* __restrict__ out, int64_t pitch, int Tn) {
+    constexpr int E = kUwE, TF = kUwTile;
+    constexpr bool FRAC = (MODE == KB2_MODE_FRACTIONAL);
+    extern __shared__ __align__(16) unsigned char uw_smem[];
+    T* raw = reinterpret_cast<T*>(uw_smem);  // [2][uw_raw_elems()]
+    double* outs = reinterpret_cast<double*>(uw_smem + ((2 * uw_raw_elems() * sizeof(T) + 15) & ~(size_t)15));
+    __shared__ double s_tot[3][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g0 = blockIdx.x * A;
-    const T* base[A];
-    bool have[A];
-#pragma unroll
-    for (int a = 0; a < A; ++a) {
-        have[a] = (g0 + a) < n_idx;
-        base[a] = coords + (size_t)(have[a] ? idx[g0 + a] : 0) * F * 3;
-    }
-    double carry[A][3];
-#pragma unroll
-    for (int a = 0; a < A; ++a) carry[a][0] = carry[a][1] = carry[a][2] = 0.0;
-    double Lconst[9];
-    if (MODE == KB2_MODE_FRACTIONAL && CONSTL) load9(latt, Lconst);
+    const int atom = blockIdx.x;
+    const T* base = coords + (size_t)idx[atom] * F * 3;
+    const int64_t n_in = (int64_t)F * 3;  // elements of this atom's row
 
-    T raw[A][NV], nxt[A][NV];
-    auto fetch = [&](int64_t t0, T (&dst)[A][NV]) {
-        const int64_t t = t0 + tid;
-#pragma unroll
-        for (int a = 0; a < A; ++a)
-#pragma unroll
-            for (int k = 0; k < NV; ++k) {
-                // fractional mode: [0..2] = frame t+1 (current), [3..5] = frame t (previous)
-                const int64_t e = (MODE == KB2_MODE_FRACTIONAL) ? (k < 3 ? (t + 1) * 3 + k : t * 3 + (k - 3)) : t * 3 + k;
-                dst[a][k] = (t < Tn && have[a]) ? base[a][e] : (T)0;
+    // raw element e of the tile starting at frame t0 is global element t0*3 + e; frame f, component k sits at
+    // f*3 + k + f/E
+    auto issue = [&](int64_t t0, int buf) {
+        T* dst = raw + (size_t)buf * uw_raw_elems();
+        const int64_t g0 = t0 * 3;
+        const int n = (TF + (FRAC ? 1 : 0)) * 3;
+        for (int e = tid; e < n; e += 256) {
+            if (g0 + e < n_in) {
+                const int f = e / 3;
+                cp_async_elem<T>(dst + e + f / E, base + g0 + e);
             }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    fetch(0, raw);
 
-    for (int64_t t0 = 0; t0 < pitch; t0 += 256) {
-        const int64_t t = t0 + tid;
-        const bool valid = t < Tn;
-        if (t0 + 256 < Tn) fetch(t0 + 256, nxt);
-        double val[A][3];
-        if (MODE == KB2_MODE_FRACTIONAL) {
-            if (t0 < Tn) {  // block-uniform: tiles that lie entirely in the pad skip the scan
-                double Lc[9], Lp[9], Ic[9];
-                if (!CONSTL && valid) {
-                    load9(latt + (size_t)(t + 1) * lstride, Lc);
-                    load9(latt + (size_t)t * lstride, Lp);
-                    load9(inv + (size_t)(t + 1) * lstride, Ic);
-                }
+    double Lconst[9];
+    if (FRAC && CONSTL) load9(latt, Lconst);
+    double carry[3] = {0.0, 0.0, 0.0};
+    const int n_tiles = (int)((pitch + TF - 1) / TF);
+    issue(0, 0);
+    for (int tile = 0; tile < n_tiles; ++tile) {
+        const int64_t t0 = (int64_t)tile * TF;
+        if (tile + 1 < n_tiles && t0 + TF < Tn) issue(t0 + TF, (tile + 1) & 1); else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const T* r = raw + (size_t)(tile & 1) * uw_raw_elems();
+        double val[E][3];
+        const int f0 = tid * E;
 #pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    if (valid && have[a]) {
-                        const T cur[3] = {raw[a][0], raw[a][1], raw[a][2]};
-                        const T prev[3] = {raw[a][3 % NV], raw[a][4 % NV], raw[a][5 % NV]};
-                        if (CONSTL)
-                            unwrapped_step_const<T>(cur, prev, Lconst, val[a]);
-                        else
-                            unwrapped_step<T>(cur, prev, Lc, Lp, Ic, val[a]);
+        for (int e = 0; e < E; ++e) {
+            const int f = f0 + e;
+            const int64_t t = t0 + f;
+            const bool valid = t < Tn;
+            double u[3] = {0.0, 0.0, 0.0};
+            if (valid) {
+                const int o0 = f * 3 + f / E;
+                if (FRAC) {
+                    const int o1 = (f + 1) * 3 + (f + 1) / E;
+                    const T prev[3] = {r[o0], r[o0 + 1], r[o0 + 2]};
+                    const T cur[3] = {r[o1], r[o1 + 1], r[o1 + 2]};
+                    if (CONSTL) {
+                        unwrapped_step_const<T>(cur, prev, Lconst, u);
                     } else {
-                        val[a][0] = val[a][1] = val[a][2] = 0.0;
+                        double Lc[9], Lp[9], Ic[9];
+                        load9(latt + (size_t)(t + 1) * lstride, Lc);
+                        load9(latt + (size_t)t * lstride, Lp);
+                        load9(inv + (size_t)(t + 1) * lstride, Ic);
+                        unwrapped_step<T>(cur, prev, Lc, Lp, Ic, u);
                     }
+                } else {
+                    u[0] = (double)r[o0];
+                    u[1] = (double)r[o0 + 1];
+                    u[2] = (double)r[o0 + 2];
                 }
+                if (step_sums) {
 #pragma unroll
-                for (int a = 0; a < A; ++a)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        val[a][c] = warp_inclusive_scan(val[a][c], lane);
-                        if (lane == 31) s_tot[a][c][warp] = val[a][c];
-                    }
-                __syncthreads();
-#pragma unroll
-                for (int a = 0; a < A; ++a)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        double pre = carry[a][c], tot = 0.0;
-#pragma unroll
-                        for (int wdx = 0; wdx < 8; ++wdx) {
-                            const double x = s_tot[a][c][wdx];
-                            if (wdx < warp) pre += x;
-                            tot += x;
-                        }
-                        val[a][c] += pre;
-                        carry[a][c] += tot;
-                    }
-                __syncthreads();
+                    for (int c = 0; c < 3; ++c) u[c] -= step_scale * __ldg(step_sums + (size_t)c * pitch + t);
+                }
             }
-        } else {
 #pragma unroll
-            for (int a = 0; a < A; ++a)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) val[a][c] = (double)raw[a][c];
+            for (int c = 0; c < 3; ++c) val[e][c] = u[c];
         }
-        if (t < pitch) {
-            double dr[3] = {0.0, 0.0, 0.0};
-            if (drift && valid) {
+        if (FRAC) {
+            // thread-sequential prefix, then the exclusive offset of this thread from a warp scan and a block scan
 #pragma unroll
-                for (int c = 0; c < 3; ++c) dr[c] = __ldg(drift + (size_t)c * pitch + t);
+            for (int e = 1; e < E; ++e)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) val[e][c] += val[e - 1][c];
+            double incl[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                incl[c] = warp_inclusive_scan(val[E - 1][c], lane);
+                if (lane == 31) s_tot[c][warp] = incl[c];
             }
+            __syncthreads();
 #pragma unroll
-            for (int a = 0; a < A; ++a) {
-                if (!have[a]) continue;
+            for (int c = 0; c < 3; ++c) {
+                double pre = carry[c], tot = 0.0;
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
-                    out[((size_t)(g0 + a) * 3 + c) * pitch + t] = valid ? (val[a][c] - dr[c]) : 0.0;
+                for (int wdx = 0; wdx < 8; ++wdx) {
+                    const double x = s_tot[c][wdx];
+                    if (wdx < warp) pre += x;
+                    tot += x;
+                }
+                const double off = pre + (incl[c] - val[E - 1][c]);
+                carry[c] += tot;
+#pragma unroll
+                for (int e = 0; e < E; ++e) val[e][c] += off;
             }
         }
 #pragma unroll
-        for (int a = 0; a < A; ++a)
+        for (int e = 0; e < E; ++e) {
+            const int f = f0 + e;
+            const bool valid = (t0 + f) < Tn;
 #pragma unroll
-            for (int k = 0; k < NV; ++k) raw[a][k] = nxt[a][k];
+            for (int c = 0; c < 3; ++c) outs[c * uw_out_elems() + f + f / E] = valid ? val[e][c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double* orow = out + ((size_t)atom * 3 + c) * pitch;
+            for (int f = tid; f < TF; f += 256) {
+                if (t0 + f < pitch) orow[t0 + f] = outs[c * uw_out_elems() + f + f / E];
+            }
+        }
+        // the next tile overwrites s_tot / outs only after its own barriers
     }
 }
 
@@ -298,19 +332,14 @@ __global__ void __launch_bounds__(256) atom_sum_kernel(const double* __restrict_
 
 template <typename T, int MODE, bool CONSTL>
 static int launch_unwrap(const void* coords, int F, const double* latt, const double* inv, int lstride,
-                         const int32_t* idx, int n_idx, const double* drift, double* out, int64_t pitch, int Tn,
-                         int sm_count, cudaStream_t st) {
+                         const int32_t* idx, int n_idx, const double* step_sums, double step_scale, double* out,
+                         int64_t pitch, int Tn, cudaStream_t st) {
     const T* c = (const T*)coords;
-    if (n_idx >= sm_count * 16) {
-        unwrap_cumsum_kernel<T, MODE, 4, CONSTL><<<ceil_div(n_idx, 4), 256, 0, st>>>(c, F, latt, inv, lstride, idx, n_idx,
-                                                                                      drift, out, pitch, Tn);
-    } else if (n_idx >= sm_count * 8) {
-        unwrap_cumsum_kernel<T, MODE, 2, CONSTL><<<ceil_div(n_idx, 2), 256, 0, st>>>(c, F, latt, inv, lstride, idx, n_idx,
-                                                                                      drift, out, pitch, Tn);
-    } else {
-        unwrap_cumsum_kernel<T, MODE, 1, CONSTL><<<n_idx, 256, 0, st>>>(c, F, latt, inv, lstride, idx, n_idx, drift, out,
-                                                                         pitch, Tn);
-    }
+    const size_t smem = uw_smem_bytes<T>();
+    KB2_CUDA(cudaFuncSetAttribute(unwrap_cumsum_kernel<T, MODE, CONSTL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    unwrap_cumsum_kernel<T, MODE, CONSTL><<<n_idx, 256, smem, st>>>(c, F, latt, inv, lstride, idx, n_idx, step_sums,
+                                                                    step_scale, out, pitch, Tn);
     KB2_LAUNCH_CHECK();
     return 0;
 }
@@ -389,17 +418,16 @@ extern "C" int kb2_scan_frames(double* buf, int n_frames, int64_t pitch, int cum
 
 extern "C" int kb2_unwrap_cumsum(const void* coords, int dtype, int mode, int n_atoms_total, int n_frames_in,
                                  const double* latt, const double* latt_inv, int latt_stride, const int32_t* idx,
-                                 int n_idx, const double* drift, double* dc_out, int64_t pitch, void* stream) {
+                                 int n_idx, const double* step_sums, double step_scale, double* dc_out, int64_t pitch,
+                                 void* stream) {
     int Tn = 0;
     if (int rc = check_stage1("kb2_unwrap_cumsum", coords, dtype, mode, n_atoms_total, n_frames_in, latt, latt_inv,
                               latt_stride, idx, n_idx, pitch, &Tn))
         return rc;
     KB2_CHECK(dc_out, "kb2_unwrap_cumsum: null output");
     cudaStream_t st = (cudaStream_t)stream;
-    int sm = 148;
-    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
 #define KB2_UC(T, M, C) \
-    return launch_unwrap<T, M, C>(coords, n_frames_in, latt, latt_inv, latt_stride, idx, n_idx, drift, dc_out, pitch, Tn, sm, st)
+    return launch_unwrap<T, M, C>(coords, n_frames_in, latt, latt_inv, latt_stride, idx, n_idx, step_sums, step_scale, dc_out, pitch, Tn, st)
     const bool constl = (mode == KB2_MODE_FRACTIONAL && latt_stride == 0);
     if (dtype == KB2_F32 && mode == KB2_MODE_FRACTIONAL) { if (constl) KB2_UC(float, KB2_MODE_FRACTIONAL, true); KB2_UC(float, KB2_MODE_FRACTIONAL, false); }
     if (dtype == KB2_F32) KB2_UC(float, KB2_MODE_DISPLACEMENT, false);

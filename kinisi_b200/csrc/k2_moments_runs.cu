@@ -200,7 +200,7 @@ template <int NDIM, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, 2)
     self_moments_runs_kernel(const double* __restrict__ dc, int n_atoms, int Tn, int64_t pitch, int c0, int c1, int c2,
                              const RunDesc* __restrict__ runs, const int2* __restrict__ pairs, int n_pairs, int batch,
-                             int K, unsigned int* work_counter, double* __restrict__ partials) {
+                             int K, unsigned int* work_counter, const int32_t* __restrict__ slot, double* __restrict__ out) {
     constexpr int M = kRunM, LG = kRunLG, NT = 32 * WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MomentSmem sm(smem_raw, K, WARPS, LG);
@@ -309,18 +309,9 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
             fold_lag_group_n<LG>(sm, warp, lane, acc_base + i_last - (i_last % LG), (i_last % LG) + 1);
     }
     __syncthreads();
+    // one FP64 reduction per lag, moment and CTA straight into the caller's array (zeroed by the host call)
 #pragma unroll 1
-    for (int i = tid; i < 2 * K; i += NT) partials[(size_t)blockIdx.x * 2 * K + i] = sm.acc[i];
-}
-
-// out[2*slot[i] + j] = sum_g partials[g][2*i + j]
-__global__ void moments_scatter_kernel(const double* __restrict__ partials, int G, int n, const int32_t* __restrict__ slot,
-                                       double* __restrict__ out) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= 2 * n) return;
-    double s = 0.0;
-    for (int g = 0; g < G; ++g) s += partials[(size_t)g * 2 * n + e];
-    out[2 * slot[e >> 1] + (e & 1)] = s;
+    for (int i = tid; i < 2 * K; i += NT) atomicAdd(out + 2 * slot[i >> 1] + (i & 1), sm.acc[i]);
 }
 
 // ---- host-side planning -------------------------------------------------------------------------
@@ -418,27 +409,26 @@ static size_t runs_pair_capacity(int K, int Tn) {
 template <int NDIM, int WARPS>
 static int launch_runs_w(int sm_count, long long n_work, cudaStream_t st, const double* dc, int n_atoms, int Tn,
                          int64_t pitch, const int comp[3], const RunDesc* runs, const int2* pairs, int n_pairs, int batch,
-                         int K, unsigned int* counter, double* partials, int* grid_out) {
-    const int grid = (int)std::min<long long>((n_work + WARPS - 1) / WARPS, std::min(2 * sm_count, kMaxGrid));
+                         int K, unsigned int* counter, const int32_t* slot, double* out) {
+    const int grid = (int)std::min<long long>((n_work + WARPS - 1) / WARPS, 2 * sm_count);
     const size_t smem = MomentSmem::bytes(K, WARPS, kRunLG) + (size_t)WARPS * kRunRingBytes;
     KB2_CUDA(cudaFuncSetAttribute(self_moments_runs_kernel<NDIM, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     self_moments_runs_kernel<NDIM, WARPS><<<grid, 32 * WARPS, smem, st>>>(dc, n_atoms, Tn, pitch, comp[0], comp[1], comp[2],
-                                                                          runs, pairs, n_pairs, batch, K, counter, partials);
+                                                                          runs, pairs, n_pairs, batch, K, counter, slot, out);
     KB2_LAUNCH_CHECK();
-    *grid_out = grid;
     return 0;
 }
 
 template <int NDIM>
 static int launch_runs(int warps, int sm_count, long long n_work, cudaStream_t st, const double* dc, int n_atoms, int Tn,
                        int64_t pitch, const int comp[3], const RunDesc* runs, const int2* pairs, int n_pairs, int batch,
-                       int K, unsigned int* counter, double* partials, int* grid_out) {
+                       int K, unsigned int* counter, const int32_t* slot, double* out) {
     if (warps == 8)
         return launch_runs_w<NDIM, 8>(sm_count, n_work, st, dc, n_atoms, Tn, pitch, comp, runs, pairs, n_pairs, batch, K,
-                                      counter, partials, grid_out);
+                                      counter, slot, out);
     return launch_runs_w<NDIM, 6>(sm_count, n_work, st, dc, n_atoms, Tn, pitch, comp, runs, pairs, n_pairs, batch, K, counter,
-                                  partials, grid_out);
+                                  slot, out);
 }
 
 // Tuning knob for experiments (tools/k2probe.py): KB2_RUNS_WARPS=6|8 picks the CTA size of the run kernel.
@@ -450,7 +440,7 @@ static int runs_warps() {
     return w;
 }
 
-// workspace layout: [partials: kMaxGrid * 2k doubles][plan: 64 ints (work counter) | runs | pairs | slots]
+// workspace layout: the plan: 64 ints (work counter) | runs | pairs | slots
 static size_t runs_plan_bytes(int k, int t) {
     return 256 + align256((size_t)k * sizeof(RunDesc)) + align256(runs_pair_capacity(k, t) * sizeof(int2)) +
            align256((size_t)k * sizeof(int32_t));
@@ -463,7 +453,7 @@ using namespace kb2;
 extern "C" size_t kb2_self_moments_runs_workspace_bytes(int n_lags, int n_frames) {
     const int k = n_lags < 1 ? 1 : (n_lags > kMaxLags ? kMaxLags : n_lags);
     const int t = n_frames < 1 ? 1 : n_frames;
-    return align256((size_t)kMaxGrid * 2 * (size_t)k * sizeof(double)) + runs_plan_bytes(k, t);
+    return runs_plan_bytes(k, t);
 }
 
 extern "C" int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames, int64_t pitch,
@@ -485,9 +475,8 @@ extern "C" int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, 0);
 
     const int kcap = n_lags > kMaxLags ? kMaxLags : n_lags;
-    char* ws = (char*)workspace;
-    double* partials = (double*)ws;
-    char* d_plan = ws + align256((size_t)kMaxGrid * 2 * (size_t)kcap * sizeof(double));
+    char* d_plan = (char*)workspace;
+    KB2_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_lags * 2 * sizeof(double), st));
     const size_t pair_cap = runs_pair_capacity(kcap, n_frames);
 
     std::vector<unsigned char> packed;
@@ -516,19 +505,17 @@ extern "C" int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames
         const RunDesc* d_runs = (const RunDesc*)(d_plan + off_runs);
         const int2* d_pairs = (const int2*)(d_plan + off_pairs);
         const int32_t* d_slot = (const int32_t*)(d_plan + off_slot);
-        int rc, grid = 0;
+        int rc;
         if (ndim == 1)
             rc = launch_runs<1>(runs_warps(), sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
-                                (int)plan.pairs.size(), batch, K, (unsigned int*)d_plan, partials, &grid);
+                                (int)plan.pairs.size(), batch, K, (unsigned int*)d_plan, d_slot, sums + 2 * l0);
         else if (ndim == 2)
             rc = launch_runs<2>(runs_warps(), sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
-                                (int)plan.pairs.size(), batch, K, (unsigned int*)d_plan, partials, &grid);
+                                (int)plan.pairs.size(), batch, K, (unsigned int*)d_plan, d_slot, sums + 2 * l0);
         else
             rc = launch_runs<3>(runs_warps(), sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
-                                (int)plan.pairs.size(), batch, K, (unsigned int*)d_plan, partials, &grid);
+                                (int)plan.pairs.size(), batch, K, (unsigned int*)d_plan, d_slot, sums + 2 * l0);
         if (rc) return rc;
-        moments_scatter_kernel<<<ceil_div(2 * K, 128), 128, 0, st>>>(partials, grid, K, d_slot, sums + 2 * l0);
-        KB2_LAUNCH_CHECK();
     }
     return 0;
 }

@@ -88,14 +88,15 @@ def scan_frames(buf, n_frames, cumulative, divide, sub=None, sub_scale=0.0):
     return buf
 
 
-def unwrap_cumsum(coords, mode, latt, latt_inv, latt_stride, idx, drift, pitch):
-    """dc [n_idx, 3, pitch] float64 component-major, drift-corrected; see kb2_unwrap_cumsum."""
+def unwrap_cumsum(coords, mode, latt, latt_inv, latt_stride, idx, step_sums, step_scale, pitch):
+    """dc [n_idx, 3, pitch] float64 component-major, drift-corrected with the per-frame framework sums;
+    see kb2_unwrap_cumsum."""
     lib = require_cuda()
     out = torch.empty((idx.numel(), 3, pitch), dtype=torch.float64, device=coords.device)
     check(
         lib.kb2_unwrap_cumsum(coords.data_ptr(), coords_dtype_code(coords), mode, coords.shape[0], coords.shape[1],
-                              _ptr(latt), _ptr(latt_inv), latt_stride, idx.data_ptr(), idx.numel(), _ptr(drift),
-                              out.data_ptr(), pitch, _stream()), 'kb2_unwrap_cumsum')
+                              _ptr(latt), _ptr(latt_inv), latt_stride, idx.data_ptr(), idx.numel(), _ptr(step_sums),
+                              float(step_scale), out.data_ptr(), pitch, _stream()), 'kb2_unwrap_cumsum')
     _count()
     return out
 
@@ -127,7 +128,7 @@ def self_moments(dc, n_frames, lags, mask=7, variant=None):
         check(
             lib.kb2_self_moments_runs(dc.data_ptr(), dc.shape[0], n_frames, dc.shape[2], lags_host.ctypes.data, K, mask,
                                       ws.data_ptr(), sums.data_ptr(), _stream()), 'kb2_self_moments_runs')
-        _count(4 * ((K + 767) // 768))
+        _count((K + 767) // 768)
         return sums
     if not isinstance(lags, torch.Tensor):
         lags = small_to_device(lags, dc.device, np.int32)

@@ -77,9 +77,12 @@ class Trajectory:
         return engine.frame_sums(self.coords, self.mode, self.latt, self.latt_inv, self.latt_stride, idx, weights, pitch)
 
     def displacement(self, idx, drift=None):
-        """dc [len(idx), 3, pitch] float64, component-major."""
+        """dc [len(idx), 3, pitch] float64, component-major.  `drift` is None or (frame_sums, n_framework): the
+        per-frame sums over the framework atoms, whose mean is removed before the cumulative sum."""
         pitch = engine.pitch_for(self.n_frames)
-        return engine.unwrap_cumsum(self.coords, self.mode, self.latt, self.latt_inv, self.latt_stride, idx, drift, pitch)
+        sums, scale = (None, 0.0) if drift is None else (drift[0], 1.0 / drift[1])
+        return engine.unwrap_cumsum(self.coords, self.mode, self.latt, self.latt_inv, self.latt_stride, idx, sums, scale,
+                                    pitch)
 
     def numpy(self, idx=None, drift=None):
         """The reference layout `[site, time step, axis]` on the host."""
@@ -232,7 +235,8 @@ class Parser:
         self.delta_t, self.disp_3d, self._n_o = self.get_disps(self.time_intervals, self._dc_sel, progress)
 
     def _framework_mean(self, traj, drift_indices):
-        """Mean displacement of the framework atoms per frame, [3, pitch] on the device, or None."""
+        """(per-frame sums over the framework atoms [3, pitch] on the device, number of framework atoms), or None.
+        The displacement kernel subtracts sums / n before its cumulative sum (kinisi/parser.py:143-145)."""
         n_fw_local = len(drift_indices)
         n_fw = int(round(dist.allreduce_sum_scalar(n_fw_local, traj.device))) if self._distributed else n_fw_local
         if n_fw == 0:
@@ -244,7 +248,7 @@ class Parser:
             sums = torch.zeros((3, engine.pitch_for(traj.n_frames)), dtype=torch.float64, device=traj.device)
         if self._distributed:
             dist.allreduce_sum_(sums)
-        return engine.scan_frames(sums, traj.n_frames, traj.mode == MODE_FRACTIONAL, float(n_fw))
+        return sums, float(n_fw)
 
     @property
     def volume(self) -> float:
@@ -290,9 +294,7 @@ class Parser:
         if len(drift_indices) == 0:
             return traj.numpy()
         fw = engine.small_to_device(drift_indices, traj.device, np.int32)
-        drift = engine.scan_frames(traj.frame_sums(fw), traj.n_frames, traj.mode == MODE_FRACTIONAL,
-                                   float(len(drift_indices)))
-        return traj.numpy(drift=drift)
+        return traj.numpy(drift=(traj.frame_sums(fw), float(len(drift_indices))))
 
     def get_time_intervals(self, n_steps: int, spacing: str) -> np.ndarray:
         """The integer time-interval grid (kinisi/parser.py:150-168).  Integer work: stays on the host."""
