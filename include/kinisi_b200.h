@@ -120,17 +120,18 @@ int kb2_self_moments(const double* dc, int n_atoms, int n_frames, int64_t pitch,
 /* The same sums through the arithmetic-run kernel (variant 2).  `lags_host` is the lag grid in HOST memory
  * (ascending): the call splits it into arithmetic progressions k0 + i*delta (kinisi's default grid,
  * np.linspace(min_dt, max_dt, n_steps, dtype=int) at kinisi/parser.py:150-168, is one up to integer
- * truncation), runs the register-window kernel on every progression of >= 3 lags (one partner sample per step
- * serves up to 8 terms) and the direct kernel on the lags left over, and enqueues the small plan copies on
- * `stream`.  workspace: kb2_self_moments_runs_workspace_bytes(n_lags, n_frames) bytes. */
+ * truncation, handled as a one-sample drift inside the run), runs the register-window kernel on every progression
+ * (one partner sample per step serves up to 8 terms; lags that fit no progression become runs of one), and enqueues
+ * one small plan copy on `stream`.  workspace: kb2_self_moments_runs_workspace_bytes(n_lags, n_frames) bytes. */
 size_t kb2_self_moments_runs_workspace_bytes(int n_lags, int n_frames);
 int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames, int64_t pitch, const int32_t* lags_host,
                           int n_lags, int dim_mask, void* workspace, double* sums, void* stream);
 /* The plan kb2_self_moments_runs makes for (the first 768 lags of) a grid, for tests and diagnostics: returns the
- * number of runs, fills up to max_runs entries of run_k0 / run_delta / run_len (host arrays, may be NULL) and
- * stores the number of lags left to the direct kernel in *n_rest. */
+ * number of runs of >= 3 lags, fills up to max_runs entries of run_k0 / run_delta / run_len / run_n_chg (host arrays,
+ * may be NULL; run_n_chg = signed number of one-sample drift changes inside the run, lags k0 + i*delta + e_i) and
+ * stores the number of lags that became runs of one in *n_rest. */
 int kb2_self_moments_plan(const int32_t* lags_host, int n_lags, int n_frames, int32_t* run_k0, int32_t* run_delta,
-                          int32_t* run_len, int max_runs, int* n_rest);
+                          int32_t* run_len, int32_t* run_n_chg, int max_runs, int* n_rest);
 
 /* The same sums from ONE materialised displacement array disp[n_atoms][n_obs][3] (float64, the
  * reference seam: an entry of disp_3d as passed to the *Bootstrap constructors,

@@ -29,7 +29,8 @@ SIGNATURES = {
     'kb2_self_moments_runs_workspace_bytes': (c_size_t, [c_int, c_int]),
     'kb2_self_moments_runs': (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p]),
-    'kb2_self_moments_plan': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_int)]),
+    'kb2_self_moments_plan': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                      POINTER(c_int)]),
     'kb2_disp_moments': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'kb2_moment_stats': (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 4 + [c_void_p]),
     'kb2_cov_build': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

@@ -22,8 +22,15 @@
 // the 8 bytes it will read itself kRunPrefetch steps later: deep prefetch (L2 latency is ~300 cycles, HBM more)
 // without spending registers, and no cross-lane synchronisation.
 //
+// Drift.  np.linspace(..., dtype=int) truncates: the spacing is D most of the time and D+1 (or D-1) every so often
+// (every 11th lag at 100,000 frames / 100 lags).  Such a grid is ONE run with drift, k_i = k0 + i*D + e_i, e_i
+// changing by delta = +-1 at a few lag indices at least M apart.  The partner of origin m at step s is then
+// x[p_s + e_(s-m)]: while a change is inside the M-lag window the step needs the two neighbouring samples
+// p_s + e and p_s + e + delta, and origin m takes the second one iff m <= s - (change index).  That is a
+// warp-uniform select per term; everything else is unchanged.
+//
 // The host splits the lag grid into arithmetic runs (greedy cover; a lag that fits no run of >= 3 becomes a run of
-// one).  Work items are (run, 32-column strip, atom); every warp of the persistent CTAs pulls its own items from
+// one) and then chains runs that continue each other's progression with a one-sample shift into drift runs.  Work items are (run, 32-column strip, atom); every warp of the persistent CTAs pulls its own items from
 // an atomic counter (no block-level barrier inside the loop).  Atoms are taken in batches whose trajectories fit
 // in L2 together (each sample is a partner in ~(M+L)/M strips, so a batch is read from HBM once and served from
 // L2 afterwards); inside a batch the strips are issued in order of decreasing cost.
@@ -44,13 +51,39 @@ constexpr int kRunCols = 32;               // columns per work item: one warp-wi
 constexpr int kRunMinLen = 3;              // shortest progression taken as a run
 constexpr int kRunSingleStride = 32;       // origin stride of a run of one lag: a strip covers 256 contiguous origins
 constexpr int kRunCandidates = 24;         // successors tried as the common difference of a run
+constexpr int kRunChainMaxSeg = 16;        // progressions longer than this are not chained into drift runs
 constexpr int kRunPrefetch = 6;            // steps between the cp.async of a partner sample and its use (< kRunM)
 constexpr long long kRunBatchBytes = 24ll << 20;  // trajectory bytes of one atom batch (L2 is 126 MB)
-constexpr int kRunRingBytes = kRunM * 3 * 32 * 8;  // per warp
+constexpr int kRunRingBytes = kRunM * 3 * 2 * 32 * 8;  // per warp: slot x component x {sample, neighbour} x lane
 constexpr int kRunMaxWarps = 8;
 
 struct RunDesc {
-    int k0, delta, len, off;  // lags k0 + i*delta, i < len; accumulator index of lag i is off + i
+    int k0, delta, len, off;  // lags k0 + i*delta + e_i, i < len; accumulator index of lag i is off + i
+    int chg_off, n_chg;       // e_i = shift * #{changes <= i}; the change indices are chg[chg_off .. chg_off + n_chg)
+    int shift, pad;           // +1 or -1
+};
+static_assert(sizeof(RunDesc) == 32, "RunDesc is read as two int4");
+
+// Warp-uniform position of a step in the drift pattern of its run.
+struct DriftCursor {
+    int e;      // sample offset of the oldest lag of the window: shift * #{changes <= s - (M-1)}
+    int cnext;  // lag index of the next change not yet absorbed into e
+    int ci;     // its position in the change list
+    __device__ __forceinline__ void init(const int32_t* chg, int n) {
+        e = 0;
+        ci = 0;
+        cnext = n > 0 ? __ldg(chg) : 0x7fffffff;
+    }
+    // at the start of step s: a change is absorbed once every lag of the window [s-(M-1), s] is at or past it
+    __device__ __forceinline__ void advance(int s, const int32_t* chg, int n, int shift) {
+        if (cnext <= s - (kRunM - 1)) {
+            e += shift;
+            ++ci;
+            cnext = ci < n ? __ldg(chg + ci) : 0x7fffffff;
+        }
+    }
+    // origins m <= mcut(s) pair with lags at or past the change inside the window: they use offset e + shift
+    __device__ __forceinline__ int mcut(int s) const { return cnext <= s ? s - cnext : -1; }
 };
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
@@ -90,49 +123,84 @@ __device__ __forceinline__ void fold_lag_group_n(MomentSmem& sm, int warp, int l
 }
 
 // State of one column while it walks its steps.
-template <int NDIM, int M>
+template <int NDIM, int M, bool DR>
 struct Column {
     double o[3][M];        // origins
     double A1[M], A2[M];   // running sums; at a step s = 0 (mod M) lag i lives in slot i mod M
-    const double* pn[3];   // address of the partner sample of the next step to prefetch
-    double* ring;          // this lane's column of the warp's ring: sample (slot, c) at ring[(slot*3 + c)*32]
-    int nvalid;            // steps whose partner lies inside the trajectory (this lane)
+    const double* pn[3];   // address of the undrifted partner sample of the next step to prefetch
+    double* ring;          // this lane's column of the warp's ring: sample (slot, c, h) at ring[((slot*3 + c)*2 + h)*32]
+                           // (h = 0 only and no factor 2 in kernels without drift, DR = false)
+    int rem;               // Tn - 1 - (undrifted partner index) of the current step: offset e is valid iff e <= rem
+    int rem_pf;            // the same for the next step to prefetch
     int fetched;           // steps prefetched so far
+    DriftCursor pf;        // drift position of the prefetch stream
 
-    __device__ __forceinline__ void prefetch(int D) {
-        if (fetched < nvalid) {
+    // Prefetch the partner sample(s) of step `fetched`: offset pf.e and, while a change is inside the window, its
+    // neighbour pf.e + shift.
+    static constexpr int H = DR ? 2 : 1;  // samples per (slot, component)
+    __device__ __forceinline__ void prefetch(int D, const int32_t* chg, int n_chg, int shift) {
+        double* dst = ring + (fetched % M) * (3 * H * 32);
+        if (DR) {
+            pf.advance(fetched, chg, n_chg, shift);
+            if (pf.e <= rem_pf) {
 #pragma unroll
-            for (int c = 0; c < NDIM; ++c) cp_async8(ring + ((fetched % M) * 3 + c) * 32, pn[c]);
+                for (int c = 0; c < NDIM; ++c) cp_async8(dst + (c * 2) * 32, pn[c] + pf.e);
+            }
+            if (pf.cnext <= fetched && pf.e + shift <= rem_pf) {
+#pragma unroll
+                for (int c = 0; c < NDIM; ++c) cp_async8(dst + (c * 2 + 1) * 32, pn[c] + pf.e + shift);
+            }
+        } else {
+            if (0 <= rem_pf) {
+#pragma unroll
+                for (int c = 0; c < NDIM; ++c) cp_async8(dst + c * 32, pn[c]);
+            }
         }
 #pragma unroll
         for (int c = 0; c < NDIM; ++c) pn[c] += D;
+        rem_pf -= D;
         ++fetched;
         cp_async_commit();
     }
 };
 
-// M consecutive steps s0 .. s0+M-1 (s0 a multiple of M) whose partners lie inside the trajectory for all lanes
-// (s0 + M <= min over lanes of nvalid) and whose (step, origin) pairs are lags of the run in a static pattern:
+struct RunCtx {  // warp-uniform description of the current item
+    int D, L, acc_base, n_chg, shift;
+    const int32_t* chg;
+};
+
+// M consecutive steps s0 .. s0+M-1 (s0 a multiple of M) whose partners lie inside the trajectory for all lanes and
+// whose (step, origin) pairs are lags of the run in a static pattern:
 //   FIRST = false: all of them (s0 >= M, s0 + M <= L);
 //   FIRST = true:  s0 = 0 and L >= M, the triangular start: origin m joins at step m, only lag 0 completes.
-template <int NDIM, int M, int LG, bool FIRST>
-__device__ __forceinline__ void run_block_interior(Column<NDIM, M>& col, int D, int s0, MomentSmem& sm, int warp,
-                                                   int lane, int acc_base) {
+// DRIFT = false requires that no change index lies in the lags these steps touch (cur.cnext > s0 + M - 1).
+template <int NDIM, int M, int LG, bool FIRST, bool DRIFT, bool DR>
+__device__ __forceinline__ void run_block_interior(Column<NDIM, M, DR>& col, DriftCursor& cur, const RunCtx& rc, int s0,
+                                                   MomentSmem& sm, int warp, int lane) {
     static_assert(M % LG == 0, "the fold group must divide the register window");
 #pragma unroll
     for (int u = 0; u < M; ++u) {
         cp_async_wait<kRunPrefetch - 1>();
-        double P[3];
+        int mc = -1;
+        if (DRIFT) {
+            cur.advance(s0 + u, rc.chg, rc.n_chg, rc.shift);
+            mc = cur.mcut(s0 + u);
+        }
+        double P[3], Q[3];
 #pragma unroll
-        for (int c = 0; c < NDIM; ++c) P[c] = col.ring[(u * 3 + c) * 32];
-        col.prefetch(D);
+        for (int c = 0; c < NDIM; ++c) {
+            P[c] = col.ring[((u * 3 + c) * (DR ? 2 : 1)) * 32];
+            if (DRIFT) Q[c] = col.ring[((u * 3 + c) * 2 + 1) * 32];
+        }
+        col.prefetch(rc.D, rc.chg, rc.n_chg, rc.shift);
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             if (FIRST && m > u) continue;
             double d2 = 0.0;
 #pragma unroll
             for (int c = 0; c < NDIM; ++c) {
-                const double d = P[c] - col.o[c][m];
+                const double partner = (DRIFT && m <= mc) ? Q[c] : P[c];  // warp-uniform select
+                const double d = partner - col.o[c][m];
                 d2 = fma(d, d, d2);
             }
             col.A1[(u - m + M) % M] += d2;
@@ -144,42 +212,54 @@ __device__ __forceinline__ void run_block_interior(Column<NDIM, M>& col, int D, 
             sm.stash_put(warp, gs, lane, col.A1[sl], col.A2[sl]);
             col.A1[sl] = 0.0;
             col.A2[sl] = 0.0;
-            if (gs == LG - 1) fold_lag_group_n<LG>(sm, warp, lane, acc_base + s0 + u - (M - 1) - (LG - 1), LG);
+            if (gs == LG - 1) fold_lag_group_n<LG>(sm, warp, lane, rc.acc_base + s0 + u - (M - 1) - (LG - 1), LG);
         }
     }
+    col.rem -= M * rc.D;
 }
 
 // One step at any position: origin m pairs with slot (M - m) % M (the layout of a step s = 0 mod M), and the
 // accumulators are rotated by one slot afterwards, so M generic steps from a block boundary restore the layout the
-// interior blocks assume.
-template <int NDIM, int M, int LG>
-__device__ __forceinline__ void run_step_generic(Column<NDIM, M>& col, int D, int s, int L, MomentSmem& sm, int warp,
-                                                 int lane, int acc_base) {
+// interior blocks assume.  Validity is checked per term (lag inside the run: warp-uniform; partner inside the
+// trajectory: per lane).
+template <int NDIM, int M, int LG, bool DR>
+__device__ __forceinline__ void run_step_generic(Column<NDIM, M, DR>& col, DriftCursor& cur, const RunCtx& rc, int s,
+                                                 MomentSmem& sm, int warp, int lane) {
     cp_async_wait<kRunPrefetch - 1>();
-    double P[3];
+    int mc = -1;
+    if (DR) {
+        cur.advance(s, rc.chg, rc.n_chg, rc.shift);
+        mc = cur.mcut(s);
+    }
+    double P[3], Q[3];
 #pragma unroll
-    for (int c = 0; c < NDIM; ++c) P[c] = col.ring[((s % M) * 3 + c) * 32];
-    col.prefetch(D);
-    const bool ok = s < col.nvalid;
+    for (int c = 0; c < NDIM; ++c) {
+        P[c] = col.ring[(((s % M) * 3 + c) * (DR ? 2 : 1)) * 32];
+        Q[c] = DR ? col.ring[(((s % M) * 3 + c) * 2 + 1) * 32] : 0.0;
+    }
+    col.prefetch(rc.D, rc.chg, rc.n_chg, rc.shift);
+    const bool ok_p = (DR ? cur.e : 0) <= col.rem, ok_q = DR && (cur.e + rc.shift <= col.rem);
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        if ((unsigned)(s - m) < (unsigned)L) {  // lag s - m belongs to the run: warp-uniform
+        if ((unsigned)(s - m) < (unsigned)rc.L) {  // lag s - m belongs to the run: warp-uniform
+            const bool hi = DR && m <= mc;          // warp-uniform
             double d2 = 0.0;
 #pragma unroll
             for (int c = 0; c < NDIM; ++c) {
-                const double d = P[c] - col.o[c][m];
+                const double d = (hi ? Q[c] : P[c]) - col.o[c][m];
                 d2 = fma(d, d, d2);
             }
-            d2 = ok ? d2 : 0.0;
+            d2 = (hi ? ok_q : ok_p) ? d2 : 0.0;
             col.A1[(M - m) % M] += d2;
             col.A2[(M - m) % M] = fma(d2, d2, col.A2[(M - m) % M]);
         }
     }
+    col.rem -= rc.D;
     const int i_f = s - (M - 1);  // complete after this step; it is the lag of origin M-1, slot 1
-    if (i_f >= 0 && i_f < L) {
+    if (i_f >= 0 && i_f < rc.L) {
         const int gs = i_f % LG;
         sm.stash_put(warp, gs, lane, col.A1[1], col.A2[1]);
-        if (gs == LG - 1 || i_f == L - 1) fold_lag_group_n<LG>(sm, warp, lane, acc_base + i_f - gs, gs + 1);
+        if (gs == LG - 1 || i_f == rc.L - 1) fold_lag_group_n<LG>(sm, warp, lane, rc.acc_base + i_f - gs, gs + 1);
     }
     // rotate by one slot: the lag of origin m becomes the lag of origin m+1 (slot j <- slot j+1); the flushed
     // slot 1 re-enters as the empty slot 0 and slot 0 moves to slot M-1
@@ -196,17 +276,19 @@ __device__ __forceinline__ void run_step_generic(Column<NDIM, M>& col, int D, in
 }
 
 // WARPS warps per CTA, two CTAs per SM: 6 warps leave 168 registers per thread (no spills), 8 warps 128.
-template <int NDIM, int WARPS>
+template <int NDIM, int WARPS, bool DR>
 __global__ void __launch_bounds__(32 * WARPS, 2)
     self_moments_runs_kernel(const double* __restrict__ dc, int n_atoms, int Tn, int64_t pitch, int c0, int c1, int c2,
                              const RunDesc* __restrict__ runs, const int2* __restrict__ pairs, int n_pairs, int batch,
-                             int K, unsigned int* work_counter, const int32_t* __restrict__ slot, double* __restrict__ out) {
+                             const int32_t* __restrict__ chg, int K, unsigned int* work_counter,
+                             const int32_t* __restrict__ slot, double* __restrict__ out) {
     constexpr int M = kRunM, LG = kRunLG, NT = 32 * WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MomentSmem sm(smem_raw, K, WARPS, LG);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    Column<NDIM, M> col;
-    col.ring = reinterpret_cast<double*>(smem_raw + MomentSmem::bytes(K, WARPS, LG)) + warp * (kRunRingBytes / 8) + lane;
+    Column<NDIM, M, DR> col;
+    col.ring = reinterpret_cast<double*>(smem_raw + MomentSmem::bytes(K, WARPS, LG)) +
+               warp * (kRunRingBytes / 8 / (DR ? 1 : 2)) + lane;
 
 #pragma unroll 1
     for (int i = tid; i < 2 * K; i += NT) sm.acc[i] = 0.0;
@@ -226,8 +308,17 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
         const int bsize = min(batch, n_atoms - bi * batch);
         const int pi = rem / bsize, atom = bi * batch + (rem - pi * bsize);
         const int2 pr = __ldg(pairs + pi);
-        const int4 rd4 = __ldg(reinterpret_cast<const int4*>(runs) + pr.x);
-        const int k0 = rd4.x, D = rd4.y, L = rd4.z, acc_base = rd4.w;
+        const int4 rd4 = __ldg(reinterpret_cast<const int4*>(runs) + 2 * pr.x);
+        const int4 rd5 = __ldg(reinterpret_cast<const int4*>(runs) + 2 * pr.x + 1);
+        const int k0 = rd4.x;
+        RunCtx rc;
+        rc.D = rd4.y;
+        rc.L = rd4.z;
+        rc.acc_base = rd4.w;
+        rc.chg = chg + rd5.x;
+        rc.n_chg = rd5.y;
+        rc.shift = rd5.z;
+        const int D = rc.D, L = rc.L;
         const double* row[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) row[c] = dc + ((size_t)atom * 3 + comp[c < NDIM ? c : 0]) * pitch;
@@ -236,36 +327,41 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
         if (pr.y == 0) {
 #pragma unroll 1
             for (int i = lane; i < L; i += 32) {
-                const int p = k0 + i * D - 1;
+                int e = 0;
+                for (int j = 0; j < rc.n_chg; ++j) e += (__ldg(rc.chg + j) <= i) ? rc.shift : 0;
+                const int p = k0 + i * D + e - 1;
                 double d2 = 0.0;
 #pragma unroll
                 for (int c = 0; c < NDIM; ++c) {
                     const double d = __ldg(row[c] + p);
                     d2 = fma(d, d, d2);
                 }
-                atomicAdd(&sm.acc[2 * (acc_base + i)], d2);
-                atomicAdd(&sm.acc[2 * (acc_base + i) + 1], d2 * d2);
+                atomicAdd(&sm.acc[2 * (rc.acc_base + i)], d2);
+                atomicAdd(&sm.acc[2 * (rc.acc_base + i) + 1], d2 * d2);
             }
         }
 
         const int g = pr.y * kRunCols + lane;  // column: tile q = g / D, offset t = g % D
         const int q = g / D, t = g - q * D;
         const long long j0 = (long long)q * M * D + t;
-        const long long p0 = j0 + k0;
-        col.nvalid = 0;
-        if (p0 < Tn) {
-            const long long room = (Tn - 1 - p0) / D + 1;
-            col.nvalid = (int)(room < (long long)(M + L - 1) ? room : (long long)(M + L - 1));
-        }
-        const int wmax = __reduce_max_sync(0xffffffffu, col.nvalid);
+        const long long p0 = j0 + k0;  // undrifted partner index of step 0
+        // steps in which this lane has at least one / only valid partners, whatever the drift (|e| <= n_chg)
+        const int e_lo = min(0, rc.shift * rc.n_chg), e_hi = max(0, rc.shift * rc.n_chg);
+        int n_any = 0, n_all = 0;
+        if (p0 + e_lo < Tn) n_any = (int)min((long long)(M + L - 1), (Tn - 1 - p0 - e_lo) / D + 1);
+        if (p0 + e_hi < Tn) n_all = (int)min((long long)(M + L - 1), (Tn - 1 - p0 - e_hi) / D + 1);
+        const int wmax = __reduce_max_sync(0xffffffffu, n_any);
         if (wmax == 0) continue;  // warp-uniform
-        const int wmin = __reduce_min_sync(0xffffffffu, col.nvalid);
+        const int wmin = __reduce_min_sync(0xffffffffu, n_all);
 
         col.fetched = 0;
+        col.pf.init(rc.chg, rc.n_chg);
+        // Tn - 1 - p0 can be far below zero for lanes past the end; clamp so that the per-step decrements cannot wrap
+        col.rem = col.rem_pf = (int)max((long long)(Tn - 1) - p0, -(1ll << 30));
 #pragma unroll
         for (int c = 0; c < NDIM; ++c) col.pn[c] = row[c] + p0;
 #pragma unroll
-        for (int f = 0; f < kRunPrefetch; ++f) col.prefetch(D);
+        for (int f = 0; f < kRunPrefetch; ++f) col.prefetch(D, rc.chg, rc.n_chg, rc.shift);
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             const long long jm = j0 + (long long)m * D;
@@ -273,19 +369,29 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
             for (int c = 0; c < NDIM; ++c) col.o[c][m] = (jm < Tn) ? __ldg(row[c] + jm) : 0.0;
             col.A1[m] = col.A2[m] = 0.0;
         }
+        DriftCursor cur;
+        cur.init(rc.chg, rc.n_chg);
 
         // steps in which at least one lane has a valid term; blocks of M steps with a static pattern run unrolled
         const int work_steps = min(M + L - 1, wmax);
         const int full = min(L, wmin);  // steps below `full` have every lane valid and lag s - m < L for all m <= s
         int s = 0;
-        if (full >= M) {
-            run_block_interior<NDIM, M, LG, true>(col, D, 0, sm, warp, lane, acc_base);
-            s = M;
 #pragma unroll 1
-            for (; s + M <= full; s += M) run_block_interior<NDIM, M, LG, false>(col, D, s, sm, warp, lane, acc_base);
+        while (s < work_steps) {
+            if ((s % M) == 0 && s + M <= full && (s > 0 || cur.cnext > M - 1)) {
+                if (s == 0)
+                    run_block_interior<NDIM, M, LG, true, false, DR>(col, cur, rc, 0, sm, warp, lane);
+                else if (!DR || cur.cnext > s + M - 1)
+                    run_block_interior<NDIM, M, LG, false, false, DR>(col, cur, rc, s, sm, warp, lane);
+                else
+                    run_block_interior<NDIM, M, LG, false, DR, DR>(col, cur, rc, s, sm, warp, lane);
+                s += M;
+            } else {
+                run_step_generic<NDIM, M, LG, DR>(col, cur, rc, s, sm, warp, lane);
+                ++s;
+            }
         }
-#pragma unroll 1
-        for (; s < work_steps; ++s) run_step_generic<NDIM, M, LG>(col, D, s, L, sm, warp, lane, acc_base);
+        const int acc_base = rc.acc_base;
         cp_async_wait<0>();  // the ring is reused by the next item
         // drain: the lags of origins M-1 .. 1 at the step after the last one are still in their slots; step on
         // without terms (flush slot 1, rotate) until they are out
@@ -319,12 +425,21 @@ struct RunPlan {
     std::vector<RunDesc> runs;
     std::vector<int2> pairs;        // (run, strip), most expensive first
     std::vector<int32_t> slot;      // accumulator index -> position in the caller's lag array
+    std::vector<int32_t> chg;       // drift change indices of all runs
 };
 
-// Greedy cover of the (ascending) lag grid by arithmetic progressions: each lag, smallest first, starts the longest
-// progression of still-uncovered lags among the differences to its next kRunCandidates successors; progressions
-// shorter than kRunMinLen are dropped and their first lag becomes a run of one.
+// Step 1, greedy cover of the (ascending) lag grid by arithmetic progressions: each lag, smallest first, starts the
+// longest progression of still-uncovered lags among the differences to its next kRunCandidates successors;
+// progressions shorter than kRunMinLen are dropped and their first lag becomes a segment of one.
+// Step 2, chaining: a segment whose first lag is (last lag of a chain) + D + shift, shift = +-1 fixed per chain, with
+// the same D (or of one lag), continues that chain as a drift change, provided the changes stay >= M lags apart.
 static void plan_runs(const int32_t* lags, int K, int Tn, RunPlan& plan) {
+    struct Segment {
+        int k0, d, len;
+        std::vector<int32_t> slots;
+        bool taken;
+    };
+    std::vector<Segment> segs;
     std::vector<char> used(K, 0);
     auto find = [&](int value, int from) -> int {  // index of an unused lag == value at or after `from`, or -1
         const int32_t* lo = std::lower_bound(lags + from, lags + K, value);
@@ -332,7 +447,6 @@ static void plan_runs(const int32_t* lags, int K, int Tn, RunPlan& plan) {
             if (!used[lo - lags]) return (int)(lo - lags);
         return -1;
     };
-    int n_acc = 0;
     for (int a = 0; a < K; ++a) {
         if (used[a]) continue;
         int best_len = 1, best_d = 0;
@@ -355,21 +469,61 @@ static void plan_runs(const int32_t* lags, int K, int Tn, RunPlan& plan) {
                 best_d = d;
             }
         }
+        Segment sg{lags[a], kRunSingleStride, 1, {a}, false};
         used[a] = 1;
-        plan.slot.push_back(a);
         if (best_len >= kRunMinLen) {
+            sg.d = best_d;
+            sg.len = best_len;
             int at = a;
             for (int i = 1; i < best_len; ++i) {
                 at = find(lags[a] + i * best_d, at + 1);
                 used[at] = 1;
-                plan.slot.push_back(at);
+                sg.slots.push_back(at);
             }
-            plan.runs.push_back(RunDesc{lags[a], best_d, best_len, n_acc});
-            n_acc += best_len;
-        } else {
-            plan.runs.push_back(RunDesc{lags[a], kRunSingleStride, 1, n_acc});
-            n_acc += 1;
         }
+        segs.push_back(std::move(sg));
+    }
+    // segments are in ascending order of their first lag (the greedy walks the grid upwards)
+    int n_acc = 0;
+    for (size_t h = 0; h < segs.size(); ++h) {
+        if (segs[h].taken) continue;
+        segs[h].taken = true;
+        RunDesc rd{segs[h].k0, segs[h].d, segs[h].len, n_acc, (int)plan.chg.size(), 0, 1, 0};
+        plan.slot.insert(plan.slot.end(), segs[h].slots.begin(), segs[h].slots.end());
+        if (segs[h].len >= kRunMinLen && segs[h].len <= kRunChainMaxSeg) {
+            int last_len = segs[h].len;  // length of the chain's last segment
+            bool first = true;           // ... which is still the chain's first segment
+            int shift = 0;
+            while (true) {
+                if (!first && last_len < kRunM) break;  // the last segment would become interior: too short
+                const long long last_lag = (long long)rd.k0 + (long long)(rd.len - 1) * rd.delta + (long long)shift * rd.n_chg;
+                size_t found = segs.size();
+                int found_shift = 0;
+                for (size_t n = h + 1; n < segs.size() && found == segs.size(); ++n) {
+                    if (segs[n].taken) continue;
+                    if (segs[n].len > 1 && (segs[n].d != rd.delta || segs[n].len > kRunChainMaxSeg)) continue;
+                    for (int sh = -1; sh <= 1; sh += 2) {
+                        if (shift != 0 && sh != shift) continue;
+                        if ((long long)segs[n].k0 == last_lag + rd.delta + sh) {
+                            found = n;
+                            found_shift = sh;
+                        }
+                    }
+                }
+                if (found == segs.size()) break;
+                shift = found_shift;
+                segs[found].taken = true;
+                plan.chg.push_back(rd.len);
+                rd.n_chg += 1;
+                rd.len += segs[found].len;
+                plan.slot.insert(plan.slot.end(), segs[found].slots.begin(), segs[found].slots.end());
+                last_len = segs[found].len;
+                first = false;
+            }
+            rd.shift = shift == 0 ? 1 : shift;
+        }
+        n_acc += rd.len;
+        plan.runs.push_back(rd);
     }
     // (run, strip) pairs with the number of steps of their first column as the cost
     struct Item {
@@ -406,29 +560,35 @@ static size_t runs_pair_capacity(int K, int Tn) {
     return long_runs * per_long + (size_t)K * per_single;
 }
 
-template <int NDIM, int WARPS>
+template <int NDIM, int WARPS, bool DR>
 static int launch_runs_w(int sm_count, long long n_work, cudaStream_t st, const double* dc, int n_atoms, int Tn,
                          int64_t pitch, const int comp[3], const RunDesc* runs, const int2* pairs, int n_pairs, int batch,
-                         int K, unsigned int* counter, const int32_t* slot, double* out) {
+                         const int32_t* chg, int K, unsigned int* counter, const int32_t* slot, double* out) {
     const int grid = (int)std::min<long long>((n_work + WARPS - 1) / WARPS, 2 * sm_count);
-    const size_t smem = MomentSmem::bytes(K, WARPS, kRunLG) + (size_t)WARPS * kRunRingBytes;
-    KB2_CUDA(cudaFuncSetAttribute(self_moments_runs_kernel<NDIM, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const size_t smem = MomentSmem::bytes(K, WARPS, kRunLG) + (size_t)WARPS * kRunRingBytes / (DR ? 1 : 2);
+    KB2_CUDA(cudaFuncSetAttribute(self_moments_runs_kernel<NDIM, WARPS, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-    self_moments_runs_kernel<NDIM, WARPS><<<grid, 32 * WARPS, smem, st>>>(dc, n_atoms, Tn, pitch, comp[0], comp[1], comp[2],
-                                                                          runs, pairs, n_pairs, batch, K, counter, slot, out);
+    self_moments_runs_kernel<NDIM, WARPS, DR><<<grid, 32 * WARPS, smem, st>>>(dc, n_atoms, Tn, pitch, comp[0], comp[1], comp[2],
+                                                                          runs, pairs, n_pairs, batch, chg, K, counter, slot, out);
     KB2_LAUNCH_CHECK();
     return 0;
 }
 
 template <int NDIM>
-static int launch_runs(int warps, int sm_count, long long n_work, cudaStream_t st, const double* dc, int n_atoms, int Tn,
-                       int64_t pitch, const int comp[3], const RunDesc* runs, const int2* pairs, int n_pairs, int batch,
-                       int K, unsigned int* counter, const int32_t* slot, double* out) {
-    if (warps == 8)
-        return launch_runs_w<NDIM, 8>(sm_count, n_work, st, dc, n_atoms, Tn, pitch, comp, runs, pairs, n_pairs, batch, K,
-                                      counter, slot, out);
-    return launch_runs_w<NDIM, 6>(sm_count, n_work, st, dc, n_atoms, Tn, pitch, comp, runs, pairs, n_pairs, batch, K, counter,
-                                  slot, out);
+static int launch_runs(int warps, bool drift, int sm_count, long long n_work, cudaStream_t st, const double* dc,
+                       int n_atoms, int Tn, int64_t pitch, const int comp[3], const RunDesc* runs, const int2* pairs,
+                       int n_pairs, int batch, const int32_t* chg, int K, unsigned int* counter, const int32_t* slot,
+                       double* out) {
+#define KB2_RUNS(W, DRF)                                                                                                \
+    return launch_runs_w<NDIM, W, DRF>(sm_count, n_work, st, dc, n_atoms, Tn, pitch, comp, runs, pairs, n_pairs, batch, chg, \
+                                       K, counter, slot, out)
+    if (warps == 8) {
+        if (drift) KB2_RUNS(8, true);
+        KB2_RUNS(8, false);
+    }
+    if (drift) KB2_RUNS(6, true);
+    KB2_RUNS(6, false);
+#undef KB2_RUNS
 }
 
 // Tuning knob for experiments (tools/k2probe.py): KB2_RUNS_WARPS=6|8 picks the CTA size of the run kernel.
@@ -440,10 +600,10 @@ static int runs_warps() {
     return w;
 }
 
-// workspace layout: the plan: 64 ints (work counter) | runs | pairs | slots
+// workspace layout: the plan: 64 ints (work counter) | runs | pairs | slots | drift change indices
 static size_t runs_plan_bytes(int k, int t) {
     return 256 + align256((size_t)k * sizeof(RunDesc)) + align256(runs_pair_capacity(k, t) * sizeof(int2)) +
-           align256((size_t)k * sizeof(int32_t));
+           2 * align256((size_t)k * sizeof(int32_t));
 }
 
 }  // namespace kb2
@@ -490,12 +650,14 @@ extern "C" int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames
         const size_t off_runs = 256;
         const size_t off_pairs = off_runs + align256(plan.runs.size() * sizeof(RunDesc));
         const size_t off_slot = off_pairs + align256(plan.pairs.size() * sizeof(int2));
-        const size_t total = off_slot + align256((size_t)K * sizeof(int32_t));
+        const size_t off_chg = off_slot + align256((size_t)K * sizeof(int32_t));
+        const size_t total = off_chg + align256((size_t)K * sizeof(int32_t));
         KB2_CHECK(total <= runs_plan_bytes(kcap, n_frames), "kb2_self_moments_runs: plan exceeds the workspace");
         packed.assign(total, 0);
         memcpy(packed.data() + off_runs, plan.runs.data(), plan.runs.size() * sizeof(RunDesc));
         memcpy(packed.data() + off_pairs, plan.pairs.data(), plan.pairs.size() * sizeof(int2));
         memcpy(packed.data() + off_slot, plan.slot.data(), (size_t)K * sizeof(int32_t));
+        if (!plan.chg.empty()) memcpy(packed.data() + off_chg, plan.chg.data(), plan.chg.size() * sizeof(int32_t));
         KB2_CUDA(cudaMemcpyAsync(d_plan, packed.data(), total, cudaMemcpyHostToDevice, st));
 
         const long long n_work = (long long)plan.pairs.size() * n_atoms;
@@ -505,25 +667,27 @@ extern "C" int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames
         const RunDesc* d_runs = (const RunDesc*)(d_plan + off_runs);
         const int2* d_pairs = (const int2*)(d_plan + off_pairs);
         const int32_t* d_slot = (const int32_t*)(d_plan + off_slot);
+        const int32_t* d_chg = (const int32_t*)(d_plan + off_chg);
         int rc;
         if (ndim == 1)
-            rc = launch_runs<1>(runs_warps(), sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
-                                (int)plan.pairs.size(), batch, K, (unsigned int*)d_plan, d_slot, sums + 2 * l0);
+            rc = launch_runs<1>(runs_warps(), !plan.chg.empty(), sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
+                                (int)plan.pairs.size(), batch, d_chg, K, (unsigned int*)d_plan, d_slot, sums + 2 * l0);
         else if (ndim == 2)
-            rc = launch_runs<2>(runs_warps(), sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
-                                (int)plan.pairs.size(), batch, K, (unsigned int*)d_plan, d_slot, sums + 2 * l0);
+            rc = launch_runs<2>(runs_warps(), !plan.chg.empty(), sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
+                                (int)plan.pairs.size(), batch, d_chg, K, (unsigned int*)d_plan, d_slot, sums + 2 * l0);
         else
-            rc = launch_runs<3>(runs_warps(), sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
-                                (int)plan.pairs.size(), batch, K, (unsigned int*)d_plan, d_slot, sums + 2 * l0);
+            rc = launch_runs<3>(runs_warps(), !plan.chg.empty(), sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
+                                (int)plan.pairs.size(), batch, d_chg, K, (unsigned int*)d_plan, d_slot, sums + 2 * l0);
         if (rc) return rc;
     }
     return 0;
 }
 
-// The plan for a lag grid, for tests and diagnostics: fills run_k0/run_delta/run_len (capacity max_runs) with the
-// runs of >= 3 lags and returns their number; *n_rest receives the number of lags that became runs of one.
+// The plan for a lag grid, for tests and diagnostics: fills run_k0/run_delta/run_len/run_n_chg (capacity max_runs)
+// with the runs of >= 3 lags (n_chg = number of one-sample drift changes inside the run) and returns their number;
+// *n_rest receives the number of lags that became runs of one.
 extern "C" int kb2_self_moments_plan(const int32_t* lags_host, int n_lags, int n_frames, int32_t* run_k0,
-                                     int32_t* run_delta, int32_t* run_len, int max_runs, int* n_rest) {
+                                     int32_t* run_delta, int32_t* run_len, int32_t* run_n_chg, int max_runs, int* n_rest) {
     if (!lags_host || n_lags <= 0) return 0;
     RunPlan plan;
     plan_runs(lags_host, std::min(n_lags, kMaxLags), n_frames, plan);
@@ -537,6 +701,7 @@ extern "C" int kb2_self_moments_plan(const int32_t* lags_host, int n_lags, int n
             if (run_k0) run_k0[n] = rd.k0;
             if (run_delta) run_delta[n] = rd.delta;
             if (run_len) run_len[n] = rd.len;
+            if (run_n_chg) run_n_chg[n] = rd.n_chg * rd.shift;
         }
         ++n;
     }

@@ -141,18 +141,17 @@ def self_moments(dc, n_frames, lags, mask=7, variant=None):
 
 
 def self_moments_plan(lags, n_frames):
-    """The arithmetic runs kb2_self_moments_runs would use: ([(k0, delta, len), ...], n_leftover_lags)."""
+    """The runs kb2_self_moments_runs would use: ([(k0, delta, len, n_chg), ...], n_lags_in_runs_of_one); a run
+    covers the lags k0 + i*delta + e_i with e_i stepping by sign(n_chg) at |n_chg| indices."""
     lib = _lib.load()
     import ctypes
     lags_host = np.ascontiguousarray(lags, dtype=np.int32)
     cap = max(1, len(lags_host))
-    k0 = np.zeros(cap, dtype=np.int32)
-    dl = np.zeros(cap, dtype=np.int32)
-    ln = np.zeros(cap, dtype=np.int32)
+    arrs = [np.zeros(cap, dtype=np.int32) for _ in range(4)]
     rest = ctypes.c_int(0)
-    n = lib.kb2_self_moments_plan(lags_host.ctypes.data, len(lags_host), int(n_frames), k0.ctypes.data, dl.ctypes.data,
-                                  ln.ctypes.data, cap, ctypes.byref(rest))
-    return [(int(k0[i]), int(dl[i]), int(ln[i])) for i in range(n)], rest.value
+    n = lib.kb2_self_moments_plan(lags_host.ctypes.data, len(lags_host), int(n_frames), arrs[0].ctypes.data,
+                                  arrs[1].ctypes.data, arrs[2].ctypes.data, arrs[3].ctypes.data, cap, ctypes.byref(rest))
+    return [tuple(int(a[i]) for a in arrs) for i in range(n)], rest.value
 
 
 def disp_moments(disp, mask=7, weights=None, coll_mask=0):

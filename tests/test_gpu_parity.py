@@ -209,6 +209,9 @@ def _device_dc(kb, dc):
 RUN_GRIDS = {
     # kinisi's default grids (parser.py:150-168) at several truncation patterns, plus adversarial ones
     'linspace_100': lambda T: np.linspace(1, T, 100, dtype=int),
+    'linspace_drift_up': lambda T: np.linspace(1, T, int(T / 12.09), dtype=int),
+    'linspace_drift_down': lambda T: np.linspace(1, T, int(T / 12.91), dtype=int),
+    'linspace_drift_fast': lambda T: np.linspace(2, T - 3, int(T / 9.13), dtype=int),
     'linspace_alternating': lambda T: np.linspace(1, T, int(T / 50.4949), dtype=int),
     'linspace_min_dt': lambda T: np.linspace(37, T - 11, 64, dtype=int),
     'geomspace': lambda T: np.unique(np.geomspace(1, T, 100, dtype=int)),

@@ -76,29 +76,33 @@ def test_lazy_displacements_materialise_like_the_reference():
 
 
 def test_lag_grid_is_split_into_arithmetic_runs():
-    """The host-side planner of kb2_self_moments_runs (no GPU needed): every lag lands in exactly one run or in
-    the leftover set, and kinisi's default linspace grids come out as a handful of long runs."""
+    """The host-side planner of kb2_self_moments_runs (no GPU needed): every lag lands in exactly one run, and
+    kinisi's default linspace grids come out as a handful of long runs (with one-sample drift where the integer
+    truncation of np.linspace shifts the progression)."""
     import numpy as np
     from kinisi_b200 import engine
 
     def check(lags, n_frames):
         lags = np.asarray(lags)
         runs, rest = engine.self_moments_plan(lags, n_frames)
-        covered = []
-        for k0, d, n in runs:
-            assert n >= 3 and d >= 1
-            covered += [k0 + i * d for i in range(n)]
-        assert len(covered) + rest == len(lags)
-        assert len(set(covered)) == len(covered)
-        assert set(covered) <= set(int(x) for x in lags)
+        for k0, d, n, n_chg in runs:
+            assert n >= 3 and d >= 1 and abs(n_chg) <= n // 8 + 2
+            assert k0 in lags
+            last = k0 + (n - 1) * d + n_chg
+            assert last in lags, (k0, d, n, n_chg)
+        assert sum(r[2] for r in runs) + rest == len(lags)
         return runs, rest
 
     runs, rest = check(np.linspace(1, 20000, 100, dtype=int), 20000)  # BASELINE configs[1]
-    assert rest <= 1 and max(r[2] for r in runs) >= 99
+    assert rest == 1 and runs == [(1, 202, 99, 0)]  # long progressions are not chained
     runs, rest = check(np.linspace(1, 5000, 100, dtype=int), 5000)  # configs[0]: alternating 50/51 spacing
     assert rest <= 2 and len(runs) <= 4
+    runs, rest = check(np.linspace(1, 100000, 100, dtype=int), 100000)  # configs[2]: +1 every 11th lag
+    assert rest == 0 and runs == [(1, 1010, 100, 9)]
+    runs, rest = check(np.linspace(1, 50000, 100, dtype=int), 50000)  # configs[4]
+    assert rest == 1 and len(runs) == 4 and all(r[1] == 505 for r in runs)
     runs, rest = check(np.linspace(1, 20000, 2000, dtype=int)[:768], 20000)  # 2000-point grid, one 768-lag launch
-    assert rest == 0 and len(runs) <= 8
+    assert rest == 0 and len(runs) <= 4
     runs, rest = check(np.unique(np.geomspace(1, 20000, 100, dtype=int)), 20000)
     assert runs[0][1] == 1  # the dense start 1, 2, 3, ...
     runs, rest = check([5], 100)
