@@ -401,7 +401,7 @@ def test_fast_reconditioning_matches_the_literal_sequence(kb, golden_dir):
     np.testing.assert_allclose(out[True][1], d_ref, rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize('n', [1, 2, 3, 17, 54, 90, 127, 128])
+@pytest.mark.parametrize('n', [1, 2, 3, 4, 5, 6, 7, 8, 17, 54, 90, 91, 92, 93, 94, 127, 128])
 def test_jacobi_spectral_kernel(kb, n):
     """kb2_spectral_prepare against numpy: spectrum, log-determinant, and the quadratic form of pinvh."""
     from scipy.linalg import pinvh
