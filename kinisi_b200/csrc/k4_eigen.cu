@@ -18,27 +18,49 @@
 // every round all seats but T_0 move one step round the circle T_1 -> ... -> T_{h-1} -> B_{h-1} -> ... -> B_0
 // -> T_1, so after m - 1 rounds (one sweep) every pair has met once and every index is back on its own seat.
 // The matrix is stored by SEAT, so every round has the same data flow: the 2x2 block between slots ka < kb is
-// four elements at fixed shared-memory addresses (four planes indexed by the block number: conflict-free for
-// consecutive lanes), it is rotated by (c, s) of the two slots and scattered to four fixed addresses of the
-// other buffer.  Each thread computes its source and destination offsets once, before the first sweep.
+// four elements at fixed shared-memory addresses (four planes indexed by the block number), it is rotated by
+// (c, s) of the two slots and scattered to four fixed addresses of the other buffer.  Every thread computes its
+// byte offsets once; the layout strides are compile-time constants and the rounds are instantiated for both
+// buffer parities, so every access of the round loop is [register + immediate].
 //
-// One barrier per round.  The element that becomes the pivot of slot k in the NEXT round sits in exactly one
-// block ("special" block of slot k).  Thread k owns that block: besides rotating it, it evaluates the two
-// diagonal entries that arrive on slot k (from the current rotations of the slots they leave) and the slot's
-// next rotation, so that serial chain (a few hundred cycles) overlaps with the other warps' block updates,
-// which are bound by shared-memory bandwidth (one read and one write of the triangle per round).
+// One barrier per round, three kinds of warps:
+//   * warps 0-1, thread k: the "special" block of slot k -- the one block that holds the element which becomes
+//     the pivot of slot k in the NEXT round.  The thread rotates it, evaluates the two diagonal entries that
+//     arrive on slot k (from the current rotations of the slots they leave) and the slot's next rotation.  This
+//     serial chain (~400 cycles, two MUFU) is the critical path of a round and runs beside
+//   * warps 2-17: the regular blocks, one task = one column slot kb x two row slots (2j, 2j+1), consecutive lanes
+//     = consecutive kb: contiguous 8-byte lanes on every load, (c, s) of kb fetched once for two blocks.  These
+//     warps are bound by shared-memory bandwidth (one read and one write of the triangle per round);
+//   * the first 4h regular threads also carry the residual pivots (the angle is inexact: the rotated pivot is
+//     kept, not dropped) and the three vectors.
 #include <math.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 
 namespace kb2 {
 
 constexpr int kJacobiMaxN = 128;
-constexpr int kJacobiThreads = 512;
+constexpr int kJacobiMaxH = kJacobiMaxN / 2;
+constexpr int kJacobiSpecial = 64;   // threads of the special warps (>= kJacobiMaxH)
+constexpr int kJacobiRegular = 512;  // threads of the regular warps
+constexpr int kJacobiThreads = kJacobiSpecial + kJacobiRegular;
 constexpr int kJacobiMaxSweeps = 40;
 constexpr int kJacobiMinH = 3;  // smaller problems are padded with zero rows (their rotations are the identity)
 
-__device__ __forceinline__ double block_sum_512(double v, double* sh) {
+// Shared-memory image of the matrix in one buffer, in doubles.
+namespace jl {
+constexpr int kPlane = 2048;                     // >= kJacobiMaxH (kJacobiMaxH - 1) / 2 = 2016 blocks per plane
+constexpr int kPiv = 4 * kPlane;                 // [kJacobiMaxH] pivots (T_k, B_k)
+constexpr int kDiagT = kPiv + kJacobiMaxH;       // [kJacobiMaxH] diagonal entries of the top seats
+constexpr int kDiagB = kDiagT + kJacobiMaxH;     // [kJacobiMaxH] ... of the bottom seats
+constexpr int kCS = kDiagB + kJacobiMaxH;        // [kJacobiMaxH][2] rotation (c, s) of every slot
+constexpr int kU = kCS + 2 * kJacobiMaxH;        // [3][2 kJacobiMaxH] vectors: top seats, then bottom seats
+constexpr int kBuf = kU + 6 * kJacobiMaxH;       // 8896 doubles = 71168 bytes
+}  // namespace jl
+
+__device__ __forceinline__ double block_sum_all(double v, double* sh) {
     v = warp_sum(v);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
@@ -49,29 +71,36 @@ __device__ __forceinline__ double block_sum_512(double v, double* sh) {
     return t;
 }
 
-// Rotation for the pivot block [[app, apq], [apq, aqq]]: t = tan(theta) is the smaller root of
-// h t^2 + 2 d t - h = 0 with d = aqq - app, h = 2 apq, i.e. t = h / (d + sign(d) sqrt(d^2 + h^2)).
-// The angle only has to be good enough for the iteration to converge (an error of 1e-7 leaves a residual pivot
-// of 1e-7 |apq| instead of zero, and the residual is kept, not dropped); what must hold to FP64 rounding is
-// c^2 + s^2 = 1.  This chain sits on the critical path of every round, so (c0, s0) are formed in single precision
-// (MUFU) on operands rescaled by an exact power of two and then renormalised in double precision with the series
+// Rotation for the pivot block [[app, apq], [apq, aqq]]: with d = aqq - app, h = 2 apq, r = sqrt(d^2 + h^2) the
+// small-angle solution has cos 2t = |d| / r, sin 2t = sign(d) h / r, c = sqrt((1 + cos 2t) / 2), s = sin 2t / (2 c).
+// The angle only has to be good enough for the iteration to converge (an error of 1e-7 leaves a residual pivot of
+// 1e-7 |apq| instead of zero, and the residual is kept); what must hold to FP64 rounding is c^2 + s^2 = 1.  The
+// chain sits on the critical path of every round, so (c0, s0) are formed in single precision (two MUFU.RSQ) on
+// operands rescaled by an exact power of two and then renormalised in double precision with the series
 // (1 + e)^-1/2 = 1 - e/2 + 3 e^2 / 8, e = c0^2 + s0^2 - 1 ~ 1e-7 (error ~e^3).
+__device__ __forceinline__ float rsqrt_approx(float v) {  // MUFU.RSQ without the denormal rescue (operands are O(1))
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 __device__ __forceinline__ void jacobi_angle(double app, double aqq, double apq, double& c, double& s) {
-    const double d = aqq - app, h = 2.0 * apq;
-    const double mx = fmax(fabs(d), fabs(h));
-    // 2^-e with e the unbiased exponent of mx: an exact rescale of (d, h) into [1, 2)
-    const int hi = __double2hiint(mx);
-    const double scale = __hiloint2double((2046 - ((hi >> 20) & 0x7ff)) << 20, 0);
+    const double d = aqq - app, h = apq + apq;
+    // 2^-E with E the larger exponent of d and h: an exact rescale of (d, h) into (-2, 2)
+    const int ed = __double2hiint(d) & 0x7ff00000, eh = __double2hiint(h) & 0x7ff00000;
+    const double scale = __hiloint2double(0x7fe00000 - max(ed, eh), 0);
     const float df = (float)(d * scale), hf = (float)(h * scale);
-    const float q = fmaf(df, df, hf * hf);
-    const float rf = q * rsqrtf(q);
-    const float tf = __fdividef(hf, df + copysignf(rf, df));
-    const float cf = rsqrtf(fmaf(tf, tf, 1.0f));
-    const double c0 = (double)cf, s0 = (double)(tf * cf);
+    const float ir = rsqrt_approx(fmaf(df, df, hf * hf));
+    const float x = fabsf(df) * ir;                                                                // cos 2t
+    const float y = __int_as_float(__float_as_int(hf * ir) ^ (__float_as_int(df) & 0x80000000));  // sin 2t
+    const float w = fmaf(0.5f, x, 0.5f);                                                           // cos^2 t
+    const float ic = rsqrt_approx(w);
+    const double c0 = (double)(w * ic), s0 = (double)(0.5f * y * ic);
     const double e = fma(c0, c0, fma(s0, s0, -1.0));
     const double g = fma(e, fma(e, 0.375, -0.5), 1.0);
-    c = c0 * g;
-    s = s0 * g;
+    const bool rot = apq != 0.0;
+    c = rot ? c0 * g : 1.0;
+    s = rot ? s0 * g : 0.0;
 }
 
 struct JacobiSeats {
@@ -91,290 +120,283 @@ struct JacobiSeats {
         return p + 1;                         // B_k <- B_{k+1}
     }
     __device__ __forceinline__ int slot(int p) const { return p < h ? p : p - h; }
+    __device__ __forceinline__ int bottom(int p) const { return p >= h; }
     __device__ __forceinline__ int tri(int ka, int kb) const { return ka * (2 * h - ka - 1) / 2 + (kb - ka - 1); }
-    // Offset of the element between seats x != y: plane * NT + block for seats of different slots, 4 NT + k for
-    // the pivot of slot k.
-    __device__ __forceinline__ int addr(int x, int y, int NT) const {
-        int sx = slot(x), sy = slot(y), tx = x >= h, ty = y >= h;
-        if (sx == sy) return 4 * NT + sx;
+    // Offset (doubles) of the element between seats x != y: plane * kPlane + block for seats of different slots,
+    // kPiv + k for the pivot of slot k.
+    __device__ __forceinline__ int addr(int x, int y) const {
+        int sx = slot(x), sy = slot(y), tx = bottom(x), ty = bottom(y);
+        if (sx == sy) return jl::kPiv + sx;
         if (sx > sy) {
             int q = sx; sx = sy; sy = q;
             q = tx; tx = ty; ty = q;
         }
-        return (tx * 2 + ty) * NT + tri(sx, sy);
+        return (tx * 2 + ty) * jl::kPlane + tri(sx, sy);
     }
-    __device__ __forceinline__ void block_of(int e, int& ka, int& kb) const {  // inverse of tri
-        ka = 0;
-        int row = h - 1;
-        while (e >= row) {
-            e -= row;
-            --row;
-            ++ka;
-        }
-        kb = ka + 1 + e;
+    __device__ __forceinline__ int diag(int p) const { return (bottom(p) ? jl::kDiagB : jl::kDiagT) + slot(p); }
+    __device__ __forceinline__ int vec(int v, int p) const { return jl::kU + v * 2 * kJacobiMaxH + bottom(p) * kJacobiMaxH + slot(p); }
+    // destination of element q = (row bottom, column bottom) of block (ka, kb)
+    __device__ __forceinline__ int block_dst(int ka, int kb, int q) const {
+        return addr(next(ka + (q >> 1) * h), next(kb + (q & 1) * h));
+    }
+    // a block is special when one of its elements lands on a pivot
+    __device__ __forceinline__ bool special(int ka, int kb) const {
+        bool sp = false;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) sp = sp || block_dst(ka, kb, q) >= jl::kPiv;
+        return sp;
     }
 };
 
-// New diagonal entry of a seat of a slot after the slot's rotation J^T [[app, apq], [apq, aqq]] J,
-// J = [[c, s], [-s, c]] (rows: T' = c T - s B, B' = s T + c B).
-__device__ __forceinline__ double rotated_diag(bool bottom, double app, double aqq, double apq, double c, double s) {
-    const double cc = c * c, ss = s * s, sc2 = 2.0 * s * c * apq;
-    return bottom ? fma(ss, app, fma(cc, aqq, sc2)) : fma(cc, app, fma(ss, aqq, -sc2));
+__device__ __forceinline__ double lds_f64(const unsigned char* sm, uint32_t off) {
+    return *reinterpret_cast<const double*>(sm + off);
+}
+__device__ __forceinline__ double2 lds_f64x2(const unsigned char* sm, uint32_t off) {
+    return *reinterpret_cast<const double2*>(sm + off);
+}
+__device__ __forceinline__ void sts_f64(unsigned char* sm, uint32_t off, double v) { *reinterpret_cast<double*>(sm + off) = v; }
+
+// M <- J_a^T M J_b for the 2x2 block (TT, TB, BT, BB) between row slot a and column slot b
+__device__ __forceinline__ void rotate_block(const double (&mm)[4], double2 ra, double2 rb, double (&ev)[4]) {
+    const double t00 = rb.x * mm[0] - rb.y * mm[1], t01 = rb.y * mm[0] + rb.x * mm[1];
+    const double t10 = rb.x * mm[2] - rb.y * mm[3], t11 = rb.y * mm[2] + rb.x * mm[3];
+    ev[0] = ra.x * t00 - ra.y * t10;
+    ev[1] = ra.x * t01 - ra.y * t11;
+    ev[2] = ra.y * t00 + ra.x * t10;
+    ev[3] = ra.y * t01 + ra.x * t11;
 }
 
-// Shared-memory image of the matrix in one buffer (doubles): elements [4 NT + h] (four planes, then the
-// pivots), diagonal [m], rotations [h][2], vectors [3][m].
-struct JacobiLayout {
-    int NT, h, m;
-    __host__ __device__ int elems() const { return 4 * NT + h; }
-    __host__ __device__ int off_diag() const { return (elems() + 1) & ~1; }
-    __host__ __device__ int off_cs() const { return off_diag() + m; }
-    __host__ __device__ int off_u() const { return off_cs() + 2 * h; }
-    __host__ __device__ int size() const { return (off_u() + 3 * m + 1) & ~1; }
-};
-
-template <int OWN>
-__global__ void __launch_bounds__(kJacobiThreads)
+template <int NTASK>
+__global__ void __launch_bounds__(kJacobiThreads, 1)
     jacobi_project_kernel(const double* __restrict__ cov, int n, int h, const double* __restrict__ x,
                           const double* __restrict__ y, double cond_max, double* __restrict__ evals,
                           double* __restrict__ proj, double* __restrict__ logdet_term, int* __restrict__ info) {
-    extern __shared__ __align__(16) double smj[];
+    extern __shared__ __align__(16) unsigned char smj[];
     __shared__ double red[kJacobiThreads / 32];
+    double* const buf0 = reinterpret_cast<double*>(smj);
     const int m = 2 * h;             // seats; indices >= n are zero padding
     const int NT = h * (h - 1) / 2;  // blocks ka < kb
     const JacobiSeats seats{h};
-    const JacobiLayout L{NT, h, m};
-    double* const buf0 = smj;
-    double* const buf1 = smj + L.size();
     const int tid = threadIdx.x;
+    constexpr uint32_t kBufBytes = jl::kBuf * 8, kPlaneBytes = jl::kPlane * 8;
 
-    // ---- load: seat p holds index p ----------------------------------------------------------------------
+    // ---- load: seat p holds index p -------------------------------------------------------------------------------
+    for (int e = tid; e < 2 * jl::kBuf; e += kJacobiThreads) buf0[e] = 0.0;
+    __syncthreads();
     for (int e = tid; e < m * m; e += kJacobiThreads) {
         const int i = e / m, j = e - i * m;
         if (i < j)
-            buf0[seats.addr(i, j, NT)] = (j < n) ? cov[(size_t)i * n + j] : 0.0;
+            buf0[seats.addr(i, j)] = (j < n) ? cov[(size_t)i * n + j] : 0.0;
         else if (i == j)
-            buf0[L.off_diag() + i] = (i < n) ? cov[(size_t)i * n + i] : 0.0;
+            buf0[seats.diag(i)] = (i < n) ? cov[(size_t)i * n + i] : 0.0;
     }
     for (int i = tid; i < m; i += kJacobiThreads) {
-        double* u = buf0 + L.off_u();
-        u[i] = i < n ? x[i] : 0.0;
-        u[m + i] = i < n ? 1.0 : 0.0;
-        u[2 * m + i] = i < n ? y[i] : 0.0;
+        buf0[seats.vec(0, i)] = i < n ? x[i] : 0.0;
+        buf0[seats.vec(1, i)] = i < n ? 1.0 : 0.0;
+        buf0[seats.vec(2, i)] = i < n ? y[i] : 0.0;
     }
 
-    // ---- static ownership ----------------------------------------------------------------------------------
-    // special block of slot k: holds the element {prev(T_k), prev(B_k)}, the pivot of slot k in the next round
-    int sp_e = -1, sp_ka = 0, sp_kb = 0, sp_q = 0, sp_dst[4] = {0, 0, 0, 0};
-    bool sp_x_bottom = false, sp_y_bottom = false, sp_x_in_ka = true;
-    int res_dst = 0;
-    if (tid < h) {
-        const int X = seats.prev(tid), Y = seats.prev(h + tid);  // X lands on T_tid, Y on B_tid
+    // ---- static roles (byte offsets into buffer 0) --------------------------------------------------------------------
+    // A thread is either special or regular, so both roles share the offset registers O[0][.]:
+    //   special thread k: block (ka, kb) holding the element {X, Y}, X = prev(T_k) -> T_k, Y = prev(B_k) -> B_k
+    //     O = {block, cs ka, cs kb, diag own a, diag other a, pivot a, diag own b, diag other b, pivot b, dst[4]}
+    //   regular thread: task o = (row pair j, column slot kb) -> blocks (2j, kb) and (2j + 1, kb)
+    //     O = {block 0, cs ka0, cs kb, block 1, cs ka1, dst 0 [4], dst 1 [4]}
+    uint32_t O[NTASK][13];
+    bool ok[NTASK][2];
+#pragma unroll
+    for (int o = 0; o < NTASK; ++o) {
+        ok[o][0] = ok[o][1] = false;
+#pragma unroll
+        for (int i = 0; i < 13; ++i) O[o][i] = 0;
+    }
+    int sp_q = 0;
+    bool sp_x_in_ka = true;
+    double sp_sga = 0.0, sp_sgb = 0.0;
+    const bool is_special = tid < h;
+    const int rt = tid - kJacobiSpecial;
+    if (is_special) {
+        const int X = seats.prev(tid), Y = seats.prev(h + tid);
         const int sX = seats.slot(X), sY = seats.slot(Y);
-        sp_ka = min(sX, sY);
-        sp_kb = max(sX, sY);
-        sp_e = seats.tri(sp_ka, sp_kb);
+        const int ka = min(sX, sY), kb = max(sX, sY);
         sp_x_in_ka = sX < sY;
-        sp_x_bottom = X >= h;
-        sp_y_bottom = Y >= h;
-        const bool row_bottom = sp_x_in_ka ? sp_x_bottom : sp_y_bottom, col_bottom = sp_x_in_ka ? sp_y_bottom : sp_x_bottom;
-        sp_q = (row_bottom ? 2 : 0) | (col_bottom ? 1 : 0);
+        const int fa = sp_x_in_ka ? seats.bottom(X) : seats.bottom(Y);  // is the element's row seat (slot ka) a bottom seat
+        const int fb = sp_x_in_ka ? seats.bottom(Y) : seats.bottom(X);  // ... its column seat (slot kb)
+        sp_q = fa * 2 + fb;
+        O[0][0] = 8u * seats.tri(ka, kb);
+        O[0][1] = 8u * (jl::kCS + 2 * ka);
+        O[0][2] = 8u * (jl::kCS + 2 * kb);
+        // new diagonal of a seat after its slot's rotation: cc * own + ss * other -/+ 2 s c pivot (top / bottom)
+        O[0][3] = 8u * ((fa ? jl::kDiagB : jl::kDiagT) + ka);
+        O[0][4] = 8u * ((fa ? jl::kDiagT : jl::kDiagB) + ka);
+        O[0][5] = 8u * (jl::kPiv + ka);
+        sp_sga = fa ? 2.0 : -2.0;
+        O[0][6] = 8u * ((fb ? jl::kDiagB : jl::kDiagT) + kb);
+        O[0][7] = 8u * ((fb ? jl::kDiagT : jl::kDiagB) + kb);
+        O[0][8] = 8u * (jl::kPiv + kb);
+        sp_sgb = fb ? 2.0 : -2.0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            sp_dst[q] = seats.addr(seats.next(sp_ka + (q >> 1) * h), seats.next(sp_kb + (q & 1) * h), NT);
-        res_dst = seats.addr(seats.next(tid), seats.next(h + tid), NT);  // where the residual pivot of slot tid goes
-    }
-    // regular blocks: all the others, dealt to the threads from the last one down so that the threads with a
-    // special block get the fewest
-    int* const s_special = reinterpret_cast<int*>(buf1);  // [NT] flags, scratch before the first round
-    for (int e = tid; e < NT; e += kJacobiThreads) s_special[e] = 0;
-    __syncthreads();
-    if (tid < h) s_special[sp_e] = 1;
-    __syncthreads();
-    int own_e[OWN], own_k[OWN], own_dst[OWN][4];
-    {
-        // list of the regular blocks (warp 0 compacts the flags); thread t takes entries (last - t) + o * threads
-        int* const s_list = s_special + NT;  // [NT]
-        if (tid < 32) {
-            int base = 0;
-            for (int e0 = 0; e0 < NT; e0 += 32) {
-                const int e = e0 + tid;
-                const bool regular = e < NT && s_special[e] == 0;
-                const unsigned mask = __ballot_sync(0xffffffffu, regular);
-                if (regular) s_list[base + __popc(mask & ((1u << tid) - 1))] = e;
-                base += __popc(mask);
+        for (int q = 0; q < 4; ++q) O[0][9 + q] = 8u * seats.block_dst(ka, kb, q);
+    } else if (rt >= 0) {
+#pragma unroll
+        for (int o = 0; o < NTASK; ++o) {
+            int li = rt + o * kJacobiRegular, j = 0;
+            while (2 * j < h - 1 && li >= h - 1 - 2 * j) {
+                li -= h - 1 - 2 * j;
+                ++j;
             }
-        }
-        __syncthreads();
-        const int n_regular = NT - h;  // the h special blocks are distinct for h >= 3
+            if (2 * j < h - 1) {
+                const int kb = 2 * j + 1 + li;
+                O[o][2] = 8u * (jl::kCS + 2 * kb);
 #pragma unroll
-        for (int o = 0; o < OWN; ++o) {
-            own_e[o] = -1;
-            own_k[o] = 0;
+                for (int r = 0; r < 2; ++r) {
+                    const int ka = 2 * j + r;
+                    if (ka < kb && !seats.special(ka, kb)) {
+                        ok[o][r] = true;
+                        O[o][3 * r] = 8u * seats.tri(ka, kb);
+                        O[o][3 * r + 1] = 8u * (jl::kCS + 2 * ka);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) own_dst[o][q] = 0;
-            const int li = (kJacobiThreads - 1 - tid) + o * kJacobiThreads;
-            if (li < n_regular) {
-                const int e = s_list[li];
-                int ka, kb;
-                seats.block_of(e, ka, kb);
-                own_e[o] = e;
-                own_k[o] = ka | (kb << 8);
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    own_dst[o][q] = seats.addr(seats.next(ka + (q >> 1) * h), seats.next(kb + (q & 1) * h), NT);
+                        for (int q = 0; q < 4; ++q) O[o][5 + 4 * r + q] = 8u * seats.block_dst(ka, kb, q);
+                    }
+                }
             }
         }
     }
-    // the three vectors: task (v, k) rotates (u[v][T_k], u[v][B_k]); given to the threads after the special ones
-    const int vt = tid - h;
-    const bool has_vec = vt >= 0 && vt < 3 * h;
-    const int vec_v = has_vec ? vt / h : 0, vec_k = has_vec ? vt - vec_v * h : 0;
-    const int vec_dt = seats.next(vec_k), vec_db = seats.next(h + vec_k);
-    __syncthreads();
-    // buf1 was scratch: clear what the rounds never write (nothing is read before being written, but keep it clean)
-    for (int e = tid; e < L.size(); e += kJacobiThreads) buf1[e] = 0.0;
+    // auxiliary task of regular thread rt < 4h: the residual pivot of slot rt (rt < h), or the pair (T_k, B_k) of vector v
+    const int aux_kind = (rt >= 0 && rt < h) ? 1 : ((rt >= h && rt < 4 * h) ? 2 : 0);
+    uint32_t aux_cs = 0, aux_l0 = 0, aux_l1 = 0, aux_l2 = 0, aux_d0 = 0, aux_d1 = 0;
+    if (aux_kind == 1) {
+        aux_cs = 8u * (jl::kCS + 2 * rt);
+        aux_l0 = 8u * (jl::kDiagT + rt);
+        aux_l1 = 8u * (jl::kDiagB + rt);
+        aux_l2 = 8u * (jl::kPiv + rt);
+        aux_d0 = 8u * seats.addr(seats.next(rt), seats.next(h + rt));
+    } else if (aux_kind == 2) {
+        const int v = (rt - h) / h, k = (rt - h) - v * h;
+        aux_cs = 8u * (jl::kCS + 2 * k);
+        aux_l0 = 8u * seats.vec(v, k);
+        aux_l1 = 8u * seats.vec(v, h + k);
+        aux_l2 = aux_l0;
+        aux_d0 = 8u * seats.vec(v, seats.next(k));
+        aux_d1 = 8u * seats.vec(v, seats.next(h + k));
+    }
     __syncthreads();
     // rotations of the first round
     if (tid < h) {
-        const double apq = buf0[4 * NT + tid];
-        double c = 1.0, s = 0.0;
-        if (apq != 0.0) jacobi_angle(buf0[L.off_diag() + tid], buf0[L.off_diag() + h + tid], apq, c, s);
-        buf0[L.off_cs() + 2 * tid] = c;
-        buf0[L.off_cs() + 2 * tid + 1] = s;
+        double c, s;
+        jacobi_angle(buf0[jl::kDiagT + tid], buf0[jl::kDiagB + tid], buf0[jl::kPiv + tid], c, s);
+        buf0[jl::kCS + 2 * tid] = c;
+        buf0[jl::kCS + 2 * tid + 1] = s;
     }
     __syncthreads();
 
-    double* cur = buf0;
-    double* nxt = buf1;
+    // ---- one round: reads buffer P, writes buffer 1 - P ------------------------------------------------------------------
+    // Loads are unconditional (offset 0 where a thread has no block) and come first: the compiler cannot move them
+    // above the scattered stores.
+    auto round = [&](auto parity) __attribute__((always_inline)) {
+        constexpr int P = decltype(parity)::value;
+        constexpr uint32_t R = P * kBufBytes, W = (1 - P) * kBufBytes;
+        if (tid < kJacobiSpecial) {
+            const double mm[4] = {lds_f64(smj, O[0][0] + R), lds_f64(smj, O[0][0] + R + kPlaneBytes),
+                                  lds_f64(smj, O[0][0] + R + 2 * kPlaneBytes), lds_f64(smj, O[0][0] + R + 3 * kPlaneBytes)};
+            const double2 ra = lds_f64x2(smj, O[0][1] + R), rb = lds_f64x2(smj, O[0][2] + R);
+            const double a1 = lds_f64(smj, O[0][3] + R), a2 = lds_f64(smj, O[0][4] + R), ap = lds_f64(smj, O[0][5] + R);
+            const double b1 = lds_f64(smj, O[0][6] + R), b2 = lds_f64(smj, O[0][7] + R), bp = lds_f64(smj, O[0][8] + R);
+            double ev[4];
+            rotate_block(mm, ra, rb, ev);
+            const double apq = (sp_q & 2) ? ((sp_q & 1) ? ev[3] : ev[2]) : ((sp_q & 1) ? ev[1] : ev[0]);
+            const double da = fma(ra.x * ra.x, a1, fma(ra.y * ra.y, a2, sp_sga * (ra.x * ra.y) * ap));
+            const double db = fma(rb.x * rb.x, b1, fma(rb.y * rb.y, b2, sp_sgb * (rb.x * rb.y) * bp));
+            const double app = sp_x_in_ka ? da : db, aqq = sp_x_in_ka ? db : da;
+            double c, s;
+            jacobi_angle(app, aqq, apq, c, s);
+            if (is_special) {
+                *reinterpret_cast<double2*>(smj + W + 8u * (jl::kCS + 2 * tid)) = make_double2(c, s);
+                sts_f64(smj, W + 8u * (jl::kDiagT + tid), app);
+                sts_f64(smj, W + 8u * (jl::kDiagB + tid), aqq);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sts_f64(smj, O[0][9 + q] + W, ev[q]);
+            }
+        } else {
+            double mm[NTASK][2][4];
+            double2 ra[NTASK][2], rb[NTASK];
+#pragma unroll
+            for (int o = 0; o < NTASK; ++o) {
+                rb[o] = lds_f64x2(smj, O[o][2] + R);
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    ra[o][r] = lds_f64x2(smj, O[o][3 * r + 1] + R);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) mm[o][r][q] = lds_f64(smj, O[o][3 * r] + R + q * kPlaneBytes);
+                }
+            }
+            const double2 ac = lds_f64x2(smj, aux_cs + R);
+            const double l0 = lds_f64(smj, aux_l0 + R), l1 = lds_f64(smj, aux_l1 + R), l2 = lds_f64(smj, aux_l2 + R);
+#pragma unroll
+            for (int o = 0; o < NTASK; ++o) {
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    double ev[4];
+                    rotate_block(mm[o][r], ra[o][r], rb[o], ev);
+                    if (ok[o][r]) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) sts_f64(smj, O[o][5 + 4 * r + q] + W, ev[q]);
+                    }
+                }
+            }
+            if (aux_kind == 1) {
+                // J^T [[app, apq], [apq, aqq]] J, off-diagonal element
+                sts_f64(smj, aux_d0 + W, fma(ac.y * ac.x, l0 - l1, (ac.x * ac.x - ac.y * ac.y) * l2));
+            } else if (aux_kind == 2) {
+                sts_f64(smj, aux_d0 + W, ac.x * l0 - ac.y * l1);
+                sts_f64(smj, aux_d1 + W, ac.y * l0 + ac.x * l1);
+            }
+        }
+        __syncthreads();
+    };
+
+    int par = 0;  // buffer holding the current matrix
     int sweeps = 0;
     bool polishing = false;
     for (; sweeps < kJacobiMaxSweeps; ++sweeps) {
         // Once the off-diagonal norm is <= 1e-9 of the matrix norm the iteration converges quadratically: ONE more
         // sweep takes it to rounding level.
+        const double* cur = buf0 + par * jl::kBuf;
         double off = 0.0, dg = 0.0;
-        for (int e = tid; e < L.elems(); e += kJacobiThreads) off = fma(cur[e], cur[e], off);
-        if (tid < m) dg = cur[L.off_diag() + tid] * cur[L.off_diag() + tid];
-        off = block_sum_512(off, red);
-        dg = block_sum_512(dg, red);
+        for (int e = tid; e < NT; e += kJacobiThreads) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) off = fma(cur[q * jl::kPlane + e], cur[q * jl::kPlane + e], off);
+        }
+        if (tid < h) {
+            off = fma(cur[jl::kPiv + tid], cur[jl::kPiv + tid], off);
+            dg = fma(cur[jl::kDiagT + tid], cur[jl::kDiagT + tid], cur[jl::kDiagB + tid] * cur[jl::kDiagB + tid]);
+        }
+        off = block_sum_all(off, red);
+        dg = block_sum_all(dg, red);
         if (polishing || off == 0.0) break;
         if (off <= 1e-18 * (dg + 2.0 * off)) polishing = true;
-
-        for (int r = 0; r < m - 1; ++r) {
-            const double* __restrict__ E = cur;
-            const double* __restrict__ Dg = cur + L.off_diag();
-            const double2* __restrict__ CS = reinterpret_cast<const double2*>(cur + L.off_cs());
-            double* __restrict__ En = nxt;
-            // ---- loads first (the compiler cannot hoist them above the scattered stores): two regular blocks, the
-            // special block with the diagonal / pivot entries its chain needs, the vector pair --------------------
-            double bm[2][4];
-            double2 b1[2], b2[2];
-#pragma unroll
-            for (int o = 0; o < 2; ++o) {
-                if (own_e[o] >= 0) {
-                    const int e = own_e[o];
-                    bm[o][0] = E[e];
-                    bm[o][1] = E[NT + e];
-                    bm[o][2] = E[2 * NT + e];
-                    bm[o][3] = E[3 * NT + e];
-                    b1[o] = CS[own_k[o] & 0xff];
-                    b2[o] = CS[own_k[o] >> 8];
-                }
+        // m - 1 rounds (an odd number): the buffers swap roles from sweep to sweep
+        if (par == 0) {
+            for (int r = 0; r < h - 1; ++r) {
+                round(std::integral_constant<int, 0>{});
+                round(std::integral_constant<int, 1>{});
             }
-            double sm4[4] = {0, 0, 0, 0}, sd[4] = {0, 0, 0, 0}, spv[2] = {0, 0}, rd[2] = {0, 0}, rp = 0;
-            double2 s1 = make_double2(1, 0), s2 = make_double2(1, 0), rcs = make_double2(1, 0);
-            if (tid < h) {
-                sm4[0] = E[sp_e];
-                sm4[1] = E[NT + sp_e];
-                sm4[2] = E[2 * NT + sp_e];
-                sm4[3] = E[3 * NT + sp_e];
-                s1 = CS[sp_ka];
-                s2 = CS[sp_kb];
-                sd[0] = Dg[sp_ka];
-                sd[1] = Dg[h + sp_ka];
-                sd[2] = Dg[sp_kb];
-                sd[3] = Dg[h + sp_kb];
-                spv[0] = E[4 * NT + sp_ka];
-                spv[1] = E[4 * NT + sp_kb];
-                rcs = CS[tid];
-                rd[0] = Dg[tid];
-                rd[1] = Dg[h + tid];
-                rp = E[4 * NT + tid];
+            round(std::integral_constant<int, 0>{});
+        } else {
+            for (int r = 0; r < h - 1; ++r) {
+                round(std::integral_constant<int, 1>{});
+                round(std::integral_constant<int, 0>{});
             }
-            double2 vcs = make_double2(1, 0);
-            double vu0 = 0, vu1 = 0;
-            if (has_vec) {
-                const double* uc = cur + L.off_u() + vec_v * m;
-                vcs = CS[vec_k];
-                vu0 = uc[vec_k];
-                vu1 = uc[h + vec_k];
-            }
-            // ---- the special block, the next pivot of slot tid and its rotation -------------------------------
-            if (tid < h) {
-                const double c1 = s1.x, sn1 = s1.y, c2 = s2.x, sn2 = s2.y;
-                const double t00 = c2 * sm4[0] - sn2 * sm4[1], t01 = sn2 * sm4[0] + c2 * sm4[1];
-                const double t10 = c2 * sm4[2] - sn2 * sm4[3], t11 = sn2 * sm4[2] + c2 * sm4[3];
-                double ev[4];
-                ev[0] = c1 * t00 - sn1 * t10;
-                ev[2] = sn1 * t00 + c1 * t10;
-                ev[1] = c1 * t01 - sn1 * t11;
-                ev[3] = sn1 * t01 + c1 * t11;
-                const double apq = sp_q == 0 ? ev[0] : (sp_q == 1 ? ev[1] : (sp_q == 2 ? ev[2] : ev[3]));
-                // new diagonal entries of the seats X (in slot ka or kb) and Y that arrive on slot tid
-                const double da = rotated_diag(sp_x_in_ka ? sp_x_bottom : sp_y_bottom, sd[0], sd[1], spv[0], c1, sn1);
-                const double db = rotated_diag(sp_x_in_ka ? sp_y_bottom : sp_x_bottom, sd[2], sd[3], spv[1], c2, sn2);
-                const double app = sp_x_in_ka ? da : db, aqq = sp_x_in_ka ? db : da;
-                double c = 1.0, s = 0.0;
-                if (apq != 0.0) jacobi_angle(app, aqq, apq, c, s);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) En[sp_dst[q]] = ev[q];
-                nxt[L.off_diag() + tid] = app;
-                nxt[L.off_diag() + h + tid] = aqq;
-                reinterpret_cast<double2*>(nxt + L.off_cs())[tid] = make_double2(c, s);
-                // residual of the current pivot of slot tid (the angle is inexact: the element is kept)
-                En[res_dst] = fma(rcs.y * rcs.x, rd[0] - rd[1], (rcs.x * rcs.x - rcs.y * rcs.y) * rp);
-            }
-            // ---- regular blocks  M <- J_ka^T M J_kb ----------------------------------------------------------------
-            auto rotate_store = [&](const double (&mm)[4], double2 r1, double2 r2, const int (&dst)[4]) {
-                const double c1 = r1.x, sn1 = r1.y, c2 = r2.x, sn2 = r2.y;
-                const double t00 = c2 * mm[0] - sn2 * mm[1], t01 = sn2 * mm[0] + c2 * mm[1];
-                const double t10 = c2 * mm[2] - sn2 * mm[3], t11 = sn2 * mm[2] + c2 * mm[3];
-                En[dst[0]] = c1 * t00 - sn1 * t10;
-                En[dst[2]] = sn1 * t00 + c1 * t10;
-                En[dst[1]] = c1 * t01 - sn1 * t11;
-                En[dst[3]] = sn1 * t01 + c1 * t11;
-            };
-#pragma unroll
-            for (int o = 0; o < 2; ++o)
-                if (own_e[o] >= 0) rotate_store(bm[o], b1[o], b2[o], own_dst[o]);
-            if (OWN > 2) {  // n > 92: two more blocks per thread, loaded late to stay inside the register budget
-#pragma unroll
-                for (int o = 2; o < OWN; ++o) {
-                    if (own_e[o] >= 0) {
-                        const int e = own_e[o];
-                        const double mm[4] = {E[e], E[NT + e], E[2 * NT + e], E[3 * NT + e]};
-                        rotate_store(mm, CS[own_k[o] & 0xff], CS[own_k[o] >> 8], own_dst[o]);
-                    }
-                }
-            }
-            if (has_vec) {
-                double* un = nxt + L.off_u() + vec_v * m;
-                un[vec_dt] = vcs.x * vu0 - vcs.y * vu1;
-                un[vec_db] = vcs.y * vu0 + vcs.x * vu1;
-            }
-            __syncthreads();
-            double* t = cur;
-            cur = nxt;
-            nxt = t;
+            round(std::integral_constant<int, 1>{});
         }
+        par ^= 1;
     }
 
     // ---- spectrum -> clipped spectrum -> pinvh cut-off -> whitened projections and log-determinant ------------
     // (whole sweeps only: every index is back on its own seat, seat p = index p; seats >= n are padding)
-    const double* D = cur + L.off_diag();
-    const double* U = cur + L.off_u();
+    const double* cur = buf0 + par * jl::kBuf;
     double lmax = -INFINITY;
-    for (int i = tid; i < n; i += kJacobiThreads) lmax = fmax(lmax, D[i]);
+    for (int i = tid; i < n; i += kJacobiThreads) lmax = fmax(lmax, cur[seats.diag(i)]);
 #pragma unroll
     for (int msk = 16; msk > 0; msk >>= 1) lmax = fmax(lmax, shfl_xor_f64(lmax, msk));
     __syncthreads();
@@ -387,18 +409,18 @@ __global__ void __launch_bounds__(kJacobiThreads)
     const double cutoff = (double)n * 2.220446049250313e-16 * fabs(lmax);  // scipy.linalg.pinvh
     double ld_sum = 0.0;
     for (int r = tid; r < n; r += kJacobiThreads) {
-        const double raw = D[r];
+        const double raw = cur[seats.diag(r)];
         const double lam = fmax(raw, floor_l);  // diffusion.py:887
         evals[r] = raw;
         ld_sum += log(lam);
         const bool keep = fabs(lam) > cutoff;
         const double s = keep ? 1.0 / sqrt(fabs(lam)) : 0.0;
-        proj[r] = s * U[r];
-        proj[n + r] = s * U[m + r];
-        proj[2 * n + r] = s * U[2 * m + r];
+        proj[r] = s * cur[seats.vec(0, r)];
+        proj[n + r] = s * cur[seats.vec(1, r)];
+        proj[2 * n + r] = s * cur[seats.vec(2, r)];
         proj[3 * n + r] = keep ? (lam > 0.0 ? 1.0 : -1.0) : 0.0;
     }
-    ld_sum = block_sum_512(ld_sum, red);
+    ld_sum = block_sum_all(ld_sum, red);
     if (tid == 0) {
         logdet_term[0] = ld_sum + (double)n * 1.8378770664093453;  // + n ln(2 pi), diffusion.py:351
         if (info) info[0] = sweeps;
@@ -422,15 +444,15 @@ extern "C" int kb2_spectral_prepare(const double* cov, const double* x, const do
     KB2_CHECK(cond_max > 0.0, "kb2_spectral_prepare: cond_max must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     const int h = (n + 1) / 2 < kJacobiMinH ? kJacobiMinH : (n + 1) / 2;
-    const JacobiLayout L{h * (h - 1) / 2, h, 2 * h};
-    const size_t smem = sizeof(double) * 2 * (size_t)L.size();
-    const int n_regular = L.NT - h;
-    if (n_regular <= 2 * kJacobiThreads) {
+    const size_t smem = sizeof(double) * 2 * (size_t)jl::kBuf;
+    int n_tasks = 0;  // (row pair, column) tasks
+    for (int j = 0; 2 * j < h - 1; ++j) n_tasks += h - 1 - 2 * j;
+    if (n_tasks <= kJacobiRegular) {
+        KB2_CUDA(cudaFuncSetAttribute(jacobi_project_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        jacobi_project_kernel<1><<<1, kJacobiThreads, smem, st>>>(cov, n, h, x, y, cond_max, evals, proj, logdet_term, info);
+    } else {
         KB2_CUDA(cudaFuncSetAttribute(jacobi_project_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         jacobi_project_kernel<2><<<1, kJacobiThreads, smem, st>>>(cov, n, h, x, y, cond_max, evals, proj, logdet_term, info);
-    } else {
-        KB2_CUDA(cudaFuncSetAttribute(jacobi_project_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        jacobi_project_kernel<4><<<1, kJacobiThreads, smem, st>>>(cov, n, h, x, y, cond_max, evals, proj, logdet_term, info);
     }
     KB2_LAUNCH_CHECK();
     return launch_gls_solve(proj, n, fit_intercept, gls, st);
