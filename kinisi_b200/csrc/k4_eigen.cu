@@ -51,8 +51,8 @@ constexpr int kJacobiMinH = 3;  // smaller problems are padded with zero rows (t
 
 // Shared-memory image of the matrix in one buffer, in doubles.
 namespace jl {
-constexpr int kPlane = 2048;                     // >= kJacobiMaxH (kJacobiMaxH - 1) / 2 = 2016 blocks per plane
-constexpr int kPiv = 4 * kPlane;                 // [kJacobiMaxH] pivots (T_k, B_k)
+constexpr int kPlane = 1024;                     // >= number of tasks; plane (q, r) holds element q of block r of every task
+constexpr int kPiv = 8 * kPlane;                 // [kJacobiMaxH] pivots (T_k, B_k)
 constexpr int kDiagT = kPiv + kJacobiMaxH;       // [kJacobiMaxH] diagonal entries of the top seats
 constexpr int kDiagB = kDiagT + kJacobiMaxH;     // [kJacobiMaxH] ... of the bottom seats
 constexpr int kCS = kDiagB + kJacobiMaxH;        // [kJacobiMaxH][2] rotation (c, s) of every slot
@@ -121,9 +121,13 @@ struct JacobiSeats {
     }
     __device__ __forceinline__ int slot(int p) const { return p < h ? p : p - h; }
     __device__ __forceinline__ int bottom(int p) const { return p >= h; }
-    __device__ __forceinline__ int tri(int ka, int kb) const { return ka * (2 * h - ka - 1) / 2 + (kb - ka - 1); }
-    // Offset (doubles) of the element between seats x != y: plane * kPlane + block for seats of different slots,
-    // kPiv + k for the pivot of slot k.
+    // task = (row pair j, column slot kb > 2j): blocks (2j, kb) and (2j + 1, kb); tasks are numbered row pair by row pair
+    __device__ __forceinline__ int task(int j, int kb) const { return j * (h - j) + (kb - 2 * j - 1); }
+    __device__ __forceinline__ int n_tasks() const { const int J = h / 2; return J * (h - J); }
+    // offset (doubles) of element TT of block (ka, kb); element q = (row bottom, column bottom) is 2 q planes further
+    __device__ __forceinline__ int block(int ka, int kb) const { return (ka & 1) * jl::kPlane + task(ka >> 1, kb); }
+    // Offset (doubles) of the element between seats x != y: for seats of different slots the planes are indexed by the
+    // task number (consecutive lanes = consecutive tasks = consecutive addresses); kPiv + k for the pivot of slot k.
     __device__ __forceinline__ int addr(int x, int y) const {
         int sx = slot(x), sy = slot(y), tx = bottom(x), ty = bottom(y);
         if (sx == sy) return jl::kPiv + sx;
@@ -131,7 +135,7 @@ struct JacobiSeats {
             int q = sx; sx = sy; sy = q;
             q = tx; tx = ty; ty = q;
         }
-        return (tx * 2 + ty) * jl::kPlane + tri(sx, sy);
+        return (tx * 2 + ty) * 2 * jl::kPlane + block(sx, sy);
     }
     __device__ __forceinline__ int diag(int p) const { return (bottom(p) ? jl::kDiagB : jl::kDiagT) + slot(p); }
     __device__ __forceinline__ int vec(int v, int p) const { return jl::kU + v * 2 * kJacobiMaxH + bottom(p) * kJacobiMaxH + slot(p); }
@@ -175,7 +179,6 @@ __global__ void __launch_bounds__(kJacobiThreads, 1)
     __shared__ double red[kJacobiThreads / 32];
     double* const buf0 = reinterpret_cast<double*>(smj);
     const int m = 2 * h;             // seats; indices >= n are zero padding
-    const int NT = h * (h - 1) / 2;  // blocks ka < kb
     const JacobiSeats seats{h};
     const int tid = threadIdx.x;
     constexpr uint32_t kBufBytes = jl::kBuf * 8, kPlaneBytes = jl::kPlane * 8;
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(kJacobiThreads, 1)
     //   special thread k: block (ka, kb) holding the element {X, Y}, X = prev(T_k) -> T_k, Y = prev(B_k) -> B_k
     //     O = {block, cs ka, cs kb, diag own a, diag other a, pivot a, diag own b, diag other b, pivot b, dst[4]}
     //   regular thread: task o = (row pair j, column slot kb) -> blocks (2j, kb) and (2j + 1, kb)
-    //     O = {block 0, cs ka0, cs kb, block 1, cs ka1, dst 0 [4], dst 1 [4]}
+    //     O = {task, cs ka0, cs kb, -, cs ka1, dst 0 [4], dst 1 [4]}
     uint32_t O[NTASK][13];
     bool ok[NTASK][2];
 #pragma unroll
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(kJacobiThreads, 1)
         const int fa = sp_x_in_ka ? seats.bottom(X) : seats.bottom(Y);  // is the element's row seat (slot ka) a bottom seat
         const int fb = sp_x_in_ka ? seats.bottom(Y) : seats.bottom(X);  // ... its column seat (slot kb)
         sp_q = fa * 2 + fb;
-        O[0][0] = 8u * seats.tri(ka, kb);
+        O[0][0] = 8u * seats.block(ka, kb);
         O[0][1] = 8u * (jl::kCS + 2 * ka);
         O[0][2] = 8u * (jl::kCS + 2 * kb);
         // new diagonal of a seat after its slot's rotation: cc * own + ss * other -/+ 2 s c pivot (top / bottom)
@@ -247,13 +250,13 @@ __global__ void __launch_bounds__(kJacobiThreads, 1)
             }
             if (2 * j < h - 1) {
                 const int kb = 2 * j + 1 + li;
+                O[o][0] = 8u * seats.task(j, kb);
                 O[o][2] = 8u * (jl::kCS + 2 * kb);
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     const int ka = 2 * j + r;
                     if (ka < kb && !seats.special(ka, kb)) {
                         ok[o][r] = true;
-                        O[o][3 * r] = 8u * seats.tri(ka, kb);
                         O[o][3 * r + 1] = 8u * (jl::kCS + 2 * ka);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) O[o][5 + 4 * r + q] = 8u * seats.block_dst(ka, kb, q);
@@ -297,8 +300,8 @@ __global__ void __launch_bounds__(kJacobiThreads, 1)
         constexpr int P = decltype(parity)::value;
         constexpr uint32_t R = P * kBufBytes, W = (1 - P) * kBufBytes;
         if (tid < kJacobiSpecial) {
-            const double mm[4] = {lds_f64(smj, O[0][0] + R), lds_f64(smj, O[0][0] + R + kPlaneBytes),
-                                  lds_f64(smj, O[0][0] + R + 2 * kPlaneBytes), lds_f64(smj, O[0][0] + R + 3 * kPlaneBytes)};
+            const double mm[4] = {lds_f64(smj, O[0][0] + R), lds_f64(smj, O[0][0] + R + 2 * kPlaneBytes),
+                                  lds_f64(smj, O[0][0] + R + 4 * kPlaneBytes), lds_f64(smj, O[0][0] + R + 6 * kPlaneBytes)};
             const double2 ra = lds_f64x2(smj, O[0][1] + R), rb = lds_f64x2(smj, O[0][2] + R);
             const double a1 = lds_f64(smj, O[0][3] + R), a2 = lds_f64(smj, O[0][4] + R), ap = lds_f64(smj, O[0][5] + R);
             const double b1 = lds_f64(smj, O[0][6] + R), b2 = lds_f64(smj, O[0][7] + R), bp = lds_f64(smj, O[0][8] + R);
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(kJacobiThreads, 1)
                 for (int r = 0; r < 2; ++r) {
                     ra[o][r] = lds_f64x2(smj, O[o][3 * r + 1] + R);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) mm[o][r][q] = lds_f64(smj, O[o][3 * r] + R + q * kPlaneBytes);
+                    for (int q = 0; q < 4; ++q) mm[o][r][q] = lds_f64(smj, O[o][0] + R + (2 * q + r) * kPlaneBytes);
                 }
             }
             const double2 ac = lds_f64x2(smj, aux_cs + R);
@@ -363,9 +366,9 @@ __global__ void __launch_bounds__(kJacobiThreads, 1)
         // sweep takes it to rounding level.
         const double* cur = buf0 + par * jl::kBuf;
         double off = 0.0, dg = 0.0;
-        for (int e = tid; e < NT; e += kJacobiThreads) {
+        for (int e = tid; e < seats.n_tasks(); e += kJacobiThreads) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) off = fma(cur[q * jl::kPlane + e], cur[q * jl::kPlane + e], off);
+            for (int q = 0; q < 8; ++q) off = fma(cur[q * jl::kPlane + e], cur[q * jl::kPlane + e], off);
         }
         if (tid < h) {
             off = fma(cur[jl::kPiv + tid], cur[jl::kPiv + tid], off);
