@@ -126,7 +126,7 @@ int kb2_self_moments(const double* dc, int n_atoms, int n_frames, int64_t pitch,
 size_t kb2_self_moments_runs_workspace_bytes(int n_lags, int n_frames);
 int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames, int64_t pitch, const int32_t* lags_host,
                           int n_lags, int dim_mask, void* workspace, double* sums, void* stream);
-/* The plan kb2_self_moments_runs makes for (the first 768 lags of) a grid, for tests and diagnostics: returns the
+/* The plan kb2_self_moments_runs makes for (the first 192 lags of -- one launch) a grid, for tests and diagnostics: returns the
  * number of runs of >= 3 lags, fills up to max_runs entries of run_k0 / run_delta / run_len / run_n_chg (host arrays,
  * may be NULL; run_n_chg = signed number of one-sample drift changes inside the run, lags k0 + i*delta + e_i) and
  * stores the number of lags that became runs of one in *n_rest. */

@@ -56,6 +56,7 @@ constexpr int kRunPrefetch = 6;            // steps between the cp.async of a pa
 constexpr long long kRunBatchBytes = 24ll << 20;  // trajectory bytes of one atom batch (L2 is 126 MB)
 constexpr int kRunRingBytes = kRunM * 3 * 2 * 32 * 8;  // per warp: slot x component x {sample, neighbour} x lane
 constexpr int kRunMaxWarps = 8;
+constexpr int kRunMaxLags = 192;           // lags per launch: every warp keeps private accumulators [K][2] in shared memory
 
 struct RunDesc {
     int k0, delta, len, off;  // lags k0 + i*delta + e_i, i < len; accumulator index of lag i is off + i
@@ -96,9 +97,11 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// As fold_lag_group, for a group whose first `cnt` stash rows are live; lag g of the group goes to acc[i0 + g].
+// As fold_lag_group, for a group whose first `cnt` stash rows are live; lag g of the group goes to the WARP's own
+// accumulators wacc[i0 + g] with a plain read-modify-write (a shared-memory FP64 atomicAdd is a compare-and-swap loop:
+// 19 % of the kernel's stall samples when all the warps of an SM fold into one array).
 template <int LG>
-__device__ __forceinline__ void fold_lag_group_n(MomentSmem& sm, int warp, int lane, int i0, int cnt) {
+__device__ __forceinline__ void fold_lag_group_n(MomentSmem& sm, double* wacc, int warp, int lane, int i0, int cnt) {
     constexpr int LPG = 32 / LG;
     __syncwarp();
     const int g = lane / LPG, q = lane % LPG;
@@ -116,8 +119,11 @@ __device__ __forceinline__ void fold_lag_group_n(MomentSmem& sm, int warp, int l
         t2 += shfl_xor_f64(t2, mask);
     }
     if (q == 0 && g < cnt) {
-        atomicAdd(&sm.acc[2 * (i0 + g)], t1);
-        atomicAdd(&sm.acc[2 * (i0 + g) + 1], t2);
+        double2* a = reinterpret_cast<double2*>(wacc) + (i0 + g);
+        double2 v = *a;
+        v.x += t1;
+        v.y += t2;
+        *a = v;
     }
     __syncwarp();
 }
@@ -176,7 +182,7 @@ struct RunCtx {  // warp-uniform description of the current item
 // DRIFT = false requires that no change index lies in the lags these steps touch (cur.cnext > s0 + M - 1).
 template <int NDIM, int M, int LG, bool FIRST, bool DRIFT, bool DR>
 __device__ __forceinline__ void run_block_interior(Column<NDIM, M, DR>& col, DriftCursor& cur, const RunCtx& rc, int s0,
-                                                   MomentSmem& sm, int warp, int lane) {
+                                                   MomentSmem& sm, double* wacc, int warp, int lane) {
     static_assert(M % LG == 0, "the fold group must divide the register window");
 #pragma unroll
     for (int u = 0; u < M; ++u) {
@@ -212,7 +218,7 @@ __device__ __forceinline__ void run_block_interior(Column<NDIM, M, DR>& col, Dri
             sm.stash_put(warp, gs, lane, col.A1[sl], col.A2[sl]);
             col.A1[sl] = 0.0;
             col.A2[sl] = 0.0;
-            if (gs == LG - 1) fold_lag_group_n<LG>(sm, warp, lane, rc.acc_base + s0 + u - (M - 1) - (LG - 1), LG);
+            if (gs == LG - 1) fold_lag_group_n<LG>(sm, wacc, warp, lane, rc.acc_base + s0 + u - (M - 1) - (LG - 1), LG);
         }
     }
     col.rem -= M * rc.D;
@@ -224,7 +230,7 @@ __device__ __forceinline__ void run_block_interior(Column<NDIM, M, DR>& col, Dri
 // trajectory: per lane).
 template <int NDIM, int M, int LG, bool DR>
 __device__ __forceinline__ void run_step_generic(Column<NDIM, M, DR>& col, DriftCursor& cur, const RunCtx& rc, int s,
-                                                 MomentSmem& sm, int warp, int lane) {
+                                                 MomentSmem& sm, double* wacc, int warp, int lane) {
     cp_async_wait<kRunPrefetch - 1>();
     int mc = -1;
     if (DR) {
@@ -259,7 +265,7 @@ __device__ __forceinline__ void run_step_generic(Column<NDIM, M, DR>& col, Drift
     if (i_f >= 0 && i_f < rc.L) {
         const int gs = i_f % LG;
         sm.stash_put(warp, gs, lane, col.A1[1], col.A2[1]);
-        if (gs == LG - 1 || i_f == rc.L - 1) fold_lag_group_n<LG>(sm, warp, lane, rc.acc_base + i_f - gs, gs + 1);
+        if (gs == LG - 1 || i_f == rc.L - 1) fold_lag_group_n<LG>(sm, wacc, warp, lane, rc.acc_base + i_f - gs, gs + 1);
     }
     // rotate by one slot: the lag of origin m becomes the lag of origin m+1 (slot j <- slot j+1); the flushed
     // slot 1 re-enters as the empty slot 0 and slot 0 moves to slot M-1
@@ -290,8 +296,12 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
     col.ring = reinterpret_cast<double*>(smem_raw + MomentSmem::bytes(K, WARPS, LG)) +
                warp * (kRunRingBytes / 8 / (DR ? 1 : 2)) + lane;
 
+    // per-warp accumulators [WARPS][K][2] behind the rings
+    double* const wacc_all = reinterpret_cast<double*>(smem_raw + MomentSmem::bytes(K, WARPS, LG) +
+                                                       (size_t)WARPS * kRunRingBytes / (DR ? 1 : 2));
+    double* const wacc = wacc_all + (size_t)warp * 2 * K;
 #pragma unroll 1
-    for (int i = tid; i < 2 * K; i += NT) sm.acc[i] = 0.0;
+    for (int i = tid; i < 2 * K * WARPS; i += NT) wacc_all[i] = 0.0;
     __syncthreads();
 
     const long long n_work = (long long)n_pairs * n_atoms;
@@ -336,9 +346,10 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
                     const double d = __ldg(row[c] + p);
                     d2 = fma(d, d, d2);
                 }
-                atomicAdd(&sm.acc[2 * (rc.acc_base + i)], d2);
-                atomicAdd(&sm.acc[2 * (rc.acc_base + i) + 1], d2 * d2);
+                wacc[2 * (rc.acc_base + i)] += d2;  // one lane per lag
+                wacc[2 * (rc.acc_base + i) + 1] += d2 * d2;
             }
+            __syncwarp();
         }
 
         const int g = pr.y * kRunCols + lane;  // column: tile q = g / D, offset t = g % D
@@ -380,14 +391,14 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
         while (s < work_steps) {
             if ((s % M) == 0 && s + M <= full && (s > 0 || cur.cnext > M - 1)) {
                 if (s == 0)
-                    run_block_interior<NDIM, M, LG, true, false, DR>(col, cur, rc, 0, sm, warp, lane);
+                    run_block_interior<NDIM, M, LG, true, false, DR>(col, cur, rc, 0, sm, wacc, warp, lane);
                 else if (!DR || cur.cnext > s + M - 1)
-                    run_block_interior<NDIM, M, LG, false, false, DR>(col, cur, rc, s, sm, warp, lane);
+                    run_block_interior<NDIM, M, LG, false, false, DR>(col, cur, rc, s, sm, wacc, warp, lane);
                 else
-                    run_block_interior<NDIM, M, LG, false, DR, DR>(col, cur, rc, s, sm, warp, lane);
+                    run_block_interior<NDIM, M, LG, false, DR, DR>(col, cur, rc, s, sm, wacc, warp, lane);
                 s += M;
             } else {
-                run_step_generic<NDIM, M, LG, DR>(col, cur, rc, s, sm, warp, lane);
+                run_step_generic<NDIM, M, LG, DR>(col, cur, rc, s, sm, wacc, warp, lane);
                 ++s;
             }
         }
@@ -401,7 +412,7 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
             if ((unsigned)i < (unsigned)L) {
                 const int gs = i % LG;
                 sm.stash_put(warp, gs, lane, col.A1[1], col.A2[1]);
-                if (gs == LG - 1 || i == L - 1) fold_lag_group_n<LG>(sm, warp, lane, acc_base + i - gs, gs + 1);
+                if (gs == LG - 1 || i == L - 1) fold_lag_group_n<LG>(sm, wacc, warp, lane, acc_base + i - gs, gs + 1);
             }
 #pragma unroll
             for (int j = 1; j < M - 1; ++j) {
@@ -412,12 +423,17 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
         // a fold group left open (the steps stopped before the run's last lag)
         const int i_last = work_steps - 1;
         if (i_last < L - 1 && (i_last % LG) != LG - 1)
-            fold_lag_group_n<LG>(sm, warp, lane, acc_base + i_last - (i_last % LG), (i_last % LG) + 1);
+            fold_lag_group_n<LG>(sm, wacc, warp, lane, acc_base + i_last - (i_last % LG), (i_last % LG) + 1);
     }
     __syncthreads();
     // one FP64 reduction per lag, moment and CTA straight into the caller's array (zeroed by the host call)
 #pragma unroll 1
-    for (int i = tid; i < 2 * K; i += NT) atomicAdd(out + 2 * slot[i >> 1] + (i & 1), sm.acc[i]);
+    for (int i = tid; i < 2 * K; i += NT) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) t += wacc_all[(size_t)w * 2 * K + i];
+        atomicAdd(out + 2 * slot[i >> 1] + (i & 1), t);
+    }
 }
 
 // ---- host-side planning -------------------------------------------------------------------------
@@ -565,7 +581,8 @@ static int launch_runs_w(int sm_count, long long n_work, cudaStream_t st, const 
                          int64_t pitch, const int comp[3], const RunDesc* runs, const int2* pairs, int n_pairs, int batch,
                          const int32_t* chg, int K, unsigned int* counter, const int32_t* slot, double* out) {
     const int grid = (int)std::min<long long>((n_work + WARPS - 1) / WARPS, 2 * sm_count);
-    const size_t smem = MomentSmem::bytes(K, WARPS, kRunLG) + (size_t)WARPS * kRunRingBytes / (DR ? 1 : 2);
+    const size_t smem = MomentSmem::bytes(K, WARPS, kRunLG) + (size_t)WARPS * kRunRingBytes / (DR ? 1 : 2) +
+                        (size_t)WARPS * 16 * K;
     KB2_CUDA(cudaFuncSetAttribute(self_moments_runs_kernel<NDIM, WARPS, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     self_moments_runs_kernel<NDIM, WARPS, DR><<<grid, 32 * WARPS, smem, st>>>(dc, n_atoms, Tn, pitch, comp[0], comp[1], comp[2],
@@ -611,7 +628,7 @@ static size_t runs_plan_bytes(int k, int t) {
 using namespace kb2;
 
 extern "C" size_t kb2_self_moments_runs_workspace_bytes(int n_lags, int n_frames) {
-    const int k = n_lags < 1 ? 1 : (n_lags > kMaxLags ? kMaxLags : n_lags);
+    const int k = n_lags < 1 ? 1 : (n_lags > kRunMaxLags ? kRunMaxLags : n_lags);
     const int t = n_frames < 1 ? 1 : n_frames;
     return runs_plan_bytes(k, t);
 }
@@ -634,14 +651,14 @@ extern "C" int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, 0);
 
-    const int kcap = n_lags > kMaxLags ? kMaxLags : n_lags;
+    const int kcap = n_lags > kRunMaxLags ? kRunMaxLags : n_lags;
     char* d_plan = (char*)workspace;
     KB2_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_lags * 2 * sizeof(double), st));
     const size_t pair_cap = runs_pair_capacity(kcap, n_frames);
 
     std::vector<unsigned char> packed;
-    for (int l0 = 0; l0 < n_lags; l0 += kMaxLags) {
-        const int K = min(kMaxLags, n_lags - l0);
+    for (int l0 = 0; l0 < n_lags; l0 += kRunMaxLags) {
+        const int K = min(kRunMaxLags, n_lags - l0);
         RunPlan plan;
         plan_runs(lags_host + l0, K, n_frames, plan);
         KB2_CHECK(plan.pairs.size() <= pair_cap && (int)plan.slot.size() == K,
@@ -690,7 +707,7 @@ extern "C" int kb2_self_moments_plan(const int32_t* lags_host, int n_lags, int n
                                      int32_t* run_delta, int32_t* run_len, int32_t* run_n_chg, int max_runs, int* n_rest) {
     if (!lags_host || n_lags <= 0) return 0;
     RunPlan plan;
-    plan_runs(lags_host, std::min(n_lags, kMaxLags), n_frames, plan);
+    plan_runs(lags_host, std::min(n_lags, kRunMaxLags), n_frames, plan);
     int n = 0, rest = 0;
     for (const RunDesc& rd : plan.runs) {
         if (rd.len < kRunMinLen) {

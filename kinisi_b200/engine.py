@@ -128,7 +128,7 @@ def self_moments(dc, n_frames, lags, mask=7, variant=None):
         check(
             lib.kb2_self_moments_runs(dc.data_ptr(), dc.shape[0], n_frames, dc.shape[2], lags_host.ctypes.data, K, mask,
                                       ws.data_ptr(), sums.data_ptr(), _stream()), 'kb2_self_moments_runs')
-        _count((K + 767) // 768)
+        _count((K + 191) // 192)
         return sums
     if not isinstance(lags, torch.Tensor):
         lags = small_to_device(lags, dc.device, np.int32)

@@ -238,13 +238,13 @@ def test_arithmetic_run_kernel_on_structured_and_irregular_grids(kb, grid, n_fra
     lags = RUN_GRIDS[grid](n_frames)
     lags = lags[(lags >= 1) & (lags <= n_frames)]
     if grid == 'all' and n_frames > 2000:
-        lags = lags[:1700]  # three chunks of the 768-lag launch limit
+        lags = lags[:1700]  # nine chunks of the 192-lag launch limit
     S1, S2, _, _ = ko.raw_sums_streaming(dc, lags)
     sums = kb.engine.self_moments(_device_dc(kb, dc), n_frames, lags, 7, kb.engine.VARIANT_RUNS).cpu().numpy()
     np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
     np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
-    runs, rest = kb.engine.self_moments_plan(lags[:768], n_frames)
-    assert sum(r[2] for r in runs) + rest == min(len(lags), 768)
+    runs, rest = kb.engine.self_moments_plan(lags[:192], n_frames)
+    assert sum(r[2] for r in runs) + rest == min(len(lags), 192)
 
 
 def test_arithmetic_run_kernel_many_atoms_and_tiles(kb):

@@ -101,7 +101,7 @@ def test_lag_grid_is_split_into_arithmetic_runs():
     assert rest == 0 and runs == [(1, 1010, 100, 9)]
     runs, rest = check(np.linspace(1, 50000, 100, dtype=int), 50000)  # configs[4]
     assert rest == 1 and len(runs) == 4 and all(r[1] == 505 for r in runs)
-    runs, rest = check(np.linspace(1, 20000, 2000, dtype=int)[:768], 20000)  # 2000-point grid, one 768-lag launch
+    runs, rest = check(np.linspace(1, 20000, 2000, dtype=int)[:192], 20000)  # 2000-point grid, one 192-lag launch
     assert rest == 0 and len(runs) <= 4
     runs, rest = check(np.unique(np.geomspace(1, 20000, 100, dtype=int)), 20000)
     assert runs[0][1] == 1  # the dense start 1, 2, 3, ...
