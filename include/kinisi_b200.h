@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KB2_ABI_VERSION 2
+#define KB2_ABI_VERSION 3
 
 /* coordinate element types */
 #define KB2_F32 0
@@ -85,10 +85,12 @@ int kb2_scan_frames(double* buf, int n_frames, int64_t pitch, int cumulative, do
  * step_scale * step_sums[c*pitch + t], summed over time in MODE_FRACTIONAL.  With step_sums = kb2_frame_sums of the
  * framework atoms and step_scale = 1/n_framework this is dc - mean(dc[framework]) of parser.py:143-145 (the sum over
  * atoms commutes with the sum over time); step_sums == NULL: no correction.  dc[:, 0] == 0 in MODE_FRACTIONAL
- * exactly as in the reference. */
+ * exactly as in the reference.  `workspace`: kb2_unwrap_cumsum_workspace_bytes(n_idx, pitch) bytes of device memory
+ * (the tiles of a trajectory exchange their totals through it); its contents need not be preserved between calls. */
+size_t kb2_unwrap_cumsum_workspace_bytes(int n_idx, int64_t pitch);
 int kb2_unwrap_cumsum(const void* coords, int dtype, int mode, int n_atoms_total, int n_frames_in, const double* latt,
                       const double* latt_inv, int latt_stride, const int32_t* idx, int n_idx, const double* step_sums,
-                      double step_scale, double* dc_out, int64_t pitch, void* stream);
+                      double step_scale, double* dc_out, int64_t pitch, void* workspace, void* stream);
 
 /* out[c*pitch + t] = sum_{a < n_atoms} w[a] * dc[(a*3 + c)*pitch + t]  (w == NULL: unit weights).
  * The collective displacement of MSTD (np.sum(disp_slice, axis=0), kinisi/diffusion.py:659) and the

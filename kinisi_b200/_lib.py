@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, 'libkinisi_b200.so')
 
 F32, F64 = 0, 1
 MODE_FRACTIONAL, MODE_DISPLACEMENT = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); mirrors include/kinisi_b200.h one to one
 SIGNATURES = {
@@ -20,8 +20,9 @@ SIGNATURES = {
     'kb2_frame_sums': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                c_void_p, c_int64, c_void_p]),
     'kb2_scan_frames': (c_int, [c_void_p, c_int, c_int64, c_int, c_double, c_void_p, c_double, c_void_p]),
+    'kb2_unwrap_cumsum_workspace_bytes': (c_size_t, [c_int, c_int64]),
     'kb2_unwrap_cumsum': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int,
-                                  c_void_p, c_double, c_void_p, c_int64, c_void_p]),
+                                  c_void_p, c_double, c_void_p, c_int64, c_void_p, c_void_p]),
     'kb2_atom_sum': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     'kb2_self_moments_workspace_bytes': (c_size_t, [c_int]),
     'kb2_self_moments': (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -9,6 +9,8 @@
 //
 // Algorithmic HBM bytes per (atom, frame): sizeof(coord)*3 read + 24 written for the scan kernel,
 // sizeof(coord)*3 read for the frame-sum kernel.  Both are HBM-bound.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace kb2 {
@@ -160,24 +162,48 @@ __global__ void __launch_bounds__(1024) scan_frames_kernel(double* __restrict__ 
     }
 }
 
-// One CTA per selected atom, walking the trajectory in tiles of kUwTile = 256 * kUwE frames with a running carry.
-//   raw tile   -> shared memory with cp.async (coalesced 4- or 8-byte copies, the next tile in flight while the
-//                 current one is scanned; the atom-major [F][3] rows are only element-aligned, so no bulk copy)
+// Persistent CTAs walk (atom, tile of kUwTile frames) work items taken from a ticket counter; the tiles of an atom are
+// processed concurrently by different CTAs and exchange their totals:
+//   raw tile   -> shared memory with 16-byte cp.async from the 16-byte-aligned address at or below the tile's first
+//                 element (the atom-major [F][3] rows are only element-aligned; the misalignment m shifts the tile by
+//                 m elements inside the buffer), double buffered: the loads of the NEXT item are issued before the
+//                 current one is scanned, and its ticket is drawn one item earlier still
 //   thread     -> kUwE consecutive frames: unwrapped steps, minus step_scale * step_sums (the per-frame framework
 //                 mean, subtracted BEFORE the cumulative sum: the sum over atoms commutes with the sum over time),
-//                 sequential prefix, then one warp scan + one block scan of the thread totals per tile
+//                 sequential prefix, then one warp scan + one block scan of the thread totals.  kUwE is odd, so the
+//                 per-thread walks through the raw buffer (stride 3 kUwE elements) and the staging buffer (stride kUwE
+//                 doubles) are bank-conflict free without padding
+//   carry      -> the tile publishes its total in the workspace and, after staging its own prefix, adds the totals of
+//                 ALL the earlier tiles of its atom, one thread per predecessor.  A total is its own ready flag (the
+//                 workspace is preset to an all-ones bit pattern no sum can produce), so publishing is three plain
+//                 stores and collecting is three L2 loads: no fences.  Tickets are drawn in order and an item only waits
+//                 for smaller tickets, so the smallest unfinished ticket always makes progress; items are numbered
+//                 tile-major (all atoms' tile 0, then tile 1, ...) so that a tile's predecessors are n_idx tickets
+//                 back: finished or running, not queued behind another item of the CTA that drew them
 //   result     -> staged through shared memory and written as full rows of the component-major dc
-// Shared-memory strides are padded by one element per kUwE frames so that the per-thread walks are conflict free.
-constexpr int kUwE = 8;
-constexpr int kUwTile = 256 * kUwE;
+// History: one CTA per atom walking its trajectory was 1.5 waves of 296 CTAs that alternated between loading and
+// scanning (1.8 TB/s); one CTA per tile exposed four dependent global latencies per tile (ticket, index, tile, flags);
+// element-wise cp.async with padded strides spent 340 instructions per frame.
+constexpr int kUwE = 5;
+constexpr int kUwThreads = 256;
+constexpr int kUwTile = kUwThreads * kUwE;
+constexpr unsigned long long kUwNotReady = 0xFFFFFFFFFFFFFFFFull;
 
-__host__ __device__ constexpr int uw_raw_elems() { return (kUwTile + 1) * 3 + (kUwTile + 1) / kUwE + 4; }
-__host__ __device__ constexpr int uw_out_elems() { return kUwTile + kUwTile / kUwE; }
 template <typename T>
-__host__ __device__ constexpr size_t uw_smem_bytes() {
-    return ((2 * uw_raw_elems() * sizeof(T) + 15) & ~(size_t)15) + 3 * uw_out_elems() * sizeof(double);
+__host__ __device__ constexpr int uw_raw_chunks() {  // 16-byte chunks that cover (kUwTile + 1) frames at any misalignment
+    return (int)(((kUwTile + 1) * 3 * sizeof(T) + 15 + 15) / 16);
 }
+template <typename T>
+__host__ __device__ constexpr size_t uw_raw_bytes() { return (size_t)uw_raw_chunks<T>() * 16; }
+template <typename T>
+__host__ __device__ constexpr size_t uw_smem_bytes() { return 2 * uw_raw_bytes<T>() + 3 * (size_t)kUwTile * sizeof(double); }
+// workspace: ticket counter (256 B) | totals [n_idx][n_tiles][3] double
+__host__ __device__ inline size_t uw_workspace_bytes(int64_t n_idx, int64_t n_tiles) { return 256 + align256(24 * n_idx * n_tiles); }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
 template <typename T>
 __device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
@@ -185,34 +211,60 @@ __device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {
                  : "memory");
 }
 
-template <typename T, int MODE, bool CONSTL>
-__global__ void __launch_bounds__(256, 2) unwrap_cumsum_kernel(const T* __restrict__ coords, int F,
-                                                               const double* __restrict__ latt,
-                                                               const double* __restrict__ inv, int lstride,
-                                                               const int32_t* __restrict__ idx, int n_idx,
-                                                               const double* __restrict__ step_sums, double step_scale,
-                                                               double* __restrict__ out, int64_t pitch, int Tn) {
-    constexpr int E = kUwE, TF = kUwTile;
-    constexpr bool FRAC = (MODE == KB2_MODE_FRACTIONAL);
-    extern __shared__ __align__(16) unsigned char uw_smem[];
-    T* raw = reinterpret_cast<T*>(uw_smem);  // [2][uw_raw_elems()]
-    double* outs = reinterpret_cast<double*>(uw_smem + ((2 * uw_raw_elems() * sizeof(T) + 15) & ~(size_t)15));
-    __shared__ double s_tot[3][8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int atom = blockIdx.x;
-    const T* base = coords + (size_t)idx[atom] * F * 3;
-    const int64_t n_in = (int64_t)F * 3;  // elements of this atom's row
+__device__ __forceinline__ unsigned long long ld_l2_u64(const double* p) {  // L2 load the compiler may not cache or hoist
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 
-    // raw element e of the tile starting at frame t0 is global element t0*3 + e; frame f, component k sits at
-    // f*3 + k + f/E
-    auto issue = [&](int64_t t0, int buf) {
-        T* dst = raw + (size_t)buf * uw_raw_elems();
-        const int64_t g0 = t0 * 3;
-        const int n = (TF + (FRAC ? 1 : 0)) * 3;
-        for (int e = tid; e < n; e += 256) {
-            if (g0 + e < n_in) {
-                const int f = e / 3;
-                cp_async_elem<T>(dst + e + f / E, base + g0 + e);
+template <typename T, int MODE, bool CONSTL>
+__global__ void __launch_bounds__(kUwThreads, 3) unwrap_cumsum_kernel(const T* __restrict__ coords, int64_t n_coords, int F,
+                                                                     const double* __restrict__ latt,
+                                                                     const double* __restrict__ inv, int lstride,
+                                                                     const int32_t* __restrict__ idx, int n_idx,
+                                                                     const double* __restrict__ step_sums, double step_scale,
+                                                                     double* __restrict__ out, int64_t pitch, int Tn,
+                                                                     int n_tiles, unsigned char* __restrict__ workspace) {
+    constexpr int E = kUwE, TF = kUwTile, NT = kUwThreads;
+    constexpr bool FRAC = (MODE == KB2_MODE_FRACTIONAL);
+    constexpr int PER16 = 16 / (int)sizeof(T);  // elements per chunk
+    extern __shared__ __align__(16) unsigned char uw_smem[];
+    double* outs = reinterpret_cast<double*>(uw_smem + 2 * uw_raw_bytes<T>());  // [3][TF]
+    __shared__ double s_tot[3][NT / 32];
+    __shared__ double s_carry[3][NT / 32];
+    __shared__ unsigned int s_ticket[4];  // ring of drawn tickets
+    __shared__ int s_mis[2];              // misalignment (elements) of the tile in each raw buffer
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int n_work = (unsigned int)n_idx * (unsigned int)n_tiles;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
+    double* totals = reinterpret_cast<double*>(workspace + 256);
+    const T* const coords_end = coords + n_coords;
+
+    // loads of work item w into raw buffer b: the tile's first element (frame t0, component 0) lands at element s_mis[b]
+    auto issue = [&](unsigned int w, int b) {
+        if (w < n_work) {
+            const int atom = (int)(w % (unsigned)n_idx), tile = (int)(w / (unsigned)n_idx);
+            const int64_t t0 = (int64_t)tile * TF;
+            if (t0 < Tn) {
+                unsigned char* dst = uw_smem + (size_t)b * uw_raw_bytes<T>();
+                const T* first = coords + ((size_t)__ldg(idx + atom) * F + t0) * 3;
+                const int mis = (int)((reinterpret_cast<uintptr_t>(first) & 15) / sizeof(T));
+                const T* src = first - mis;  // 16-byte aligned
+                // elements needed: [0, 3 * frames) past `first`, frames = min(TF, Tn - t0) (+ 1 in fractional mode)
+                const int n_el = mis + 3 * ((int)min((int64_t)TF, (int64_t)Tn - t0) + (FRAC ? 1 : 0));
+                const int n_chunks = (n_el + PER16 - 1) / PER16;
+                if (tid == 0) s_mis[b] = mis;
+                for (int ch = tid; ch < n_chunks; ch += NT) {
+                    const T* g = src + (size_t)ch * PER16;
+                    if (g >= coords && g + PER16 <= coords_end) {
+                        cp_async16(dst + (size_t)ch * 16, g);
+                    } else {  // the first / last chunk of the whole array: element by element
+#pragma unroll
+                        for (int k = 0; k < PER16; ++k)
+                            if (g + k >= coords && g + k < coords_end)
+                                cp_async_elem<T>(reinterpret_cast<T*>(dst + (size_t)ch * 16) + k, g + k);
+                    }
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -220,50 +272,74 @@ __global__ void __launch_bounds__(256, 2) unwrap_cumsum_kernel(const T* __restri
 
     double Lconst[9];
     if (FRAC && CONSTL) load9(latt, Lconst);
-    double carry[3] = {0.0, 0.0, 0.0};
-    const int n_tiles = (int)((pitch + TF - 1) / TF);
-    issue(0, 0);
-    for (int tile = 0; tile < n_tiles; ++tile) {
+    if (tid == 0) {
+        s_ticket[0] = atomicAdd(counter, 1u);
+        s_ticket[1] = atomicAdd(counter, 1u);
+    }
+    __syncthreads();
+    issue(s_ticket[0], 0);
+    for (int it = 0;; ++it) {
+        const unsigned int w = s_ticket[it & 3];
+        if (w >= n_work) break;
+        const unsigned int w_next = s_ticket[(it + 1) & 3];
+        issue(w_next, (it + 1) & 1);                                      // in flight while this item is scanned
+        if (tid == 0) s_ticket[(it + 2) & 3] = atomicAdd(counter, 1u);  // read two barriers from here at the earliest
+        const int atom = (int)(w % (unsigned)n_idx), tile = (int)(w / (unsigned)n_idx);  // tile-major order (see above)
         const int64_t t0 = (int64_t)tile * TF;
-        if (tile + 1 < n_tiles && t0 + TF < Tn) issue(t0 + TF, (tile + 1) & 1); else asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncthreads();
-        const T* r = raw + (size_t)(tile & 1) * uw_raw_elems();
-        double val[E][3];
+        double* tot_atom = totals + (size_t)atom * n_tiles * 3;
+        // the drift of this thread's frames: L2 loads that land while the tile is unwrapped
         const int f0 = tid * E;
+        double drift[E][3];
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const int f = f0 + e;
-            const int64_t t = t0 + f;
-            const bool valid = t < Tn;
-            double u[3] = {0.0, 0.0, 0.0};
-            if (valid) {
-                const int o0 = f * 3 + f / E;
-                if (FRAC) {
-                    const int o1 = (f + 1) * 3 + (f + 1) / E;
-                    const T prev[3] = {r[o0], r[o0 + 1], r[o0 + 2]};
-                    const T cur[3] = {r[o1], r[o1 + 1], r[o1 + 2]};
-                    if (CONSTL) {
-                        unwrapped_step_const<T>(cur, prev, Lconst, u);
+            const int64_t t = t0 + f0 + e;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                drift[e][c] = (step_sums && t < Tn) ? step_scale * __ldg(step_sums + (size_t)c * pitch + t) : 0.0;
+        }
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const T* raw = reinterpret_cast<const T*>(uw_smem + (size_t)(it & 1) * uw_raw_bytes<T>()) + s_mis[it & 1];
+
+        double val[E][3];
+        if (t0 + f0 < Tn) {
+            // the thread's frames f0 .. f0 + E (one more than it owns in fractional mode), read once
+            T r[E + 1][3];
+#pragma unroll
+            for (int e = 0; e < E + (FRAC ? 1 : 0); ++e)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) r[e][k] = (t0 + f0 + e < Tn + (FRAC ? 1 : 0)) ? raw[(f0 + e) * 3 + k] : (T)0;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int64_t t = t0 + f0 + e;
+                double u[3] = {0.0, 0.0, 0.0};
+                if (t < Tn) {
+                    if (FRAC) {
+                        if (CONSTL) {
+                            unwrapped_step_const<T>(r[e + 1], r[e], Lconst, u);
+                        } else {
+                            double Lc[9], Lp[9], Ic[9];
+                            load9(latt + (size_t)(t + 1) * lstride, Lc);
+                            load9(latt + (size_t)t * lstride, Lp);
+                            load9(inv + (size_t)(t + 1) * lstride, Ic);
+                            unwrapped_step<T>(r[e + 1], r[e], Lc, Lp, Ic, u);
+                        }
                     } else {
-                        double Lc[9], Lp[9], Ic[9];
-                        load9(latt + (size_t)(t + 1) * lstride, Lc);
-                        load9(latt + (size_t)t * lstride, Lp);
-                        load9(inv + (size_t)(t + 1) * lstride, Ic);
-                        unwrapped_step<T>(cur, prev, Lc, Lp, Ic, u);
+                        u[0] = (double)r[e][0];
+                        u[1] = (double)r[e][1];
+                        u[2] = (double)r[e][2];
                     }
-                } else {
-                    u[0] = (double)r[o0];
-                    u[1] = (double)r[o0 + 1];
-                    u[2] = (double)r[o0 + 2];
-                }
-                if (step_sums) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) u[c] -= step_scale * __ldg(step_sums + (size_t)c * pitch + t);
+                    for (int c = 0; c < 3; ++c) u[c] -= drift[e][c];
                 }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) val[e][c] = u[c];
             }
+        } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) val[e][c] = u[c];
+            for (int e = 0; e < E; ++e)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) val[e][c] = 0.0;
         }
         if (FRAC) {
             // thread-sequential prefix, then the exclusive offset of this thread from a warp scan and a block scan
@@ -278,38 +354,67 @@ __global__ void __launch_bounds__(256, 2) unwrap_cumsum_kernel(const T* __restri
                 if (lane == 31) s_tot[c][warp] = incl[c];
             }
             __syncthreads();
+            // publish the tile total before collecting: no tile ever waits for another tile's wait
+            if (tid >= NT - 3 && n_tiles > 1) {
+                const int c = tid - (NT - 3);
+                double tot = 0.0;
+#pragma unroll
+                for (int wdx = 0; wdx < NT / 32; ++wdx) tot += s_tot[c][wdx];
+                __stcg(tot_atom + tile * 3 + c, tot);
+            }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                double pre = carry[c], tot = 0.0;
+                double pre = 0.0;
 #pragma unroll
-                for (int wdx = 0; wdx < 8; ++wdx) {
-                    const double x = s_tot[c][wdx];
-                    if (wdx < warp) pre += x;
-                    tot += x;
-                }
+                for (int wdx = 0; wdx < NT / 32; ++wdx) pre += (wdx < warp) ? s_tot[c][wdx] : 0.0;
                 const double off = pre + (incl[c] - val[E - 1][c]);
-                carry[c] += tot;
 #pragma unroll
                 for (int e = 0; e < E; ++e) val[e][c] += off;
             }
         }
+        // the prefix inside the tile goes to the staging buffer ...
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int f = f0 + e;
-            const bool valid = (t0 + f) < Tn;
+        for (int e = 0; e < E; ++e)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) outs[c * uw_out_elems() + f + f / E] = valid ? val[e][c] : 0.0;
+            for (int c = 0; c < 3; ++c) outs[c * TF + f0 + e] = val[e][c];
+        // ... and only now the totals of the earlier tiles of this atom are collected, one thread per predecessor
+        if (FRAC && tile > 0) {
+            double pc[3] = {0.0, 0.0, 0.0};
+            for (int j = tid; j < tile; j += NT) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    unsigned long long bits;
+                    while ((bits = ld_l2_u64(tot_atom + j * 3 + c)) == kUwNotReady) __nanosleep(32);
+                    pc[c] += __longlong_as_double((long long)bits);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                pc[c] = warp_sum(pc[c]);
+                if (lane == 0) s_carry[c][warp] = pc[c];
+            }
         }
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            double* orow = out + ((size_t)atom * 3 + c) * pitch;
-            for (int f = tid; f < TF; f += 256) {
-                if (t0 + f < pitch) orow[t0 + f] = outs[c * uw_out_elems() + f + f / E];
+            double carry = 0.0;
+            if (FRAC && tile > 0) {
+#pragma unroll
+                for (int wdx = 0; wdx < NT / 32; ++wdx) carry += s_carry[c][wdx];
+            }
+            double* orow = out + ((size_t)atom * 3 + c) * pitch + t0;
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const int f = tid + i * NT;
+                const int64_t t = t0 + f;
+                if (t < pitch) orow[f] = (t < Tn) ? outs[c * TF + f] + carry : 0.0;
             }
         }
-        // the next tile overwrites s_tot / outs only after its own barriers
+        // the next item overwrites outs / s_tot / s_carry only after its own first barrier; its raw buffer is the one
+        // this item read, refilled by the issue() at the top of the NEXT iteration, after every thread passed the
+        // barrier above
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // Weighted sum over atoms of a component-major displacement array: out[c][t] += sum_a w[a] dc[a][c][t].
@@ -331,15 +436,24 @@ __global__ void __launch_bounds__(256) atom_sum_kernel(const double* __restrict_
 }
 
 template <typename T, int MODE, bool CONSTL>
-static int launch_unwrap(const void* coords, int F, const double* latt, const double* inv, int lstride,
+static int launch_unwrap(const void* coords, int n_atoms_total, int F, const double* latt, const double* inv, int lstride,
                          const int32_t* idx, int n_idx, const double* step_sums, double step_scale, double* out,
-                         int64_t pitch, int Tn, cudaStream_t st) {
+                         int64_t pitch, int Tn, void* workspace, cudaStream_t st) {
     const T* c = (const T*)coords;
     const size_t smem = uw_smem_bytes<T>();
+    const int n_tiles = ceil_div(pitch, kUwTile);
+    KB2_CHECK((int64_t)n_idx * n_tiles < (1ll << 31), "kb2_unwrap_cumsum: too many (atom, tile) pairs for one call");
     KB2_CUDA(cudaFuncSetAttribute(unwrap_cumsum_kernel<T, MODE, CONSTL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-    unwrap_cumsum_kernel<T, MODE, CONSTL><<<n_idx, 256, smem, st>>>(c, F, latt, inv, lstride, idx, n_idx, step_sums,
-                                                                    step_scale, out, pitch, Tn);
+    // ticket counter = 0; totals = the "not ready" pattern
+    KB2_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
+    KB2_CUDA(cudaMemsetAsync((unsigned char*)workspace + 256, 0xFF, uw_workspace_bytes(n_idx, n_tiles) - 256, st));
+    int sm = 148;
+    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
+    const int grid = (int)std::min<int64_t>((int64_t)n_idx * n_tiles, (int64_t)sm * 3);
+    unwrap_cumsum_kernel<T, MODE, CONSTL><<<grid, kUwThreads, smem, st>>>(
+        c, (int64_t)n_atoms_total * F * 3, F, latt, inv, lstride, idx, n_idx, step_sums, step_scale, out, pitch, Tn, n_tiles,
+        (unsigned char*)workspace);
     KB2_LAUNCH_CHECK();
     return 0;
 }
@@ -416,18 +530,23 @@ extern "C" int kb2_scan_frames(double* buf, int n_frames, int64_t pitch, int cum
     return 0;
 }
 
+extern "C" size_t kb2_unwrap_cumsum_workspace_bytes(int n_idx, int64_t pitch) {
+    if (n_idx < 1 || pitch < 1) return 256;
+    return uw_workspace_bytes(n_idx, ceil_div(pitch, kUwTile));
+}
+
 extern "C" int kb2_unwrap_cumsum(const void* coords, int dtype, int mode, int n_atoms_total, int n_frames_in,
                                  const double* latt, const double* latt_inv, int latt_stride, const int32_t* idx,
                                  int n_idx, const double* step_sums, double step_scale, double* dc_out, int64_t pitch,
-                                 void* stream) {
+                                 void* workspace, void* stream) {
     int Tn = 0;
     if (int rc = check_stage1("kb2_unwrap_cumsum", coords, dtype, mode, n_atoms_total, n_frames_in, latt, latt_inv,
                               latt_stride, idx, n_idx, pitch, &Tn))
         return rc;
-    KB2_CHECK(dc_out, "kb2_unwrap_cumsum: null output");
+    KB2_CHECK(dc_out && workspace, "kb2_unwrap_cumsum: null output or workspace");
     cudaStream_t st = (cudaStream_t)stream;
 #define KB2_UC(T, M, C) \
-    return launch_unwrap<T, M, C>(coords, n_frames_in, latt, latt_inv, latt_stride, idx, n_idx, step_sums, step_scale, dc_out, pitch, Tn, st)
+    return launch_unwrap<T, M, C>(coords, n_atoms_total, n_frames_in, latt, latt_inv, latt_stride, idx, n_idx, step_sums, step_scale, dc_out, pitch, Tn, workspace, st)
     const bool constl = (mode == KB2_MODE_FRACTIONAL && latt_stride == 0);
     if (dtype == KB2_F32 && mode == KB2_MODE_FRACTIONAL) { if (constl) KB2_UC(float, KB2_MODE_FRACTIONAL, true); KB2_UC(float, KB2_MODE_FRACTIONAL, false); }
     if (dtype == KB2_F32) KB2_UC(float, KB2_MODE_DISPLACEMENT, false);

@@ -93,10 +93,11 @@ def unwrap_cumsum(coords, mode, latt, latt_inv, latt_stride, idx, step_sums, ste
     see kb2_unwrap_cumsum."""
     lib = require_cuda()
     out = torch.empty((idx.numel(), 3, pitch), dtype=torch.float64, device=coords.device)
+    ws = torch.empty(lib.kb2_unwrap_cumsum_workspace_bytes(idx.numel(), pitch), dtype=torch.uint8, device=coords.device)
     check(
         lib.kb2_unwrap_cumsum(coords.data_ptr(), coords_dtype_code(coords), mode, coords.shape[0], coords.shape[1],
                               _ptr(latt), _ptr(latt_inv), latt_stride, idx.data_ptr(), idx.numel(), _ptr(step_sums),
-                              float(step_scale), out.data_ptr(), pitch, _stream()), 'kb2_unwrap_cumsum')
+                              float(step_scale), out.data_ptr(), pitch, ws.data_ptr(), _stream()), 'kb2_unwrap_cumsum')
     _count()
     return out
 
