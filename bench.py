@@ -156,48 +156,84 @@ def run_reference(args):
 # own arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-              'clocks_event_reasons.sw_power_cap')
+    """SM clock and throttle reasons sampled DURING the timed region.  In-process NVML on a background thread (a query
+    costs tens of microseconds); the nvidia-smi subprocess it replaces takes driver-wide locks for milliseconds per
+    query, which stalled kernel launches inside a timed region that is only tens of milliseconds long."""
+    BAD = {'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40, 'sw_power_cap': 0x4}
 
-    def __init__(self, index):
-        self.proc, self.path = None, None
+    def __init__(self, index, period_s=0.004):
+        import threading
+        self.samples, self.max_clock, self.reasons = [], [], set()
+        self._stop = threading.Event()
+        self._thread = None
+        self._smi = None
         try:
-            fd, self.path = tempfile.mkstemp(suffix='.csv')
-            os.close(fd)
-            self.proc = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={self.FIELDS}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._thread = threading.Thread(target=self._run, args=(period_s, ), daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._nv = None
+            self._start_smi(index)
+
+    def _run(self, period_s):
+        nv, h = self._nv, self._h
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.max_clock.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for name, bit in self.BAD.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(period_s)
+
+    def _start_smi(self, index):
+        fields = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+                  'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+                  'clocks_event_reasons.sw_power_cap')
+        try:
+            fd, self._path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self._smi = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={fields}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=open(self._path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self._smi = None
 
     def stop(self):
-        if self.proc is None:
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        elif self._smi is not None:
+            self._smi.terminate()
+            try:
+                self._smi.wait(timeout=5)
+            except Exception:
+                self._smi.kill()
+            names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+            try:
+                for line in open(self._path):
+                    f = [x.strip() for x in line.split(',')]
+                    if len(f) < 7:
+                        continue
+                    self.samples.append(float(f[0]))
+                    self.max_clock.append(float(f[1]))
+                    for name, val in zip(names, f[3:7]):
+                        if val.lower().startswith('active'):
+                            self.reasons.add(name)
+                os.unlink(self._path)
+            except Exception:
+                pass
+        if not self.samples:
             return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        try:
-            for line in open(self.path):
-                f = [x.strip() for x in line.split(',')]
-                if len(f) < 7:
-                    continue
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-                for name, val in zip(names, f[3:7]):
-                    if val.lower().startswith('active'):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if not sm:
-            return None
-        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
-                'samples': len(sm)}
+        return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': float(max(self.max_clock)),
+                'reasons': sorted(self.reasons), 'samples': len(self.samples),
+                'source': 'nvml' if self._thread is not None else 'nvidia-smi'}
 
 
 def run_own(args):
@@ -301,7 +337,7 @@ def run_own(args):
     launches0 = engine.LAUNCHES['n']
     k2_events.clear()
     stage_events.clear()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if rank == 0 and not os.environ.get('KB2_BENCH_NO_CLOCKS') else None
     ms_total, wall_total, b = timed(resident, args.steps)
     launches = engine.LAUNCHES['n'] - launches0
     k2_ms = [a.elapsed_time(z) for a, z, n in k2_events if n == n_mob]

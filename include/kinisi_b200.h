@@ -128,6 +128,17 @@ int kb2_self_moments(const double* dc, int n_atoms, int n_frames, int64_t pitch,
 size_t kb2_self_moments_runs_workspace_bytes(int n_lags, int n_frames);
 int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames, int64_t pitch, const int32_t* lags_host,
                           int n_lags, int dim_mask, void* workspace, double* sums, void* stream);
+/* The same in two steps, for callers that keep the plan: it depends on (lags, n_frames) only.
+ *   kb2_self_moments_runs_plan_pack   plans on the host into plan_host (kb2_self_moments_runs_workspace_bytes bytes of
+ *                                     HOST memory, pinned if its upload is to be asynchronous); no device work.
+ *   kb2_self_moments_runs_planned     launches the kernels of a packed plan: plan_host = the host copy (its headers are
+ *                                     read by the call), plan_dev = the same bytes in device memory (uploaded by the caller
+ *                                     earlier in stream order; never written), counters = one 256-byte device slot per
+ *                                     block of 192 lags (zeroed by the call; not shared between concurrent calls).
+ * The convenience form above re-plans and uploads from pageable memory on every call, which synchronises the stream. */
+int kb2_self_moments_runs_plan_pack(const int32_t* lags_host, int n_lags, int n_frames, void* plan_host);
+int kb2_self_moments_runs_planned(const double* dc, int n_atoms, int n_frames, int64_t pitch, int n_lags, int dim_mask,
+                                  const void* plan_host, const void* plan_dev, void* counters, double* sums, void* stream);
 /* The plan kb2_self_moments_runs makes for (the first 192 lags of -- one launch) a grid, for tests and diagnostics: returns the
  * number of runs of >= 3 lags, fills up to max_runs entries of run_k0 / run_delta / run_len / run_n_chg (host arrays,
  * may be NULL; run_n_chg = signed number of one-sample drift changes inside the run, lags k0 + i*delta + e_i) and

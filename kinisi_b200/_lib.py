@@ -27,6 +27,9 @@ SIGNATURES = {
     'kb2_self_moments_workspace_bytes': (c_size_t, [c_int]),
     'kb2_self_moments': (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p,
                                  c_void_p]),
+    'kb2_self_moments_runs_plan_pack': (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    'kb2_self_moments_runs_planned': (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p]),
     'kb2_self_moments_runs_workspace_bytes': (c_size_t, [c_int, c_int]),
     'kb2_self_moments_runs': (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p]),

@@ -617,10 +617,27 @@ static int runs_warps() {
     return w;
 }
 
-// workspace layout: the plan: 64 ints (work counter) | runs | pairs | slots | drift change indices
+// Packed plan of one launch (<= kRunMaxLags lags): header (256 B) | runs | pairs | slots | drift change indices.
+// A grid longer than kRunMaxLags is a sequence of such blocks at a fixed stride.
+struct PlanHeader {
+    int K, n_runs, n_pairs, drift;
+    int off_runs, off_pairs, off_slot, off_chg;
+    int l0, pad[7];
+};
+static_assert(sizeof(PlanHeader) <= 256, "the header has 256 bytes");
+
 static size_t runs_plan_bytes(int k, int t) {
     return 256 + align256((size_t)k * sizeof(RunDesc)) + align256(runs_pair_capacity(k, t) * sizeof(int2)) +
            2 * align256((size_t)k * sizeof(int32_t));
+}
+
+static int check_lags(const char* fn, const int32_t* lags_host, int n_lags, int n_frames) {
+    KB2_CHECK(lags_host && n_lags > 0 && n_frames > 0, "%s: empty problem", fn);
+    for (int i = 0; i < n_lags; ++i) {
+        KB2_CHECK(lags_host[i] >= 1 && lags_host[i] <= n_frames, "%s: lag %d out of range", fn, i);
+        KB2_CHECK(i == 0 || lags_host[i] >= lags_host[i - 1], "%s: lags must ascend", fn);
+    }
+    return 0;
 }
 
 }  // namespace kb2
@@ -628,74 +645,134 @@ static size_t runs_plan_bytes(int k, int t) {
 using namespace kb2;
 
 extern "C" size_t kb2_self_moments_runs_workspace_bytes(int n_lags, int n_frames) {
-    const int k = n_lags < 1 ? 1 : (n_lags > kRunMaxLags ? kRunMaxLags : n_lags);
     const int t = n_frames < 1 ? 1 : n_frames;
-    return runs_plan_bytes(k, t);
+    const int n = n_lags < 1 ? 1 : n_lags;
+    const int blocks = (n + kRunMaxLags - 1) / kRunMaxLags;
+    return (size_t)blocks * runs_plan_bytes(n > kRunMaxLags ? kRunMaxLags : n, t);
 }
 
-extern "C" int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames, int64_t pitch,
-                                     const int32_t* lags_host, int n_lags, int dim_mask, void* workspace, double* sums,
-                                     void* stream) {
-    KB2_CHECK(dc && lags_host && workspace && sums, "kb2_self_moments_runs: null pointer");
-    KB2_CHECK(n_atoms > 0 && n_frames > 0 && n_lags > 0, "kb2_self_moments_runs: empty problem");
-    KB2_CHECK(pitch >= n_frames && pitch % 2 == 0, "kb2_self_moments_runs: pitch must be even and >= n_frames");
-    KB2_CHECK(dim_mask >= 1 && dim_mask <= 7, "kb2_self_moments_runs: dim_mask must be in 1..7");
-    for (int i = 0; i < n_lags; ++i) {
-        KB2_CHECK(lags_host[i] >= 1 && lags_host[i] <= n_frames, "kb2_self_moments_runs: lag %d out of range", i);
-        KB2_CHECK(i == 0 || lags_host[i] >= lags_host[i - 1], "kb2_self_moments_runs: lags must ascend");
+// Plans the lag grid on the host into `plan_host` (kb2_self_moments_runs_workspace_bytes bytes of HOST memory; pinned
+// if the caller wants its upload to be asynchronous).  The plan depends on (lags, n_frames) only: callers cache it.
+extern "C" int kb2_self_moments_runs_plan_pack(const int32_t* lags_host, int n_lags, int n_frames, void* plan_host) {
+    if (int rc = check_lags("kb2_self_moments_runs_plan_pack", lags_host, n_lags, n_frames)) return rc;
+    KB2_CHECK(plan_host, "kb2_self_moments_runs_plan_pack: null pointer");
+    const int kcap = n_lags > kRunMaxLags ? kRunMaxLags : n_lags;
+    const size_t stride = runs_plan_bytes(kcap, n_frames);
+    const size_t pair_cap = runs_pair_capacity(kcap, n_frames);
+    unsigned char* base = (unsigned char*)plan_host;
+    int b = 0;
+    for (int l0 = 0; l0 < n_lags; l0 += kRunMaxLags, ++b) {
+        const int K = std::min(kRunMaxLags, n_lags - l0);
+        RunPlan plan;
+        plan_runs(lags_host + l0, K, n_frames, plan);
+        KB2_CHECK(plan.pairs.size() <= pair_cap && (int)plan.slot.size() == K,
+                  "kb2_self_moments_runs_plan_pack: internal planning error");
+        PlanHeader h{};
+        h.K = K;
+        h.n_runs = (int)plan.runs.size();
+        h.n_pairs = (int)plan.pairs.size();
+        h.drift = plan.chg.empty() ? 0 : 1;
+        h.off_runs = 256;
+        h.off_pairs = h.off_runs + (int)align256(plan.runs.size() * sizeof(RunDesc));
+        h.off_slot = h.off_pairs + (int)align256(plan.pairs.size() * sizeof(int2));
+        h.off_chg = h.off_slot + (int)align256((size_t)K * sizeof(int32_t));
+        h.l0 = l0;
+        const size_t total = h.off_chg + align256((size_t)K * sizeof(int32_t));
+        KB2_CHECK(total <= stride, "kb2_self_moments_runs_plan_pack: plan exceeds the workspace");
+        unsigned char* p = base + (size_t)b * stride;
+        memset(p, 0, stride);
+        memcpy(p, &h, sizeof(h));
+        memcpy(p + h.off_runs, plan.runs.data(), plan.runs.size() * sizeof(RunDesc));
+        memcpy(p + h.off_pairs, plan.pairs.data(), plan.pairs.size() * sizeof(int2));
+        memcpy(p + h.off_slot, plan.slot.data(), (size_t)K * sizeof(int32_t));
+        if (!plan.chg.empty()) memcpy(p + h.off_chg, plan.chg.data(), plan.chg.size() * sizeof(int32_t));
     }
+    return 0;
+}
+
+// Launches the run kernels of a packed plan: `plan_host` is the host copy (its headers are read here), `plan_dev` the
+// same bytes in device memory (uploaded by the caller, before this call in stream order), `counters` one zero-initialised
+// 256-byte slot of device memory per block of kRunMaxLags lags (zeroed by this call).  sums[n_lags][2] is zeroed first.
+extern "C" int kb2_self_moments_runs_planned(const double* dc, int n_atoms, int n_frames, int64_t pitch, int n_lags,
+                                             int dim_mask, const void* plan_host, const void* plan_dev, void* counters,
+                                             double* sums, void* stream) {
+    KB2_CHECK(dc && plan_host && plan_dev && counters && sums, "kb2_self_moments_runs_planned: null pointer");
+    KB2_CHECK(n_atoms > 0 && n_frames > 0 && n_lags > 0, "kb2_self_moments_runs_planned: empty problem");
+    KB2_CHECK(pitch >= n_frames && pitch % 2 == 0, "kb2_self_moments_runs_planned: pitch must be even and >= n_frames");
+    KB2_CHECK(dim_mask >= 1 && dim_mask <= 7, "kb2_self_moments_runs_planned: dim_mask must be in 1..7");
     cudaStream_t st = (cudaStream_t)stream;
     int comp[3] = {0, 0, 0}, ndim = 0;
     for (int c = 0; c < 3; ++c)
         if (dim_mask & (1 << c)) comp[ndim++] = c;
     int sm_count = 148;
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, 0);
-
     const int kcap = n_lags > kRunMaxLags ? kRunMaxLags : n_lags;
-    char* d_plan = (char*)workspace;
+    const size_t stride = runs_plan_bytes(kcap, n_frames);
+    const int blocks = (n_lags + kRunMaxLags - 1) / kRunMaxLags;
     KB2_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_lags * 2 * sizeof(double), st));
-    const size_t pair_cap = runs_pair_capacity(kcap, n_frames);
-
-    std::vector<unsigned char> packed;
-    for (int l0 = 0; l0 < n_lags; l0 += kRunMaxLags) {
-        const int K = min(kRunMaxLags, n_lags - l0);
-        RunPlan plan;
-        plan_runs(lags_host + l0, K, n_frames, plan);
-        KB2_CHECK(plan.pairs.size() <= pair_cap && (int)plan.slot.size() == K,
-                  "kb2_self_moments_runs: internal planning error");
-        // one packed upload: zeroed work counter, runs, pairs, slots
-        const size_t off_runs = 256;
-        const size_t off_pairs = off_runs + align256(plan.runs.size() * sizeof(RunDesc));
-        const size_t off_slot = off_pairs + align256(plan.pairs.size() * sizeof(int2));
-        const size_t off_chg = off_slot + align256((size_t)K * sizeof(int32_t));
-        const size_t total = off_chg + align256((size_t)K * sizeof(int32_t));
-        KB2_CHECK(total <= runs_plan_bytes(kcap, n_frames), "kb2_self_moments_runs: plan exceeds the workspace");
-        packed.assign(total, 0);
-        memcpy(packed.data() + off_runs, plan.runs.data(), plan.runs.size() * sizeof(RunDesc));
-        memcpy(packed.data() + off_pairs, plan.pairs.data(), plan.pairs.size() * sizeof(int2));
-        memcpy(packed.data() + off_slot, plan.slot.data(), (size_t)K * sizeof(int32_t));
-        if (!plan.chg.empty()) memcpy(packed.data() + off_chg, plan.chg.data(), plan.chg.size() * sizeof(int32_t));
-        KB2_CUDA(cudaMemcpyAsync(d_plan, packed.data(), total, cudaMemcpyHostToDevice, st));
-
-        const long long n_work = (long long)plan.pairs.size() * n_atoms;
-        KB2_CHECK(n_work < (1ll << 31) - (1 << 20), "kb2_self_moments_runs: too many work items");
+    KB2_CUDA(cudaMemsetAsync(counters, 0, (size_t)blocks * 256, st));
+    for (int b = 0; b < blocks; ++b) {
+        const unsigned char* ph = (const unsigned char*)plan_host + (size_t)b * stride;
+        const char* pd = (const char*)plan_dev + (size_t)b * stride;
+        PlanHeader h;
+        memcpy(&h, ph, sizeof(h));
+        KB2_CHECK(h.K > 0 && h.K <= kRunMaxLags && h.l0 == b * kRunMaxLags && h.l0 + h.K <= n_lags,
+                  "kb2_self_moments_runs_planned: the plan does not match the lag count");
+        const long long n_work = (long long)h.n_pairs * n_atoms;
+        KB2_CHECK(n_work < (1ll << 31) - (1 << 20), "kb2_self_moments_runs_planned: too many work items");
         // atoms per batch: their trajectories (3 * pitch * 8 B each) fit in a fraction of the L2 together
         const int batch = (int)std::max<long long>(1, std::min<long long>(n_atoms, kRunBatchBytes / (3 * pitch * 8)));
-        const RunDesc* d_runs = (const RunDesc*)(d_plan + off_runs);
-        const int2* d_pairs = (const int2*)(d_plan + off_pairs);
-        const int32_t* d_slot = (const int32_t*)(d_plan + off_slot);
-        const int32_t* d_chg = (const int32_t*)(d_plan + off_chg);
+        const RunDesc* d_runs = (const RunDesc*)(pd + h.off_runs);
+        const int2* d_pairs = (const int2*)(pd + h.off_pairs);
+        const int32_t* d_slot = (const int32_t*)(pd + h.off_slot);
+        const int32_t* d_chg = (const int32_t*)(pd + h.off_chg);
+        unsigned int* counter = (unsigned int*)((char*)counters + (size_t)b * 256);
         int rc;
         if (ndim == 1)
-            rc = launch_runs<1>(runs_warps(), !plan.chg.empty(), sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
-                                (int)plan.pairs.size(), batch, d_chg, K, (unsigned int*)d_plan, d_slot, sums + 2 * l0);
+            rc = launch_runs<1>(runs_warps(), h.drift != 0, sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
+                                h.n_pairs, batch, d_chg, h.K, counter, d_slot, sums + 2 * h.l0);
         else if (ndim == 2)
-            rc = launch_runs<2>(runs_warps(), !plan.chg.empty(), sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
-                                (int)plan.pairs.size(), batch, d_chg, K, (unsigned int*)d_plan, d_slot, sums + 2 * l0);
+            rc = launch_runs<2>(runs_warps(), h.drift != 0, sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
+                                h.n_pairs, batch, d_chg, h.K, counter, d_slot, sums + 2 * h.l0);
         else
-            rc = launch_runs<3>(runs_warps(), !plan.chg.empty(), sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
-                                (int)plan.pairs.size(), batch, d_chg, K, (unsigned int*)d_plan, d_slot, sums + 2 * l0);
+            rc = launch_runs<3>(runs_warps(), h.drift != 0, sm_count, n_work, st, dc, n_atoms, n_frames, pitch, comp, d_runs, d_pairs,
+                                h.n_pairs, batch, d_chg, h.K, counter, d_slot, sums + 2 * h.l0);
         if (rc) return rc;
+    }
+    return 0;
+}
+
+// Convenience form: plan, upload (a pageable copy: it synchronises the stream) and launch.  `workspace` holds the
+// device copy of the plan; its first 256 bytes per block double as the work counters.
+extern "C" int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames, int64_t pitch,
+                                     const int32_t* lags_host, int n_lags, int dim_mask, void* workspace, double* sums,
+                                     void* stream) {
+    KB2_CHECK(dc && lags_host && workspace && sums, "kb2_self_moments_runs: null pointer");
+    const size_t bytes = kb2_self_moments_runs_workspace_bytes(n_lags, n_frames);
+    std::vector<unsigned char> packed(bytes);
+    if (int rc = kb2_self_moments_runs_plan_pack(lags_host, n_lags, n_frames, packed.data())) return rc;
+    KB2_CUDA(cudaMemcpyAsync(workspace, packed.data(), bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    // the header of each block is host-only information: its 256 bytes serve as the block's work counter slot
+    const int kcap = n_lags > kRunMaxLags ? kRunMaxLags : n_lags;
+    const size_t stride = runs_plan_bytes(kcap, n_frames);
+    const int blocks = (n_lags + kRunMaxLags - 1) / kRunMaxLags;
+    KB2_CHECK(stride % 256 == 0, "kb2_self_moments_runs: internal layout error");
+    // counters must be contiguous 256-byte slots: use a small array behind the packed plan when there are several blocks
+    if (blocks == 1)
+        return kb2_self_moments_runs_planned(dc, n_atoms, n_frames, pitch, n_lags, dim_mask, packed.data(), workspace, workspace,
+                                             sums, stream);
+    for (int b = 0; b < blocks; ++b) {
+        const int l0 = b * kRunMaxLags, K = std::min(kRunMaxLags, n_lags - l0);
+        // one block at a time: shift the views so that the block looks like a single-block plan starting at lag 0
+        std::vector<unsigned char> one(packed.begin() + (size_t)b * stride, packed.begin() + (size_t)(b + 1) * stride);
+        PlanHeader h;
+        memcpy(&h, one.data(), sizeof(h));
+        h.l0 = 0;
+        memcpy(one.data(), &h, sizeof(h));
+        char* wd = (char*)workspace + (size_t)b * stride;
+        if (int rc = kb2_self_moments_runs_planned(dc, n_atoms, n_frames, pitch, K, dim_mask, one.data(), wd, wd, sums + 2 * l0,
+                                                   stream))
+            return rc;
     }
     return 0;
 }

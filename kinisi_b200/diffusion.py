@@ -90,9 +90,11 @@ class Bootstrap:
         self._diffusion_coefficient = None
         self._jump_diffusion_coefficient = None
         self._sigma = None
-        self._intercept = None
-        self.gradient = None
-        self.flatchain = None
+        self._intercept_dist = None
+        self._gradient = None
+        self._flatchain = None
+        self._flat_pending = None  # (pinned buffer, event, shape, fit_intercept): the flat chain on its way to the host
+        self._coefficient = None   # (attribute, factor): unit conversion applied to the gradient on first access
         self._covariance_matrix_dev = None
         self._npd_covariance_matrix_dev = None
         self._eig = None
@@ -109,7 +111,7 @@ class Bootstrap:
         self._stats_dev = None  # [4, n] = n, v, s, ngp on the device
         self._stats_host = None
         self._dt = np.array([])
-        self._device = self._displacements.dc.device if self._lazy else torch.device('cuda',
+        self._device = self._displacements.dc_unsynchronised.device if self._lazy else torch.device('cuda',
                                                                                      torch.cuda.current_device())
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -138,8 +140,14 @@ class Bootstrap:
         if self._lazy and not isinstance(d, SingleOriginDisplacements):
             lags = d.lags[used]
             order = np.argsort(lags, kind='stable')
-            if d.dc.shape[0] > 0:
-                sums = engine.self_moments(d.dc, d.n_frames, lags[order], mask)
+            if d.n_atoms > 0:
+                # atoms are additive: with a staged ingest the kernel follows the transfer block by block
+                sums = None
+                for r0, r1, ev in d.row_blocks():
+                    if ev is not None:
+                        torch.cuda.current_stream(self._device).wait_event(ev)
+                    part = engine.self_moments(d.dc_unsynchronised[r0:r1], d.n_frames, lags[order], mask)
+                    sums = part if sums is None else sums.add_(part)
             else:
                 sums = torch.zeros((len(used), 2), dtype=torch.float64, device=self._device)
             if dist.active():
@@ -242,10 +250,72 @@ class Bootstrap:
         """:return: Non-Gaussian parameter as a function of dt."""
         return self._ngp
 
+    # ---- results of the regression: copied to the host asynchronously, materialised on first access -----------
+    def _materialise(self):
+        if self._flat_pending is not None:
+            pinned, event, shape, fit_intercept = self._flat_pending
+            self._flat_pending = None
+            event.synchronize()
+            n = int(np.prod(shape))
+            self._flatchain = pinned[:n * 8].view(torch.float64).reshape(shape).numpy().copy()
+            engine.pinned_give(pinned)
+            self._gradient = Distribution(self._flatchain[:, 0])
+            self._intercept_dist = Distribution(self._flatchain[:, 1]) if fit_intercept else None
+
+    def __del__(self):
+        # results that were never read: the buffer goes back to the pool once its copy has landed (waiting here also
+        # keeps a caller that drops its results from queueing more than one analysis ahead of the device)
+        pending = getattr(self, '_flat_pending', None)
+        if pending is not None:
+            try:
+                pending[1].synchronize()
+                engine.pinned_give(pending[0])
+            except Exception:
+                pass
+
+    @property
+    def flatchain(self):
+        """:return: The flat MCMC chain `[(n_samples / thin) * n_walkers, ndim]` (None before the regression)."""
+        self._materialise()
+        return self._flatchain
+
+    @flatchain.setter
+    def flatchain(self, value):
+        self._flat_pending = None
+        self._flatchain = value
+
+    @property
+    def gradient(self) -> Union[Distribution, None]:
+        """:return: The samples of the gradient of the straight line."""
+        self._materialise()
+        return self._gradient
+
+    @gradient.setter
+    def gradient(self, value):
+        self._gradient = value
+
+    @property
+    def _intercept(self):
+        self._materialise()
+        return self._intercept_dist
+
+    @_intercept.setter
+    def _intercept(self, value):
+        self._intercept_dist = value
+
     @property
     def intercept(self) -> Union[Distribution, None]:
         """:return: The estimated intercept (None if fit_intercept was False)."""
         return self._intercept
+
+    def _converted(self, attribute):
+        """D / D_J / sigma: the gradient samples times the unit conversion of the last regression call."""
+        if self._coefficient is not None and self._coefficient[0] == attribute:
+            g = self.gradient
+            self._coefficient_cache = Distribution(g.samples * self._coefficient[1])
+            setattr(self, attribute, self._coefficient_cache)
+            self._coefficient = None
+        return getattr(self, attribute)
 
     def _covariance_device(self):
         """The reconditioned covariance on the device; on the default path the sampler does not need the
@@ -379,11 +449,16 @@ class Bootstrap:
         chain, logp = engine.ensemble_sample(theta_ml, ndim, n_walkers, n_samples + n_burn, logdet_term, seed)
         self._chain_dev, self._logp_dev = chain, logp
         # emcee get_chain(flat=True, thin=thin, discard=n_burn)
-        self.flatchain = chain[n_burn + thin - 1::thin].reshape(-1, ndim).cpu().numpy()
-        self.gradient = Distribution(self.flatchain[:, 0])
-        self._intercept = None
-        if fit_intercept:
-            self._intercept = Distribution(self.flatchain[:, 1])
+        # The device->host copy of the flat chain goes to pinned memory without waiting for it: the host is free to
+        # queue the next analysis (its transfer overlaps this regression); `flatchain`, `gradient`, `intercept`, `D`,
+        # `D_J`, `sigma` wait for the copy when they are first read.
+        flat = chain[n_burn + thin - 1::thin].reshape(-1, ndim)
+        pinned = engine.pinned_take(flat.numel() * 8)
+        pinned[:flat.numel() * 8].view(torch.float64).reshape(flat.shape).copy_(flat, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(torch.cuda.current_stream(self._device))
+        self._flatchain = self._gradient = self._intercept_dist = None
+        self._flat_pending = (pinned, event, tuple(flat.shape), bool(fit_intercept))
 
     def log_likelihood(self, theta) -> np.ndarray:
         """Batched log-likelihood (kinisi/diffusion.py:354-365) of parameter vectors `[n, ndim]`."""
@@ -393,35 +468,37 @@ class Bootstrap:
     def diffusion(self, start_dt: float, **kwargs):
         """Diffusion coefficient in cm^2/s (kinisi/diffusion.py:427-436)."""
         self.bootstrap_GLS(start_dt, **kwargs)
-        self._diffusion_coefficient = Distribution(self.gradient.samples / (2e4 * self.dims))
+        self._diffusion_coefficient = None
+        self._coefficient = ('_diffusion_coefficient', 1.0 / (2e4 * self.dims))
 
     @property
     def D(self) -> Union[Distribution, None]:
         """:return: Diffusion coefficient, with units of cm^2 s^-1."""
-        return self._diffusion_coefficient
+        return self._converted('_diffusion_coefficient')
 
     def jump_diffusion(self, start_dt: float, **kwargs):
         """Jump diffusion coefficient in cm^2/s (kinisi/diffusion.py:447-457)."""
         self.bootstrap_GLS(start_dt, **kwargs)
-        self._jump_diffusion_coefficient = Distribution(self.gradient.samples / (2e4 * self.dims * self._n_atoms()))
+        self._jump_diffusion_coefficient = None
+        self._coefficient = ('_jump_diffusion_coefficient', 1.0 / (2e4 * self.dims * self._n_atoms()))
 
     @property
     def D_J(self) -> Union[Distribution, None]:
         """:return: Jump diffusion coefficient, with units of cm^2 s^-1."""
-        return self._jump_diffusion_coefficient
+        return self._converted('_jump_diffusion_coefficient')
 
     def conductivity(self, start_dt: float, temperature: float, volume: float, **kwargs):
         """Ionic conductivity in mS/cm (kinisi/diffusion.py:468-482)."""
         self.bootstrap_GLS(start_dt, **kwargs)
         volume = volume * 1e-24  # cm^3
-        D = self.gradient.samples / (2e4 * self.dims)  # cm^2s^-1
         conversion = 1000 / (volume * const.N_A) * (const.N_A * const.e)**2 / (const.R * temperature)
-        self._sigma = Distribution(D * conversion)
+        self._sigma = None
+        self._coefficient = ('_sigma', conversion / (2e4 * self.dims))  # D [cm^2 s^-1] = gradient / (2e4 dims)
 
     @property
     def sigma(self) -> Union[Distribution, None]:
         """:return: The estimated conductivity, with units mS cm^-1."""
-        return self._sigma
+        return self._converted('_sigma')
 
     def posterior_predictive(self, n_posterior_samples: int = None, n_predictive_samples: int = 256,
                              progress: bool = True) -> np.ndarray:
@@ -496,16 +573,14 @@ class MSDBootstrap(Bootstrap):
         super().__init__(delta_t, disp_3d, n_o, sub_sample_dt, dimension)
         self._reject_unsupported(bootstrap, block)
         n_atoms = self._n_atoms()
-        used, cnt, div = [], [], []
-        for i in range(len(self._displacements)):
-            shp = self._shape_of(i)
-            n_local = shp[0] if not self._lazy else n_atoms
-            size = n_local * shp[1]
-            if size <= 1:  # diffusion.py:575
-                continue
-            used.append(i)
-            cnt.append(float(size))
-            div.append(float(n_o[i]))  # diffusion.py:598: n_o is NOT strided by sub_sample_dt
+        if self._lazy:
+            sizes = n_atoms * self._displacements.n_obs_all()
+        else:
+            sizes = np.array([self._shape_of(i)[0] * self._shape_of(i)[1] for i in range(len(self._displacements))],
+                             dtype=np.int64)
+        used = [int(i) for i in np.flatnonzero(sizes > 1)]  # diffusion.py:575
+        cnt = [float(sizes[i]) for i in used]
+        div = [float(n_o[i]) for i in used]  # diffusion.py:598: n_o is NOT strided by sub_sample_dt
         if used:
             sums = self._self_sums(np.array(used), self._mask)
             self._finish(used, sums, cnt, div, sums, cnt)
@@ -590,6 +665,6 @@ class MSCDBootstrap(_CollectiveBootstrap):
             _ = len(ionic_charge)
             ionic_charge = np.asarray(ionic_charge, dtype=np.float64)
         except TypeError:
-            n_local = self._displacements.dc.shape[0] if self._lazy else self._shape_of(0)[0]
+            n_local = self._displacements.n_atoms if self._lazy else self._shape_of(0)[0]
             ionic_charge = np.ones(n_local) * ionic_charge
         self._run(n_o, ionic_charge, 7)

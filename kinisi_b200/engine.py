@@ -25,14 +25,21 @@ def _count(n=1):
     LAUNCHES['n'] += n
 
 
+_LIB = None
+
+
 def require_cuda():
-    if not torch.cuda.is_available():
-        raise RuntimeError('kinisi_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.')
-    return _lib.load()
+    global _LIB
+    if _LIB is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError('kinisi_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.')
+        _LIB = _lib.load()
+    return _LIB
 
 
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    # the raw handle of torch's current stream (the python Stream object costs ~15 us to build, per launch)
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
 def _ptr(t):
@@ -88,11 +95,13 @@ def scan_frames(buf, n_frames, cumulative, divide, sub=None, sub_scale=0.0):
     return buf
 
 
-def unwrap_cumsum(coords, mode, latt, latt_inv, latt_stride, idx, step_sums, step_scale, pitch):
+def unwrap_cumsum(coords, mode, latt, latt_inv, latt_stride, idx, step_sums, step_scale, pitch, out=None):
     """dc [n_idx, 3, pitch] float64 component-major, drift-corrected with the per-frame framework sums;
-    see kb2_unwrap_cumsum."""
+    see kb2_unwrap_cumsum.  `out`: a contiguous [n_idx, 3, pitch] block to fill instead of a new tensor."""
     lib = require_cuda()
-    out = torch.empty((idx.numel(), 3, pitch), dtype=torch.float64, device=coords.device)
+    if out is None:
+        out = torch.empty((idx.numel(), 3, pitch), dtype=torch.float64, device=coords.device)
+    assert out.is_contiguous() and tuple(out.shape) == (idx.numel(), 3, pitch)
     ws = torch.empty(lib.kb2_unwrap_cumsum_workspace_bytes(idx.numel(), pitch), dtype=torch.uint8, device=coords.device)
     check(
         lib.kb2_unwrap_cumsum(coords.data_ptr(), coords_dtype_code(coords), mode, coords.shape[0], coords.shape[1],
@@ -125,11 +134,14 @@ def self_moments(dc, n_frames, lags, mask=7, variant=None):
     sums = torch.empty((K, 2), dtype=torch.float64, device=dc.device)
     if (variant & 0xff) == VARIANT_RUNS:
         lags_host = np.ascontiguousarray(lags.cpu().numpy() if isinstance(lags, torch.Tensor) else lags, dtype=np.int32)
-        ws = torch.empty(lib.kb2_self_moments_runs_workspace_bytes(K, n_frames), dtype=torch.uint8, device=dc.device)
+        plan_host, plan_dev = _runs_plan(lib, lags_host, n_frames, dc.device)
+        blocks = (K + 191) // 192
+        counters = torch.empty(256 * blocks, dtype=torch.uint8, device=dc.device)
         check(
-            lib.kb2_self_moments_runs(dc.data_ptr(), dc.shape[0], n_frames, dc.shape[2], lags_host.ctypes.data, K, mask,
-                                      ws.data_ptr(), sums.data_ptr(), _stream()), 'kb2_self_moments_runs')
-        _count((K + 191) // 192)
+            lib.kb2_self_moments_runs_planned(dc.data_ptr(), dc.shape[0], n_frames, dc.shape[2], K, mask,
+                                              plan_host.data_ptr(), plan_dev.data_ptr(), counters.data_ptr(),
+                                              sums.data_ptr(), _stream()), 'kb2_self_moments_runs_planned')
+        _count(blocks)
         return sums
     if not isinstance(lags, torch.Tensor):
         lags = small_to_device(lags, dc.device, np.int32)
@@ -139,6 +151,27 @@ def self_moments(dc, n_frames, lags, mask=7, variant=None):
                              ws.data_ptr(), sums.data_ptr(), _stream()), 'kb2_self_moments')
     _count(3 * ((K + 767) // 768))
     return sums
+
+
+_RUNS_PLANS = {}  # (lags, n_frames, device) -> (pinned host plan, device plan); the plan depends on nothing else
+
+
+def _runs_plan(lib, lags_host, n_frames, device):
+    """The packed plan of the arithmetic-run kernel for a lag grid, planned once and kept on the device: repeated
+    analyses of trajectories of one shape (and the blocks of a staged ingest) only launch."""
+    key = (lags_host.tobytes(), int(n_frames), device.type, device.index)
+    hit = _RUNS_PLANS.get(key)
+    if hit is not None:
+        return hit
+    nbytes = lib.kb2_self_moments_runs_workspace_bytes(len(lags_host), int(n_frames))
+    plan_host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    check(lib.kb2_self_moments_runs_plan_pack(lags_host.ctypes.data, len(lags_host), int(n_frames), plan_host.data_ptr()),
+          'kb2_self_moments_runs_plan_pack')
+    plan_dev = plan_host.to(device, non_blocking=True)
+    if len(_RUNS_PLANS) >= 32:
+        _RUNS_PLANS.pop(next(iter(_RUNS_PLANS)))
+    _RUNS_PLANS[key] = (plan_host, plan_dev)
+    return plan_host, plan_dev
 
 
 def self_moments_plan(lags, n_frames):
@@ -268,10 +301,62 @@ def device_info():
     return {'sm_count': vals[0].value, 'max_smem_optin': vals[1].value, 'cc': (vals[2].value, vals[3].value)}
 
 
+class _PinnedRing:
+    """Page-locked staging ring for small host->device copies.  cudaMemcpyAsync from PAGEABLE memory synchronises the
+    stream before it starts, which stops the host from running ahead of the device and exposes every launch latency
+    of the step; a copy from this ring is enqueued like a kernel.  A slot is reused one lap later."""
+
+    def __init__(self, nbytes=8 << 20):
+        self.buf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        self.view = self.buf.numpy()
+        self.size = nbytes
+        self.off = 0
+
+    def put(self, a, device):
+        n = a.nbytes
+        start = (self.off + 63) & ~63
+        if start + n > self.size:
+            # wrap: everything queued from this lap must have left the ring before it is overwritten
+            # (any stream may have used the ring: a device-wide wait, once per lap of 8 MB of small arrays)
+            torch.cuda.synchronize(device)
+            start = 0
+        self.view[start:start + n] = a.reshape(-1).view(np.uint8)
+        self.off = start + n
+        src = self.buf[start:start + n].view(torch.from_numpy(a).dtype).reshape(a.shape)
+        out = torch.empty(a.shape, dtype=src.dtype, device=device)
+        out.copy_(src, non_blocking=True)
+        return out
+
+
+_RINGS = {}
+_PINNED_POOL = {}  # size -> free page-locked buffers (cudaHostAlloc is slow: results buffers are recycled)
+
+
+def pinned_take(nbytes):
+    """A page-locked uint8 buffer of at least `nbytes` (rounded up to 64 KiB) from the pool."""
+    size = (int(nbytes) + 65535) & ~65535
+    free = _PINNED_POOL.setdefault(size, [])
+    return free.pop() if free else torch.empty(size, dtype=torch.uint8).pin_memory()
+
+
+def pinned_give(buf):
+    free = _PINNED_POOL.setdefault(buf.numel(), [])
+    if len(free) < 8:
+        free.append(buf)
+
+
 def small_to_device(a, device, np_dtype=np.float64):
-    """Small host array -> CUDA tensor without a stream synchronisation (the driver stages small
-    pageable copies, so the call returns as soon as the copy is enqueued)."""
-    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np_dtype))).to(device, non_blocking=True)
+    """Small host array -> CUDA tensor through a pinned staging ring: enqueued on the current stream, no stream
+    synchronisation (see _PinnedRing)."""
+    a = np.ascontiguousarray(np.asarray(a, dtype=np_dtype))
+    device = torch.device(device)
+    if a.nbytes == 0 or a.nbytes > (1 << 20):
+        return torch.from_numpy(a).to(device, non_blocking=True)
+    key = (device.type, device.index)
+    ring = _RINGS.get(key)
+    if ring is None:
+        ring = _RINGS[key] = _PinnedRing()
+    return ring.put(a, device)
 
 
 def to_device(a, device, dtype=None):
@@ -282,4 +367,6 @@ def to_device(a, device, dtype=None):
         t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None and t.dtype != dtype:
         t = t.to(dtype)
+    if t.device.type == 'cpu' and not t.is_pinned() and 0 < t.numel() * t.element_size() <= (1 << 20):
+        return small_to_device(t.contiguous().numpy(), device, t.contiguous().numpy().dtype)
     return t.to(device, non_blocking=True).contiguous()

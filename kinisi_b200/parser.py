@@ -22,6 +22,19 @@ from . import dist, engine
 from ._lib import MODE_DISPLACEMENT, MODE_FRACTIONAL
 
 
+_SIDE_STREAMS = {}
+STAGE_BYTES = 32 << 20  # host->device copy granularity of the staged ingest (about 0.6 ms of PCIe time)
+
+
+def _side_streams(device):
+    """(copy stream, ingest stream) of a device: transfers and the stage-1 kernels that consume them run beside the
+    caller's stream."""
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = (torch.cuda.Stream(device), torch.cuda.Stream(device))
+    return _SIDE_STREAMS[key]
+
+
 def _default_device(device=None):
     if device is not None:
         return torch.device(device)
@@ -39,28 +52,93 @@ class Trajectory:
     def __init__(self, coords, latt=None, mode=MODE_FRACTIONAL, device=None):
         device = _default_device(device)
         self.mode = mode
-        self.coords = engine.to_device(coords, device)
-        if self.coords.dtype not in (torch.float32, torch.float64):
-            self.coords = self.coords.to(torch.float64)
-        if self.coords.dim() != 3 or self.coords.shape[2] != 3:
+        self._host = None      # host copy still to be staged (None: the coordinates are resident)
+        self._staged = None    # per atom: its row has been queued for the device
+        if not isinstance(coords, torch.Tensor):
+            coords = torch.from_numpy(np.ascontiguousarray(coords))
+        if coords.dtype not in (torch.float32, torch.float64):
+            coords = coords.to(torch.float64)
+        if coords.dim() != 3 or coords.shape[2] != 3:
             raise ValueError('coordinates must have the shape [site, frame, 3]')
+        if coords.device.type == 'cpu':
+            # Host input: rows are copied atom block by atom block on a side stream, in the order the parser needs
+            # them, so that the stage-1 kernels overlap the transfer (see Parser._build_displacement_staged).
+            # The staged ingest lives on its own two streams and never waits for the caller's stream, so the transfer
+            # of one trajectory overlaps whatever the caller's stream is still doing (the regression of the previous one).
+            self._host = coords.contiguous()
+            self._staged = np.zeros(self._host.shape[0], dtype=bool)
+            self._side = _side_streams(device)
+            with torch.cuda.stream(self._side[0]):  # from the copy stream's pool: no cross-stream reuse hazard
+                self.coords = torch.empty(self._host.shape, dtype=self._host.dtype, device=device)
+            self.coords.record_stream(self._side[1])
+            self.coords.record_stream(torch.cuda.current_stream(device))
+        else:
+            self.coords = coords.to(device).contiguous()
         self.latt = self.latt_inv = None
         self.latt_stride = 9
+        self._latt_event = None
         if mode == MODE_FRACTIONAL:
             latt_host = latt if isinstance(latt, np.ndarray) else None
-            latt = engine.to_device(latt, device, torch.float64).reshape(-1, 3, 3)
-            if latt.shape[0] == 1:
-                self.latt_stride = 0
-            elif latt.shape[0] != self.coords.shape[1]:
-                raise ValueError('one lattice per frame is required')
-            elif latt_host is not None and np.all(latt_host == latt_host[0]):
-                self.latt_stride = 0  # constant cell: every frame reads latt[0]
-            self.latt = latt
-            self.latt_inv = engine.invert_lattice(latt)
+            # with a staged ingest the lattices are prepared on the ingest stream, like everything else of stage 1
+            work = self._side[1] if self._host is not None else torch.cuda.current_stream(device)
+            with torch.cuda.stream(work):
+                latt = engine.to_device(latt, device, torch.float64).reshape(-1, 3, 3)
+                if latt.shape[0] == 1:
+                    self.latt_stride = 0
+                elif latt.shape[0] != self.coords.shape[1]:
+                    raise ValueError('one lattice per frame is required')
+                elif latt_host is not None and np.all(latt_host == latt_host[0]):
+                    self.latt_stride = 0  # constant cell: every frame reads latt[0]
+                self.latt = latt
+                self.latt_inv = engine.invert_lattice(latt)
+                if self._host is not None:
+                    self._latt_event = torch.cuda.Event()
+                    self._latt_event.record(work)
+            if self._host is not None:
+                self.latt.record_stream(torch.cuda.current_stream(device))
+                self.latt_inv.record_stream(torch.cuda.current_stream(device))
 
     @property
     def device(self):
         return self.coords.device
+
+    @property
+    def resident(self):
+        return self._host is None
+
+    def stage(self, rows):
+        """Queue the host->device copy of the atom rows `rows` (host integers) on the copy stream, contiguous runs as
+        single copies; returns an event that fires when they have landed (None: nothing left to copy)."""
+        if self._host is None:
+            return None
+        rows = np.unique(np.asarray(rows, dtype=np.int64))
+        rows = rows[~self._staged[rows]]
+        if rows.size == 0:
+            return None
+        copy = self._side[0]
+        breaks = np.flatnonzero(np.diff(rows) != 1) + 1
+        with torch.cuda.stream(copy):
+            for run in np.split(rows, breaks):
+                a, b = int(run[0]), int(run[-1]) + 1
+                self.coords[a:b].copy_(self._host[a:b], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+        self._staged[rows] = True
+        if self._staged.all():
+            self._host_keepalive = self._host  # the copies may still be in flight
+            self._host = None
+        return ev
+
+    def make_resident(self, rows=None):
+        """Stage `rows` (default: every atom) and make the current stream wait for the copy."""
+        if self._latt_event is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._latt_event)
+            self._latt_event = None
+        if self._host is None:
+            return
+        ev = self.stage(np.arange(self.coords.shape[0]) if rows is None else rows)
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
 
     @property
     def n_atoms(self):
@@ -72,13 +150,15 @@ class Trajectory:
         return self.coords.shape[1] - (1 if self.mode == MODE_FRACTIONAL else 0)
 
     def frame_sums(self, idx, weights=None):
-        """Per-frame (weighted) displacement sums over atoms idx, all-reduced over ranks."""
+        """Per-frame (weighted) displacement sums over atoms idx (an int32 device tensor)."""
+        self.make_resident()
         pitch = engine.pitch_for(self.n_frames)
         return engine.frame_sums(self.coords, self.mode, self.latt, self.latt_inv, self.latt_stride, idx, weights, pitch)
 
     def displacement(self, idx, drift=None):
         """dc [len(idx), 3, pitch] float64, component-major.  `drift` is None or (frame_sums, n_framework): the
         per-frame sums over the framework atoms, whose mean is removed before the cumulative sum."""
+        self.make_resident()
         pitch = engine.pitch_for(self.n_frames)
         sums, scale = (None, 0.0) if drift is None else (drift[0], 1.0 / drift[1])
         return engine.unwrap_cumsum(self.coords, self.mode, self.latt, self.latt_inv, self.latt_stride, idx, sums, scale,
@@ -108,12 +188,35 @@ class LazyDisplacements:
     kernels never do that.
     """
 
-    def __init__(self, dc, n_frames, lags, n_atoms_global=None, stride=1):
-        self.dc = dc  # [n_local_atoms, 3, pitch] float64 CUDA
+    def __init__(self, dc, n_frames, lags, n_atoms_global=None, stride=1, ready=None):
+        self._dc = dc  # [n_local_atoms, 3, pitch] float64 CUDA
+        # staged ingest: [(row0, row1, event)] -- rows [row0, row1) of dc are valid once the event has fired
+        self._ready = list(ready) if ready else []
         self.n_frames = int(n_frames)
         self.lags = np.asarray(lags, dtype=np.int64)
         self.n_atoms = dc.shape[0]
         self.n_atoms_global = int(n_atoms_global if n_atoms_global is not None else dc.shape[0])
+
+    @property
+    def dc(self):
+        """The whole array, valid on the current stream (waits for a staged ingest to finish)."""
+        if self._ready:
+            stream = torch.cuda.current_stream(self._dc.device)
+            for _, _, ev in self._ready:
+                stream.wait_event(ev)
+            self._ready = []
+        return self._dc
+
+    def row_blocks(self):
+        """[(row0, row1, event or None)]: blocks of atoms in the order they become valid.  A consumer that reduces
+        over atoms (the moment kernels) can work block by block behind the transfer."""
+        if not self._ready:
+            return [(0, self.n_atoms, None)]
+        return list(self._ready)
+
+    @property
+    def dc_unsynchronised(self):
+        return self._dc
 
     def __len__(self):
         return len(self.lags)
@@ -125,9 +228,13 @@ class LazyDisplacements:
     def shapes(self):
         return [self.shape_of(i) for i in range(len(self))]
 
+    def n_obs_all(self):
+        """Number of observations of every entry (shape_of(i)[1]) as one array."""
+        return self.n_frames - self.lags + 1
+
     def __getitem__(self, i):
         if isinstance(i, slice):
-            return LazyDisplacements(self.dc, self.n_frames, self.lags[i], self.n_atoms_global)
+            return LazyDisplacements(self._dc, self.n_frames, self.lags[i], self.n_atoms_global, ready=self._ready)
         k = int(self.lags[i])
         x = self.dc[:, :, :self.n_frames]
         first = x[:, :, k - 1:k]
@@ -215,11 +322,15 @@ class Parser:
                               "https://kinisi.readthedocs.io/en/latest/memory_limit.html).")
 
         # drift correction (kinisi/parser.py:131-148) fused with the displacement construction
-        self._drift = self._framework_mean(traj, drift_indices)
-        if n_sel_local > 0:
-            self._dc_sel = traj.displacement(idx, self._drift)
+        self._dc_ready = None
+        if not traj.resident and n_sel_local > 0:
+            self._build_displacement_staged(traj, indices, drift_indices)
         else:
-            self._dc_sel = torch.zeros((0, 3, engine.pitch_for(n_frames)), dtype=torch.float64, device=dev)
+            self._drift = self._framework_mean(traj, drift_indices)
+            if n_sel_local > 0:
+                self._dc_sel = traj.displacement(idx, self._drift)
+            else:
+                self._dc_sel = torch.zeros((0, 3, engine.pitch_for(n_frames)), dtype=torch.float64, device=dev)
 
         if self.max_dt is None:
             self.max_dt = n_frames * (self.step_skip * self.time_step)
@@ -232,7 +343,76 @@ class Parser:
             n_steps = int(n_frames - min_dt_int) + 1
 
         self.time_intervals = self.get_time_intervals(n_steps, spacing)
-        self.delta_t, self.disp_3d, self._n_o = self.get_disps(self.time_intervals, self._dc_sel, progress)
+        self.delta_t, self.disp_3d, self._n_o = self.get_disps(self.time_intervals, self._dc_sel_staged, progress)
+
+    def _build_displacement_staged(self, traj, indices, drift_indices):
+        """Stage 1 behind the host->device transfer.  The rows are copied in the order they are needed -- framework
+        atoms first (their per-frame sums are the drift), then the selected atoms, block by block -- on a copy stream;
+        an ingest stream runs the frame-sum / unwrap kernels of a block as soon as it has landed and records one event
+        per block of the displacement array, so a consumer on the caller's stream (the moment kernels) can follow
+        block by block.  Atoms that are neither selected nor framework are never transferred."""
+        dev = traj.device
+        main = torch.cuda.current_stream(dev)
+        _, ingest = _side_streams(dev)
+        n_frames, pitch = traj.n_frames, engine.pitch_for(traj.n_frames)
+        row_bytes = traj.coords.shape[1] * 3 * traj.coords.element_size()
+        per_block = max(1, int(STAGE_BYTES // row_bytes))
+        sel = np.asarray(indices, dtype=np.int64)
+        fw = np.asarray(drift_indices, dtype=np.int64)
+        n_fw_local = len(fw)
+        n_fw = int(round(dist.allreduce_sum_scalar(n_fw_local, dev))) if self._distributed else n_fw_local
+        fw_sorted = np.sort(fw)
+        with torch.cuda.stream(ingest):
+            idx_dev = engine.small_to_device(np.concatenate([fw_sorted, sel]), dev, np.int32)  # one upload for every block
+            fw_dev, sel_dev = idx_dev[:n_fw_local], idx_dev[n_fw_local:]
+            sums = None
+            if n_fw > 0:
+                for b0 in range(0, n_fw_local, per_block):
+                    block = fw_sorted[b0:b0 + per_block]
+                    ev = traj.stage(block)
+                    if ev is not None:
+                        ingest.wait_event(ev)
+                    part = engine.frame_sums(traj.coords, traj.mode, traj.latt, traj.latt_inv, traj.latt_stride,
+                                             fw_dev[b0:b0 + len(block)], None, pitch)
+                    sums = part if sums is None else sums.add_(part)
+                if sums is None:
+                    sums = torch.zeros((3, pitch), dtype=torch.float64, device=dev)
+                if self._distributed:
+                    dist.allreduce_sum_(sums)
+            self._drift = None if n_fw == 0 else (sums, float(n_fw))
+            step_sums, scale = (None, 0.0) if self._drift is None else (sums, 1.0 / n_fw)
+            dc = torch.empty((len(sel), 3, pitch), dtype=torch.float64, device=dev)
+            dc.record_stream(main)  # allocated for the ingest stream, consumed on the caller's
+            if sums is not None:
+                sums.record_stream(main)
+            ready = []
+            for b0 in range(0, len(sel), per_block):
+                block = sel[b0:b0 + per_block]
+                ev = traj.stage(block)
+                if ev is not None:
+                    ingest.wait_event(ev)
+                engine.unwrap_cumsum(traj.coords, traj.mode, traj.latt, traj.latt_inv, traj.latt_stride,
+                                     sel_dev[b0:b0 + len(block)], step_sums, scale, pitch, out=dc[b0:b0 + len(block)])
+                done = torch.cuda.Event()
+                done.record(ingest)
+                ready.append((b0, b0 + len(block), done))
+        self._dc_sel_staged = dc
+        self._dc_ready = ready
+
+    @property
+    def _dc_sel(self):
+        """The drift-corrected displacement of the selected atoms, valid on the current stream."""
+        if self._dc_ready:
+            stream = torch.cuda.current_stream(self._dc_sel_staged.device)
+            for _, _, ev in self._dc_ready:
+                stream.wait_event(ev)
+            self._dc_ready = None
+        return self._dc_sel_staged
+
+    @_dc_sel.setter
+    def _dc_sel(self, value):
+        self._dc_sel_staged = value
+        self._dc_ready = None
 
     def _framework_mean(self, traj, drift_indices):
         """(per-frame sums over the framework atoms [3, pitch] on the device, number of framework atoms), or None.
@@ -323,35 +503,35 @@ class Parser:
                              "please use 'multi-origin' or 'single-origin'.")
         if np.any(time_intervals > n_frames):
             raise IndexError('a time interval exceeds the length of the trajectory')
-        kept, n_samples = [], []
-        for i, k in enumerate(time_intervals):
-            n_obs = 1 if self.sampling == 'single-origin' else n_frames - int(k) + 1
-            if n_atoms * len(range(0, n_obs, int(k))) <= 1:  # parser.py:204-205, 214-215
-                continue
-            kept.append(i)
-            n_samples.append(n_atoms * time_intervals[-1] / k)  # parser.py:221
-        kept = np.array(kept, dtype=int)
+        ks = np.asarray(time_intervals, dtype=np.int64)
+        n_obs = np.ones_like(ks) if self.sampling == 'single-origin' else n_frames - ks + 1
+        # parser.py:204-205, 214-215: an interval is kept if atoms x len(range(0, n_obs, k)) > 1
+        kept = np.flatnonzero(n_atoms * np.maximum(0, -(-n_obs // ks)) > 1)
+        n_samples = n_atoms * time_intervals[-1] / time_intervals[kept]  # parser.py:221
         if self.sampling == 'single-origin':
             # parser.py:203: entry i is the single frame dc[:, i] (indexed by grid position, not by lag)
-            disp_3d = SingleOriginDisplacements(drift_corrected, n_frames, kept, n_atoms)
+            disp_3d = SingleOriginDisplacements(drift_corrected, n_frames, kept, n_atoms, ready=getattr(self, '_dc_ready', None))
         else:
-            disp_3d = LazyDisplacements(drift_corrected, n_frames, time_intervals[kept], n_atoms)
+            disp_3d = LazyDisplacements(drift_corrected, n_frames, time_intervals[kept], n_atoms, ready=getattr(self, '_dc_ready', None))
         return delta_t, disp_3d, np.array(n_samples, dtype=float)
 
 
 class SingleOriginDisplacements(LazyDisplacements):
     """`sampling='single-origin'` (kinisi/parser.py:202-206): entry i is `dc[:, i:i+1]`."""
 
-    def __init__(self, dc, n_frames, frames, n_atoms_global=None):
-        super().__init__(dc, n_frames, np.ones(len(frames), dtype=np.int64), n_atoms_global)
+    def __init__(self, dc, n_frames, frames, n_atoms_global=None, ready=None):
+        super().__init__(dc, n_frames, np.ones(len(frames), dtype=np.int64), n_atoms_global, ready=ready)
         self.frames = np.asarray(frames, dtype=np.int64)
 
     def shape_of(self, i):
         return (self.n_atoms, 1, 3)
 
+    def n_obs_all(self):
+        return np.ones(len(self.lags), dtype=np.int64)
+
     def __getitem__(self, i):
         if isinstance(i, slice):
-            return SingleOriginDisplacements(self.dc, self.n_frames, self.frames[i], self.n_atoms_global)
+            return SingleOriginDisplacements(self._dc, self.n_frames, self.frames[i], self.n_atoms_global, ready=self._ready)
         f = int(self.frames[i])
         return self.dc[:, :, f:f + 1].permute(0, 2, 1).contiguous().cpu().numpy()
 

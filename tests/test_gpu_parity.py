@@ -285,6 +285,39 @@ def test_stage1_dtypes_and_collective(kb, dtype):
         np.testing.assert_allclose(b.ngp, ref['ngp'], rtol=1e-8, atol=1e-10)
 
 
+def test_staged_ingest_matches_resident_input(kb, monkeypatch):
+    """Host input is transferred block by block behind the stage-1 / stage-2 kernels (Parser._build_displacement_staged);
+    the result must not depend on the blocking, on the order of the indices, or on where the input lives."""
+    n_all, n_frames = 37, 2500
+    frac, latt = ko.synthetic_walk(n_all, n_frames, box=11.0, sigma=0.12, seed=5, dtype=np.float32)
+    rng = np.random.RandomState(3)
+    perm = rng.permutation(n_all)
+    idx, fw = list(perm[:17]), list(perm[17:30])  # scattered, unsorted; 7 atoms are neither (never transferred)
+    dev = torch.device('cuda')
+    ref = kb.parser.Parser(kb.parser.Parser.get_disp(torch.from_numpy(frac).to(dev), latt), idx, fw, 0.001, 1, n_steps=50,
+                           progress=False)
+    ref_b = kb.diffusion.MSDBootstrap(ref.delta_t, ref.disp_3d, ref._n_o, progress=False)
+    row_bytes = (n_frames + 1) * 3 * 4
+    for block_rows, pinned in ((1, True), (4, True), (5, False), (1000, True)):
+        monkeypatch.setattr(kb.parser, 'STAGE_BYTES', block_rows * row_bytes)
+        host = torch.from_numpy(frac.copy())
+        if pinned:
+            host = host.pin_memory()
+        traj = kb.parser.Parser.get_disp(host, latt)
+        assert not traj.resident
+        p = kb.parser.Parser(traj, idx, fw, 0.001, 1, n_steps=50, progress=False)
+        assert len(p.disp_3d.row_blocks()) == -(-17 // block_rows)
+        b = kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False)
+        np.testing.assert_allclose(b.n, ref_b.n, rtol=1e-13)
+        np.testing.assert_allclose(b.v, ref_b.v, rtol=1e-11)
+        np.testing.assert_array_equal(p.disp_3d.dc.cpu().numpy(), ref.disp_3d.dc.cpu().numpy())
+        assert traj._staged is not None and int(traj._staged.sum()) == 30
+        np.testing.assert_array_equal(p.disp_3d[3], ref.disp_3d[3])
+        # a later consumer of the whole array (here the all-atom view) stages the rest
+        np.testing.assert_allclose(p.dc, ref.dc, rtol=0, atol=0)
+        assert traj.resident
+
+
 def test_identical_trajectories_stack(kb):
     """dtype='identical' (kinisi/analyzer.py:111-116, 274-290): more atoms, n_o summed."""
     symbols = ['Li'] * 6 + ['O'] * 3
