@@ -34,6 +34,16 @@ UNIT = 'terms/s'
 WORKLOAD = 'configs[1]: LLZO-like 1536 atoms (448 Li) x 20000 steps, 100 dt, MSD+covariance+emcee D'
 
 
+def k2_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the stage-2 kernel on this workload, from the
+    ncu --set full capture summarised in profiles/ (None if the summary is missing)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'r01_k2_runs_traffic.json')))
+        return float(d['dram_bytes_read'] + d['dram_bytes_write'])
+    except Exception:
+        return None
+
+
 def lag_grid(n_frames, n_steps):
     return np.linspace(1, n_frames, n_steps, dtype=int)
 
@@ -414,7 +424,7 @@ def run_own(args):
                 'peak': fp64_peak_tflops,
                 'unit': 'TFLOP/s',
                 'frac': achieved / fp64_peak_tflops,
-                'traffic': None,
+                'traffic': k2_traffic_bytes(),
                 'note': '8 FP64 instructions per term counted as 2 flop each; peak = DFMA micro-benchmark measured '
                         'in this run (MEASURED_PEAKS.json has no FP64 figure); kernel time = CUDA events on the '
                         'launching stream, 10 back-to-back launches on the last timed step\'s data (in-step interval reported beside it)',
@@ -438,7 +448,7 @@ def run_own(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--variant', type=int, default=None, help='self-moment kernel: 0 direct, 1 TMA ring, 2 arithmetic runs (default)')

@@ -24,13 +24,32 @@ def allreduce_sum_(t):
     return t
 
 
-def allreduce_sum_scalar(x, device=None):
-    """Sum of a host scalar over ranks (atom counts, charge sums)."""
+_SCALAR_STREAMS = {}
+
+
+def allreduce_sum_scalars(values, device=None):
+    """Sums of host scalars over ranks (atom counts, charge sums), all in one collective.  On a CUDA device the
+    collective and the read-back run on a stream of their own, so the host only waits for this tiny all-reduce and
+    not for whatever is queued on the caller's stream (the previous analysis)."""
     if not active():
-        return x
-    t = torch.tensor([float(x)], dtype=torch.float64, device=device if device is not None else 'cpu')
+        return list(values)
+    if device is not None and torch.device(device).type == 'cuda':
+        device = torch.device(device)
+        key = device.index
+        if key not in _SCALAR_STREAMS:
+            _SCALAR_STREAMS[key] = torch.cuda.Stream(device)
+        with torch.cuda.stream(_SCALAR_STREAMS[key]):
+            t = torch.tensor([float(v) for v in values], dtype=torch.float64).to(device)
+            td.all_reduce(t, op=td.ReduceOp.SUM)
+            return [float(v) for v in t.cpu().tolist()]
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64)
     td.all_reduce(t, op=td.ReduceOp.SUM)
-    return float(t.item())
+    return [float(v) for v in t.tolist()]
+
+
+def allreduce_sum_scalar(x, device=None):
+    """Sum of one host scalar over ranks."""
+    return allreduce_sum_scalars([x], device)[0]
 
 
 def shard_bounds(n, r=None, w=None):

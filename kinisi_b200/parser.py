@@ -310,7 +310,12 @@ class Parser:
 
         idx = engine.small_to_device(indices, dev, np.int32)
         n_sel_local = idx.numel()
-        n_sel = int(round(dist.allreduce_sum_scalar(n_sel_local, dev))) if self._distributed else n_sel_local
+        # global atom counts (selected, framework): one small collective
+        if self._distributed:
+            n_sel, self._n_fw_global = (int(round(v)) for v in dist.allreduce_sum_scalars(
+                [n_sel_local, len(drift_indices)], dev))
+        else:
+            n_sel, self._n_fw_global = n_sel_local, len(drift_indices)
         self._n_atoms_global = n_sel
 
         # memory guard (kinisi/parser.py:190-200), applied to what this build keeps resident
@@ -360,7 +365,7 @@ class Parser:
         sel = np.asarray(indices, dtype=np.int64)
         fw = np.asarray(drift_indices, dtype=np.int64)
         n_fw_local = len(fw)
-        n_fw = int(round(dist.allreduce_sum_scalar(n_fw_local, dev))) if self._distributed else n_fw_local
+        n_fw = self._n_fw_global
         fw_sorted = np.sort(fw)
         with torch.cuda.stream(ingest):
             idx_dev = engine.small_to_device(np.concatenate([fw_sorted, sel]), dev, np.int32)  # one upload for every block
@@ -418,7 +423,7 @@ class Parser:
         """(per-frame sums over the framework atoms [3, pitch] on the device, number of framework atoms), or None.
         The displacement kernel subtracts sums / n before its cumulative sum (kinisi/parser.py:143-145)."""
         n_fw_local = len(drift_indices)
-        n_fw = int(round(dist.allreduce_sum_scalar(n_fw_local, traj.device))) if self._distributed else n_fw_local
+        n_fw = self._n_fw_global
         if n_fw == 0:
             return None
         if n_fw_local > 0:
