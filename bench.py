@@ -366,6 +366,31 @@ def run_own(args):
     i1.record()
     torch.cuda.synchronize()
     k2_isolated = i0.elapsed_time(i1) / 10
+    # the two stage-1 kernels the same way (HBM-bound: algorithmic bytes / time against the measured HBM peak)
+    from kinisi_b200._lib import MODE_FRACTIONAL
+    tr = pz._traj
+    pitch = engine.pitch_for(T)
+    idx_d = engine.small_to_device(idx, dev, np.int32)
+    fw_d = engine.small_to_device(fw, dev, np.int32)
+
+    def isolated(fn, n=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        z.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(z) / n
+
+    fs_ms = isolated(lambda: engine.frame_sums(resident, MODE_FRACTIONAL, tr.latt, tr.latt_inv, tr.latt_stride, fw_d, None, pitch))
+    fsum = engine.frame_sums(resident, MODE_FRACTIONAL, tr.latt, tr.latt_inv, tr.latt_stride, fw_d, None, pitch)
+    uw_out = torch.empty((n_mob, 3, pitch), dtype=torch.float64, device=dev)
+    uw_ms = isolated(lambda: engine.unwrap_cumsum(resident, MODE_FRACTIONAL, tr.latt, tr.latt_inv, tr.latt_stride, idx_d, fsum,
+                                                  1.0 / n_fw, pitch, out=uw_out))
+    del uw_out
     e2e_ms, _, b2 = timed(host, args.steps)
     clocks = sampler.stop() if sampler is not None else None
 
@@ -434,6 +459,17 @@ def run_own(args):
                 'hbm_peak_gbs': peaks.get('hbm_gbs', 6650.0),
                 'hbm_peak_source': 'measured' if 'hbm_gbs' in peaks else 'fallback',
             },
+            'other_kernels': [
+                {'kernel': 'frame_sums (stage 1, framework drift)', 'bound': 'hbm', 'ms': fs_ms,
+                 'achieved_gbs': n_fw * (T + 1) * 12 / (fs_ms * 1e-3) / 1e9, 'peak_gbs': peaks.get('hbm_gbs', 6650.0),
+                 'algorithmic_bytes': n_fw * (T + 1) * 12},
+                {'kernel': 'unwrap_cumsum (stage 1, displacement)', 'bound': 'hbm', 'ms': uw_ms,
+                 'achieved_gbs': (n_mob * (T + 1) * 12 + n_mob * 3 * pitch * 8) / (uw_ms * 1e-3) / 1e9,
+                 'peak_gbs': peaks.get('hbm_gbs', 6650.0),
+                 'algorithmic_bytes': n_mob * (T + 1) * 12 + n_mob * 3 * pitch * 8},
+                {'kernel': 'jacobi_project + ensemble_sample (stage 3)', 'bound': 'latency (one CTA / one warp)',
+                 'ms': float(stages[2])},
+            ],
             'stage_ms': {'stage1_parser': float(stages[0]), 'stage2_moments': float(stages[1]),
                          'stage3_cov_mcmc': float(stages[2])},
             'cpu_baseline': cpu,

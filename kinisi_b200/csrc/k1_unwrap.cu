@@ -92,23 +92,35 @@ __global__ void __launch_bounds__(256) frame_sums_kernel(const T* __restrict__ c
     const int i0 = blockIdx.y * per_chunk;
     const int i1 = min(n_idx, i0 + per_chunk);
     double acc[3] = {0.0, 0.0, 0.0};
-    if (MODE == KB2_MODE_FRACTIONAL) {
+    if (MODE == KB2_MODE_FRACTIONAL && CONSTL) {
+        // constant cell: sum_i w_i (frac diff - image) @ L = (sum_i w_i (frac diff - image)) @ L -- the lattice product
+        // leaves the atom loop (12 FP64 operations per atom and frame instead of 24)
+        double L[9];
+        load9(latt, L);
+        double aw[3] = {0.0, 0.0, 0.0};
+#pragma unroll 8
+        for (int i = i0; i < i1; ++i) {
+            const T* base = coords + ((size_t)idx[i] * F + t) * 3;
+            const double wi = w ? w[i] : 1.0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double d = (double)base[3 + k] - (double)base[k];
+                const double wk = d - floor(d + 0.5);
+                aw[k] = w ? fma(wi, wk, aw[k]) : aw[k] + wk;
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < 3; ++l) acc[l] = aw[0] * L[l] + aw[1] * L[3 + l] + aw[2] * L[6 + l];
+    } else if (MODE == KB2_MODE_FRACTIONAL) {
         double Lc[9], Lp[9], Ic[9];
         load9(latt + (size_t)(t + 1) * lstride, Lc);
-        if (!CONSTL) {
-            load9(latt + (size_t)t * lstride, Lp);
-            load9(inv + (size_t)(t + 1) * lstride, Ic);
-        }
+        load9(latt + (size_t)t * lstride, Lp);
+        load9(inv + (size_t)(t + 1) * lstride, Ic);
 #pragma unroll 4
         for (int i = i0; i < i1; ++i) {
             const T* base = coords + ((size_t)idx[i] * F + t) * 3;
             double u[3];
-            if (CONSTL) {
-                const T cur[3] = {base[3], base[4], base[5]}, prev[3] = {base[0], base[1], base[2]};
-                unwrapped_step_const<T>(cur, prev, Lc, u);
-            } else {
-                unwrapped_step<T>(base + 3, base, Lc, Lp, Ic, u);
-            }
+            unwrapped_step<T>(base + 3, base, Lc, Lp, Ic, u);
             const double wi = w ? w[i] : 1.0;
             acc[0] += wi * u[0];
             acc[1] += wi * u[1];

@@ -411,6 +411,40 @@ def test_covariance_likelihood_and_posterior(kb, golden_dir, name):
     assert ppd.shape == (128, b.dt.size - dr)
 
 
+def test_long_grid_regression_takes_the_library_eigensolver(kb):
+    """A 300-point dt grid (BASELINE configs[3] in small): the moment kernel runs in two 192-lag launches and the
+    regression has n > 128, so the spectrum comes from the library eigensolver + kb2_gls_prepare instead of the Jacobi
+    kernel.  Moments, covariance, the quadratic form and the posterior against the oracle."""
+    n_atoms, n_frames, n_steps = 20, 4000, 300
+    frac, latt = ko.synthetic_walk(n_atoms, n_frames, box=12.0, sigma=0.1, seed=21)
+    dc = ko.get_disp(frac, latt)
+    parsed = ko.parse(dc, list(range(n_atoms)), [], 0.002, 1, n_steps=n_steps)
+    ref = ko.bootstrap_streaming(parsed, 'msd')
+    p = kb.parser.Parser(kb.parser.Parser.get_disp(frac, latt), list(range(n_atoms)), [], 0.002, 1, n_steps=n_steps,
+                         progress=False)
+    b = kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False)
+    for key in ('dt', 'n', 'v'):
+        np.testing.assert_allclose(getattr(b, key), ref[key], rtol=RTOL_MOMENT, err_msg=key)
+    start = 40
+    b.diffusion(float(b.dt[start]), progress=False, random_state=np.random.RandomState(5))
+    n_dt = len(b.dt) - start
+    assert n_dt > kb.engine.spectral_prepare_max_n()
+    cov_ref = ko.generate_covariance_matrix(ref['v'], ref['n_o'], start)
+    scale = np.abs(cov_ref).max()
+    np.testing.assert_allclose(b.covariance_matrix, cov_ref, rtol=1e-6, atol=1e-9 * scale)
+    _, _, inv = ko.make_log_likelihood(ref['dt'][start:], ref['n'][start:], cov_ref)
+    thetas = np.array([[0.18, 0.0], [0.17, 0.05], [0.19, -0.04], [0.2, 0.1]])
+    x, y = ref['dt'][start:], ref['n'][start:]
+    q_ref = np.array([(t[0] * x + t[1] - y) @ inv @ (t[0] * x + t[1] - y) for t in thetas])
+    ll = b.log_likelihood(thetas)
+    np.testing.assert_allclose(-2.0 * (ll - ll[0]), q_ref - q_ref[0], rtol=1e-5, atol=1e-5 * np.abs(q_ref).max())
+    mean, cov_theta = ko.gls_posterior(x, y, inv)
+    sd = np.sqrt(np.diag(cov_theta))
+    assert b.flatchain.shape == (3200, 2)
+    assert abs(b.gradient.samples.mean() - mean[0]) < 0.25 * sd[0]
+    assert b.gradient.samples.std() == pytest.approx(sd[0], rel=0.15)
+
+
 def test_fast_reconditioning_matches_the_literal_sequence(kb, golden_dir):
     """The default stage-3 path factorises the covariance once; the literal path repeats the reference's
     eigh / cov_nearest / slogdet / pinvh sequence.  Both must give the same matrix and likelihood."""
