@@ -556,6 +556,38 @@ def test_errors(kb):
 # ---------------------------------------------------------------------------------------------
 # full-size properties (BASELINE.json configs[1]): no oracle at this size, so size-independent checks
 # ---------------------------------------------------------------------------------------------
+def test_full_size_stage1_against_torch_fp64(kb):
+    """BASELINE configs[1] shape (1536 atoms, 448 mobile, 20 000 frames, f32 wrapped coordinates): stage 1 against a
+    plain PyTorch float64 restatement of kinisi/parser.py:101-148 on the device.  Exercises 16 tiles per atom of the
+    persistent unwrap kernel (totals exchanged between CTAs) and the staged ingest from pinned host memory."""
+    n_mob, n_fw, n_frames, box = 448, 1088, 20000, 26.0
+    dev = torch.device('cuda')
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(7)
+    steps = torch.randn((n_mob + n_fw, n_frames + 1, 3), dtype=torch.float64, device=dev, generator=gen) * (0.1 / box)
+    steps[:, 0] = torch.rand((n_mob + n_fw, 3), dtype=torch.float64, device=dev, generator=gen)
+    steps[:, 1] = 0.0  # the front-ends duplicate the first frame
+    frac32 = (torch.cumsum(steps, dim=1) % 1.0).to(torch.float32)
+    latt = np.eye(3)[None] * box
+    idx, fw = np.arange(n_mob), np.arange(n_mob, n_mob + n_fw)
+    # reference: float64 torch ops on the same float32 input
+    f64 = frac32.to(torch.float64)
+    d = f64[:, 1:] - f64[:, :-1]
+    u = (d - torch.floor(d + 0.5)) * box
+    dc_all = torch.cumsum(u, dim=1)
+    ref = (dc_all[:n_mob] - dc_all[n_mob:].mean(dim=0, keepdim=True)).permute(0, 2, 1)  # [atom, axis, frame]
+    scale = float(ref.abs().max())
+    for source in ('device', 'pinned host'):
+        coords = frac32 if source == 'device' else frac32.cpu().pin_memory()
+        p = kb.parser.Parser(kb.parser.Parser.get_disp(coords, latt), idx, fw, 0.001, 1, n_steps=100, memory_limit=64.,
+                             progress=False)
+        dc = p.disp_3d.dc[:, :, :n_frames]
+        err = float((dc - ref).abs().max())
+        assert err <= 1e-11 * scale, (source, err, scale)
+        pad = p.disp_3d.dc[:, :, n_frames:]
+        assert pad.numel() == 0 or float(pad.abs().max()) == 0.0  # the row padding stays zero
+
+
 def test_full_size_properties(kb):
     n_atoms, n_frames = 448, 20000
     dev = torch.device('cuda')
