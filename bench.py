@@ -273,7 +273,8 @@ def run_own(args):
     fw = np.arange(n_mob, n_mob + n_fw)
     host = torch.from_numpy(frac).pin_memory()
     resident = host.to(dev)
-    pkw = dict(n_steps=CFG['n_steps'], memory_limit=64., progress=False, distributed=world > 1)
+    pkw = dict(n_steps=CFG['n_steps'], memory_limit=64., progress=False, distributed=world > 1,
+               global_counts=(world * n_mob, world * n_fw) if world > 1 else None)
     gkw = dict(progress=False)
 
     k2_events = []

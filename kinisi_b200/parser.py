@@ -272,6 +272,8 @@ class Parser:
     :param device: CUDA device. Optional, defaults to the current device.
     :param distributed: If True and torch.distributed is initialised, `disp` holds this rank's shard of
         the atoms; drift sums, atom counts and (later) moment sums are all-reduced.
+    :param global_counts: Optional `(selected atoms, framework atoms)` summed over all ranks.  When given, the
+        collective (and the host synchronisation) that would count them is skipped.
     """
 
     def __init__(self,
@@ -288,7 +290,8 @@ class Parser:
                  memory_limit: float = 8.,
                  progress: bool = True,
                  device=None,
-                 distributed: bool = False):
+                 distributed: bool = False,
+                 global_counts: Tuple[int, int] = None):
         self.time_step = time_step
         self.step_skip = step_skip
         self.indices = indices
@@ -311,7 +314,9 @@ class Parser:
         idx = engine.small_to_device(indices, dev, np.int32)
         n_sel_local = idx.numel()
         # global atom counts (selected, framework): one small collective
-        if self._distributed:
+        if self._distributed and global_counts is not None:
+            n_sel, self._n_fw_global = int(global_counts[0]), int(global_counts[1])
+        elif self._distributed:
             n_sel, self._n_fw_global = (int(round(v)) for v in dist.allreduce_sum_scalars(
                 [n_sel_local, len(drift_indices)], dev))
         else:
