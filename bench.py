@@ -291,6 +291,7 @@ def run_own(args):
     engine.self_moments = timed_self_moments
 
     stage_events = []
+    lanes = [torch.cuda.Stream(dev) for _ in range(max(1, args.in_flight))]
 
     def step(coords):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -313,8 +314,22 @@ def run_own(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
-        for _ in range(steps):
-            b = step(coords)
+        if args.in_flight > 1:
+            # consecutive analyses on alternating streams: everything of one analysis is in order on its stream, the
+            # regression of one (a single CTA, then a single warp) runs beside stages 1-2 of the next
+            main = torch.cuda.current_stream(dev)
+            for st in lanes:
+                st.wait_stream(main)
+            held = [None] * args.in_flight
+            for i in range(steps):
+                with torch.cuda.stream(lanes[i % args.in_flight]):
+                    held[i % args.in_flight] = step(coords)
+            for st in lanes:
+                main.wait_stream(st)
+            b = held[(steps - 1) % args.in_flight]
+        else:
+            for _ in range(steps):
+                b = step(coords)
         e1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -331,6 +346,9 @@ def run_own(args):
         step(resident)
     step(host)
     torch.cuda.synchronize()
+    if args.in_flight > 1:  # the streams of the timed loops have their own allocator pools: warm them too
+        timed(resident, 2 * args.in_flight)
+        timed(host, 2 * args.in_flight)
 
     # FP64-pipe peak of this device, measured live (16 independent DFMA chains per thread)
     sink = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -438,6 +456,7 @@ def run_own(args):
                       'exceed the 126 MB L2; no flush needed',
                 'self_moment_variant': {0: 'direct', 1: 'tma-ring', 2: 'arithmetic-runs'}[engine.DEFAULT_VARIANT & 0xff],
                 'wall_ms_per_step': wall_total / args.steps,
+                'analyses_in_flight': args.in_flight,
             },
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                     'ms_per_step': e2e_ms / args.steps},
@@ -490,6 +509,8 @@ def main():
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--variant', type=int, default=None, help='self-moment kernel: 0 direct, 1 TMA ring, 2 arithmetic runs (default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--in-flight', type=int, default=2,
+                    help='analyses in flight: consecutive trajectories go to alternating CUDA streams (1 = one stream)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
