@@ -192,8 +192,9 @@ class Bootstrap:
         if len(used) == 0:
             self._stats_dev = torch.zeros((4, 0), dtype=torch.float64, device=self._device)
         else:
-            self._stats_dev = engine.moment_stats(main_sums, self._dev(cnt), self._dev(divisor), ngp_sums,
-                                                  self._dev(gcnt))
+            packed = self._dev(np.stack([np.asarray(cnt, dtype=np.float64), np.asarray(divisor, dtype=np.float64),
+                                         np.asarray(gcnt, dtype=np.float64)]))  # one upload: counts, divisors, NGP counts
+            self._stats_dev = engine.moment_stats(main_sums, packed[0], packed[1], ngp_sums, packed[2])
         self._dt = np.array([self._delta_t[i] for i in used], dtype=float)
         self._n_o = self._n_o[:len(used)]  # diffusion.py:602
         self._euclidian_displacements = _LazyEuclidian(self._displacements, used, self._slice, self.dims)
@@ -417,7 +418,9 @@ class Bootstrap:
 
         diff_regime = np.argwhere(self._dt >= self._start_dt)[0][0]
 
-        x = self._dev(self._dt[diff_regime:])
+        xn = self._dev(np.stack([np.asarray(self._dt[diff_regime:], dtype=np.float64),
+                                 np.asarray(self._n_o[diff_regime:], dtype=np.float64)]))  # one upload: dt and n_o
+        x, n_o_dev = xn[0], xn[1]
         y = self._stats_dev[0, diff_regime:].contiguous()
         n_dt = x.numel()
         self._cov_regime = diff_regime
@@ -427,7 +430,7 @@ class Bootstrap:
             # model, log-determinant and the GLS expansion (csrc/k4_eigen.cu).  The reconditioned matrix itself
             # is only materialised if `covariance_matrix` is read.
             v = self._stats_dev[1, diff_regime:].contiguous()
-            cov0 = engine.cov_build(v, self._dev(self._n_o[diff_regime:]))
+            cov0 = engine.cov_build(v, n_o_dev)
             self._npd_covariance_matrix_dev = cov0
             self._evals, proj, theta_ml, logdet_term, self._sweeps = engine.spectral_prepare(
                 cov0, x, y, cond_max, fit_intercept)

@@ -311,8 +311,7 @@ class Parser:
         dev = traj.device
         n_frames = traj.n_frames
 
-        idx = engine.small_to_device(indices, dev, np.int32)
-        n_sel_local = idx.numel()
+        n_sel_local = len(indices)
         # global atom counts (selected, framework): one small collective
         if self._distributed and global_counts is not None:
             n_sel, self._n_fw_global = int(global_counts[0]), int(global_counts[1])
@@ -336,7 +335,11 @@ class Parser:
         if not traj.resident and n_sel_local > 0:
             self._build_displacement_staged(traj, indices, drift_indices)
         else:
-            self._drift = self._framework_mean(traj, drift_indices)
+            # one upload for both index lists
+            both = engine.small_to_device(np.concatenate([np.asarray(indices, dtype=np.int64).reshape(-1),
+                                                          np.asarray(drift_indices, dtype=np.int64).reshape(-1)]), dev, np.int32)
+            idx, fw_idx = both[:n_sel_local], both[n_sel_local:]
+            self._drift = self._framework_mean(traj, drift_indices, fw_idx)
             if n_sel_local > 0:
                 self._dc_sel = traj.displacement(idx, self._drift)
             else:
@@ -424,7 +427,7 @@ class Parser:
         self._dc_sel_staged = value
         self._dc_ready = None
 
-    def _framework_mean(self, traj, drift_indices):
+    def _framework_mean(self, traj, drift_indices, fw=None):
         """(per-frame sums over the framework atoms [3, pitch] on the device, number of framework atoms), or None.
         The displacement kernel subtracts sums / n before its cumulative sum (kinisi/parser.py:143-145)."""
         n_fw_local = len(drift_indices)
@@ -432,7 +435,8 @@ class Parser:
         if n_fw == 0:
             return None
         if n_fw_local > 0:
-            fw = engine.small_to_device(drift_indices, traj.device, np.int32)
+            if fw is None:
+                fw = engine.small_to_device(drift_indices, traj.device, np.int32)
             sums = traj.frame_sums(fw)
         else:
             sums = torch.zeros((3, engine.pitch_for(traj.n_frames)), dtype=torch.float64, device=traj.device)
