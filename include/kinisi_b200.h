@@ -60,6 +60,20 @@ int kb2_device_info(int* sm_count, int* max_smem_optin, int* cc_major, int* cc_m
  *         `latt_stride` = 9 for per-frame lattices or 0 when every frame shares latt[0].
  * ------------------------------------------------------------------------------------------- */
 
+/* Frame-major -> atom-major (replaces np.concatenate(coords, axis=1), parser.py:120, and the per-frame
+ * loops of the front-ends, :309-325, 458-473): frames[n_frames][n_atoms][3] goes to
+ * coords_out[(a * n_frames_out + frame_offset + f) * 3 + k]; duplicate_first != 0 also writes frame 0 to
+ * frame_offset - 1 (the front-ends insert a copy of the first frame, parser.py:323-324).  Blocks of frames may be
+ * transposed by successive calls (frame_offset).  Both arrays have the element type `dtype`. */
+int kb2_frames_to_atoms(const void* frames, int dtype, int n_atoms, int n_frames, void* coords_out, int64_t n_frames_out,
+                        int64_t frame_offset, int duplicate_first, void* stream);
+
+/* Pseudo-centre-of-mass of groups of atoms in fractional coordinates (_get_molecules, parser.py:674-738,
+ * arXiv:2501.14578): members[n_molecules][molecule_size] are 0-based atom rows of coords[n_atoms_total][n_frames_in][3],
+ * weights[molecule_size] the masses (NULL: centre of geometry); centres[n_molecules][n_frames_in][3] float64 in [0, 1). */
+int kb2_molecule_centres(const void* coords, int dtype, int n_atoms_total, int64_t n_frames_in, const int32_t* members,
+                         int n_molecules, int molecule_size, const double* weights, double* centres, void* stream);
+
 /* inv[f] = latt[f]^-1 for f < n (np.linalg.inv at parser.py:121). */
 int kb2_invert_lattice(const double* latt, double* latt_inv, int n, void* stream);
 

@@ -74,6 +74,33 @@ def invert_lattice(latt):
     return inv
 
 
+def frames_to_atoms(frames, out, frame_offset, duplicate_first=False):
+    """Transposes frame-major frames [n_frames, n_atoms, 3] into the atom-major array out [n_atoms, F_out, 3] at
+    frame_offset; see kb2_frames_to_atoms."""
+    lib = require_cuda()
+    assert frames.is_contiguous() and out.is_contiguous() and frames.dtype == out.dtype
+    check(
+        lib.kb2_frames_to_atoms(frames.data_ptr(), coords_dtype_code(frames), frames.shape[1], frames.shape[0],
+                                out.data_ptr(), out.shape[1], int(frame_offset), int(bool(duplicate_first)), _stream()),
+        'kb2_frames_to_atoms')
+    _count()
+    return out
+
+
+def molecule_centres(coords, members, weights=None):
+    """Pseudo-centres of mass [n_molecules, F, 3] (float64, fractional) of the atom groups members [n_mol, m] (int32
+    device tensor) of coords [n_atoms, F, 3]; see kb2_molecule_centres."""
+    lib = require_cuda()
+    n_mol, m = members.shape
+    out = torch.empty((n_mol, coords.shape[1], 3), dtype=torch.float64, device=coords.device)
+    check(
+        lib.kb2_molecule_centres(coords.data_ptr(), coords_dtype_code(coords), coords.shape[0], coords.shape[1],
+                                 members.data_ptr(), n_mol, m, _ptr(weights), out.data_ptr(), _stream()),
+        'kb2_molecule_centres')
+    _count()
+    return out
+
+
 def frame_sums(coords, mode, latt, latt_inv, latt_stride, idx, weights, pitch):
     """[3, pitch] per-frame (weighted) sums over the atoms in idx; see kb2_frame_sums."""
     lib = require_cuda()

@@ -77,7 +77,7 @@ class Trajectory:
         self.latt = self.latt_inv = None
         self.latt_stride = 9
         self._latt_event = None
-        if mode == MODE_FRACTIONAL:
+        if mode == MODE_FRACTIONAL and latt is not None:
             latt_host = latt if isinstance(latt, np.ndarray) else None
             # with a staged ingest the lattices are prepared on the ingest stream, like everything else of stage 1
             work = self._side[1] if self._host is not None else torch.cuda.current_stream(device)
@@ -148,6 +148,64 @@ class Trajectory:
     def n_frames(self):
         """Number of displacement frames (the reference's drift_corrected.shape[1])."""
         return self.coords.shape[1] - (1 if self.mode == MODE_FRACTIONAL else 0)
+
+    @classmethod
+    def from_frames(cls, frames, latt=None, mode=MODE_FRACTIONAL, device=None, duplicate_first=True):
+        """
+        A trajectory from FRAME-major coordinates `[frame, site, 3]` (how MD codes write them and how the front-ends
+        collect them, kinisi/parser.py:309-325, 458-473).  The transposition to the atom-major layout of the kernels
+        runs on the device (kb2_frames_to_atoms); host input is transferred in blocks of frames on the copy stream
+        and transposed on the ingest stream behind the transfer.  `duplicate_first` inserts the copy of the first
+        frame the reference's front-ends prepend (parser.py:323-324).
+        """
+        device = _default_device(device)
+        if not isinstance(frames, torch.Tensor):
+            frames = torch.from_numpy(np.ascontiguousarray(frames))
+        if frames.dtype not in (torch.float32, torch.float64):
+            frames = frames.to(torch.float64)
+        if frames.dim() != 3 or frames.shape[2] != 3:
+            raise ValueError('frames must have the shape [frame, site, 3]')
+        frames = frames.contiguous()
+        n_f, n_a = int(frames.shape[0]), int(frames.shape[1])
+        off = 1 if duplicate_first else 0
+        copy, ingest = _side_streams(device)
+        main = torch.cuda.current_stream(device)
+        if frames.device.type == 'cpu':
+            with torch.cuda.stream(ingest):
+                coords = torch.empty((n_a, n_f + off, 3), dtype=frames.dtype, device=device)
+            per = max(1, int(STAGE_BYTES // max(1, n_a * 3 * frames.element_size())))
+            with torch.cuda.stream(copy):
+                stage = [torch.empty((min(per, n_f), n_a, 3), dtype=frames.dtype, device=device) for _ in range(2)]
+            free = [None, None]  # event: the transpose that read staging buffer i has been queued and finished
+            for i, f0 in enumerate(range(0, n_f, per)):
+                f1 = min(n_f, f0 + per)
+                buf = stage[i & 1][:f1 - f0]
+                with torch.cuda.stream(copy):
+                    if free[i & 1] is not None:
+                        copy.wait_event(free[i & 1])
+                    buf.copy_(frames[f0:f1], non_blocking=True)
+                    landed = torch.cuda.Event()
+                    landed.record(copy)
+                with torch.cuda.stream(ingest):
+                    ingest.wait_event(landed)
+                    engine.frames_to_atoms(buf, coords, off + f0, duplicate_first and f0 == 0)
+                    free[i & 1] = torch.cuda.Event()
+                    free[i & 1].record(ingest)
+            for t in stage:
+                t.record_stream(ingest)
+            coords.record_stream(main)
+            main.wait_stream(ingest)
+            keep = frames  # the transfer reads the caller's memory until the streams have drained
+        else:
+            frames = frames.to(device)
+            coords = torch.empty((n_a, n_f + off, 3), dtype=frames.dtype, device=device)
+            for f0 in range(0, n_f, 65535 * 32):
+                f1 = min(n_f, f0 + 65535 * 32)
+                engine.frames_to_atoms(frames[f0:f1], coords, off + f0, duplicate_first and f0 == 0)
+            keep = None
+        traj = cls(coords, latt, mode, device)
+        traj._frames_keepalive = keep
+        return traj
 
     def frame_sums(self, idx, weights=None):
         """Per-frame (weighted) displacement sums over atoms idx (an int32 device tensor)."""
@@ -478,6 +536,23 @@ class Parser:
         return Trajectory(coords, latt_np.reshape(-1, 3, 3), MODE_FRACTIONAL, device)
 
     @staticmethod
+    def get_disp_from_frames(frames, latt, progress: bool = True, device=None) -> Trajectory:
+        """As :py:meth:`get_disp` for FRAME-major fractional coordinates `[frame, site, 3]` WITHOUT the duplicated first
+        frame (it is inserted on the device): see :py:meth:`Trajectory.from_frames`."""
+        if isinstance(latt, (list, tuple)):
+            latt = np.array(latt)
+        latt_np = latt.detach().cpu().numpy() if isinstance(latt, torch.Tensor) else np.asarray(latt)
+        latt_np = latt_np.reshape(-1, 3, 3)
+        off_diags = np.array([[False, True, True], [True, False, True], [True, True, False]])
+        if np.any(latt_np[:, off_diags] != 0):
+            warnings.warn(
+                'Converting triclinic cell to orthorhombic this may have unexpected results. '
+                'Triclinic a, b, c are not equilivalent to orthorhombic x, y, z.', UserWarning)
+        if latt_np.shape[0] > 1:
+            latt_np = np.concatenate([latt_np[:1], latt_np], axis=0)  # the duplicated first frame has its lattice too
+        return Trajectory.from_frames(frames, latt_np, MODE_FRACTIONAL, device, duplicate_first=True)
+
+    @staticmethod
     def correct_drift(drift_indices, disp) -> np.ndarray:
         """
         Drift correction on its own (kinisi/parser.py:131-148): `disp - mean(disp[drift_indices])`.
@@ -569,12 +644,82 @@ def _frames_to_arrays(frames, get_frac, get_cell, sub_sample_traj, progress):
     return structure, np.stack(coords, axis=1), np.stack(latt, axis=0)
 
 
+def _walk_frames(frames, get_frac, get_cell, sub_sample_traj):
+    """The same walk collecting FRAME-major arrays `[frame, site, 3]`, `[frame, 3, 3]` (no duplicated first frame): the
+    frames are appended as they come and transposed on the device."""
+    structure = None
+    coords, latt = [], []
+    for struct in frames[::sub_sample_traj]:
+        if structure is None:
+            structure = struct
+        coords.append(np.asarray(get_frac(struct), dtype=np.float64))
+        latt.append(np.asarray(get_cell(struct), dtype=np.float64))
+    return structure, np.stack(coords, axis=0), np.stack(latt, axis=0)
+
+
+def _get_molecules(structure, traj, indices, masses, framework_indices):
+    """
+    Centres of groups of atoms by the pseudo-centre-of-mass approach (kinisi/parser.py:674-738, arXiv:2501.14578), on
+    the device (kb2_molecule_centres).  `indices` are 1-based lists of equal length, one per molecule; `masses` has one
+    entry per member (None: centre of geometry); `framework_indices` 1-based or None (every atom outside the molecules).
+
+    :return: a Trajectory whose first rows are the centres followed by the framework atoms, and the index lists
+        `(centres, framework)` into it.
+    """
+    try:
+        members = np.array(indices) - 1
+        if members.ndim != 2:
+            raise ValueError
+    except Exception:
+        raise ValueError('Molecules must be of same length')
+    n_molecules = members.shape[0]
+    if isinstance(framework_indices, (list, tuple)):
+        drift_indices = np.array(framework_indices, dtype=np.int64) - 1
+    else:
+        inside = set(int(i) for i in members.reshape(-1))
+        drift_indices = np.array([i for i, _ in enumerate(structure) if i not in inside], dtype=np.int64)
+    weights = None
+    if masses is not None:
+        if len(masses) != members.shape[-1]:
+            raise ValueError('Masses must be the same length as a molecule')
+        weights = engine.small_to_device(np.asarray(masses, dtype=np.float64), traj.device, np.float64)
+    traj.make_resident()
+    centres = engine.molecule_centres(traj.coords, engine.small_to_device(members, traj.device, np.int32), weights)
+    rows = [centres]
+    if len(drift_indices):
+        sel = engine.small_to_device(drift_indices, traj.device, np.int64)
+        rows.append(traj.coords.index_select(0, sel).to(torch.float64))
+    new = Trajectory(torch.cat(rows, dim=0), None, traj.mode, traj.device)
+    new.latt, new.latt_inv, new.latt_stride, new._latt_event = traj.latt, traj.latt_inv, traj.latt_stride, traj._latt_event
+    return new, (list(range(n_molecules)), list(range(n_molecules, n_molecules + len(drift_indices))))
+
+
 def _get_framework(structure, indices, framework_indices):
     """kinisi/parser.py:741-764 (1-based `framework_indices`, as the reference subtracts one)."""
     if isinstance(framework_indices, (list, tuple)):
         return indices, list(np.array(framework_indices, dtype=int) - 1)
     chosen = set(int(i) for i in indices)
     return indices, [i for i, _ in enumerate(structure) if i not in chosen]
+
+
+def _front_end_trajectory(parser, structure, frames, latt, specie, specie_indices, masses, framework_indices, progress,
+                          device):
+    """Shared body of the front-end constructors (kinisi/parser.py:266-293, 406-435): index selection, molecule
+    centres, `coords_check`, and the device trajectory built from the frame-major walk."""
+    traj = Parser.get_disp_from_frames(frames, latt, progress=progress, device=device)
+    if specie is not None:
+        indices = parser.get_indices(structure, specie, framework_indices)
+        parser.coords_check = frames[0][:, None, :]
+    elif isinstance(specie_indices, (list, tuple)):
+        if isinstance(specie_indices[0], (list, tuple)):
+            traj, indices = _get_molecules(structure, traj, specie_indices, masses, framework_indices)
+            parser.coords_check = traj.coords[:, 0:1].cpu().numpy()
+        else:
+            indices = _get_framework(structure, specie_indices, framework_indices)
+            parser.coords_check = frames[0][:, None, :]
+    else:
+        raise TypeError('Unrecognized type for specie or specie_indices')
+    return traj, indices
 
 
 class ASEParser(Parser):
@@ -588,7 +733,8 @@ class ASEParser(Parser):
     :param step_skip: Sampling frequency of the trajectory.
     :param sub_sample_traj: Multiple of the time_step to sub sample at. Optional, defaults to 1.
     :param specie_indices: Optional, list of indices to calculate diffusivity for. Specie must be None.
-    :param masses: Optional, masses for molecule centres (not on the displacement-statistics path).
+    :param masses: Optional, masses of the members of a molecule when `specie_indices` is a list of 1-based lists
+        (centres by the pseudo-centre-of-mass approach, kinisi/parser.py:674-738).
     :param framework_indices: Optional, indices used to correct framework drift; [] disables the correction.
     (min_dt, max_dt, n_steps, spacing, sampling, memory_limit, progress as for :py:class:`Parser`.)
     """
@@ -610,23 +756,13 @@ class ASEParser(Parser):
                  masses: List[float] = None,
                  framework_indices: List[int] = None,
                  device=None):
-        structure, coords, latt = self.get_structure_coords_latt(atoms, sub_sample_traj, progress)
-
-        if specie is not None:
-            indices = self.get_indices(structure, specie, framework_indices)
-        elif isinstance(specie_indices, (list, tuple)):
-            if isinstance(specie_indices[0], (list, tuple)):
-                raise NotImplementedError('molecular centres of mass (kinisi/parser.py:674-738) are outside the '
-                                          'displacement-statistics path of kinisi_b200')
-            indices = _get_framework(structure, specie_indices, framework_indices)
-        else:
-            raise TypeError('Unrecognized type for specie or specie_indices')
-
-        self.coords_check = coords[:, 0:1]
-
+        structure, frames, latt = _walk_frames(atoms, lambda s: s.get_scaled_positions(), lambda s: s.cell[:],
+                                               sub_sample_traj)
+        traj, indices = _front_end_trajectory(self, structure, frames, latt, specie, specie_indices, masses,
+                                              framework_indices, progress, device)
         # note: like the reference (parser.py:291) sub_sample_traj is NOT folded into step_skip here
-        super().__init__(self.get_disp(coords, latt, progress=progress, device=device), indices[0], indices[1], time_step,
-                         step_skip, min_dt, max_dt, n_steps, spacing, sampling, memory_limit, progress, device=device)
+        super().__init__(traj, indices[0], indices[1], time_step, step_skip, min_dt, max_dt, n_steps, spacing, sampling,
+                         memory_limit, progress, device=device)
         self._volume = structure.get_volume()
 
     @staticmethod
@@ -678,20 +814,12 @@ class PymatgenParser(Parser):
                  masses: List[float] = None,
                  framework_indices: List[int] = None,
                  device=None):
-        structure, coords, latt = self.get_structure_coords_latt(structures, sub_sample_traj, progress)
-        if specie is not None:
-            indices = self.get_indices(structure, specie, framework_indices)
-        elif isinstance(specie_indices, (list, tuple)):
-            if isinstance(specie_indices[0], (list, tuple)):
-                raise NotImplementedError('molecular centres of mass (kinisi/parser.py:674-738) are outside the '
-                                          'displacement-statistics path of kinisi_b200')
-            indices = _get_framework(structure, specie_indices, framework_indices)
-        else:
-            raise TypeError('Unrecognized type for specie or specie_indices')
-        self.coords_check = coords[:, 0:1]
-        super().__init__(self.get_disp(coords, latt, progress=progress, device=device), indices[0], indices[1], time_step,
-                         step_skip * sub_sample_traj, min_dt, max_dt, n_steps, spacing, sampling, memory_limit, progress,
-                         device=device)
+        structure, frames, latt = _walk_frames(structures, lambda s: s.frac_coords, lambda s: s.lattice.matrix,
+                                               sub_sample_traj)
+        traj, indices = _front_end_trajectory(self, structure, frames, latt, specie, specie_indices, masses,
+                                              framework_indices, progress, device)
+        super().__init__(traj, indices[0], indices[1], time_step, step_skip * sub_sample_traj, min_dt, max_dt, n_steps,
+                         spacing, sampling, memory_limit, progress, device=device)
         self._volume = structure.volume
         warnings.warn("UserWarning: Be aware that the expected input unit for 'time_step' is femtoseconds, not picoseconds.")
         self.delta_t = self.delta_t * 1e-3

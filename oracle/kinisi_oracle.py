@@ -70,6 +70,27 @@ def correct_drift(drift_indices, disp):
     return disp
 
 
+def molecule_centres(coords, members, masses=None):
+    """kinisi/parser.py:706-724 (_get_molecules): pseudo-centre-of-mass of groups of atoms (arXiv:2501.14578).
+
+    coords: fractional coordinates [N, F, 3] (site-major, this module's layout); members: 0-based [n_mol, m];
+    masses: [m] or None.  Returns the centres [n_mol, F, 3] in [0, 1)."""
+    coords = np.asarray(coords, dtype=np.float64)
+    members = np.asarray(members)
+    s_coords = np.transpose(coords[members], (2, 0, 1, 3))  # [F, n_mol, m, 3] as sq_coords[:, indices]
+    theta = s_coords * (2 * np.pi)
+    xi = np.cos(theta)
+    zeta = np.sin(theta)
+    xi_bar = np.average(xi, axis=-2, weights=masses)
+    zeta_bar = np.average(zeta, axis=-2, weights=masses)
+    theta_bar = np.arctan2(-zeta_bar, -xi_bar) + np.pi
+    new_s_coords = theta_bar / (2 * np.pi)
+    recentred = (s_coords - (new_s_coords + 0.5)[:, :, np.newaxis]) % 1
+    com_pseudo_space = np.average(recentred, weights=masses, axis=2)
+    corrected = (com_pseudo_space + (new_s_coords + 0.5)) % 1
+    return np.transpose(corrected, (1, 0, 2))
+
+
 def time_intervals(n_frames, time_step, step_skip, min_dt=None, max_dt=None, n_steps=100, spacing='linear'):
     """kinisi/parser.py:80-90 (defaults and clamps) + :150-168 (get_time_intervals).
 

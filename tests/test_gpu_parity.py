@@ -285,6 +285,85 @@ def test_stage1_dtypes_and_collective(kb, dtype):
         np.testing.assert_allclose(b.ngp, ref['ngp'], rtol=1e-8, atol=1e-10)
 
 
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_frame_major_ingest(kb, dtype, monkeypatch):
+    """kb2_frames_to_atoms: frame-major input, from the device and from the host in several blocks, gives
+    the atom-major array with the duplicated first frame that np.concatenate builds in the reference (parser.py:120,
+    323-324); the parser on top of it gives the same displacements."""
+    n_atoms, n_frames = 37, 131
+    frac, latt = ko.synthetic_walk(n_atoms, n_frames, box=9.0, sigma=0.2, seed=8, dtype=dtype)
+    frames = np.ascontiguousarray(np.transpose(frac[:, 1:], (1, 0, 2)))  # [frame, site, 3] without the duplicate
+    dev = torch.device('cuda')
+    t_dev = kb.parser.Trajectory.from_frames(torch.from_numpy(frames).to(dev), latt[:1], device=dev)
+    np.testing.assert_array_equal(t_dev.coords.cpu().numpy(), frac)
+    monkeypatch.setattr(kb.parser, 'STAGE_BYTES', 10 * n_atoms * 3 * frames.itemsize)  # 14 blocks of 10 frames
+    t_host = kb.parser.Trajectory.from_frames(frames, latt[:1], device=dev)
+    np.testing.assert_array_equal(t_host.coords.cpu().numpy(), frac)
+    t_nodup = kb.parser.Trajectory.from_frames(frames, None, mode=kb.parser.MODE_DISPLACEMENT, device=dev,
+                                               duplicate_first=False)
+    np.testing.assert_array_equal(t_nodup.coords.cpu().numpy(), frac[:, 1:])
+    idx = list(range(0, n_atoms, 2))
+    fw = list(range(1, n_atoms, 2))
+    a = kb.parser.Parser(kb.parser.Parser.get_disp_from_frames(frames, latt[1:]), idx, fw, 0.001, 1, n_steps=20, progress=False)
+    b = kb.parser.Parser(kb.parser.Parser.get_disp(frac, latt), idx, fw, 0.001, 1, n_steps=20, progress=False)
+    # (the framework sums of the two runs are accumulated in a different order: rounding-level differences)
+    np.testing.assert_allclose(a.disp_3d.dc.cpu().numpy(), b.disp_3d.dc.cpu().numpy(), rtol=1e-12, atol=1e-12)
+
+
+def test_molecule_centres(kb):
+    """kb2_molecule_centres against the oracle's restatement of kinisi/parser.py:706-724, the reference's
+    KAT (kinisi/tests/test_parser.py:127-149) through the pymatgen front-end, and its error behaviour."""
+    rng = np.random.RandomState(4)
+    n_atoms, n_frames = 23, 300
+    coords = rng.uniform(0, 1, size=(n_atoms, 1, 3)) + np.cumsum(rng.normal(0, 0.02, size=(n_atoms, n_frames, 3)), axis=1)
+    coords = coords % 1.0
+    members = np.array([[0, 5, 7, 2], [11, 12, 13, 14], [22, 1, 3, 20]])
+    masses = np.array([1.0, 16.0, 12.0, 1.0])
+    dev = torch.device('cuda')
+    for dtype in (np.float32, np.float64):
+        c = coords.astype(dtype)
+        for w in (None, masses):
+            ref = ko.molecule_centres(c.astype(np.float64), members, w)
+            got = kb.engine.molecule_centres(torch.from_numpy(c).to(dev), torch.from_numpy(members.astype(np.int32)).to(dev),
+                                             None if w is None else torch.from_numpy(w).to(dev)).cpu().numpy()
+            d = np.abs(got - ref)
+            assert np.minimum(d, 1.0 - d).max() < 1e-12  # equal up to the periodic image
+    # the reference's KAT through the front-end (1-based indices, duck-typed pymatgen structures)
+    class Site:
+        def __init__(self, s):
+            self.specie = s
+
+    class Lattice:
+        matrix = np.eye(3) * 5.0
+
+    class Structure:
+        lattice, volume = Lattice(), 125.0
+
+        def __init__(self, frac):
+            self.frac_coords = np.asarray(frac, dtype=float)
+
+        def __iter__(self):
+            return iter([Site('H'), Site('He'), Site('H')])
+
+    f0 = [[0.2, 0.2, 0.2], [0.4, 0.2, 0.2], [0.22, 0.4, 0.2]]
+    f1 = [[0.4, 0.2, 0.2], [0.4, 0.2, 0.2], [0.2, 0.4, 0.2]]
+    structs = [Structure(f0), Structure(f1), Structure(f1), Structure(f1)]
+    pk = dict(specie=None, time_step=1.0, step_skip=1, specie_indices=[[1, 2, 3]], progress=False)
+    with pytest.warns(UserWarning):
+        data = kb.parser.PymatgenParser(structs, **pk)
+    assert data.indices == [0] and data.drift_indices == []
+    np.testing.assert_array_almost_equal(data.coords_check, [[[0.2733333, 0.2666667, 0.2]]])
+    with pytest.warns(UserWarning):
+        data = kb.parser.PymatgenParser(structs, masses=[1, 16, 1], **pk)
+    np.testing.assert_array_almost_equal(data.coords_check, [[[0.3788889, 0.2111111, 0.2]]])
+    with pytest.raises(ValueError), warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        kb.parser.PymatgenParser(structs, masses=[1, 16], **pk)
+    with pytest.raises(ValueError), warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        kb.parser.PymatgenParser(structs, **dict(pk, specie_indices=[[1, 2], [3]]))
+
+
 def test_staged_ingest_matches_resident_input(kb, monkeypatch):
     """Host input is transferred block by block behind the stage-1 / stage-2 kernels (Parser._build_displacement_staged);
     the result must not depend on the blocking, on the order of the indices, or on where the input lives."""

@@ -148,3 +148,18 @@ def test_reference_kats(golden_dir):
     res = ko.bootstrap_streaming(parsed, 'msd')
     for key in ('dt', 'n', 'v', 's', 'ngp', 'n_o'):
         np.testing.assert_allclose(res[key], g[f'lips_msd_{key}'], rtol=1e-11)
+
+
+def test_molecule_centres_reference_kat():
+    """kinisi/tests/test_parser.py:127-149 (example_center.XDATCAR, first frame): centre of geometry and centre of mass
+    (masses 1, 16, 1) of the three atoms."""
+    frame0 = np.array([[0.2, 0.2, 0.2], [0.4, 0.2, 0.2], [0.22, 0.4, 0.2]])
+    coords = frame0[:, None, :]
+    cog = ko.molecule_centres(coords, [[0, 1, 2]])
+    np.testing.assert_array_almost_equal(cog[0, 0], [0.2733333, 0.2666667, 0.2])
+    com = ko.molecule_centres(coords, [[0, 1, 2]], masses=np.array([1.0, 16.0, 1.0]))
+    np.testing.assert_array_almost_equal(com[0, 0], [0.3788889, 0.2111111, 0.2])
+    # across the periodic boundary: members at 0.95 and 0.05 have their centre at 0.0, not 0.5
+    wrap = np.array([[0.95, 0.5, 0.5], [0.05, 0.5, 0.5]])[:, None, :]
+    c = ko.molecule_centres(wrap, [[0, 1]])[0, 0]
+    assert min(c[0], 1 - c[0]) < 1e-12 and abs(c[1] - 0.5) < 1e-12
