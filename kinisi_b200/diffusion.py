@@ -9,7 +9,7 @@ displacement list is never materialised) or a plain list of `[atom, observation,
 reference's seam, kinisi/diffusion.py:552-564; each entry is reduced by one kernel).
 
 Not provided (off the default path): `bootstrap=True` resampling (diffusion.py:258-289,
-783-835), `block=True` (pyblock) and `model=True` variance smoothing (:406-420).
+783-835) and `block=True` (pyblock).
 """
 from typing import List, Union
 
@@ -360,9 +360,7 @@ class Bootstrap:
         `_populate_covariance_matrix` (:838-854) -> `minimum_eigenvalue_method` (:870-888) ->
         `cov_nearest` (statsmodels, clipped-correlation repair).
         """
-        if self._model:
-            raise NotImplementedError('model=True variance smoothing (kinisi/diffusion.py:406-420) is not built here')
-        v = self._stats_dev[1, diff_regime:].contiguous()
+        v = self._variances_for_covariance(diff_regime)
         n_o = self._dev(self._n_o[diff_regime:])
         cov = engine.cov_build(v, n_o)
         self._npd_covariance_matrix_dev = cov
@@ -389,6 +387,22 @@ class Bootstrap:
         repaired = repaired / rstd / rstd[:, None]
         corr = torch.where((ev < 1e-15).any(), repaired, corr)
         return corr * torch.outer(std, std)
+
+    def _variances_for_covariance(self, diff_regime: int):
+        """The variances that enter the covariance model: the measured ones, or with `model=True` the fitted
+        `a / n_o * dt**2` (kinisi/diffusion.py:406-420).  The reference fits `a` with `scipy.optimize.curve_fit` under
+        the bound a >= 0; the model is linear in `a`, so the least-squares solution is closed form,
+        a = max(0, sum(v f) / sum(f f)) with f = dt**2 / n_o, evaluated on the device."""
+        v = self._stats_dev[1, diff_regime:].contiguous()
+        if not self._model:
+            self._model_v_dev = v
+            return v
+        f = self._dev(np.asarray(self._dt[diff_regime:], dtype=np.float64)**2 /
+                      np.asarray(self._n_o[diff_regime:], dtype=np.float64))
+        a = torch.clamp((v * f).sum() / (f * f).sum(), min=0.0)
+        self._popt_dev = a
+        self._model_v_dev = (a * f).contiguous()
+        return self._model_v_dev
 
     def bootstrap_GLS(self,
                       start_dt: float,
@@ -425,11 +439,11 @@ class Bootstrap:
         n_dt = x.numel()
         self._cov_regime = diff_regime
         self._covariance_matrix_dev = None
-        if not LITERAL_RECONDITIONING and not model and n_dt <= engine.spectral_prepare_max_n():
+        if not LITERAL_RECONDITIONING and n_dt <= engine.spectral_prepare_max_n():
             # One kernel: Jacobi spectrum of the model covariance -> clipped spectrum, pinvh cut-off, whitened
             # model, log-determinant and the GLS expansion (csrc/k4_eigen.cu).  The reconditioned matrix itself
             # is only materialised if `covariance_matrix` is read.
-            v = self._stats_dev[1, diff_regime:].contiguous()
+            v = self._variances_for_covariance(diff_regime)
             cov0 = engine.cov_build(v, n_o_dev)
             self._npd_covariance_matrix_dev = cov0
             self._evals, proj, theta_ml, logdet_term, self._sweeps = engine.spectral_prepare(

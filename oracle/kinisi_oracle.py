@@ -328,9 +328,21 @@ def cov_nearest(cov, threshold=1e-15):
     return corr * np.outer(std, std)
 
 
-def generate_covariance_matrix(v, n_o, diff_regime, cond_max=1e16):
-    """kinisi/diffusion.py:397-425 with model=False."""
-    cov = populate_covariance_matrix(v[diff_regime:], n_o[diff_regime:])
+def model_variance(dt, v, n_o, diff_regime):
+    """kinisi/diffusion.py:406-420 with model=True: v ~ a / n_o * dt**2, `a` fitted with curve_fit under a >= 0."""
+    from scipy.optimize import curve_fit
+
+    def _model_variance(x, a):
+        return a / n_o[diff_regime:] * x**2
+
+    popt, _ = curve_fit(_model_variance, dt[diff_regime:], v[diff_regime:], bounds=(0, np.inf))
+    return _model_variance(dt[diff_regime:], *popt)
+
+
+def generate_covariance_matrix(v, n_o, diff_regime, cond_max=1e16, dt=None, model=False):
+    """kinisi/diffusion.py:397-425."""
+    model_v = model_variance(dt, v, n_o, diff_regime) if model else v[diff_regime:]
+    cov = populate_covariance_matrix(model_v, n_o[diff_regime:])
     return cov_nearest(minimum_eigenvalue_method(cov, cond_max))
 
 

@@ -524,6 +524,29 @@ def test_long_grid_regression_takes_the_library_eigensolver(kb):
     assert b.gradient.samples.std() == pytest.approx(sd[0], rel=0.15)
 
 
+def test_model_variance(kb):
+    """model=True (kinisi/diffusion.py:406-420): the covariance is built from the fitted variances a / n_o * dt**2;
+    the closed-form fit against the oracle's scipy curve_fit, on both spectral routes."""
+    n_atoms, n_frames = 24, 3000
+    frac, latt = ko.synthetic_walk(n_atoms, n_frames, box=12.0, sigma=0.1, seed=31)
+    parsed = ko.parse(ko.get_disp(frac, latt), list(range(n_atoms)), [], 0.002, 1, n_steps=60)
+    ref = ko.bootstrap_streaming(parsed, 'msd')
+    p = kb.parser.Parser(kb.parser.Parser.get_disp(frac, latt), list(range(n_atoms)), [], 0.002, 1, n_steps=60,
+                         progress=False)
+    start = 8
+    cov_ref = ko.generate_covariance_matrix(ref['v'], ref['n_o'], start, dt=ref['dt'], model=True)
+    scale = np.abs(cov_ref).max()
+    for literal in (False, True):
+        kb.diffusion.LITERAL_RECONDITIONING = literal
+        try:
+            b = kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False)
+            b.diffusion(float(b.dt[start]), model=True, progress=False, n_samples=200, n_burn=100)
+            np.testing.assert_allclose(b.covariance_matrix, cov_ref, rtol=1e-6, atol=1e-9 * scale)
+        finally:
+            kb.diffusion.LITERAL_RECONDITIONING = False
+        assert b.D.n > 0 and b.flatchain.shape == (32 * 20, 2)
+
+
 def test_fast_reconditioning_matches_the_literal_sequence(kb, golden_dir):
     """The default stage-3 path factorises the covariance once; the literal path repeats the reference's
     eigh / cov_nearest / slogdet / pinvh sequence.  Both must give the same matrix and likelihood."""
