@@ -10,6 +10,7 @@
 // Algorithmic HBM bytes per (atom, frame): sizeof(coord)*3 read + 24 written for the scan kernel,
 // sizeof(coord)*3 read for the frame-sum kernel.  Both are HBM-bound.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -299,33 +300,46 @@ __global__ void __launch_bounds__(kUwThreads, 3) unwrap_cumsum_kernel(const T* _
         const int atom = (int)(w % (unsigned)n_idx), tile = (int)(w / (unsigned)n_idx);  // tile-major order (see above)
         const int64_t t0 = (int64_t)tile * TF;
         double* tot_atom = totals + (size_t)atom * n_tiles * 3;
+        // the body of an item, instantiated without bounds tests for tiles that lie fully inside the trajectory
+        auto body = [&](auto full_tag) __attribute__((always_inline)) {
+            constexpr bool FULL = decltype(full_tag)::value;
         // the drift of this thread's frames: L2 loads that land while the tile is unwrapped
         const int f0 = tid * E;
+        // look back early: thread j asks for the total of tile j of this atom now (an L2 round trip that overlaps the
+        // unwrapping); whatever is not ready yet is asked for again after the tile's own prefix has been staged
+        unsigned long long early[3] = {kUwNotReady, kUwNotReady, kUwNotReady};
+        if (FRAC && tid < tile) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) early[c] = ld_l2_u64(tot_atom + tid * 3 + c);
+        }
         double drift[E][3];
+        {
+            const double* ds[3] = {step_sums + t0 + f0, step_sums + pitch + t0 + f0, step_sums + 2 * pitch + t0 + f0};
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int64_t t = t0 + f0 + e;
+            for (int e = 0; e < E; ++e) {
+                const int64_t t = t0 + f0 + e;
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                drift[e][c] = (step_sums && t < Tn) ? step_scale * __ldg(step_sums + (size_t)c * pitch + t) : 0.0;
+                for (int c = 0; c < 3; ++c)
+                    drift[e][c] = (step_sums && (FULL || t < Tn)) ? step_scale * __ldg(ds[c] + e) : 0.0;
+            }
         }
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
         const T* raw = reinterpret_cast<const T*>(uw_smem + (size_t)(it & 1) * uw_raw_bytes<T>()) + s_mis[it & 1];
 
         double val[E][3];
-        if (t0 + f0 < Tn) {
+        if (FULL || t0 + f0 < Tn) {
             // the thread's frames f0 .. f0 + E (one more than it owns in fractional mode), read once
             T r[E + 1][3];
 #pragma unroll
             for (int e = 0; e < E + (FRAC ? 1 : 0); ++e)
 #pragma unroll
-                for (int k = 0; k < 3; ++k) r[e][k] = (t0 + f0 + e < Tn + (FRAC ? 1 : 0)) ? raw[(f0 + e) * 3 + k] : (T)0;
+                for (int k = 0; k < 3; ++k) r[e][k] = (FULL || t0 + f0 + e < Tn + (FRAC ? 1 : 0)) ? raw[(f0 + e) * 3 + k] : (T)0;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int64_t t = t0 + f0 + e;
                 double u[3] = {0.0, 0.0, 0.0};
-                if (t < Tn) {
+                if (FULL || t < Tn) {
                     if (FRAC) {
                         if (CONSTL) {
                             unwrapped_step_const<T>(r[e + 1], r[e], Lconst, u);
@@ -393,12 +407,16 @@ __global__ void __launch_bounds__(kUwThreads, 3) unwrap_cumsum_kernel(const T* _
         if (FRAC && tile > 0) {
             double pc[3] = {0.0, 0.0, 0.0};
             for (int j = tid; j < tile; j += NT) {
+                unsigned long long bits[3];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    unsigned long long bits;
-                    while ((bits = ld_l2_u64(tot_atom + j * 3 + c)) == kUwNotReady) __nanosleep(32);
-                    pc[c] += __longlong_as_double((long long)bits);
+                for (int c = 0; c < 3; ++c) bits[c] = (j == tid) ? early[c] : ld_l2_u64(tot_atom + j * 3 + c);
+                while (bits[0] == kUwNotReady || bits[1] == kUwNotReady || bits[2] == kUwNotReady) {
+                    __nanosleep(32);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) bits[c] = ld_l2_u64(tot_atom + j * 3 + c);  // three loads in flight
                 }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) pc[c] += __longlong_as_double((long long)bits[c]);
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -419,9 +437,17 @@ __global__ void __launch_bounds__(kUwThreads, 3) unwrap_cumsum_kernel(const T* _
             for (int i = 0; i < E; ++i) {
                 const int f = tid + i * NT;
                 const int64_t t = t0 + f;
-                if (t < pitch) orow[f] = (t < Tn) ? outs[c * TF + f] + carry : 0.0;
+                if (FULL)
+                    orow[f] = outs[c * TF + f] + carry;
+                else if (t < pitch)
+                    orow[f] = (t < Tn) ? outs[c * TF + f] + carry : 0.0;
             }
         }
+        };
+        if (t0 + TF <= Tn)
+            body(std::true_type{});
+        else
+            body(std::false_type{});
         // the next item overwrites outs / s_tot / s_carry only after its own first barrier; its raw buffer is the one
         // this item read, refilled by the issue() at the top of the NEXT iteration, after every thread passed the
         // barrier above
