@@ -506,7 +506,8 @@ static void plan_runs(const int32_t* lags, int K, int Tn, RunPlan& plan) {
         segs[h].taken = true;
         RunDesc rd{segs[h].k0, segs[h].d, segs[h].len, n_acc, (int)plan.chg.size(), 0, 1, 0};
         plan.slot.insert(plan.slot.end(), segs[h].slots.begin(), segs[h].slots.end());
-        if (segs[h].len >= kRunMinLen && segs[h].len <= kRunChainMaxSeg) {
+        static const int chain_max = [] { const char* e = getenv("KB2_RUNS_CHAIN_MAX"); return e ? atoi(e) : kRunChainMaxSeg; }();
+        if (segs[h].len >= kRunMinLen && segs[h].len <= chain_max) {
             int last_len = segs[h].len;  // length of the chain's last segment
             bool first = true;           // ... which is still the chain's first segment
             int shift = 0;
@@ -517,7 +518,7 @@ static void plan_runs(const int32_t* lags, int K, int Tn, RunPlan& plan) {
                 int found_shift = 0;
                 for (size_t n = h + 1; n < segs.size() && found == segs.size(); ++n) {
                     if (segs[n].taken) continue;
-                    if (segs[n].len > 1 && (segs[n].d != rd.delta || segs[n].len > kRunChainMaxSeg)) continue;
+                    if (segs[n].len > 1 && (segs[n].d != rd.delta || segs[n].len > chain_max)) continue;
                     for (int sh = -1; sh <= 1; sh += 2) {
                         if (shift != 0 && sh != shift) continue;
                         if ((long long)segs[n].k0 == last_lag + rd.delta + sh) {
