@@ -189,15 +189,20 @@ def _runs_plan(lib, lags_host, n_frames, device):
     key = (lags_host.tobytes(), int(n_frames), device.type, device.index)
     hit = _RUNS_PLANS.get(key)
     if hit is not None:
-        return hit
+        plan_host, plan_dev, uploaded = hit
+        if not uploaded.query():  # uploaded on another stream and still in flight
+            torch.cuda.current_stream(device).wait_event(uploaded)
+        return plan_host, plan_dev
     nbytes = lib.kb2_self_moments_runs_workspace_bytes(len(lags_host), int(n_frames))
     plan_host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     check(lib.kb2_self_moments_runs_plan_pack(lags_host.ctypes.data, len(lags_host), int(n_frames), plan_host.data_ptr()),
           'kb2_self_moments_runs_plan_pack')
     plan_dev = plan_host.to(device, non_blocking=True)
+    uploaded = torch.cuda.Event()
+    uploaded.record(torch.cuda.current_stream(device))
     if len(_RUNS_PLANS) >= 32:
         _RUNS_PLANS.pop(next(iter(_RUNS_PLANS)))
-    _RUNS_PLANS[key] = (plan_host, plan_dev)
+    _RUNS_PLANS[key] = (plan_host, plan_dev, uploaded)
     return plan_host, plan_dev
 
 
