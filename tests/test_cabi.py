@@ -47,6 +47,39 @@ def test_argument_errors_are_reported_without_a_gpu(lib_path):
     assert rc != 0 and b'kb2_cov_build' in lib.kb2_last_error()
     rc = lib.kb2_self_moments(None, 1, 1, 2, None, 1, 7, 0, None, None, None)
     assert rc != 0 and b'null pointer' in lib.kb2_last_error()
+    import numpy as np
+    lags = np.array([5, 3, 9], dtype=np.int32)  # not ascending
+    buf = np.zeros(lib.kb2_self_moments_runs_workspace_bytes(3, 100), dtype=np.uint8)
+    rc = lib.kb2_self_moments_runs_plan_pack(lags.ctypes.data, 3, 100, buf.ctypes.data)
+    assert rc != 0 and b'ascend' in lib.kb2_last_error()
+    lags = np.array([1, 50, 101], dtype=np.int32)  # beyond the trajectory
+    rc = lib.kb2_self_moments_runs_plan_pack(lags.ctypes.data, 3, 100, buf.ctypes.data)
+    assert rc != 0 and b'out of range' in lib.kb2_last_error()
+    rc = lib.kb2_spectral_prepare(1, 1, 1, 129, 1e16, 1, 1, 1, 1, 1, None, None)
+    assert rc != 0 and b'[1, 128]' in lib.kb2_last_error()
+    rc = lib.kb2_ensemble_sample(1, 2, 33, 10, 1, 0, 1, 1, 1, None)
+    assert rc != 0 and b'even' in lib.kb2_last_error()
+    rc = lib.kb2_unwrap_cumsum(1, 0, 0, 4, 10, 1, 1, 0, 1, 2, None, 0.0, 1, 9, None, None)  # odd pitch, no workspace
+    assert rc != 0
+    rc = lib.kb2_frames_to_atoms(1, 0, 4, 10, 1, 10, 0, 1, None)  # no room for the duplicated first frame
+    assert rc != 0 and b'do not fit' in lib.kb2_last_error()
+    rc = lib.kb2_molecule_centres(1, 7, 4, 10, 1, 1, 3, None, 1, None)
+    assert rc != 0 and b'dtype' in lib.kb2_last_error()
+
+
+def test_run_plan_is_host_only(lib_path):
+    """kb2_self_moments_runs_plan_pack needs no device: the packed plan of BASELINE configs[1]'s grid has one block with
+    one 99-lag progression and one single lag."""
+    import numpy as np
+    from kinisi_b200 import _lib
+    lib = _lib.load()
+    lags = np.linspace(1, 20000, 100, dtype=int).astype(np.int32)
+    n = lib.kb2_self_moments_runs_workspace_bytes(100, 20000)
+    buf = np.zeros(n, dtype=np.uint8)
+    assert lib.kb2_self_moments_runs_plan_pack(lags.ctypes.data, 100, 20000, buf.ctypes.data) == 0
+    header = buf[:32].view(np.int32)
+    assert header[0] == 100 and header[1] == 2 and header[3] == 0  # K, runs, no drift
+    assert header[2] > 80  # (run, strip) pairs
 
 
 def test_sass_has_tma_and_fp64(lib_path):
