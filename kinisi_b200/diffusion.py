@@ -134,6 +134,10 @@ class Bootstrap:
     def _dev(self, a):
         return engine.small_to_device(a, self._device, np.float64)
 
+    def _const(self, a):
+        """Upload of an array the kernels only read (content-addressed: see engine.const_to_device)."""
+        return engine.const_to_device(a, self._device, np.float64)
+
     def _self_sums(self, used, mask):
         """[len(used), 2] sums of d^2, d^4 over atoms x observations for the entries in `used`."""
         d = self._displacements
@@ -192,10 +196,10 @@ class Bootstrap:
         if len(used) == 0:
             self._stats_dev = torch.zeros((4, 0), dtype=torch.float64, device=self._device)
         else:
-            packed = self._dev(np.stack([np.asarray(cnt, dtype=np.float64), np.asarray(divisor, dtype=np.float64),
-                                         np.asarray(gcnt, dtype=np.float64)]))  # one upload: counts, divisors, NGP counts
+            packed = self._const(np.stack([np.asarray(cnt, dtype=np.float64), np.asarray(divisor, dtype=np.float64),
+                                           np.asarray(gcnt, dtype=np.float64)]))  # one upload: counts, divisors, NGP counts
             self._stats_dev = engine.moment_stats(main_sums, packed[0], packed[1], ngp_sums, packed[2])
-        self._dt = np.array([self._delta_t[i] for i in used], dtype=float)
+        self._dt = np.asarray(self._delta_t, dtype=float)[np.asarray(used, dtype=np.int64)] if len(used) else np.array([])
         self._n_o = self._n_o[:len(used)]  # diffusion.py:602
         self._euclidian_displacements = _LazyEuclidian(self._displacements, used, self._slice, self.dims)
 
@@ -432,8 +436,8 @@ class Bootstrap:
 
         diff_regime = np.argwhere(self._dt >= self._start_dt)[0][0]
 
-        xn = self._dev(np.stack([np.asarray(self._dt[diff_regime:], dtype=np.float64),
-                                 np.asarray(self._n_o[diff_regime:], dtype=np.float64)]))  # one upload: dt and n_o
+        xn = self._const(np.stack([np.asarray(self._dt[diff_regime:], dtype=np.float64),
+                                   np.asarray(self._n_o[diff_regime:], dtype=np.float64)]))  # one upload: dt and n_o
         x, n_o_dev = xn[0], xn[1]
         y = self._stats_dev[0, diff_regime:].contiguous()
         n_dt = x.numel()
@@ -595,9 +599,10 @@ class MSDBootstrap(Bootstrap):
         else:
             sizes = np.array([self._shape_of(i)[0] * self._shape_of(i)[1] for i in range(len(self._displacements))],
                              dtype=np.int64)
-        used = [int(i) for i in np.flatnonzero(sizes > 1)]  # diffusion.py:575
-        cnt = [float(sizes[i]) for i in used]
-        div = [float(n_o[i]) for i in used]  # diffusion.py:598: n_o is NOT strided by sub_sample_dt
+        used = np.flatnonzero(sizes > 1)  # diffusion.py:575
+        cnt = sizes[used].astype(np.float64)
+        div = np.asarray(n_o, dtype=np.float64)[used]  # diffusion.py:598: n_o is NOT strided by sub_sample_dt
+        used = used.tolist()
         if used:
             sums = self._self_sums(np.array(used), self._mask)
             self._finish(used, sums, cnt, div, sums, cnt)

@@ -391,6 +391,33 @@ def small_to_device(a, device, np_dtype=np.float64):
     return ring.put(a, device)
 
 
+_CONST_CACHE = {}  # (bytes, dtype, shape, device) -> (tensor, upload event); read-only inputs only
+
+
+def const_to_device(a, device, np_dtype=np.float64):
+    """As small_to_device for arrays the kernels only READ (index lists, grids, counts, lattices): identical content is
+    uploaded once and shared afterwards -- repeated analyses of trajectories of one shape upload nothing.  The caller must
+    not write to the returned tensor."""
+    a = np.ascontiguousarray(np.asarray(a, dtype=np_dtype))
+    if a.nbytes == 0 or a.nbytes > (64 << 10):
+        return small_to_device(a, device, np_dtype)
+    device = torch.device(device)
+    key = (a.tobytes(), a.dtype.str, a.shape, device.type, device.index)
+    hit = _CONST_CACHE.get(key)
+    if hit is not None:
+        t, uploaded = hit
+        if not uploaded.query():  # uploaded on another stream and still in flight
+            torch.cuda.current_stream(device).wait_event(uploaded)
+        return t
+    t = small_to_device(a, device, np_dtype)
+    uploaded = torch.cuda.Event()
+    uploaded.record(torch.cuda.current_stream(device))
+    if len(_CONST_CACHE) >= 256:
+        _CONST_CACHE.pop(next(iter(_CONST_CACHE)))
+    _CONST_CACHE[key] = (t, uploaded)
+    return t
+
+
 def to_device(a, device, dtype=None):
     """numpy / torch -> contiguous CUDA tensor (float32 stays float32 unless dtype is given)."""
     if isinstance(a, torch.Tensor):

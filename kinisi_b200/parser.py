@@ -23,6 +23,7 @@ from ._lib import MODE_DISPLACEMENT, MODE_FRACTIONAL
 
 
 _SIDE_STREAMS = {}
+_LATTICES = {}  # (lattice bytes, device) -> (lattices, inverses, upload event) on the device
 STAGE_BYTES = 32 << 20  # host->device copy granularity of the staged ingest (about 0.6 ms of PCIe time)
 
 
@@ -82,7 +83,18 @@ class Trajectory:
             # with a staged ingest the lattices are prepared on the ingest stream, like everything else of stage 1
             work = self._side[1] if self._host is not None else torch.cuda.current_stream(device)
             with torch.cuda.stream(work):
-                latt = engine.to_device(latt, device, torch.float64).reshape(-1, 3, 3)
+                cached = None
+                if latt_host is not None and latt_host.nbytes <= (64 << 10):
+                    # small lattices (the constant cell above all) and their inverses are kept on the device by content
+                    key = (np.ascontiguousarray(latt_host, dtype=np.float64).tobytes(), device.index)
+                    cached = _LATTICES.get(key)
+                if cached is not None:
+                    latt, inv, uploaded = cached
+                    if not uploaded.query():
+                        work.wait_event(uploaded)
+                else:
+                    latt = engine.to_device(latt, device, torch.float64).reshape(-1, 3, 3)
+                    inv = None
                 if latt.shape[0] == 1:
                     self.latt_stride = 0
                 elif latt.shape[0] != self.coords.shape[1]:
@@ -90,7 +102,13 @@ class Trajectory:
                 elif latt_host is not None and np.all(latt_host == latt_host[0]):
                     self.latt_stride = 0  # constant cell: every frame reads latt[0]
                 self.latt = latt
-                self.latt_inv = engine.invert_lattice(latt)
+                self.latt_inv = inv if inv is not None else engine.invert_lattice(latt)
+                if cached is None and latt_host is not None and latt_host.nbytes <= (64 << 10):
+                    uploaded = torch.cuda.Event()
+                    uploaded.record(work)
+                    if len(_LATTICES) >= 64:
+                        _LATTICES.pop(next(iter(_LATTICES)))
+                    _LATTICES[key] = (self.latt, self.latt_inv, uploaded)
                 if self._host is not None:
                     self._latt_event = torch.cuda.Event()
                     self._latt_event.record(work)
@@ -394,7 +412,7 @@ class Parser:
             self._build_displacement_staged(traj, indices, drift_indices)
         else:
             # one upload for both index lists
-            both = engine.small_to_device(np.concatenate([np.asarray(indices, dtype=np.int64).reshape(-1),
+            both = engine.const_to_device(np.concatenate([np.asarray(indices, dtype=np.int64).reshape(-1),
                                                           np.asarray(drift_indices, dtype=np.int64).reshape(-1)]), dev, np.int32)
             idx, fw_idx = both[:n_sel_local], both[n_sel_local:]
             self._drift = self._framework_mean(traj, drift_indices, fw_idx)
@@ -434,7 +452,7 @@ class Parser:
         n_fw = self._n_fw_global
         fw_sorted = np.sort(fw)
         with torch.cuda.stream(ingest):
-            idx_dev = engine.small_to_device(np.concatenate([fw_sorted, sel]), dev, np.int32)  # one upload for every block
+            idx_dev = engine.const_to_device(np.concatenate([fw_sorted, sel]), dev, np.int32)  # one upload for every block
             fw_dev, sel_dev = idx_dev[:n_fw_local], idx_dev[n_fw_local:]
             sums = None
             if n_fw > 0:
