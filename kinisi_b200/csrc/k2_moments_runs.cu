@@ -55,7 +55,7 @@ constexpr int kRunChainMaxSeg = 16;        // progressions longer than this are 
 constexpr int kRunPrefetch = 6;            // steps between the cp.async of a partner sample and its use (< kRunM)
 constexpr long long kRunBatchBytes = 24ll << 20;  // trajectory bytes of one atom batch (L2 is 126 MB)
 constexpr int kRunRingBytes = kRunM * 3 * 2 * 32 * 8;  // per warp: slot x component x {sample, neighbour} x lane
-constexpr int kRunMaxWarps = 8;
+
 constexpr int kRunMaxLags = 192;           // lags per launch: every warp keeps private accumulators [K][2] in shared memory
 
 struct RunDesc {
@@ -66,25 +66,29 @@ struct RunDesc {
 static_assert(sizeof(RunDesc) == 32, "RunDesc is read as two int4");
 
 // Warp-uniform position of a step in the drift pattern of its run.
+//
+// Lags k_i = k0 + i*D + shift * E_i, E_i = #{changes <= i}.  The PARTNER stream of a column is fixed for the whole run,
+// x[j + k0 + s*D + e_fix] with e_fix = max_i (shift * E_i); the ORIGIN of slot m for lag i = s - m is then
+// x[j + m*D + sigma_i], sigma_i = e_fix - shift * E_i >= 0: when the lag of a slot passes a change (at step c + m for the
+// change at lag index c) the slot takes the neighbouring origin, one frame down (shift = +1) or up (shift = -1).  So a
+// change costs one origin reload per step for M steps and no per-term work.  The origins [0, sigma_i) of lag i that no
+// column reaches are added by the strip that also adds the first-observation terms.
 struct DriftCursor {
-    int e;      // sample offset of the oldest lag of the window: shift * #{changes <= s - (M-1)}
-    int cnext;  // lag index of the next change not yet absorbed into e
+    int cnext;  // lag index of the change whose slots are being switched, or of the next one
     int ci;     // its position in the change list
     __device__ __forceinline__ void init(const int32_t* chg, int n) {
-        e = 0;
         ci = 0;
         cnext = n > 0 ? __ldg(chg) : 0x7fffffff;
     }
-    // at the start of step s: a change is absorbed once every lag of the window [s-(M-1), s] is at or past it
-    __device__ __forceinline__ void advance(int s, const int32_t* chg, int n, int shift) {
-        if (cnext <= s - (kRunM - 1)) {
-            e += shift;
+    // at the start of step s: a change is done once all M slots have switched (steps cnext .. cnext + M - 1)
+    __device__ __forceinline__ void advance(int s, const int32_t* chg, int n) {
+        if (s - cnext >= kRunM) {
             ++ci;
             cnext = ci < n ? __ldg(chg + ci) : 0x7fffffff;
         }
     }
-    // origins m <= mcut(s) pair with lags at or past the change inside the window: they use offset e + shift
-    __device__ __forceinline__ int mcut(int s) const { return cnext <= s ? s - cnext : -1; }
+    // the slot that switches at step s, or a value outside [0, M)
+    __device__ __forceinline__ int slot(int s) const { return s - cnext; }
 };
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
@@ -141,25 +145,26 @@ struct Column {
     int fetched;           // steps prefetched so far
     DriftCursor pf;        // drift position of the prefetch stream
 
-    // Prefetch the partner sample(s) of step `fetched`: offset pf.e and, while a change is inside the window, its
-    // neighbour pf.e + shift.
+    // Prefetch the partner sample of step `fetched` and, if a slot switches its origin in that step, the new origin
+    // (h = 1 of the ring slot): its address is the partner's plus a warp-uniform offset,
+    //   j + m*D + sigma - (j + k0 + e_fix + fetched*D) = sigma_after - k0 - e_fix - c*D   with m = fetched - c.
     static constexpr int H = DR ? 2 : 1;  // samples per (slot, component)
-    __device__ __forceinline__ void prefetch(int D, const int32_t* chg, int n_chg, int shift) {
+    __device__ __forceinline__ void prefetch(int D, const int32_t* chg, int n_chg, int shift, int k0, int e_fix) {
         double* dst = ring + (fetched % M) * (3 * H * 32);
+        if (0 <= rem_pf) {
+#pragma unroll
+            for (int c = 0; c < NDIM; ++c) cp_async8(dst + (c * H) * 32, pn[c]);
+        }
         if (DR) {
-            pf.advance(fetched, chg, n_chg, shift);
-            if (pf.e <= rem_pf) {
+            pf.advance(fetched, chg, n_chg);
+            const int ms = pf.slot(fetched);
+            if (ms >= 0 && ms < M) {
+                const int sigma_after = e_fix - shift * (pf.ci + 1);
+                const int ooff = sigma_after - k0 - e_fix - pf.cnext * D;  // < 0: the origin precedes the partner
+                if (ooff <= rem_pf) {
 #pragma unroll
-                for (int c = 0; c < NDIM; ++c) cp_async8(dst + (c * 2) * 32, pn[c] + pf.e);
-            }
-            if (pf.cnext <= fetched && pf.e + shift <= rem_pf) {
-#pragma unroll
-                for (int c = 0; c < NDIM; ++c) cp_async8(dst + (c * 2 + 1) * 32, pn[c] + pf.e + shift);
-            }
-        } else {
-            if (0 <= rem_pf) {
-#pragma unroll
-                for (int c = 0; c < NDIM; ++c) cp_async8(dst + c * 32, pn[c]);
+                    for (int c = 0; c < NDIM; ++c) cp_async8(dst + (c * 2 + 1) * 32, pn[c] + ooff);
+                }
             }
         }
 #pragma unroll
@@ -168,10 +173,22 @@ struct Column {
         ++fetched;
         cp_async_commit();
     }
+
+    // slot ms takes the origin staged at h = 1 of ring slot `rs`: M predicated loads straight into the slot's registers
+    // (a register cannot be indexed at run time; a switch is if-converted into twice as many predicated moves)
+    __device__ __forceinline__ void switch_origin(int ms, int rs) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            if (m == ms) {
+#pragma unroll
+                for (int c = 0; c < NDIM; ++c) o[c][m] = ring[((rs * 3 + c) * 2 + 1) * 32];
+            }
+        }
+    }
 };
 
 struct RunCtx {  // warp-uniform description of the current item
-    int D, L, acc_base, n_chg, shift;
+    int D, L, acc_base, n_chg, shift, k0, e_fix;
     const int32_t* chg;
 };
 
@@ -179,7 +196,8 @@ struct RunCtx {  // warp-uniform description of the current item
 // whose (step, origin) pairs are lags of the run in a static pattern:
 //   FIRST = false: all of them (s0 >= M, s0 + M <= L);
 //   FIRST = true:  s0 = 0 and L >= M, the triangular start: origin m joins at step m, only lag 0 completes.
-// DRIFT = false requires that no change index lies in the lags these steps touch (cur.cnext > s0 + M - 1).
+// DRIFT = false requires that no slot switches its origin in these steps (the previous change is done and
+// cur.cnext > s0 + M - 1).
 template <int NDIM, int M, int LG, bool FIRST, bool DRIFT, bool DR>
 __device__ __forceinline__ void run_block_interior(Column<NDIM, M, DR>& col, DriftCursor& cur, const RunCtx& rc, int s0,
                                                    MomentSmem& sm, double* wacc, int warp, int lane) {
@@ -187,26 +205,22 @@ __device__ __forceinline__ void run_block_interior(Column<NDIM, M, DR>& col, Dri
 #pragma unroll
     for (int u = 0; u < M; ++u) {
         cp_async_wait<kRunPrefetch - 1>();
-        int mc = -1;
-        if (DRIFT) {
-            cur.advance(s0 + u, rc.chg, rc.n_chg, rc.shift);
-            mc = cur.mcut(s0 + u);
-        }
-        double P[3], Q[3];
+        double P[3];
 #pragma unroll
-        for (int c = 0; c < NDIM; ++c) {
-            P[c] = col.ring[((u * 3 + c) * (DR ? 2 : 1)) * 32];
-            if (DRIFT) Q[c] = col.ring[((u * 3 + c) * 2 + 1) * 32];
+        for (int c = 0; c < NDIM; ++c) P[c] = col.ring[((u * 3 + c) * (DR ? 2 : 1)) * 32];
+        if (DRIFT) {
+            cur.advance(s0 + u, rc.chg, rc.n_chg);
+            const int ms = cur.slot(s0 + u);
+            if (ms >= 0 && ms < M) col.switch_origin(ms, u);  // warp-uniform
         }
-        col.prefetch(rc.D, rc.chg, rc.n_chg, rc.shift);
+        col.prefetch(rc.D, rc.chg, rc.n_chg, rc.shift, rc.k0, rc.e_fix);
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             if (FIRST && m > u) continue;
             double d2 = 0.0;
 #pragma unroll
             for (int c = 0; c < NDIM; ++c) {
-                const double partner = (DRIFT && m <= mc) ? Q[c] : P[c];  // warp-uniform select
-                const double d = partner - col.o[c][m];
+                const double d = P[c] - col.o[c][m];
                 d2 = fma(d, d, d2);
             }
             col.A1[(u - m + M) % M] += d2;
@@ -232,30 +246,26 @@ template <int NDIM, int M, int LG, bool DR>
 __device__ __forceinline__ void run_step_generic(Column<NDIM, M, DR>& col, DriftCursor& cur, const RunCtx& rc, int s,
                                                  MomentSmem& sm, double* wacc, int warp, int lane) {
     cp_async_wait<kRunPrefetch - 1>();
-    int mc = -1;
-    if (DR) {
-        cur.advance(s, rc.chg, rc.n_chg, rc.shift);
-        mc = cur.mcut(s);
-    }
-    double P[3], Q[3];
+    double P[3];
 #pragma unroll
-    for (int c = 0; c < NDIM; ++c) {
-        P[c] = col.ring[(((s % M) * 3 + c) * (DR ? 2 : 1)) * 32];
-        Q[c] = DR ? col.ring[(((s % M) * 3 + c) * 2 + 1) * 32] : 0.0;
+    for (int c = 0; c < NDIM; ++c) P[c] = col.ring[(((s % M) * 3 + c) * (DR ? 2 : 1)) * 32];
+    if (DR) {
+        cur.advance(s, rc.chg, rc.n_chg);
+        const int ms = cur.slot(s);
+        if (ms >= 0 && ms < M) col.switch_origin(ms, s % M);  // warp-uniform
     }
-    col.prefetch(rc.D, rc.chg, rc.n_chg, rc.shift);
-    const bool ok_p = (DR ? cur.e : 0) <= col.rem, ok_q = DR && (cur.e + rc.shift <= col.rem);
+    col.prefetch(rc.D, rc.chg, rc.n_chg, rc.shift, rc.k0, rc.e_fix);
+    const bool ok_p = 0 <= col.rem;
 #pragma unroll
     for (int m = 0; m < M; ++m) {
         if ((unsigned)(s - m) < (unsigned)rc.L) {  // lag s - m belongs to the run: warp-uniform
-            const bool hi = DR && m <= mc;          // warp-uniform
             double d2 = 0.0;
 #pragma unroll
             for (int c = 0; c < NDIM; ++c) {
-                const double d = (hi ? Q[c] : P[c]) - col.o[c][m];
+                const double d = P[c] - col.o[c][m];
                 d2 = fma(d, d, d2);
             }
-            d2 = (hi ? ok_q : ok_p) ? d2 : 0.0;
+            d2 = ok_p ? d2 : 0.0;
             col.A1[(M - m) % M] += d2;
             col.A2[(M - m) % M] = fma(d2, d2, col.A2[(M - m) % M]);
         }
@@ -328,26 +338,44 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
         rc.chg = chg + rd5.x;
         rc.n_chg = rd5.y;
         rc.shift = rd5.z;
+        rc.k0 = k0;
+        rc.e_fix = rc.shift > 0 ? rc.n_chg : 0;  // max_i shift * E_i
         const int D = rc.D, L = rc.L;
         const double* row[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) row[c] = dc + ((size_t)atom * 3 + comp[c < NDIM ? c : 0]) * pitch;
 
-        // the extra first observation dc[a][k-1] of every lag of the run (kinisi/parser.py:209)
+        // the extra first observation dc[a][k-1] of every lag of the run (kinisi/parser.py:209), and the origins
+        // [0, sigma_i) of a drifting run that no column reaches (see DriftCursor)
         if (pr.y == 0) {
 #pragma unroll 1
             for (int i = lane; i < L; i += 32) {
                 int e = 0;
                 for (int j = 0; j < rc.n_chg; ++j) e += (__ldg(rc.chg + j) <= i) ? rc.shift : 0;
-                const int p = k0 + i * D + e - 1;
-                double d2 = 0.0;
+                const int k = k0 + i * D + e;
+                double s1 = 0.0, s2 = 0.0;
+                {
+                    double d2 = 0.0;
 #pragma unroll
-                for (int c = 0; c < NDIM; ++c) {
-                    const double d = __ldg(row[c] + p);
-                    d2 = fma(d, d, d2);
+                    for (int c = 0; c < NDIM; ++c) {
+                        const double d = __ldg(row[c] + k - 1);
+                        d2 = fma(d, d, d2);
+                    }
+                    s1 = d2;
+                    s2 = d2 * d2;
                 }
-                wacc[2 * (rc.acc_base + i)] += d2;  // one lane per lag
-                wacc[2 * (rc.acc_base + i) + 1] += d2 * d2;
+                for (int jj = 0; jj < rc.e_fix - e && jj + k < Tn; ++jj) {
+                    double d2 = 0.0;
+#pragma unroll
+                    for (int c = 0; c < NDIM; ++c) {
+                        const double d = __ldg(row[c] + jj + k) - __ldg(row[c] + jj);
+                        d2 = fma(d, d, d2);
+                    }
+                    s1 += d2;
+                    s2 = fma(d2, d2, s2);
+                }
+                wacc[2 * (rc.acc_base + i)] += s1;  // one lane per lag
+                wacc[2 * (rc.acc_base + i) + 1] += s2;
             }
             __syncwarp();
         }
@@ -355,15 +383,13 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
         const int g = pr.y * kRunCols + lane;  // column: tile q = g / D, offset t = g % D
         const int q = g / D, t = g - q * D;
         const long long j0 = (long long)q * M * D + t;
-        const long long p0 = j0 + k0;  // undrifted partner index of step 0
-        // steps in which this lane has at least one / only valid partners, whatever the drift (|e| <= n_chg)
-        const int e_lo = min(0, rc.shift * rc.n_chg), e_hi = max(0, rc.shift * rc.n_chg);
-        int n_any = 0, n_all = 0;
-        if (p0 + e_lo < Tn) n_any = (int)min((long long)(M + L - 1), (Tn - 1 - p0 - e_lo) / D + 1);
-        if (p0 + e_hi < Tn) n_all = (int)min((long long)(M + L - 1), (Tn - 1 - p0 - e_hi) / D + 1);
-        const int wmax = __reduce_max_sync(0xffffffffu, n_any);
+        const long long p0 = j0 + k0 + rc.e_fix;  // partner index of step 0 (the partner stream never drifts)
+        // steps in which this lane has a valid partner
+        int n_ok = 0;
+        if (p0 < Tn) n_ok = (int)min((long long)(M + L - 1), (Tn - 1 - p0) / D + 1);
+        const int wmax = __reduce_max_sync(0xffffffffu, n_ok);
         if (wmax == 0) continue;  // warp-uniform
-        const int wmin = __reduce_min_sync(0xffffffffu, n_all);
+        const int wmin = __reduce_min_sync(0xffffffffu, n_ok);
 
         col.fetched = 0;
         col.pf.init(rc.chg, rc.n_chg);
@@ -372,10 +398,10 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
 #pragma unroll
         for (int c = 0; c < NDIM; ++c) col.pn[c] = row[c] + p0;
 #pragma unroll
-        for (int f = 0; f < kRunPrefetch; ++f) col.prefetch(D, rc.chg, rc.n_chg, rc.shift);
+        for (int f = 0; f < kRunPrefetch; ++f) col.prefetch(D, rc.chg, rc.n_chg, rc.shift, rc.k0, rc.e_fix);
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            const long long jm = j0 + (long long)m * D;
+            const long long jm = j0 + (long long)m * D + rc.e_fix;  // sigma of lag 0 is e_fix
 #pragma unroll
             for (int c = 0; c < NDIM; ++c) col.o[c][m] = (jm < Tn) ? __ldg(row[c] + jm) : 0.0;
             col.A1[m] = col.A2[m] = 0.0;
@@ -389,6 +415,7 @@ __global__ void __launch_bounds__(32 * WARPS, 2)
         int s = 0;
 #pragma unroll 1
         while (s < work_steps) {
+            if (DR) cur.advance(s, rc.chg, rc.n_chg);  // (idempotent) so that the dispatch below sees the current change
             if ((s % M) == 0 && s + M <= full && (s > 0 || cur.cnext > M - 1)) {
                 if (s == 0)
                     run_block_interior<NDIM, M, LG, true, false, DR>(col, cur, rc, 0, sm, wacc, warp, lane);
