@@ -24,10 +24,9 @@
 //
 // Drift.  np.linspace(..., dtype=int) truncates: the spacing is D most of the time and D+1 (or D-1) every so often
 // (every 11th lag at 100,000 frames / 100 lags).  Such a grid is ONE run with drift, k_i = k0 + i*D + e_i, e_i
-// changing by delta = +-1 at a few lag indices at least M apart.  The partner of origin m at step s is then
-// x[p_s + e_(s-m)]: while a change is inside the M-lag window the step needs the two neighbouring samples
-// p_s + e and p_s + e + delta, and origin m takes the second one iff m <= s - (change index).  That is a
-// warp-uniform select per term; everything else is unchanged.
+// changing by delta = +-1 at a few lag indices at least M apart.  The partner stream of a column stays where it is,
+// x[j + k0 + s*D + e_fix]; what moves is the ORIGIN of a slot, by one frame, when the lag of that slot passes a change
+// (see DriftCursor): one origin reload per step for the M steps after a change, nothing per term.
 //
 // The host splits the lag grid into arithmetic runs (greedy cover; a lag that fits no run of >= 3 becomes a run of
 // one) and then chains runs that continue each other's progression with a one-sample shift into drift runs.  Work items are (run, 32-column strip, atom); every warp of the persistent CTAs pulls its own items from
