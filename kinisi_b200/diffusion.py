@@ -154,7 +154,7 @@ class Bootstrap:
                     sums = part if sums is None else sums.add_(part)
             else:
                 sums = torch.zeros((len(used), 2), dtype=torch.float64, device=self._device)
-            if dist.active():
+            if d.distributed:
                 dist.allreduce_sum_(sums)
             if not np.array_equal(order, np.arange(len(order))):
                 inv = np.empty_like(order)
@@ -167,7 +167,7 @@ class Bootstrap:
                 d[i], self._device, torch.float64)
             rows.append(engine.disp_moments(arr, mask)[:2])
         sums = torch.stack(rows)
-        if self._lazy and dist.active():
+        if self._lazy and d.distributed:
             dist.allreduce_sum_(sums)
         return sums
 
@@ -180,7 +180,7 @@ class Bootstrap:
                 S = engine.atom_sum(d.dc, w)
             else:
                 S = torch.zeros((3, d.dc.shape[2]), dtype=torch.float64, device=self._device)
-            if dist.active():
+            if d.distributed:
                 dist.allreduce_sum_(S)
             return engine.self_moments(S.unsqueeze(0), d.n_frames, d.lags[used], coll_mask)
         w = None if weights is None else self._dev(weights)

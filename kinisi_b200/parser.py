@@ -264,8 +264,10 @@ class LazyDisplacements:
     kernels never do that.
     """
 
-    def __init__(self, dc, n_frames, lags, n_atoms_global=None, stride=1, ready=None):
+    def __init__(self, dc, n_frames, lags, n_atoms_global=None, stride=1, ready=None, distributed=False):
         self._dc = dc  # [n_local_atoms, 3, pitch] float64 CUDA
+        # True: dc holds this rank's shard of the atoms; sums over atoms are all-reduced (set by a distributed Parser)
+        self.distributed = bool(distributed) and dist.active()
         # staged ingest: [(row0, row1, event)] -- rows [row0, row1) of dc are valid once the event has fired
         self._ready = list(ready) if ready else []
         self.n_frames = int(n_frames)
@@ -310,7 +312,8 @@ class LazyDisplacements:
 
     def __getitem__(self, i):
         if isinstance(i, slice):
-            return LazyDisplacements(self._dc, self.n_frames, self.lags[i], self.n_atoms_global, ready=self._ready)
+            return LazyDisplacements(self._dc, self.n_frames, self.lags[i], self.n_atoms_global, ready=self._ready,
+                                     distributed=self.distributed)
         k = int(self.lags[i])
         x = self.dc[:, :, :self.n_frames]
         first = x[:, :, k - 1:k]
@@ -323,7 +326,8 @@ class LazyDisplacements:
     def stacked_with(self, others):
         """`Analyzer._stack_trajectories` (kinisi/analyzer.py:274-290): more atoms, same lags."""
         dc = torch.cat([self.dc] + [o.dc for o in others], dim=0)
-        return LazyDisplacements(dc, self.n_frames, self.lags, self.n_atoms_global + sum(o.n_atoms_global for o in others))
+        return LazyDisplacements(dc, self.n_frames, self.lags, self.n_atoms_global + sum(o.n_atoms_global for o in others),
+                                 distributed=self.distributed)
 
 
 class Parser:
@@ -617,17 +621,20 @@ class Parser:
         n_samples = n_atoms * time_intervals[-1] / time_intervals[kept]  # parser.py:221
         if self.sampling == 'single-origin':
             # parser.py:203: entry i is the single frame dc[:, i] (indexed by grid position, not by lag)
-            disp_3d = SingleOriginDisplacements(drift_corrected, n_frames, kept, n_atoms, ready=getattr(self, '_dc_ready', None))
+            disp_3d = SingleOriginDisplacements(drift_corrected, n_frames, kept, n_atoms, ready=getattr(self, '_dc_ready', None),
+                                                distributed=getattr(self, '_distributed', False))
         else:
-            disp_3d = LazyDisplacements(drift_corrected, n_frames, time_intervals[kept], n_atoms, ready=getattr(self, '_dc_ready', None))
+            disp_3d = LazyDisplacements(drift_corrected, n_frames, time_intervals[kept], n_atoms, ready=getattr(self, '_dc_ready', None),
+                                        distributed=getattr(self, '_distributed', False))
         return delta_t, disp_3d, np.array(n_samples, dtype=float)
 
 
 class SingleOriginDisplacements(LazyDisplacements):
     """`sampling='single-origin'` (kinisi/parser.py:202-206): entry i is `dc[:, i:i+1]`."""
 
-    def __init__(self, dc, n_frames, frames, n_atoms_global=None, ready=None):
-        super().__init__(dc, n_frames, np.ones(len(frames), dtype=np.int64), n_atoms_global, ready=ready)
+    def __init__(self, dc, n_frames, frames, n_atoms_global=None, ready=None, distributed=False):
+        super().__init__(dc, n_frames, np.ones(len(frames), dtype=np.int64), n_atoms_global, ready=ready,
+                         distributed=distributed)
         self.frames = np.asarray(frames, dtype=np.int64)
 
     def shape_of(self, i):
@@ -638,7 +645,8 @@ class SingleOriginDisplacements(LazyDisplacements):
 
     def __getitem__(self, i):
         if isinstance(i, slice):
-            return SingleOriginDisplacements(self._dc, self.n_frames, self.frames[i], self.n_atoms_global, ready=self._ready)
+            return SingleOriginDisplacements(self._dc, self.n_frames, self.frames[i], self.n_atoms_global, ready=self._ready,
+                                             distributed=self.distributed)
         f = int(self.frames[i])
         return self.dc[:, :, f:f + 1].permute(0, 2, 1).contiguous().cpu().numpy()
 
