@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KB2_ABI_VERSION 3
+#define KB2_ABI_VERSION 4
 
 /* coordinate element types */
 #define KB2_F32 0
@@ -227,6 +227,30 @@ int kb2_mvn_loglike(const double* theta, int n_walkers, int ndim, const double* 
 size_t kb2_sampler_workspace_bytes(int n_steps, int n_walkers);
 int kb2_ensemble_sample(const double* gls, int ndim, int n_walkers, int n_steps, const double* logdet_term,
                         uint64_t seed, void* workspace, double* chain, double* logp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * `bootstrap=True`: the resampled means of diffusion.py:258-289, 783-801.
+ * ------------------------------------------------------------------------------------------- */
+/* The population of one lag from the cumulative displacements (the array d_squared of diffusion.py:574, without the
+ * list of parser.py:205-207): out[a * (n_frames - lag + 1) + m] = |dc[a][lag - 1 + m] - dc[a][m - 1]|^2 over dim_mask,
+ * the m = 0 entry being the first-observation term |dc[a][lag - 1]|^2.  With n_atoms = 1 on the atom sum of
+ * kb2_atom_sum this is coll_motion (diffusion.py:659, 751). */
+int kb2_lag_squares(const double* dc, int n_atoms, int n_frames, int64_t pitch, int lag, int dim_mask, double* out,
+                    void* stream);
+
+/* The same populations from ONE materialised displacement array disp[n_atoms][n_obs][3] (an entry of disp_3d):
+ * collective == 0: out[a * n_obs + j] = |disp[a][j]|^2 over dim_mask (diffusion.py:574);
+ * collective != 0: out[j] = |sum_a w_a disp[a][j]|^2 over dim_mask (diffusion.py:659, 751; w == NULL: unit weights). */
+int kb2_disp_squares(const double* disp, int n_atoms, int n_obs, int dim_mask, const double* w, int collective,
+                     double* out, void* stream);
+
+/* _bootstrap (diffusion.py:783-801): means[i] = mean of n_draws values drawn with replacement from
+ * values[n_values], for the resamples first_resample + i, i < n_resamples.  Draw d of resample r takes the index
+ * floor(u * n_values / 2^64) with u the 64-bit half (d & 1) of Philox4x32-10(counter {d >> 1 (64 bit), r, stream_id},
+ * key seed): a pure function of its arguments, so a later call continues the sequence of an earlier one
+ * (sample_until_normal, diffusion.py:258-289) and the same seed reproduces the same bits. */
+int kb2_resample_means(const double* values, int64_t n_values, int64_t n_draws, int n_resamples, int first_resample,
+                       uint64_t seed, int stream_id, double* means, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): a dependent-free DFMA loop and a streaming copy, to measure the

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, 'libkinisi_b200.so')
 
 F32, F64 = 0, 1
 MODE_FRACTIONAL, MODE_DISPLACEMENT = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # name -> (restype, argtypes); mirrors include/kinisi_b200.h one to one
 SIGNATURES = {
@@ -49,6 +49,9 @@ SIGNATURES = {
     'kb2_sampler_workspace_bytes': (c_size_t, [c_int, c_int]),
     'kb2_ensemble_sample': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_uint64, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    'kb2_lag_squares': (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    'kb2_disp_squares': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    'kb2_resample_means': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_uint64, c_int, c_void_p, c_void_p]),
     'kb2_fp64_peak': (c_int, [c_int, c_int, c_void_p, c_void_p]),
     'kb2_stream_copy': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
 }

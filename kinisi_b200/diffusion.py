@@ -8,9 +8,10 @@ behaviour; the arithmetic runs in the sm_100a kernels behind include/kinisi_b200
 displacement list is never materialised) or a plain list of `[atom, observation, axis]` arrays (the
 reference's seam, kinisi/diffusion.py:552-564; each entry is reduced by one kernel).
 
-Not provided (off the default path): `bootstrap=True` resampling (diffusion.py:258-289,
-783-835) and `block=True` (pyblock).
+`bootstrap=True` (diffusion.py:258-289, 783-801) resamples on the device (csrc/k6_resample.cu).  Not provided
+(see DESIGN.md): `block=True`, which needs pyblock.
 """
+import warnings
 from typing import List, Union
 
 import numpy as np
@@ -62,6 +63,43 @@ class _LazyEuclidian:
 
     def __iter__(self):
         return (self[i] for i in range(len(self)))
+
+
+def _seed_from(random_state):
+    """64 seed bits for the device resampler, drawn from the caller's RandomState (numpy's global one when None, as
+    sklearn.utils.check_random_state does for the reference, kinisi/diffusion.py:799)."""
+    rs = np.random.mtrand._rand if random_state is None else random_state
+    w = rs.randint(0, 2**32, size=2, dtype=np.uint64)
+    return int(w[0]) | (int(w[1]) << 32)
+
+
+def _resample_until_normal(values, n_samples, n_resamples, max_resamples, alpha, seed):
+    """kinisi/diffusion.py:280-289 on a device population: n_resamples means, then 100 more at a time while
+    normaltest rejects and max_resamples is not reached.  The sequence is indexed by the resample number, so the
+    batches made ahead of the test (up to 1000 per launch) are the values one-hundred-at-a-time calls would give."""
+    from scipy.stats import normaltest
+    n_draws = int(n_samples)
+
+    def batch(first, count):
+        if n_draws < 1 or values.numel() == 0:
+            return np.full(count, np.nan)  # the mean of an empty resample
+        return engine.resample_means(values, n_draws, count, first, seed).cpu().numpy()
+
+    have = batch(0, int(n_resamples))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        p_value = normaltest(have)[1]
+        while p_value < alpha and have.size < max_resamples:
+            ahead = int(min(1000, 100 * -(-(max_resamples - have.size) // 100)))
+            extra = batch(have.size, ahead)
+            for u in range(0, ahead, 100):
+                have = np.concatenate([have, extra[u:u + 100]])
+                p_value = normaltest(have)[1]
+                if not (p_value < alpha and have.size < max_resamples):
+                    break
+    if have.size >= max_resamples:
+        warnings.warn("The maximum number of resamples has been reached, and the distribution is not yet normal.")
+    return Distribution(have)
 
 
 class Bootstrap:
@@ -124,12 +162,71 @@ class Bootstrap:
         """disp.shape[0] in the reference: the (global) number of atoms of entry 0."""
         return self._displacements.n_atoms_global if self._lazy else self._shape_of(0)[0]
 
-    def _reject_unsupported(self, bootstrap, block):
-        if bootstrap:
-            raise NotImplementedError('bootstrap=True (kinisi/diffusion.py:258-289) is not on the default '
-                                      'displacement-statistics path built here')
+    def _resampling(self, bootstrap, block, n_resamples, max_resamples, alpha, random_state):
+        """`bootstrap=True` is provided (device resampler, see sample_until_normal); `block=True` needs pyblock."""
         if block:
             raise NotImplementedError('block=True needs pyblock (kinisi/diffusion.py:584-595); not built here')
+        if bootstrap and self._lazy and self._displacements.distributed:
+            raise NotImplementedError('bootstrap=True resamples one population: gather the atoms on one rank first')
+        self._resample = (int(n_resamples), int(max_resamples), alpha, random_state) if bootstrap else None
+        self._atom_sum_cache = None
+
+    def _population(self, i, mask, weights=None, collective=False):
+        """Device array of the squared displacements of entry i: d_squared (kinisi/diffusion.py:574) or, collective,
+        coll_motion (:659, 751)."""
+        d = self._displacements
+        if self._lazy and not isinstance(d, SingleOriginDisplacements):
+            lag = int(d.lags[i])
+            if not collective:
+                return engine.lag_squares(d.dc, d.n_frames, lag, mask)
+            if self._atom_sum_cache is None:
+                self._atom_sum_cache = engine.atom_sum(d.dc, None if weights is None else self._dev(weights))
+            return engine.lag_squares(self._atom_sum_cache.unsqueeze(0), d.n_frames, lag, mask)
+        arr = d.device_entry(i) if isinstance(d, SingleOriginDisplacements) else engine.to_device(
+            d[i], self._device, torch.float64)
+        w = None if (weights is None or not collective) else self._dev(weights)
+        return engine.disp_squares(arr, mask, w, collective)
+
+    def _resample_entry(self, values, n_samples):
+        """The `if bootstrap:` block of kinisi/diffusion.py:578-583, 663-669, 755-761."""
+        n_resamples, max_resamples, alpha, random_state = self._resample
+        distro = _resample_until_normal(values, n_samples, n_resamples, max_resamples, alpha, _seed_from(random_state))
+        self._distributions.append(distro)
+        self._n_bootstrap = np.append(self._n_bootstrap, np.mean(distro.samples))
+        self._v_bootstrap = np.append(self._v_bootstrap, np.var(distro.samples, ddof=1))
+        self._s_bootstrap = np.append(self._s_bootstrap, np.std(distro.samples, ddof=1))
+
+    @staticmethod
+    def sample_until_normal(array: np.ndarray,
+                            n_samples: float,
+                            n_resamples: int,
+                            max_resamples: int,
+                            alpha: float = 1e-3,
+                            random_state: np.random.mtrand.RandomState = None) -> Distribution:
+        """
+        Resample from the distribution until a normal distribution is obtained or a maximum is reached
+        (kinisi/diffusion.py:258-289).  Every resample is the mean of int(n_samples) values drawn with replacement;
+        all resamples of a batch are made by one kernel launch (csrc/k6_resample.cu) from a counter-based generator
+        seeded from `random_state` (or numpy's global state), so a RandomState in the same state gives the same
+        samples, though not the values the reference's Mersenne-twister indices would give.
+
+        :param array: The array to sample from (numpy array or CUDA tensor).
+        :param n_samples: Number of samples.
+        :param n_resamples: Number of resamples to perform initially.
+        :param max_resamples: The maximum number of resamples to perform.
+        :param alpha: Level that the p-value of :py:func:`scipy.stats.normaltest` should be below for more
+            resamples to be drawn. Optional, default is :py:attr:`1e-3`.
+        :param random_state: A :py:attr:`RandomState` object to be used to ensure reproducibility.
+
+        :return: The resampled distribution.
+        """
+        engine.require_cuda()
+        if isinstance(array, torch.Tensor):
+            values = array.to(torch.float64).reshape(-1).contiguous()
+        else:
+            values = engine.to_device(np.asarray(array, dtype=np.float64).reshape(-1),
+                                      torch.device('cuda', torch.cuda.current_device()), torch.float64)
+        return _resample_until_normal(values, n_samples, n_resamples, max_resamples, alpha, _seed_from(random_state))
 
     def _dev(self, a):
         return engine.small_to_device(a, self._device, np.float64)
@@ -555,6 +652,10 @@ class Bootstrap:
             'n': self._n,
             's': self._s,
             'v': self._v,
+            'n_bootstrap': self._n_bootstrap,
+            's_bootstrap': self._s_bootstrap,
+            'v_bootstrap': self._v_bootstrap,
+            'distributions': [d.to_dict() for d in self._distributions] if len(self._distributions) else None,
             'sub_sample_dt': self._sub_sample_dt,
             'dimension': self._dimension,
             'ngp': self._ngp,
@@ -574,8 +675,10 @@ class MSDBootstrap(Bootstrap):
     :param disp_3d: The displacements (see :py:class:`Bootstrap`).
     :param n_o: Number of statistically independent observations of the MSD at each time interval.
     :param sub_sample_dt, dimension, progress: as in the reference.
-    :param bootstrap, block, n_resamples, max_resamples, alpha, random_state: accepted for signature
-        compatibility; `bootstrap=True` / `block=True` raise NotImplementedError.
+    :param bootstrap, n_resamples, max_resamples, alpha, random_state: `bootstrap=True` adds the resampled
+        distributions of the mean (`_distributions`, `_n_bootstrap`, `_v_bootstrap`, `_s_bootstrap`;
+        kinisi/diffusion.py:578-583), see :py:meth:`Bootstrap.sample_until_normal`.
+    :param block: `block=True` raises NotImplementedError (pyblock is not available).
     """
 
     def __init__(self,
@@ -592,7 +695,7 @@ class MSDBootstrap(Bootstrap):
                  random_state: np.random.mtrand.RandomState = None,
                  progress: bool = True):
         super().__init__(delta_t, disp_3d, n_o, sub_sample_dt, dimension)
-        self._reject_unsupported(bootstrap, block)
+        self._resampling(bootstrap, block, n_resamples, max_resamples, alpha, random_state)
         n_atoms = self._n_atoms()
         if self._lazy:
             sizes = n_atoms * self._displacements.n_obs_all()
@@ -606,6 +709,9 @@ class MSDBootstrap(Bootstrap):
         if used:
             sums = self._self_sums(np.array(used), self._mask)
             self._finish(used, sums, cnt, div, sums, cnt)
+            if self._resample is not None:
+                for i in used:
+                    self._resample_entry(self._population(i, self._mask), n_o[i])  # diffusion.py:579
         else:
             self._finish(used, None, cnt, div, None, cnt)
 
@@ -630,6 +736,9 @@ class _CollectiveBootstrap(Bootstrap):
             self_sums = self._self_sums(u, self._mask)
             coll = self._collective_sums(u, weights, coll_mask)
             self._finish(used, coll, m, div, self_sums, gcnt)
+            if self._resample is not None:
+                for i, n_samples in zip(used, div):  # diffusion.py:664, 756: n_o[i] / d_squared.shape[0]
+                    self._resample_entry(self._population(i, coll_mask, weights, collective=True), n_samples)
         else:
             self._finish(used, None, m, div, None, gcnt)
 
@@ -654,7 +763,7 @@ class MSTDBootstrap(_CollectiveBootstrap):
                  random_state: np.random.mtrand.RandomState = None,
                  progress: bool = True):
         super().__init__(delta_t, disp_3d, n_o, sub_sample_dt, dimension)
-        self._reject_unsupported(bootstrap, block)
+        self._resampling(bootstrap, block, n_resamples, max_resamples, alpha, random_state)
         self._run(n_o, None, self._mask)
 
 
@@ -682,7 +791,7 @@ class MSCDBootstrap(_CollectiveBootstrap):
                  random_state: np.random.mtrand.RandomState = None,
                  progress: bool = True):
         super().__init__(delta_t, disp_3d, n_o, sub_sample_dt, dimension)
-        self._reject_unsupported(bootstrap, block)
+        self._resampling(bootstrap, block, n_resamples, max_resamples, alpha, random_state)
         try:
             _ = len(ionic_charge)
             ionic_charge = np.asarray(ionic_charge, dtype=np.float64)

@@ -231,6 +231,39 @@ def disp_moments(disp, mask=7, weights=None, coll_mask=0):
     return out
 
 
+def lag_squares(dc, n_frames, lag, mask=7):
+    """The squared displacements of one lag, [n_atoms * (n_frames - lag + 1)], from a component-major displacement
+    array [n_atoms, 3, pitch] (first-observation term included); see kb2_lag_squares."""
+    lib = require_cuda()
+    out = torch.empty(dc.shape[0] * (n_frames - lag + 1), dtype=torch.float64, device=dc.device)
+    check(lib.kb2_lag_squares(dc.data_ptr(), dc.shape[0], n_frames, dc.shape[2], int(lag), mask, out.data_ptr(), _stream()),
+          'kb2_lag_squares')
+    _count()
+    return out
+
+
+def disp_squares(disp, mask=7, weights=None, collective=False):
+    """|disp[a][j]|^2 ([N * M]) or |sum_a w_a disp[a][j]|^2 ([M]) of one materialised array [N, M, 3]."""
+    lib = require_cuda()
+    n, m = disp.shape[0], disp.shape[1]
+    out = torch.empty(m if collective else n * m, dtype=torch.float64, device=disp.device)
+    check(lib.kb2_disp_squares(disp.data_ptr(), n, m, mask, _ptr(weights), int(bool(collective)), out.data_ptr(), _stream()),
+          'kb2_disp_squares')
+    _count()
+    return out
+
+
+def resample_means(values, n_draws, n_resamples, first_resample=0, seed=0, stream_id=0):
+    """[n_resamples] means of n_draws values drawn with replacement from `values`; see kb2_resample_means."""
+    lib = require_cuda()
+    out = torch.empty(n_resamples, dtype=torch.float64, device=values.device)
+    check(lib.kb2_resample_means(values.data_ptr(), values.numel(), int(n_draws), int(n_resamples), int(first_resample),
+                                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_id), out.data_ptr(), _stream()),
+          'kb2_resample_means')
+    _count()
+    return out
+
+
 def moment_stats(main_sums, cnt, divisor, ngp_sums, gcnt):
     lib = require_cuda()
     n = cnt.numel()

@@ -291,6 +291,83 @@ def raw_sums_streaming(dc_sel, lags, dimension='xyz', weights=None, collective=F
 
 
 # --------------------------------------------------------------------------------------------
+# bootstrap=True: resampled means
+# --------------------------------------------------------------------------------------------
+def bootstrap_means(array, n_samples, n_resamples, random_state=None):
+    """kinisi/diffusion.py:783-801 (`_bootstrap`).  The reference calls sklearn.utils.resample(values,
+    n_samples=int(n_samples), random_state=rs) per resample, which for replace=True takes
+    `rs.randint(0, len(values), size=(n,))` and indexes (scikit-learn, sklearn/utils/_indexing.py `resample`;
+    pinned bit for bit against the reference + scikit-learn 1.9 in tests/golden/resample_reference.npz)."""
+    rs = np.random.mtrand._rand if random_state is None else random_state
+    values = np.asarray(array).flatten()
+    return [float(np.mean(values[rs.randint(0, values.shape[0], size=(int(n_samples), ))])) for _ in range(n_resamples)]
+
+
+def sample_until_normal(array, n_samples, n_resamples, max_resamples, alpha=1e-3, random_state=None):
+    """kinisi/diffusion.py:258-289: resample, then add 100 at a time until scipy.stats.normaltest passes or
+    max_resamples is reached.  Returns (values, reached_max)."""
+    from scipy.stats import normaltest
+    values = bootstrap_means(array, n_samples, n_resamples, random_state)
+    p_value = normaltest(values)[1]
+    while p_value < alpha and len(values) < max_resamples:
+        values += bootstrap_means(array, n_samples, 100, random_state)
+        p_value = normaltest(values)[1]
+    return np.array(values), len(values) >= max_resamples
+
+
+_PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_PHILOX_W0, _PHILOX_W1 = 0x9E3779B9, 0xBB67AE85
+_U32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11), vectorised over uint64-held 32-bit words: the published
+    generator the device resampler draws from (no counterpart in the reference, whose indices come from numpy's
+    Mersenne twister; the two can only agree in distribution)."""
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & _U32 for c in (c0, c1, c2, c3))
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    for _ in range(10):
+        p0 = _PHILOX_M0 * c0
+        p1 = _PHILOX_M1 * c2
+        hi0, lo0 = p0 >> np.uint64(32), p0 & _U32
+        hi1, lo1 = p1 >> np.uint64(32), p1 & _U32
+        c0, c1, c2, c3 = (hi1 ^ c1 ^ np.uint64(k0)) & _U32, lo1, (hi0 ^ c3 ^ np.uint64(k1)) & _U32, lo0
+        k0, k1 = (k0 + _PHILOX_W0) & 0xFFFFFFFF, (k1 + _PHILOX_W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def _mulhi64(u, m):
+    """floor(u * m / 2^64) for uint64 arrays u and an integer m < 2^64, by 32-bit limbs."""
+    m = int(m)
+    ul, uh = u & _U32, u >> np.uint64(32)
+    ml, mh = np.uint64(m & 0xFFFFFFFF), np.uint64(m >> 32)
+    ll, lh, hl, hh = ul * ml, ul * mh, uh * ml, uh * mh
+    mid = (ll >> np.uint64(32)) + (lh & _U32) + (hl & _U32)
+    return hh + (lh >> np.uint64(32)) + (hl >> np.uint64(32)) + (mid >> np.uint64(32))
+
+
+def counter_resample_indices(n_values, n_draws, resample, seed, stream_id=0):
+    """The indices draw 0 .. n_draws - 1 of one resample take in kb2_resample_means (include/kinisi_b200.h): draw d
+    uses half (d & 1) of Philox4x32-10(counter {d >> 1 lo, d >> 1 hi, resample, stream_id}, key seed)."""
+    pairs = np.arange((n_draws + 1) // 2, dtype=np.uint64)
+    x = philox4x32_10(pairs & _U32, pairs >> np.uint64(32), np.full_like(pairs, resample), np.full_like(pairs, stream_id),
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    u = np.empty(2 * pairs.size, dtype=np.uint64)
+    u[0::2] = (x[1] << np.uint64(32)) | x[0]
+    u[1::2] = (x[3] << np.uint64(32)) | x[2]
+    return _mulhi64(u[:n_draws], n_values).astype(np.int64)
+
+
+def counter_resample_means(values, n_draws, n_resamples, first_resample=0, seed=0, stream_id=0):
+    """`_bootstrap` (kinisi/diffusion.py:783-801) with the counter-based indices above instead of numpy's."""
+    values = np.asarray(values, dtype=np.float64).flatten()
+    return np.array([
+        np.mean(values[counter_resample_indices(values.size, int(n_draws), first_resample + r, seed, stream_id)])
+        for r in range(n_resamples)
+    ])
+
+
+# --------------------------------------------------------------------------------------------
 # Stage 3: covariance + Bayesian regression
 # --------------------------------------------------------------------------------------------
 def populate_covariance_matrix(variances, n_samples):

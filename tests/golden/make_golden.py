@@ -233,7 +233,40 @@ def case_reference_kats():
     print('reference_kats ok', out['docs_msd'], out['docs_var_over_384'], out['docs_ngp'])
 
 
+def case_resample():
+    """`bootstrap=True` (kinisi/diffusion.py:258-289, 578-583, 783-801) run by the reference + scikit-learn with seeded
+    RandomStates, on the inputs of kinisi/tests/test_diffusion.py:86-103, 192-208, 451-466, 839-842."""
+    out = {}
+    out['bootstrap_arange'] = np.array(diffusion._bootstrap(np.arange(1, 100, 1), 200, 100, np.random.RandomState(0)))
+    d = diffusion.Bootstrap.sample_until_normal(np.arange(1, 10, 1), 5, 100, 100, random_state=np.random.RandomState(0))
+    out['until_normal_small'] = d.samples
+    rng = np.random.RandomState(5)
+    skewed = rng.exponential(size=(40, 25))**2
+    out['skewed_population'] = skewed
+    d = diffusion.Bootstrap.sample_until_normal(skewed, 7, 200, 2000, random_state=np.random.RandomState(1))
+    out['until_normal_skewed'] = d.samples
+    dt, disp_3d, n_o, _ = list_bootstrap_inputs()
+    for kind, cls, args in (('msd', diffusion.MSDBootstrap, ()), ('mstd', diffusion.MSTDBootstrap, ())):
+        b = cls(dt, disp_3d, *args, n_o, bootstrap=True, random_state=np.random.RandomState(0), progress=False)
+        out[f'{kind}_n_bootstrap'] = b._n_bootstrap
+        out[f'{kind}_v_bootstrap'] = b._v_bootstrap
+        out[f'{kind}_s_bootstrap'] = b._s_bootstrap
+        out[f'{kind}_sizes'] = np.array([x.size for x in b._distributions])
+        out[f'{kind}_first_distribution'] = b._distributions[0].samples
+        for k, v in boot_arrays(b).items():
+            out[f'{kind}_{k}'] = v
+    b = diffusion.MSCDBootstrap(dt, disp_3d, 1, n_o, bootstrap=True, random_state=np.random.RandomState(0), progress=False)
+    out['mscd_n_bootstrap'] = b._n_bootstrap
+    out['mscd_v_bootstrap'] = b._v_bootstrap
+    out['mscd_sizes'] = np.array([x.size for x in b._distributions])
+    np.savez_compressed(os.path.join(HERE, 'resample_reference.npz'), **out)
+    print('resample_reference ok', out['msd_sizes'], out['mstd_sizes'], out['until_normal_skewed'].size)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'resample':  # only the fixture added for SURVEY 8f-4
+        case_resample()
+        sys.exit(0)
     for name in ASE_CASES:
         case_ase(name, CHARGES12)
     case_parser_random()
@@ -241,3 +274,4 @@ if __name__ == '__main__':
     for name in REGRESS_CASES:
         case_regression(name)
     case_reference_kats()
+    case_resample()

@@ -25,7 +25,7 @@ def declared_symbols():
 def test_header_symbols_are_exported(lib_path):
     lib = ctypes.CDLL(lib_path)
     names = declared_symbols()
-    assert len(names) >= 19
+    assert len(names) >= 22
     for name in names:
         assert hasattr(lib, name), f'{name} is declared in include/kinisi_b200.h but not exported'
 
@@ -65,6 +65,14 @@ def test_argument_errors_are_reported_without_a_gpu(lib_path):
     assert rc != 0 and b'do not fit' in lib.kb2_last_error()
     rc = lib.kb2_molecule_centres(1, 7, 4, 10, 1, 1, 3, None, 1, None)
     assert rc != 0 and b'dtype' in lib.kb2_last_error()
+    rc = lib.kb2_lag_squares(1, 2, 10, 10, 11, 7, 1, None)
+    assert rc != 0 and b'out of range' in lib.kb2_last_error()
+    rc = lib.kb2_disp_squares(1, 2, 10, 0, None, 0, 1, None)
+    assert rc != 0 and b'dim_mask' in lib.kb2_last_error()
+    rc = lib.kb2_resample_means(1, 0, 5, 10, 0, 1, 0, 1, None)
+    assert rc != 0 and b'empty population' in lib.kb2_last_error()
+    rc = lib.kb2_resample_means(1, 10, 0, 10, 0, 1, 0, 1, None)
+    assert rc != 0 and b'n_draws' in lib.kb2_last_error()
 
 
 def test_run_plan_is_host_only(lib_path):

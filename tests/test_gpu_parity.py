@@ -442,6 +442,136 @@ def test_analyses_in_flight_on_two_streams(kb, monkeypatch):
         assert abs(b.flatchain[:, 0].mean() - fc[:, 0].mean()) < 0.5 * sd
         assert b.flatchain[:, 0].std() == pytest.approx(sd, rel=0.35)
 
+# ---------------------------------------------------------------------------------------------
+# bootstrap=True: the device resampler
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n_values,n_draws', [(1, 1), (9, 5), (1000, 2), (1000, 4097), (123457, 50001), (77, 2048)])
+def test_resample_means_match_the_counter_restatement(kb, n_values, n_draws):
+    """kb2_resample_means against the numpy restatement of the same counter-based draws: the indices are exact, the
+    means agree to the reordering of a float64 sum; batches continue each other and repeat bit for bit."""
+    rng = np.random.default_rng(n_values + n_draws)
+    values = rng.exponential(size=n_values)**2
+    dev = torch.from_numpy(values).cuda()
+    seed = 0x9E3779B97F4A7C15 ^ n_draws
+    got = kb.engine.resample_means(dev, n_draws, 12, 0, seed, 3).cpu().numpy()
+    want = ko.counter_resample_means(values, n_draws, 12, 0, seed, 3)
+    np.testing.assert_allclose(got, want, rtol=1e-13)
+    again = kb.engine.resample_means(dev, n_draws, 12, 0, seed, 3).cpu().numpy()
+    assert np.array_equal(got, again)
+    tail = kb.engine.resample_means(dev, n_draws, 5, 7, seed, 3).cpu().numpy()
+    assert np.array_equal(tail, got[7:])
+    other = kb.engine.resample_means(dev, n_draws, 12, 0, seed + 1, 3).cpu().numpy()
+    if n_values > 1:
+        assert not np.array_equal(other, got)
+    idx = ko.counter_resample_indices(n_values, n_draws, 4, seed, 3)
+    assert idx.min() >= 0 and idx.max() < n_values
+
+
+def test_resample_populations(kb):
+    """kb2_lag_squares / kb2_disp_squares against the reference's per-lag arrays (parser.py:205-207, diffusion.py:574, 659)."""
+    rng = np.random.default_rng(5)
+    dc = np.cumsum(rng.normal(size=(7, 300, 3)), axis=1)
+    dct = _device_dc(kb, dc)
+    w = rng.normal(size=7)
+    for lag in (1, 2, 37, 299, 300):
+        disp = ko.displacements_for_lag(dc, lag)
+        for mask, dims in ((7, [0, 1, 2]), (5, [0, 2]), (2, [1])):
+            want = np.sum(disp[:, :, dims]**2, axis=-1)
+            got = kb.engine.lag_squares(dct, 300, lag, mask).cpu().numpy()
+            np.testing.assert_allclose(got, want.flatten(), rtol=1e-13, atol=1e-300)
+            arr = torch.from_numpy(np.ascontiguousarray(disp)).cuda()
+            np.testing.assert_allclose(kb.engine.disp_squares(arr, mask).cpu().numpy(), want.flatten(), rtol=1e-14)
+            coll = np.sum(np.sum(disp * w[:, None, None], axis=0)[:, dims]**2, axis=-1)
+            wd = torch.from_numpy(w).cuda()
+            np.testing.assert_allclose(kb.engine.disp_squares(arr, mask, wd, True).cpu().numpy(), coll, rtol=1e-12)
+            S = kb.engine.atom_sum(dct, wd)
+            np.testing.assert_allclose(kb.engine.lag_squares(S.unsqueeze(0), 300, lag, mask).cpu().numpy(), coll, rtol=1e-11,
+                                       atol=1e-18)
+
+
+def test_sample_until_normal(kb, golden_dir):
+    """The reference's own tests of sample_until_normal (kinisi/tests/test_diffusion.py:83-103) and the distribution of
+    the resampled means against the reference's (tests/golden/resample_reference.npz, made with numpy's generator:
+    only the statistics can agree)."""
+    B = kb.diffusion.Bootstrap
+    rng = np.random.RandomState(42)
+    d1 = B.sample_until_normal(rng.normal(0, 1, size=2000), 50, 1000, 100000, random_state=np.random.RandomState(1))
+    assert d1.size == 1000  # test_diffusion.py:83-89: normal at the first test
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        a = B.sample_until_normal(np.arange(1, 10, 1), 5, 100, 100, random_state=np.random.RandomState(0))
+        b = B.sample_until_normal(np.arange(1, 10, 1), 5, 100, 100, random_state=np.random.RandomState(0))
+    assert any('maximum number of resamples' in str(x.message) for x in w)
+    assert a.size == 100 and np.array_equal(a.samples, b.samples)  # test_diffusion.py:91-103
+    g = load(golden_dir, 'resample_reference')
+    ref = g['until_normal_small']
+    assert abs(a.samples.mean() - 5.0) < 5 * ref.std() / 10 and 0.6 < a.samples.std() / ref.std() < 1.6
+    # a skewed population with few draws per resample: the loop adds hundreds until the test passes or the cap is hit
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter('always')
+        d = B.sample_until_normal(g['skewed_population'], 7, 200, 2000, random_state=np.random.RandomState(1))
+    ref = g['until_normal_skewed']
+    assert d.size == ref.size == 2000
+    pop = g['skewed_population']
+    assert abs(d.samples.mean() - pop.mean()) < 5 * pop.std() / np.sqrt(7 * 2000)
+    assert 0.8 < d.samples.std() / ref.std() < 1.25
+    assert 0.5 < np.percentile(d.samples, 97.5) / np.percentile(ref, 97.5) < 2.0
+
+
+def test_bootstrap_true(kb, golden_dir):
+    """`bootstrap=True` through the constructors (kinisi/diffusion.py:578-583, 663-669, 755-761), on the inputs of
+    kinisi/tests/test_diffusion.py:192-208, 451-466, against the reference's resampled moments."""
+    g = load(golden_dir, 'resample_reference')
+    dt, disp_3d, n_o, _ = list_bootstrap_inputs()
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter('always')
+        b1 = kb.diffusion.MSDBootstrap(dt, disp_3d, n_o, bootstrap=True, random_state=np.random.RandomState(0), progress=False)
+        b2 = kb.diffusion.MSDBootstrap(dt, disp_3d, n_o, bootstrap=True, random_state=np.random.RandomState(0), progress=False)
+        t1 = kb.diffusion.MSTDBootstrap(dt, disp_3d, n_o, bootstrap=True, random_state=np.random.RandomState(0), progress=False)
+        c1 = kb.diffusion.MSCDBootstrap(dt, disp_3d, 1, n_o, bootstrap=True, random_state=np.random.RandomState(0),
+                                        progress=False)
+    check_boot(b1, g, 'msd_')  # n, v, s, ngp are the unresampled ones (diffusion.py:596-600)
+    assert len(b1._distributions) == 10 and all(d.size >= 1000 for d in b1._distributions)
+    assert b1._distributions[-1].size == b2._distributions[-1].size
+    assert np.array_equal(b1._distributions[-1].samples, b2._distributions[-1].samples)  # test_diffusion.py:206-208
+    sizes = np.array([d.size for d in b1._distributions])
+    se = np.sqrt(g['msd_v_bootstrap'] / sizes)
+    assert np.all(np.abs(b1._n_bootstrap - b1.n) < 5 * se)
+    assert np.all(np.abs(b1._v_bootstrap / g['msd_v_bootstrap'] - 1) < 0.3)
+    np.testing.assert_allclose(b1._s_bootstrap**2, b1._v_bootstrap, rtol=1e-12)
+    d = b1.to_dict()
+    assert len(d['distributions']) == 10 and d['n_bootstrap'].shape == (10, )
+    # collective: 20..16 values with one draw per resample never look normal: the cap is reached, as in the reference
+    check_boot(t1, g, 'mstd_')
+    assert np.array_equal(np.array([d.size for d in t1._distributions]), g['mstd_sizes'])
+    assert np.all(np.abs(t1._n_bootstrap - t1.n) < 5 * np.sqrt(g['mstd_v_bootstrap'] / 10000))
+    assert np.all(np.abs(t1._v_bootstrap / g['mstd_v_bootstrap'] - 1) < 0.15)
+    assert np.array_equal(np.array([d.size for d in c1._distributions]), g['mscd_sizes'])
+    assert np.all(np.abs(c1._v_bootstrap / g['mscd_v_bootstrap'] - 1) < 0.15)
+
+
+def test_bootstrap_true_fused_path_equals_list_seam(kb):
+    """From the parser's lazy sequence the populations come straight from the cumulative displacements
+    (kb2_lag_squares): same values in the same order as the materialised list, hence the same resamples."""
+    rng = np.random.default_rng(2)
+    dc = np.cumsum(rng.normal(scale=0.1, size=(24, 400, 3)), axis=1)
+    dc[:, 0] = 0.0
+    charges = np.where(np.arange(24) % 2, 1.0, -1.0)
+    p = kb.parser.Parser(dc, np.arange(24), [], 1.0, 1, n_steps=12, progress=False)
+    listed = [np.asarray(d) for d in p.disp_3d]
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter('always')
+        for cls, args in ((kb.diffusion.MSDBootstrap, ()), (kb.diffusion.MSTDBootstrap, ()),
+                          (kb.diffusion.MSCDBootstrap, (charges, ))):
+            kw = dict(bootstrap=True, n_resamples=300, max_resamples=1000, progress=False)
+            a = cls(p.delta_t, p.disp_3d, *args, p._n_o, random_state=np.random.RandomState(7), **kw)
+            b = cls(p.delta_t, listed, *args, p._n_o, random_state=np.random.RandomState(7), **kw)
+            assert len(a._distributions) == len(b._distributions) == a.n.size
+            for x, y in zip(a._distributions, b._distributions):
+                assert x.size == y.size
+                np.testing.assert_allclose(x.samples, y.samples, rtol=1e-9)
+            np.testing.assert_allclose(a._n_bootstrap, a.n, rtol=0.2)
+
 
 def test_identical_trajectories_stack(kb):
     """dtype='identical' (kinisi/analyzer.py:111-116, 274-290): more atoms, n_o summed."""

@@ -163,3 +163,44 @@ def test_molecule_centres_reference_kat():
     wrap = np.array([[0.95, 0.5, 0.5], [0.05, 0.5, 0.5]])[:, None, :]
     c = ko.molecule_centres(wrap, [[0, 1]])[0, 0]
     assert min(c[0], 1 - c[0]) < 1e-12 and abs(c[1] - 0.5) < 1e-12
+
+
+def test_resampling_restatement_is_pinned_to_the_reference(golden_dir):
+    """`_bootstrap` / `sample_until_normal` (kinisi/diffusion.py:258-289, 783-801) restated in the oracle give, with the
+    same seeded RandomState, the values the reference + scikit-learn gave (tests/golden/make_golden.py resample)."""
+    from synth_inputs import list_bootstrap_inputs
+    g = np.load(os.path.join(golden_dir, 'resample_reference.npz'))
+    a = np.array(ko.bootstrap_means(np.arange(1, 100, 1), 200, 100, np.random.RandomState(0)))
+    assert np.array_equal(a, g['bootstrap_arange'])
+    v, capped = ko.sample_until_normal(np.arange(1, 10, 1), 5, 100, 100, random_state=np.random.RandomState(0))
+    assert capped and np.array_equal(v, g['until_normal_small'])
+    v, capped = ko.sample_until_normal(g['skewed_population'], 7, 200, 2000, random_state=np.random.RandomState(1))
+    assert capped and np.array_equal(v, g['until_normal_skewed'])
+    dt, disp_3d, n_o, _ = list_bootstrap_inputs()
+    rs = np.random.RandomState(0)
+    means = []
+    for i, d in enumerate(disp_3d):
+        v, _ = ko.sample_until_normal(np.sum(d**2, axis=-1), n_o[i], 1000, 10000, 1e-3, rs)
+        means.append(np.mean(v))
+        if i == 0:
+            assert np.array_equal(v, g['msd_first_distribution'])
+    assert np.array_equal(np.array(means), g['msd_n_bootstrap'])
+
+
+def test_counter_generator_known_answers():
+    """Philox4x32-10 against the known answers published with Random123 (kat_vectors: all-zero and all-one inputs)
+    and the multiply-high range reduction against exact integer arithmetic."""
+    x = ko.philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(v[0]) for v in x] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xffffffff
+    x = ko.philox4x32_10([f], [f], [f], [f], f, f)
+    assert [int(v[0]) for v in x] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    u = np.array([2**64 - 1, 12345678901234567890, 7, 2**63], dtype=np.uint64)
+    for m in (1, 10, 2**40 + 3, 2**63 + 5):
+        assert [int(a) for a in ko._mulhi64(u, m)] == [(int(a) * m) >> 64 for a in u]
+    idx = ko.counter_resample_indices(1000, 20001, 5, 1234567)
+    assert idx.size == 20001 and idx.min() >= 0 and idx.max() < 1000
+    counts = np.bincount(idx, minlength=1000)
+    assert abs(counts.mean() - 20.001) < 1e-9 and counts.std() < 6.0  # ~ Poisson(20)
+    m = ko.counter_resample_means(np.arange(10.0), 64, 400, seed=3)
+    assert abs(m.mean() - 4.5) < 5 * np.sqrt(8.25 / 64 / 400)
