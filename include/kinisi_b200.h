@@ -252,6 +252,17 @@ int kb2_disp_squares(const double* disp, int n_atoms, int n_obs, int dim_mask, c
 int kb2_resample_means(const double* values, int64_t n_values, int64_t n_draws, int n_resamples, int first_resample,
                        uint64_t seed, int stream_id, double* means, void* stream);
 
+/* `block=True` (diffusion.py:584-595, 670-681, 762-773): the statistics of pyblock.blocking.reblock (pyblock is not part
+ * of the reference tree; Flyvbjerg & Petersen, J. Chem. Phys. 91, 461 (1989)) for one population.  Level 0 is the data;
+ * level l + 1 holds the means of neighbouring pairs of level l, the last point of an odd level being dropped.  For
+ * each of the kb2_reblock_levels(n_values) levels (those with at least two points) stats[2 l] = sum of the level and
+ * stats[2 l + 1] = sum of squared deviations from its mean; the level has n_values >> l points.  stats holds
+ * 2 * (levels + 1) doubles (device), workspace kb2_reblock_workspace_bytes(n_values) bytes (device, 16-byte aligned,
+ * as `values`). */
+int kb2_reblock_levels(int64_t n_values);
+size_t kb2_reblock_workspace_bytes(int64_t n_values);
+int kb2_reblock(const double* values, int64_t n_values, double* workspace, double* stats, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): a dependent-free DFMA loop and a streaming copy, to measure the
  * FP64-pipe and HBM rooflines on the device the bench runs on.

@@ -52,6 +52,9 @@ SIGNATURES = {
     'kb2_lag_squares': (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'kb2_disp_squares': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'kb2_resample_means': (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_uint64, c_int, c_void_p, c_void_p]),
+    'kb2_reblock_levels': (c_int, [c_int64]),
+    'kb2_reblock_workspace_bytes': (c_size_t, [c_int64]),
+    'kb2_reblock': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'kb2_fp64_peak': (c_int, [c_int, c_int, c_void_p, c_void_p]),
     'kb2_stream_copy': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
 }

@@ -10,6 +10,8 @@
 //   index(d) = floor(u64(d) * M / 2^64),  u64 = one half of Philox4x32-10(counter = {d/2 lo, d/2 hi, r, stream}, key = seed)
 // (multiply-high range reduction: the bias is M / 2^64 < 2^-30 for any population that fits the device).
 // The per-thread partial sums are reduced in a fixed order: the same seed gives the same bits.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace kb2 {
@@ -111,9 +113,99 @@ __global__ void __launch_bounds__(kRsThreads) resample_means_kernel(const double
     }
 }
 
+// ---- block=True: Flyvbjerg-Petersen reblocking (kinisi/diffusion.py:584-595 via pyblock.blocking.reblock) ----------------
+// One launch per level: with the level's sum known (acc[0], finished by the previous launch), accumulate the sum of
+// squared deviations from the level's mean into acc[1] (the two-pass variance numpy.cov computes), write the next level
+// y[i] = (x[2i] + x[2i+1]) / 2 -- the last point of an odd level takes part in its statistics and is then dropped -- and
+// accumulate the next level's sum into acc[2].
+__global__ void __launch_bounds__(256) reblock_level_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ acc,
+                                                            double* __restrict__ y) {
+    __shared__ double s_part[2][8];
+    const double mean = acc[0] / (double)n;
+    const int64_t n_pairs = n >> 1;
+    double ssd = 0.0, sy = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_pairs; i += (int64_t)gridDim.x * 256) {
+        const double2 v = *reinterpret_cast<const double2*>(x + 2 * i);
+        const double da = v.x - mean, db = v.y - mean;
+        ssd = fma(da, da, ssd);
+        ssd = fma(db, db, ssd);
+        const double m = 0.5 * (v.x + v.y);
+        y[i] = m;
+        sy += m;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const double d = x[n - 1] - mean;
+        ssd = fma(d, d, ssd);
+    }
+    ssd = warp_sum(ssd);
+    sy = warp_sum(sy);
+    if ((threadIdx.x & 31) == 0) {
+        s_part[0][threadIdx.x >> 5] = ssd;
+        s_part[1][threadIdx.x >> 5] = sy;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s_part[threadIdx.x][i];
+        atomicAdd(acc + 1 + threadIdx.x, t);
+    }
+}
+
+__global__ void __launch_bounds__(256) reblock_sum_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ acc) {
+    __shared__ double s_part[8];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) s += x[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += s_part[i];
+        atomicAdd(acc, t);
+    }
+}
+
 }  // namespace kb2
 
 using namespace kb2;
+
+extern "C" int kb2_reblock_levels(int64_t n_values) {
+    int levels = 0;
+    for (int64_t n = n_values; n >= 2; n >>= 1) ++levels;
+    return levels;
+}
+
+extern "C" size_t kb2_reblock_workspace_bytes(int64_t n_values) {
+    size_t n = 0;
+    for (int64_t m = n_values; m >= 2; m >>= 1) n += (size_t)(((m >> 1) + 1) & ~(int64_t)1);
+    return sizeof(double) * (n + 2);
+}
+
+extern "C" int kb2_reblock(const double* values, int64_t n_values, double* workspace, double* stats, void* stream) {
+    KB2_CHECK(n_values >= 2, "kb2_reblock: at least two values are needed");
+    KB2_CHECK(values && workspace && stats, "kb2_reblock: null pointer");
+    KB2_CHECK(((uintptr_t)values & 15) == 0 && ((uintptr_t)workspace & 15) == 0, "kb2_reblock: values and workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int levels = kb2_reblock_levels(n_values);
+    KB2_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (levels + 1), st));
+    auto grid_for = [](int64_t n) { return (int)std::min<int64_t>(std::max<int64_t>((n + 255) / 256, 1), 148 * 8); };
+    reblock_sum_kernel<<<grid_for(n_values), 256, 0, st>>>(values, n_values, stats);
+    KB2_LAUNCH_CHECK();
+    const double* x = values;
+    double* y = workspace;
+    int64_t n = n_values;
+    for (int l = 0; l < levels; ++l) {
+        // stats[2l] = sum of level l, stats[2l + 1] = its sum of squared deviations, stats[2l + 2] = sum of level l + 1
+        reblock_level_kernel<<<grid_for(n >> 1), 256, 0, st>>>(x, n, stats + 2 * l, y);
+        KB2_LAUNCH_CHECK();
+        x = y;
+        y += ((n >> 1) + 1) & ~(int64_t)1;  // keep every level 16-byte aligned
+        n >>= 1;
+    }
+    return 0;
+}
 
 extern "C" int kb2_lag_squares(const double* dc, int n_atoms, int n_frames, int64_t pitch, int lag, int dim_mask,
                                double* out, void* stream) {

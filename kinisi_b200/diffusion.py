@@ -8,8 +8,8 @@ behaviour; the arithmetic runs in the sm_100a kernels behind include/kinisi_b200
 displacement list is never materialised) or a plain list of `[atom, observation, axis]` arrays (the
 reference's seam, kinisi/diffusion.py:552-564; each entry is reduced by one kernel).
 
-`bootstrap=True` (diffusion.py:258-289, 783-801) resamples on the device (csrc/k6_resample.cu).  Not provided
-(see DESIGN.md): `block=True`, which needs pyblock.
+`bootstrap=True` (diffusion.py:258-289, 783-801) resamples and `block=True` (diffusion.py:584-595) reblocks on the
+device (csrc/k6_resample.cu).
 """
 import warnings
 from typing import List, Union
@@ -163,13 +163,38 @@ class Bootstrap:
         return self._displacements.n_atoms_global if self._lazy else self._shape_of(0)[0]
 
     def _resampling(self, bootstrap, block, n_resamples, max_resamples, alpha, random_state):
-        """`bootstrap=True` is provided (device resampler, see sample_until_normal); `block=True` needs pyblock."""
+        """`bootstrap=True`: device resampler (see sample_until_normal); `block=True`: device reblocking (_blocked)."""
+        if (bootstrap or block) and self._lazy and self._displacements.distributed:
+            raise NotImplementedError('bootstrap=True / block=True work on one population: gather the atoms on one rank')
         if block:
-            raise NotImplementedError('block=True needs pyblock (kinisi/diffusion.py:584-595); not built here')
-        if bootstrap and self._lazy and self._displacements.distributed:
-            raise NotImplementedError('bootstrap=True resamples one population: gather the atoms on one rank first')
+            print('You are using the blocking method to estimate variances, please cite '
+                  'doi:10.1063/1.457480 and the pyblock pacakge.')  # the reference's message, diffusion.py:572-573
         self._resample = (int(n_resamples), int(max_resamples), alpha, random_state) if bootstrap else None
+        self._block = bool(block)
         self._atom_sum_cache = None
+
+    @staticmethod
+    def _blocked(values):
+        """Mean and variance of the mean by the blocking method (kinisi/diffusion.py:584-595; pyblock.blocking.reblock
+        and find_optimal_block restated -- pyblock itself is not available): every reblocking level is
+        reduced on the device (kb2_reblock); the optimal level is the smallest one whose block size B = 2^level
+        satisfies B^3 > 2 n (std_err(B) / std_err(0))^4, the last level when none does."""
+        n0 = values.numel()
+        acc = engine.reblock(values).cpu().numpy()
+        ndata = np.array([n0 >> l for l in range(acc.shape[0])], dtype=np.float64)
+        mean = acc[:, 0] / ndata
+        with np.errstate(all='ignore'):
+            std_err = np.sqrt(acc[:, 1] / (ndata - 1) / ndata)
+            ok = np.power(2.0, 3 * np.arange(acc.shape[0])) > 2 * n0 * (std_err / std_err[0])**4
+        lvl = int(np.flatnonzero(ok)[0]) if ok.any() else acc.shape[0] - 1
+        return mean[lvl], std_err[lvl]**2
+
+    def _apply_blocking(self, populations):
+        """Replace n, v, s by the blocked estimates (the `if block:` branch; the NGP stays, diffusion.py:600)."""
+        est = np.array([self._blocked(v) for v in populations], dtype=np.float64).reshape(-1, 2)
+        rows = np.stack([est[:, 0], est[:, 1], np.sqrt(est[:, 1])])
+        self._stats_dev[0:3] = self._dev(rows)
+        self._stats_host = None
 
     def _population(self, i, mask, weights=None, collective=False):
         """Device array of the squared displacements of entry i: d_squared (kinisi/diffusion.py:574) or, collective,
@@ -195,6 +220,7 @@ class Bootstrap:
         self._n_bootstrap = np.append(self._n_bootstrap, np.mean(distro.samples))
         self._v_bootstrap = np.append(self._v_bootstrap, np.var(distro.samples, ddof=1))
         self._s_bootstrap = np.append(self._s_bootstrap, np.std(distro.samples, ddof=1))
+        return values
 
     @staticmethod
     def sample_until_normal(array: np.ndarray,
@@ -678,7 +704,8 @@ class MSDBootstrap(Bootstrap):
     :param bootstrap, n_resamples, max_resamples, alpha, random_state: `bootstrap=True` adds the resampled
         distributions of the mean (`_distributions`, `_n_bootstrap`, `_v_bootstrap`, `_s_bootstrap`;
         kinisi/diffusion.py:578-583), see :py:meth:`Bootstrap.sample_until_normal`.
-    :param block: `block=True` raises NotImplementedError (pyblock is not available).
+    :param block: `block=True` replaces the mean and variance by the blocking-method estimates
+        (kinisi/diffusion.py:584-595), see :py:meth:`Bootstrap._blocked`.
     """
 
     def __init__(self,
@@ -709,9 +736,12 @@ class MSDBootstrap(Bootstrap):
         if used:
             sums = self._self_sums(np.array(used), self._mask)
             self._finish(used, sums, cnt, div, sums, cnt)
-            if self._resample is not None:
-                for i in used:
-                    self._resample_entry(self._population(i, self._mask), n_o[i])  # diffusion.py:579
+            if self._resample is not None or self._block:
+                pops = (self._population(i, self._mask) for i in used)
+                if self._resample is not None:
+                    pops = [self._resample_entry(v, n_o[i]) for i, v in zip(used, pops)]  # diffusion.py:579
+                if self._block:
+                    self._apply_blocking(pops)
         else:
             self._finish(used, None, cnt, div, None, cnt)
 
@@ -736,9 +766,12 @@ class _CollectiveBootstrap(Bootstrap):
             self_sums = self._self_sums(u, self._mask)
             coll = self._collective_sums(u, weights, coll_mask)
             self._finish(used, coll, m, div, self_sums, gcnt)
-            if self._resample is not None:
-                for i, n_samples in zip(used, div):  # diffusion.py:664, 756: n_o[i] / d_squared.shape[0]
-                    self._resample_entry(self._population(i, coll_mask, weights, collective=True), n_samples)
+            if self._resample is not None or self._block:
+                pops = (self._population(i, coll_mask, weights, collective=True) for i in used)
+                if self._resample is not None:  # diffusion.py:664, 756: n_samples = n_o[i] / d_squared.shape[0]
+                    pops = [self._resample_entry(v, n_samples) for v, n_samples in zip(pops, div)]
+                if self._block:
+                    self._apply_blocking(pops)
         else:
             self._finish(used, None, m, div, None, gcnt)
 

@@ -264,6 +264,18 @@ def resample_means(values, n_draws, n_resamples, first_resample=0, seed=0, strea
     return out
 
 
+def reblock(values):
+    """[levels, 2] = (sum, sum of squared deviations) of every reblocking level of `values`; see kb2_reblock."""
+    lib = require_cuda()
+    n = values.numel()
+    levels = lib.kb2_reblock_levels(n)
+    ws = torch.empty(lib.kb2_reblock_workspace_bytes(n) // 8, dtype=torch.float64, device=values.device)
+    stats = torch.empty((levels + 1, 2), dtype=torch.float64, device=values.device)
+    check(lib.kb2_reblock(values.data_ptr(), n, ws.data_ptr(), stats.data_ptr(), _stream()), 'kb2_reblock')
+    _count(levels + 1)
+    return stats[:levels]
+
+
 def moment_stats(main_sums, cnt, divisor, ngp_sums, gcnt):
     lib = require_cuda()
     n = cnt.numel()

@@ -19,7 +19,11 @@ Parity status
   installed here nor vendored in /root/reference and whose results the reference's tests do not pin:
   `emcee.EnsembleSampler` (stretch move; unpinned version, the RNG is unseedable from kinisi,
   diffusion.py:386-389) and `statsmodels.stats.correlation_tools.cov_nearest` (statsmodels>=0.14).
-  Both are restated from their published algorithms (see oracle/shims/README.md).
+  Both are restated from their published algorithms (see oracle/shims/README.md).  The same holds for
+  `pyblock.blocking.reblock` / `find_optimal_block` behind `block=True` (diffusion.py:584-595): pyblock is absent, no
+  reference test pins a blocked result; `reblock` / `find_optimal_block` below restate Flyvbjerg & Petersen (1989).
+* PINNED bit for bit for `bootstrap=True`: `bootstrap_means` / `sample_until_normal` against the reference +
+  scikit-learn with seeded RandomStates (tests/golden/resample_reference.npz).
 
 Every function cites the reference file:line it follows (paths relative to /root/reference).
 The restatement is *streaming*: it evaluates the same numpy expressions one dt at a time and never
@@ -313,6 +317,48 @@ def sample_until_normal(array, n_samples, n_resamples, max_resamples, alpha=1e-3
         values += bootstrap_means(array, n_samples, 100, random_state)
         p_value = normaltest(values)[1]
     return np.array(values), len(values) >= max_resamples
+
+
+def reblock(data, ddof=1):
+    """pyblock.blocking.reblock for one variable (the call at kinisi/diffusion.py:585, 671, 763).  PARITY UNPINNED: pyblock
+    (unpinned in the reference's pyproject.toml, imported lazily) is neither installed here nor vendored under
+    /root/reference and no reference test pins a `block=True` result; restated from the published algorithm
+    (Flyvbjerg & Petersen, J. Chem. Phys. 91, 461 (1989); pyblock 0.6 documentation): at every level the mean, the
+    ddof=1 variance, std_err = sqrt(var / n) and std_err_err = std_err / sqrt(2 (n - ddof)); the next level averages
+    neighbouring pairs, dropping the last point of an odd level.  Returns [(block, ndata, mean, cov, std_err, std_err_err)]."""
+    data = np.asarray(data, dtype=np.float64).flatten()
+    stats, iblock = [], 0
+    while data.shape[0] >= 2:
+        n = data.shape[0]
+        mean = data.mean()
+        cov = float(np.cov(data, ddof=ddof))
+        std_err = np.sqrt(cov / n)
+        stats.append((iblock, n, mean, cov, std_err, std_err / np.sqrt(2 * (n - ddof))))
+        last = 2 * (n // 2)
+        data = (data[:last:2] + data[1:last:2]) / 2
+        iblock += 1
+    return stats
+
+
+def find_optimal_block(ndata, stats):
+    """pyblock.blocking.find_optimal_block for one variable (same status as `reblock`): the smallest level whose block
+    size B = 2^level satisfies B^3 > 2 n (std_err(B) / std_err(0))^4 (Wolff; Lee et al.), nan when no level does."""
+    optimal = float('inf')
+    first = stats[0][4]
+    with np.errstate(all='ignore'):
+        for (iblock, _, _, _, std_err, _) in reversed(stats):
+            if 2**(3 * iblock) > 2 * ndata * (std_err / first)**4:
+                optimal = iblock
+    return float('nan') if np.isinf(optimal) else optimal
+
+
+def blocked_mean_and_variance(values):
+    """kinisi/diffusion.py:584-595: mean and squared standard error at the optimal block, the last level when there is
+    none (the reference's `except TypeError` on a nan index)."""
+    stats = reblock(values)
+    opt = find_optimal_block(np.asarray(values).size, stats)
+    lvl = stats[-1] if np.isnan(opt) else stats[int(opt)]
+    return lvl[2], lvl[4]**2
 
 
 _PHILOX_M0, _PHILOX_M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)

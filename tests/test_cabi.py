@@ -73,6 +73,12 @@ def test_argument_errors_are_reported_without_a_gpu(lib_path):
     assert rc != 0 and b'empty population' in lib.kb2_last_error()
     rc = lib.kb2_resample_means(1, 10, 0, 10, 0, 1, 0, 1, None)
     assert rc != 0 and b'n_draws' in lib.kb2_last_error()
+    rc = lib.kb2_reblock(16, 1, 16, 16, None)
+    assert rc != 0 and b'two values' in lib.kb2_last_error()
+    rc = lib.kb2_reblock(24, 8, 16, 16, None)
+    assert rc != 0 and b'aligned' in lib.kb2_last_error()
+    assert lib.kb2_reblock_levels(1) == 0 and lib.kb2_reblock_levels(2) == 1 and lib.kb2_reblock_levels(7) == 2
+    assert lib.kb2_reblock_workspace_bytes(7) >= 8 * (4 + 2)
 
 
 def test_run_plan_is_host_only(lib_path):

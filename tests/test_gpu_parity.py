@@ -573,6 +573,64 @@ def test_bootstrap_true_fused_path_equals_list_seam(kb):
             np.testing.assert_allclose(a._n_bootstrap, a.n, rtol=0.2)
 
 
+@pytest.mark.parametrize('n_values', [2, 3, 5, 64, 1000, 4097, 100003])
+def test_reblock_levels_match_the_restatement(kb, n_values):
+    """kb2_reblock against the numpy restatement of pyblock.blocking.reblock (oracle; parity unpinned: pyblock is absent)."""
+    rng = np.random.default_rng(n_values)
+    x = np.cumsum(rng.normal(size=n_values)) * 0.1 + rng.exponential(size=n_values)  # serially correlated
+    want = ko.reblock(x)
+    acc = kb.engine.reblock(torch.from_numpy(x).cuda()).cpu().numpy()
+    assert acc.shape[0] == len(want)
+    for lvl, (block, ndata, mean, cov, std_err, _) in enumerate(want):
+        assert ndata == n_values >> lvl
+        np.testing.assert_allclose(acc[lvl, 0] / ndata, mean, rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(acc[lvl, 1] / (ndata - 1), cov, rtol=1e-10)
+    mean, var = kb.diffusion.Bootstrap._blocked(torch.from_numpy(x).cuda())
+    wm, wv = ko.blocked_mean_and_variance(x)
+    np.testing.assert_allclose([mean, var], [wm, wv], rtol=1e-10)
+
+
+def test_block_true(kb):
+    """`block=True` through the constructors (kinisi/diffusion.py:584-595, 670-681, 762-773): n, v, s become the blocked
+    estimates of the flattened population of every lag; the NGP and dt are untouched; the fused path agrees with the list."""
+    rng = np.random.default_rng(3)
+    dc = np.cumsum(rng.normal(scale=0.1, size=(16, 600, 3)), axis=1)
+    dc[:, 0] = 0.0
+    charges = np.where(np.arange(16) % 2, 1.0, -1.0)
+    p = kb.parser.Parser(dc, np.arange(16), [], 1.0, 1, n_steps=10, progress=False)
+    listed = [np.asarray(d) for d in p.disp_3d]
+    plain = kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False)
+    for dimension, sl in (('xyz', [0, 1, 2]), ('xz', [0, 2])):
+        a = kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, block=True, dimension=dimension, progress=False)
+        b = kb.diffusion.MSDBootstrap(p.delta_t, listed, p._n_o, block=True, dimension=dimension, progress=False)
+        want = np.array([ko.blocked_mean_and_variance(np.sum(d[:, :, sl]**2, axis=-1)) for d in listed])
+        for x in (a, b):
+            np.testing.assert_allclose(x.n, want[:, 0], rtol=1e-9)
+            np.testing.assert_allclose(x.v, want[:, 1], rtol=1e-9)
+            np.testing.assert_allclose(x.s, np.sqrt(want[:, 1]), rtol=1e-9)
+            np.testing.assert_allclose(x.dt, plain.dt)
+    np.testing.assert_allclose(a.ngp[0], kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, dimension='xz',
+                                                                    progress=False).ngp[0], rtol=1e-12)
+    # overlapping origins are serially correlated: the blocked variance of the mean must exceed the naive one
+    naive = np.array([np.var(np.sum(d**2, axis=-1), ddof=1) / d[..., 0].size for d in listed])
+    a = kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, block=True, progress=False)
+    assert np.all(a.v[1:5] > 2 * naive[1:5])
+    half = len(listed) // 2
+    for cls, args, w, sl in ((kb.diffusion.MSTDBootstrap, (), np.ones(16), [0, 1, 2]),
+                             (kb.diffusion.MSCDBootstrap, (charges, ), charges, [0, 1, 2])):
+        a = cls(p.delta_t, p.disp_3d, *args, p._n_o, block=True, progress=False)
+        b = cls(p.delta_t, listed, *args, p._n_o, block=True, progress=False)
+        want = np.array([ko.blocked_mean_and_variance(np.sum(np.sum(d * w[:, None, None], axis=0)[:, sl]**2, axis=-1))
+                         for d in listed[:half]])
+        for x in (a, b):
+            np.testing.assert_allclose(x.n, want[:, 0], rtol=1e-8)
+            np.testing.assert_allclose(x.v, want[:, 1], rtol=1e-8)
+    # the regression runs on the blocked variances
+    a = kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, block=True, progress=False)
+    a.diffusion(p.delta_t[2], progress=False, n_samples=200, n_burn=100)
+    assert a.D.samples.size == 200 * 32 // 10 and np.isfinite(a.D.n)  # thin = 10
+
+
 def test_identical_trajectories_stack(kb):
     """dtype='identical' (kinisi/analyzer.py:111-116, 274-290): more atoms, n_o summed."""
     symbols = ['Li'] * 6 + ['O'] * 3

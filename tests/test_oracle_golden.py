@@ -204,3 +204,25 @@ def test_counter_generator_known_answers():
     assert abs(counts.mean() - 20.001) < 1e-9 and counts.std() < 6.0  # ~ Poisson(20)
     m = ko.counter_resample_means(np.arange(10.0), 64, 400, seed=3)
     assert abs(m.mean() - 4.5) < 5 * np.sqrt(8.25 / 64 / 400)
+
+
+def test_reblocking_restatement_on_correlated_data():
+    """The restated blocking method (pyblock is absent: unpinned) recovers the standard error of an AR(1) series, which
+    the naive estimate misses by the correlation factor, and has no optimal block for constant data."""
+    rng = np.random.default_rng(0)
+    phi, n = 0.9, 2**15
+    e = rng.normal(size=n)
+    x = np.empty(n)
+    x[0] = e[0]
+    for i in range(1, n):
+        x[i] = phi * x[i - 1] + e[i]
+    stats = ko.reblock(x)
+    assert [s[1] for s in stats] == [n >> l for l in range(15)]
+    opt = ko.find_optimal_block(n, stats)
+    true_se = np.sqrt(1.0 / (1 - phi)**2 / n)
+    assert abs(stats[int(opt)][4] / true_se - 1) < 0.15 and stats[0][4] < 0.3 * true_se
+    mean, var = ko.blocked_mean_and_variance(x)
+    assert var == stats[int(opt)][4]**2 and mean == stats[int(opt)][2]
+    assert np.isnan(ko.find_optimal_block(5, ko.reblock(np.ones(5))))
+    odd = ko.reblock(np.arange(7.0))
+    assert [s[1] for s in odd] == [7, 3] and odd[1][2] == 2.5  # (0.5, 2.5, 4.5): the 7th point is dropped
