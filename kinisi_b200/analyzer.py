@@ -46,7 +46,13 @@ class Analyzer:
 
     @classmethod
     def from_dict(cls, my_dict: dict) -> 'Analyzer':
-        return cls(**my_dict)
+        """An analyzer from its dictionary (kinisi/analyzer.py:75-85; with the bootstrap under 'diff' as in
+        kinisi/diffusion_analyzer.py:46-57 and the two sibling classes)."""
+        an = cls(my_dict['delta_t'], my_dict['disp_3d'], my_dict['n_o'], my_dict['volume'])
+        if my_dict.get('diff') is not None:
+            from . import diffusion
+            an._diff = diffusion.Bootstrap.from_dict(my_dict['diff'])
+        return an
 
     @classmethod
     def _from_parser(cls, make_parser, trajectory, dtype, flatten, **kwargs):

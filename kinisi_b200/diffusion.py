@@ -450,11 +450,17 @@ class Bootstrap:
         matrix itself (only its spectrum), so it is rebuilt here on first use."""
         if self._covariance_matrix_dev is None and self._cov_regime is not None:
             self._covariance_matrix_dev = self.generate_covariance_matrix(self._cov_regime)
+        host = getattr(self, '_covariance_matrix_host', None)
+        if self._covariance_matrix_dev is None and host is not None:  # an object restored by from_dict
+            self._covariance_matrix_dev = engine.to_device(np.asarray(host), self._device, torch.float64)
         return self._covariance_matrix_dev
 
     @property
     def covariance_matrix(self) -> np.ndarray:
         """:return: The covariance matrix for the trajectories."""
+        host = getattr(self, '_covariance_matrix_host', None)
+        if host is not None and self._covariance_matrix_dev is None:
+            return host
         cov = self._covariance_device()
         return None if cov is None else cov.cpu().numpy()
 
@@ -669,8 +675,15 @@ class Bootstrap:
         return ppd.reshape(-1, x.numel()).cpu().numpy()
 
     def to_dict(self) -> dict:
-        """:return: Dictionary description of the statistics (arrays only; the displacements stay on the device)."""
+        """:return: Dictionary description of the :py:class:`Bootstrap` (kinisi/diffusion.py:84-122): the statistics
+        and the regression results as host arrays.  `displacements` is None: the displacement sequence stays on the
+        device (the reference stores the whole O(N T n_dt) list)."""
+
+        def dump(d):
+            return None if d is None else d.to_dict()
+
         return {
+            'displacements': None,
             'delta_t': self._delta_t,
             'n_o': np.asarray(self._n_o),
             'max_obs': self._max_obs,
@@ -682,15 +695,79 @@ class Bootstrap:
             's_bootstrap': self._s_bootstrap,
             'v_bootstrap': self._v_bootstrap,
             'distributions': [d.to_dict() for d in self._distributions] if len(self._distributions) else None,
+            'euclidian_displacements': self._euclidian_displacements,  # the lazy sequence itself, not its O(N T) values
             'sub_sample_dt': self._sub_sample_dt,
             'dimension': self._dimension,
             'ngp': self._ngp,
             'covariance_matrix': self.covariance_matrix,
+            'diffusion_coefficient': dump(self.D),
+            'jump_diffusion_coefficient': dump(self.D_J),
+            'sigma': dump(self.sigma),
+            'intercept': dump(self.intercept),
+            'gradient': dump(self.gradient),
             'flatchain': self.flatchain,
             'start_dt': self._start_dt,
             'model': self._model,
             'cond_max': self._cond_max
         }
+
+    @classmethod
+    def from_dict(cls, my_dict: dict) -> 'Bootstrap':
+        """
+        Generate a :py:class:`Bootstrap` object from a dictionary (kinisi/diffusion.py:124-176): a host-side object
+        holding the stored statistics and regression results; nothing is recomputed and no device is needed.
+
+        :param my_dict: The input dictionary.
+
+        :return: New :py:class:`Bootstrap` object.
+        """
+
+        def restore(d):
+            return None if d is None else Distribution.from_dict(d)
+
+        boot = object.__new__(Bootstrap)
+        dimension = my_dict['dimension']
+        if isinstance(dimension, bytes):
+            dimension = dimension.decode()
+        boot._displacements = my_dict.get('displacements')
+        boot._delta_t = np.asarray(my_dict['delta_t'])
+        boot._lazy = False
+        boot._max_obs = my_dict['max_obs']
+        boot._n_o = my_dict['n_o']
+        boot._sub_sample_dt = my_dict['sub_sample_dt']
+        boot._dimension = dimension
+        boot._slice = DIMENSIONALITY[dimension.lower()]
+        boot._mask = engine.dim_mask(dimension)
+        boot.dims = len(dimension.lower())
+        boot._dt = my_dict['dt']
+        boot._stats_dev = None
+        boot._stats_host = np.stack([np.asarray(my_dict[k], dtype=np.float64) for k in ('n', 'v', 's', 'ngp')])
+        boot._n_bootstrap = my_dict['n_bootstrap']
+        boot._s_bootstrap = my_dict['s_bootstrap']
+        boot._v_bootstrap = my_dict['v_bootstrap']
+        boot._distributions = ([Distribution.from_dict(d) for d in my_dict['distributions']]
+                               if my_dict.get('distributions') is not None else [])
+        ed = my_dict.get('euclidian_displacements', [])
+        boot._euclidian_displacements = ed if isinstance(ed, _LazyEuclidian) else [Distribution.from_dict(d) for d in ed]
+        boot._flat_pending = None
+        boot._flatchain = my_dict['flatchain']
+        boot._gradient = restore(my_dict['gradient'])
+        boot._intercept_dist = restore(my_dict['intercept'])
+        boot._coefficient = None
+        boot._diffusion_coefficient = restore(my_dict['diffusion_coefficient'])
+        boot._jump_diffusion_coefficient = restore(my_dict['jump_diffusion_coefficient'])
+        boot._sigma = restore(my_dict['sigma'])
+        boot._covariance_matrix_dev = None
+        boot._npd_covariance_matrix_dev = None
+        boot._covariance_matrix_host = my_dict['covariance_matrix']
+        boot._cov_regime = None
+        boot._eig = None
+        boot._start_dt = my_dict['start_dt']
+        boot._model = my_dict['model']
+        boot._cond_max = my_dict['cond_max']
+        boot._resample, boot._block, boot._atom_sum_cache = None, False, None
+        boot._device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else None
+        return boot
 
 
 class MSDBootstrap(Bootstrap):

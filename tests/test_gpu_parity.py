@@ -631,6 +631,47 @@ def test_block_true(kb):
     assert a.D.samples.size == 200 * 32 // 10 and np.isfinite(a.D.n)  # thin = 10
 
 
+def test_dictionary_roundtrip(kb):
+    """to_dict / from_dict of the analyzers and the bootstrap (kinisi/tests/test_analyze.py:59-90, 255-275;
+    kinisi/diffusion.py:84-176): the restored object answers from the stored host arrays."""
+    symbols, frac, latt, pp, start_idx, kind = regress_case_inputs('regress_msd')
+    traj = trajectory_from_arrays(symbols, frac, latt)
+    A = kb.analyze.DiffusionAnalyzer
+    a = A.from_ase(traj, parser_params=pp, uncertainty_params={'progress': False, 'bootstrap': True, 'n_resamples': 200,
+                                                              'max_resamples': 400,
+                                                              'random_state': np.random.RandomState(0)})
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter('always')
+        a.diffusion(a.dt[start_idx], {'progress': False, 'n_samples': 300, 'n_burn': 100})
+    d = a.to_dict()
+    assert set(['delta_t', 'disp_3d', 'n_o', 'volume', 'diff']) == set(d.keys())
+    for key in ('displacements', 'delta_t', 'n_o', 'max_obs', 'dt', 'n', 's', 'v', 'n_bootstrap', 's_bootstrap', 'v_bootstrap',
+                'sub_sample_dt', 'dimension', 'ngp', 'covariance_matrix', 'distributions', 'diffusion_coefficient',
+                'jump_diffusion_coefficient', 'sigma', 'intercept', 'gradient', 'start_dt', 'model', 'cond_max',
+                'euclidian_displacements', 'flatchain'):
+        assert key in d['diff'], key  # the keys of kinisi/diffusion.py:88-122
+    b = A.from_dict(d)
+    np.testing.assert_array_equal(a.dt, b.dt)
+    np.testing.assert_array_equal(a.msd, b.msd)
+    np.testing.assert_array_equal(a.msd_std, b.msd_std)
+    assert a.ngp_max == b.ngp_max and a.volume == b.volume
+    np.testing.assert_array_equal(a.D.samples, b.D.samples)
+    np.testing.assert_array_equal(a.intercept.samples, b.intercept.samples)
+    np.testing.assert_array_equal(a.flatchain, b.flatchain)
+    np.testing.assert_array_equal(a._diff.covariance_matrix, b._diff.covariance_matrix)
+    np.testing.assert_array_equal(a.distribution, b.distribution)
+    np.testing.assert_array_equal(a._diff._n_bootstrap, b._diff._n_bootstrap)
+    assert len(b._diff._distributions) == len(a._diff._distributions) > 0
+    np.testing.assert_array_equal(a.dr[0].samples, b.dr[0].samples)
+    assert b._diff.D_J is None and b._diff.sigma is None
+    ppd = b.posterior_predictive({'n_posterior_samples': 8, 'n_predictive_samples': 4, 'progress': False})
+    assert ppd.shape == (32, a.dt[start_idx:].size)
+    base = kb.analyze.DiffusionAnalyzer.__mro__[1]
+    plain = base.from_dict(base(a._delta_t, a._disp_3d, a._n_o, a._volume).to_dict())
+    np.testing.assert_array_equal(plain._delta_t, a._delta_t)
+    assert plain._volume == a._volume
+
+
 def test_identical_trajectories_stack(kb):
     """dtype='identical' (kinisi/analyzer.py:111-116, 274-290): more atoms, n_o summed."""
     symbols = ['Li'] * 6 + ['O'] * 3

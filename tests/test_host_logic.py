@@ -109,3 +109,26 @@ def test_lag_grid_is_split_into_arithmetic_runs():
     assert runs == [] and rest == 1
     runs, rest = check([2, 3, 5, 7, 11, 13, 17, 19, 23], 100)
     assert rest + sum(r[2] for r in runs) == 9
+
+
+def test_bootstrap_from_dict_needs_no_device():
+    """Bootstrap.from_dict (kinisi/diffusion.py:124-176) restores the stored statistics and regression results on the host."""
+    from kinisi_b200 import diffusion
+    from kinisi_b200.distribution import Distribution
+    rng = np.random.default_rng(0)
+    grad = Distribution(rng.normal(3.0, 0.1, size=640))
+    d = {
+        'displacements': None, 'delta_t': np.arange(1.0, 6.0), 'n_o': np.arange(5.0, 0.0, -1.0), 'max_obs': 40,
+        'dt': np.arange(1.0, 6.0), 'n': np.arange(5.0), 's': np.ones(5), 'v': np.ones(5), 'ngp': np.array([0.1, 0.5, 0.2, 0.0, -0.1]),
+        'n_bootstrap': np.array([]), 's_bootstrap': np.array([]), 'v_bootstrap': np.array([]), 'distributions': None,
+        'sub_sample_dt': 1, 'dimension': 'xy', 'covariance_matrix': np.eye(3), 'diffusion_coefficient': grad.to_dict(),
+        'jump_diffusion_coefficient': None, 'sigma': None, 'intercept': None, 'gradient': grad.to_dict(),
+        'flatchain': grad.samples[:, None], 'start_dt': 3.0, 'model': True, 'cond_max': 1e16, 'euclidian_displacements': []
+    }
+    b = diffusion.Bootstrap.from_dict(d)
+    assert b.dims == 2 and b.n[3] == 3.0 and b.ngp.argmax() == 1 and b.intercept is None
+    np.testing.assert_array_equal(b.D.samples, grad.samples)
+    np.testing.assert_array_equal(b.covariance_matrix, np.eye(3))
+    again = b.to_dict()
+    np.testing.assert_array_equal(again['gradient']['samples'], grad.samples)
+    assert again['start_dt'] == 3.0 and again['sigma'] is None
