@@ -68,6 +68,14 @@ int kb2_device_info(int* sm_count, int* max_smem_optin, int* cc_major, int* cc_m
 int kb2_frames_to_atoms(const void* frames, int dtype, int n_atoms, int n_frames, void* coords_out, int64_t n_frames_out,
                         int64_t frame_offset, int duplicate_first, void* stream);
 
+/* The same transposition for CARTESIAN frames (the MDAnalysis front-end, parser.py:620-638, whose per-frame
+ * np.dot(positions, np.linalg.inv(cell)) runs on the host in the reference): coords_out (always float64) receives
+ * frames[f][a] . cell_inv[f] (row vector times matrix); cell_inv[n_frames][3][3] with cell_stride = 9, or one matrix
+ * with cell_stride = 0. */
+int kb2_frames_to_atoms_fractional(const void* frames, int dtype, int n_atoms, int n_frames, const double* cell_inv,
+                                   int cell_stride, double* coords_out, int64_t n_frames_out, int64_t frame_offset,
+                                   int duplicate_first, void* stream);
+
 /* Pseudo-centre-of-mass of groups of atoms in fractional coordinates (_get_molecules, parser.py:674-738,
  * arXiv:2501.14578): members[n_molecules][molecule_size] are 0-based atom rows of coords[n_atoms_total][n_frames_in][3],
  * weights[molecule_size] the masses (NULL: centre of geometry); centres[n_molecules][n_frames_in][3] float64 in [0, 1). */

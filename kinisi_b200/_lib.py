@@ -18,6 +18,8 @@ SIGNATURES = {
     'kb2_device_info': (c_int, [POINTER(c_int)] * 4),
     'kb2_invert_lattice': (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     'kb2_frames_to_atoms': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    'kb2_frames_to_atoms_fractional': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int64, c_int64,
+                                               c_int, c_void_p]),
     'kb2_molecule_centres': (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                      c_void_p]),
     'kb2_frame_sums': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,

@@ -8,7 +8,7 @@ from typing import List, Union
 
 import numpy as np
 
-from .parser import ASEParser, LazyDisplacements, PymatgenParser
+from .parser import MDAnalysisParser, ASEParser, LazyDisplacements, PymatgenParser
 
 
 def _flatten_list(this_list: list) -> list:
@@ -106,13 +106,10 @@ class Analyzer:
 
     @classmethod
     def _from_universe(cls, trajectory, parser_params: dict, dtype: str = None, **kwargs):
-        """MDAnalysis front-end (kinisi/analyzer.py:236-271): needs MDAnalysis like the reference."""
-        try:
-            import MDAnalysis  # noqa: F401
-        except ModuleNotFoundError:  # pragma: no cover
-            raise ModuleNotFoundError(
-                "To use the MDAnalysis from file parsing, MDAnalysis must be installed.")  # pragma: no cover
-        raise NotImplementedError('the MDAnalysis front-end is outside the path kinisi_b200 builds')  # pragma: no cover
+        """From an MDAnalysis Universe-like object, or a list of them with dtype='identical' (kinisi/analyzer.py:236-271;
+        'consecutive' is not offered for universes, as in the reference).  MDAnalysis itself is not imported: any object
+        with the attributes :py:class:`MDAnalysisParser` reads will do."""
+        return cls._from_parser(lambda t: MDAnalysisParser(t, **parser_params), trajectory, dtype, None, **kwargs)
 
     @staticmethod
     def _stack_trajectories(u) -> LazyDisplacements:

@@ -40,6 +40,35 @@ __global__ void __launch_bounds__(256) frames_to_atoms_kernel(const T* __restric
     }
 }
 
+// The MDAnalysis front-end (kinisi/parser.py:620-638) holds CARTESIAN positions and the cell of every frame: the reference
+// computes np.dot(positions, inv(cell)) per frame on the host.  Same tiled transpose, with the product by the frame's
+// inverse cell (row vector times matrix, float64 whatever the input type) applied on the way out.
+template <typename T>
+__global__ void __launch_bounds__(256) frames_to_atoms_fractional_kernel(const T* __restrict__ in, int n_atoms, int n_frames,
+                                                                         const double* __restrict__ cell_inv, int cell_stride,
+                                                                         double* __restrict__ out, int64_t F_out, int64_t f_off,
+                                                                         int dup_first) {
+    __shared__ T tile[kTrTile][kTrTile * 3 + 1];
+    __shared__ double inv[kTrTile][9];
+    const int a0 = blockIdx.x * kTrTile, f0 = blockIdx.y * kTrTile;
+    const int na = min(kTrTile, n_atoms - a0), nf = min(kTrTile, n_frames - f0);
+    for (int e = threadIdx.x; e < nf * na * 3; e += 256) {
+        const int f = e / (na * 3), r = e - f * (na * 3);
+        tile[f][r] = in[((size_t)(f0 + f) * n_atoms + a0) * 3 + r];
+    }
+    for (int e = threadIdx.x; e < nf * 9; e += 256) inv[e / 9][e % 9] = cell_inv[(size_t)(f0 + e / 9) * cell_stride + e % 9];
+    __syncthreads();
+    for (int e = threadIdx.x; e < na * nf * 3; e += 256) {
+        const int a = e / (nf * 3), r = e - a * (nf * 3);
+        const int f = r / 3, k = r - f * 3;
+        const double x = (double)tile[f][a * 3], y = (double)tile[f][a * 3 + 1], z = (double)tile[f][a * 3 + 2];
+        const double v = fma(z, inv[f][6 + k], fma(y, inv[f][3 + k], x * inv[f][k]));
+        double* row = out + (size_t)(a0 + a) * F_out * 3;
+        row[(f_off + f0 + f) * 3 + k] = v;
+        if (dup_first && f0 + f == 0) row[(f_off - 1) * 3 + k] = v;
+    }
+}
+
 // one thread per (molecule, frame): members[mol * m + j] are atom rows of coords [n_atoms][F][3]
 template <typename T>
 __global__ void __launch_bounds__(128) molecule_centres_kernel(const T* __restrict__ coords, int64_t F,
@@ -108,6 +137,30 @@ extern "C" int kb2_frames_to_atoms(const void* frames, int dtype, int n_atoms, i
     else
         frames_to_atoms_kernel<double><<<grid, 256, 0, st>>>((const double*)frames, n_atoms, n_frames, (double*)coords_out,
                                                              n_frames_out, frame_offset, duplicate_first);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int kb2_frames_to_atoms_fractional(const void* frames, int dtype, int n_atoms, int n_frames, const double* cell_inv,
+                                              int cell_stride, double* coords_out, int64_t n_frames_out, int64_t frame_offset,
+                                              int duplicate_first, void* stream) {
+    KB2_CHECK(frames && coords_out && cell_inv, "kb2_frames_to_atoms_fractional: null pointer");
+    KB2_CHECK(dtype == KB2_F32 || dtype == KB2_F64, "kb2_frames_to_atoms_fractional: dtype must be KB2_F32 or KB2_F64");
+    KB2_CHECK(cell_stride == 0 || cell_stride == 9, "kb2_frames_to_atoms_fractional: cell_stride must be 0 or 9");
+    KB2_CHECK(n_atoms > 0 && n_frames > 0, "kb2_frames_to_atoms_fractional: empty input");
+    KB2_CHECK(frame_offset >= (duplicate_first ? 1 : 0) && frame_offset + n_frames <= n_frames_out,
+              "kb2_frames_to_atoms_fractional: the frames do not fit the output rows");
+    dim3 grid(ceil_div(n_atoms, kTrTile), ceil_div(n_frames, kTrTile));
+    KB2_CHECK(grid.y <= 65535, "kb2_frames_to_atoms_fractional: at most %d frames per call", 65535 * kTrTile);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == KB2_F32)
+        frames_to_atoms_fractional_kernel<float><<<grid, 256, 0, st>>>((const float*)frames, n_atoms, n_frames, cell_inv,
+                                                                       cell_stride, coords_out, n_frames_out, frame_offset,
+                                                                       duplicate_first);
+    else
+        frames_to_atoms_fractional_kernel<double><<<grid, 256, 0, st>>>((const double*)frames, n_atoms, n_frames, cell_inv,
+                                                                        cell_stride, coords_out, n_frames_out, frame_offset,
+                                                                        duplicate_first);
     KB2_LAUNCH_CHECK();
     return 0;
 }

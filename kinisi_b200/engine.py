@@ -74,10 +74,21 @@ def invert_lattice(latt):
     return inv
 
 
-def frames_to_atoms(frames, out, frame_offset, duplicate_first=False):
+def frames_to_atoms(frames, out, frame_offset, duplicate_first=False, cell_inv=None):
     """Transposes frame-major frames [n_frames, n_atoms, 3] into the atom-major array out [n_atoms, F_out, 3] at
-    frame_offset; see kb2_frames_to_atoms."""
+    frame_offset; see kb2_frames_to_atoms.  With cell_inv ([n_frames, 3, 3] or [1, 3, 3] float64) the frames are Cartesian
+    and out (float64) receives the fractional coordinates; see kb2_frames_to_atoms_fractional."""
     lib = require_cuda()
+    if cell_inv is not None:
+        assert frames.is_contiguous() and out.is_contiguous() and out.dtype == torch.float64 and cell_inv.is_contiguous()
+        stride = 9 if cell_inv.shape[0] > 1 else 0
+        assert stride == 0 or cell_inv.shape[0] == frames.shape[0]
+        check(
+            lib.kb2_frames_to_atoms_fractional(frames.data_ptr(), coords_dtype_code(frames), frames.shape[1], frames.shape[0],
+                                               cell_inv.data_ptr(), stride, out.data_ptr(), out.shape[1], int(frame_offset),
+                                               int(bool(duplicate_first)), _stream()), 'kb2_frames_to_atoms_fractional')
+        _count()
+        return out
     assert frames.is_contiguous() and out.is_contiguous() and frames.dtype == out.dtype
     check(
         lib.kb2_frames_to_atoms(frames.data_ptr(), coords_dtype_code(frames), frames.shape[1], frames.shape[0],

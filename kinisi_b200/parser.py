@@ -168,13 +168,15 @@ class Trajectory:
         return self.coords.shape[1] - (1 if self.mode == MODE_FRACTIONAL else 0)
 
     @classmethod
-    def from_frames(cls, frames, latt=None, mode=MODE_FRACTIONAL, device=None, duplicate_first=True):
+    def from_frames(cls, frames, latt=None, mode=MODE_FRACTIONAL, device=None, duplicate_first=True, cartesian_cells=None):
         """
         A trajectory from FRAME-major coordinates `[frame, site, 3]` (how MD codes write them and how the front-ends
         collect them, kinisi/parser.py:309-325, 458-473).  The transposition to the atom-major layout of the kernels
         runs on the device (kb2_frames_to_atoms); host input is transferred in blocks of frames on the copy stream
         and transposed on the ingest stream behind the transfer.  `duplicate_first` inserts the copy of the first
-        frame the reference's front-ends prepend (parser.py:323-324).
+        frame the reference's front-ends prepend (parser.py:323-324).  `cartesian_cells` ([frame, 3, 3], or [1, 3, 3] for a
+        constant cell; without the duplicated frame): the frames hold Cartesian positions and are multiplied by the
+        inverse cell of their frame on the way (the MDAnalysis front-end, parser.py:630-635); the result is float64.
         """
         device = _default_device(device)
         if not isinstance(frames, torch.Tensor):
@@ -188,9 +190,23 @@ class Trajectory:
         off = 1 if duplicate_first else 0
         copy, ingest = _side_streams(device)
         main = torch.cuda.current_stream(device)
+        out_dtype = frames.dtype if cartesian_cells is None else torch.float64
+        inv = None
+        if cartesian_cells is not None:
+            work = ingest if frames.device.type == 'cpu' else main
+            with torch.cuda.stream(work):
+                cells = engine.to_device(np.ascontiguousarray(cartesian_cells, dtype=np.float64).reshape(-1, 3, 3), device,
+                                         torch.float64)
+                if cells.shape[0] not in (1, n_f):
+                    raise ValueError('one cell per frame is required')
+                inv = engine.invert_lattice(cells)
+
+        def inv_of(f0, f1):
+            return None if inv is None else (inv if inv.shape[0] == 1 else inv[f0:f1])
+
         if frames.device.type == 'cpu':
             with torch.cuda.stream(ingest):
-                coords = torch.empty((n_a, n_f + off, 3), dtype=frames.dtype, device=device)
+                coords = torch.empty((n_a, n_f + off, 3), dtype=out_dtype, device=device)
             per = max(1, int(STAGE_BYTES // max(1, n_a * 3 * frames.element_size())))
             with torch.cuda.stream(copy):
                 stage = [torch.empty((min(per, n_f), n_a, 3), dtype=frames.dtype, device=device) for _ in range(2)]
@@ -206,7 +222,7 @@ class Trajectory:
                     landed.record(copy)
                 with torch.cuda.stream(ingest):
                     ingest.wait_event(landed)
-                    engine.frames_to_atoms(buf, coords, off + f0, duplicate_first and f0 == 0)
+                    engine.frames_to_atoms(buf, coords, off + f0, duplicate_first and f0 == 0, inv_of(f0, f1))
                     free[i & 1] = torch.cuda.Event()
                     free[i & 1].record(ingest)
             for t in stage:
@@ -216,10 +232,10 @@ class Trajectory:
             keep = frames  # the transfer reads the caller's memory until the streams have drained
         else:
             frames = frames.to(device)
-            coords = torch.empty((n_a, n_f + off, 3), dtype=frames.dtype, device=device)
+            coords = torch.empty((n_a, n_f + off, 3), dtype=out_dtype, device=device)
             for f0 in range(0, n_f, 65535 * 32):
                 f1 = min(n_f, f0 + 65535 * 32)
-                engine.frames_to_atoms(frames[f0:f1], coords, off + f0, duplicate_first and f0 == 0)
+                engine.frames_to_atoms(frames[f0:f1], coords, off + f0, duplicate_first and f0 == 0, inv_of(f0, f1))
             keep = None
         traj = cls(coords, latt, mode, device)
         traj._frames_keepalive = keep
@@ -558,9 +574,10 @@ class Parser:
         return Trajectory(coords, latt_np.reshape(-1, 3, 3), MODE_FRACTIONAL, device)
 
     @staticmethod
-    def get_disp_from_frames(frames, latt, progress: bool = True, device=None) -> Trajectory:
+    def get_disp_from_frames(frames, latt, progress: bool = True, device=None, cartesian: bool = False) -> Trajectory:
         """As :py:meth:`get_disp` for FRAME-major fractional coordinates `[frame, site, 3]` WITHOUT the duplicated first
-        frame (it is inserted on the device): see :py:meth:`Trajectory.from_frames`."""
+        frame (it is inserted on the device): see :py:meth:`Trajectory.from_frames`.  `cartesian`: the frames hold
+        Cartesian positions, converted with the inverse of their frame's cell on the device."""
         if isinstance(latt, (list, tuple)):
             latt = np.array(latt)
         latt_np = latt.detach().cpu().numpy() if isinstance(latt, torch.Tensor) else np.asarray(latt)
@@ -570,9 +587,12 @@ class Parser:
             warnings.warn(
                 'Converting triclinic cell to orthorhombic this may have unexpected results. '
                 'Triclinic a, b, c are not equilivalent to orthorhombic x, y, z.', UserWarning)
+        cells = latt_np if cartesian else None
+        if cells is not None and cells.shape[0] > 1 and np.all(cells == cells[0]):
+            cells = cells[:1]
         if latt_np.shape[0] > 1:
             latt_np = np.concatenate([latt_np[:1], latt_np], axis=0)  # the duplicated first frame has its lattice too
-        return Trajectory.from_frames(frames, latt_np, MODE_FRACTIONAL, device, duplicate_first=True)
+        return Trajectory.from_frames(frames, latt_np, MODE_FRACTIONAL, device, duplicate_first=True, cartesian_cells=cells)
 
     @staticmethod
     def correct_drift(drift_indices, disp) -> np.ndarray:
@@ -729,20 +749,21 @@ def _get_framework(structure, indices, framework_indices):
 
 
 def _front_end_trajectory(parser, structure, frames, latt, specie, specie_indices, masses, framework_indices, progress,
-                          device):
+                          device, cartesian=False):
     """Shared body of the front-end constructors (kinisi/parser.py:266-293, 406-435): index selection, molecule
     centres, `coords_check`, and the device trajectory built from the frame-major walk."""
-    traj = Parser.get_disp_from_frames(frames, latt, progress=progress, device=device)
+    traj = Parser.get_disp_from_frames(frames, latt, progress=progress, device=device, cartesian=cartesian)
+    first = (np.dot(frames[0], np.linalg.inv(latt[0])) if cartesian else frames[0])[:, None, :]
     if specie is not None:
         indices = parser.get_indices(structure, specie, framework_indices)
-        parser.coords_check = frames[0][:, None, :]
+        parser.coords_check = first
     elif isinstance(specie_indices, (list, tuple)):
         if isinstance(specie_indices[0], (list, tuple)):
             traj, indices = _get_molecules(structure, traj, specie_indices, masses, framework_indices)
             parser.coords_check = traj.coords[:, 0:1].cpu().numpy()
         else:
             indices = _get_framework(structure, specie_indices, framework_indices)
-            parser.coords_check = frames[0][:, None, :]
+            parser.coords_check = first
     else:
         raise TypeError('Unrecognized type for specie or specie_indices')
     return traj, indices
@@ -862,6 +883,94 @@ class PymatgenParser(Parser):
             specie = [specie]
         for i, site in enumerate(structure):
             if site.specie.__str__() in specie:
+                indices.append(i)
+            else:
+                drift_indices.append(i)
+        if len(indices) == 0:
+            raise ValueError("There are no species selected to calculate the mean-squared displacement of.")
+        if isinstance(framework_indices, (list, tuple)):
+            drift_indices = framework_indices
+        return indices, drift_indices
+
+
+class MDAnalysisParser(Parser):
+    """
+    A parser that consumes an MDAnalysis.Universe object (kinisi/parser.py:511-672).  Any object exposing
+    `.trajectory[::n]` yielding timesteps with `.volume` and `.triclinic_dimensions`, and `.atoms[::n]` with `.positions`
+    (Cartesian, of the current timestep) and iteration over sites with `.type` works.  The positions are collected as
+    they are read and the per-frame product with the inverse cell (parser.py:630-634) runs on the device.
+
+    :param universe: The MDAnalysis object of interest.
+    :param specie: Specie to calculate diffusivity for as a String, e.g. 'Li'.
+    :param time_step: Time step, in picoseconds, between steps in trajectory.
+    :param step_skip: Sampling frequency of the trajectory.
+    :param sub_sample_atoms: The sampling rate to sample the atoms in the system. Optional, defaults to 1.
+    :param sub_sample_traj: Multiple of the time_step to sub sample at (folded into step_skip, parser.py:593).
+    :param specie_indices, masses, framework_indices: as for :py:class:`ASEParser`.
+    (min_dt, max_dt, n_steps, spacing, sampling, memory_limit, progress as for :py:class:`Parser`.)
+    """
+
+    def __init__(self,
+                 universe,
+                 specie: str,
+                 time_step: float,
+                 step_skip: int,
+                 sub_sample_atoms: int = 1,
+                 sub_sample_traj: int = 1,
+                 min_dt: float = None,
+                 max_dt: float = None,
+                 n_steps: int = 100,
+                 spacing: str = 'linear',
+                 sampling: str = 'multi-origin',
+                 memory_limit: float = 8.,
+                 progress: bool = True,
+                 specie_indices: List[int] = None,
+                 masses: List[float] = None,
+                 framework_indices: List[int] = None,
+                 device=None):
+        if sub_sample_atoms != 1 and specie_indices is not None:
+            raise ValueError(
+                'sub_sample_atom cannot be used with specie_indices. Please specify only inidices you wish to sample.')
+        structure, frames, cells, volume = self._walk_universe(universe, sub_sample_atoms, sub_sample_traj)
+        traj, indices = _front_end_trajectory(self, structure, frames, cells, specie, specie_indices, masses,
+                                              framework_indices, progress, device, cartesian=True)
+        super().__init__(traj, indices[0], indices[1], time_step, step_skip * sub_sample_traj, min_dt, max_dt, n_steps,
+                         spacing, sampling, memory_limit, progress, device=device)
+        self._volume = volume
+
+    @staticmethod
+    def _walk_universe(universe, sub_sample_atoms, sub_sample_traj):
+        """The walk of kinisi/parser.py:620-636 collecting FRAME-major Cartesian positions `[frame, site, 3]` (in the
+        universe's own element type, float32 for MDAnalysis) and the cells `[frame, 3, 3]`."""
+        structure, volume = None, 0
+        positions, cells = [], []
+        for timestep in universe.trajectory[::sub_sample_traj]:
+            if structure is None:
+                structure = universe.atoms[::sub_sample_atoms]
+                volume = timestep.volume
+            cells.append(np.array(timestep.triclinic_dimensions, dtype=np.float64))
+            positions.append(np.array(universe.atoms[::sub_sample_atoms].positions))  # a copy: readers reuse the buffer
+        return structure, np.stack(positions, axis=0), np.stack(cells, axis=0), volume
+
+    @staticmethod
+    def get_structure_coords_latt(universe, sub_sample_atoms: int = 1, sub_sample_traj: int = 1, progress: bool = True):
+        """:return: initial structure, fractional coordinates as the reference's list of `[site, 1, 3]` arrays (first
+        frame duplicated), the list of cells, and the cell volume (kinisi/parser.py:600-638; host arithmetic)."""
+        structure, positions, cells, volume = MDAnalysisParser._walk_universe(universe, sub_sample_atoms, sub_sample_traj)
+        coords = [np.dot(p, np.linalg.inv(m))[:, None] for p, m in zip(positions, cells)]
+        latt = list(cells)
+        coords.insert(0, coords[0])
+        latt.insert(0, latt[0])
+        return structure, coords, latt, volume
+
+    @staticmethod
+    def get_indices(structure, specie, framework_indices) -> Tuple[list, list]:
+        """Framework and non-framework indices by atom type (kinisi/parser.py:640-672)."""
+        indices, drift_indices = [], []
+        if not isinstance(specie, list):
+            specie = [specie]
+        for i, site in enumerate(structure):
+            if site.type in specie:
                 indices.append(i)
             else:
                 drift_indices.append(i)

@@ -67,6 +67,21 @@ def get_disp(coords, latt):
     return np.cumsum(unwrapped, axis=1)
 
 
+def universe_coords_latt(positions, cells):
+    """kinisi/parser.py:620-638 (MDAnalysisParser.get_structure_coords_latt): per frame, Cartesian positions times the
+    inverse cell, in the arrays' own precision (MDAnalysis hands out float32: numpy then inverts and multiplies in
+    single precision); the first frame is duplicated.  positions [F, N, 3], cells [F, 3, 3] -> (coords [N, F + 1, 3],
+    latt [F + 1, 3, 3])."""
+    coords, latt = [], []
+    for pos, matrix in zip(positions, cells):
+        inv_matrix = np.linalg.inv(matrix)
+        coords.append(np.array(np.dot(pos, inv_matrix))[:, None])
+        latt.append(matrix)
+    coords.insert(0, coords[0])
+    latt.insert(0, latt[0])
+    return np.concatenate(coords, axis=1), np.array(latt)
+
+
 def correct_drift(drift_indices, disp):
     """kinisi/parser.py:131-148 (Parser.correct_drift)."""
     if len(drift_indices) > 0:

@@ -263,7 +263,45 @@ def case_resample():
     print('resample_reference ok', out['msd_sizes'], out['mstd_sizes'], out['until_normal_skewed'].size)
 
 
+def case_universe():
+    """The MDAnalysis front-end (kinisi/parser.py:511-672) run by the reference on a duck-typed universe
+    (tests/duck_atoms.py): float64 positions (tight parity) and float32 ones (what MDAnalysis hands out: the reference
+    then inverts the cell and forms the fractional coordinates in single precision)."""
+    from duck_atoms import universe_from_arrays
+    out = {}
+    for name in ('ase_nvt', 'ase_npt_triclinic'):
+        symbols, frac, latt, pp = ase_case_inputs(name)
+        for tag, dtype in (('f64', np.float64), ('f32', np.float32)):
+            p = parser.MDAnalysisParser(universe_from_arrays(symbols, frac, latt, dtype), **pp)
+            key = f'{name}_{tag}_'
+            out[key + 'dc'] = p.dc
+            out[key + 'delta_t'] = p.delta_t
+            out[key + 'n_o'] = p._n_o
+            out[key + 'volume'] = p.volume
+            out[key + 'coords_check'] = p.coords_check
+            b = diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False)
+            for k, v in boot_arrays(b).items():
+                out[key + 'msd_' + k] = v
+    symbols, frac, latt, pp = ase_case_inputs('ase_npt_triclinic')
+    pp = dict(pp, sub_sample_atoms=2, sub_sample_traj=3)
+    p = parser.MDAnalysisParser(universe_from_arrays(symbols, frac, latt, np.float64), **pp)
+    out['sub_dc'], out['sub_delta_t'], out['sub_n_o'] = p.dc, p.delta_t, p._n_o
+    b = diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False)
+    for k, v in boot_arrays(b).items():
+        out['sub_msd_' + k] = v
+    pp = dict(ase_case_inputs('ase_nvt')[3], specie=None, specie_indices=[0, 2, 3, 5])
+    symbols, frac, latt, _ = ase_case_inputs('ase_nvt')
+    p = parser.MDAnalysisParser(universe_from_arrays(symbols, frac, latt, np.float64), **pp)
+    out['idx_dc'], out['idx_delta_t'], out['idx_n_o'] = p.dc, p.delta_t, p._n_o
+    out['idx_indices'], out['idx_drift_indices'] = np.array(p.indices), np.array(p.drift_indices)
+    np.savez_compressed(os.path.join(HERE, 'universe_reference.npz'), **out)
+    print('universe_reference ok', out['sub_dc'].shape, out['idx_dc'].shape)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'universe':  # only the fixture added for the MDAnalysis front-end
+        case_universe()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'resample':  # only the fixture added for SURVEY 8f-4
         case_resample()
         sys.exit(0)
@@ -275,3 +313,4 @@ if __name__ == '__main__':
         case_regression(name)
     case_reference_kats()
     case_resample()
+    case_universe()

@@ -63,6 +63,8 @@ def test_argument_errors_are_reported_without_a_gpu(lib_path):
     assert rc != 0
     rc = lib.kb2_frames_to_atoms(1, 0, 4, 10, 1, 10, 0, 1, None)  # no room for the duplicated first frame
     assert rc != 0 and b'do not fit' in lib.kb2_last_error()
+    rc = lib.kb2_frames_to_atoms_fractional(1, 0, 4, 10, 1, 3, 1, 11, 1, 1, None)
+    assert rc != 0 and b'cell_stride' in lib.kb2_last_error()
     rc = lib.kb2_molecule_centres(1, 7, 4, 10, 1, 1, 3, None, 1, None)
     assert rc != 0 and b'dtype' in lib.kb2_last_error()
     rc = lib.kb2_lag_squares(1, 2, 10, 10, 11, 7, 1, None)

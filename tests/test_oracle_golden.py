@@ -2,6 +2,8 @@
 (tests/golden/make_golden.py) and against the reference's own known-answer tests."""
 import os
 
+import warnings
+
 import numpy as np
 import pytest
 
@@ -226,3 +228,22 @@ def test_reblocking_restatement_on_correlated_data():
     assert np.isnan(ko.find_optimal_block(5, ko.reblock(np.ones(5))))
     odd = ko.reblock(np.arange(7.0))
     assert [s[1] for s in odd] == [7, 3] and odd[1][2] == 2.5  # (0.5, 2.5, 4.5): the 7th point is dropped
+
+
+def test_universe_front_end_restatement(golden_dir):
+    """The MDAnalysis walk (kinisi/parser.py:620-638) restated in the oracle against the reference run on a duck-typed
+    universe: exact for float64 input, single-precision noise for the float32 arrays MDAnalysis hands out (the
+    reference then works in float32; the oracle's unwrapping is float64)."""
+    from synth_inputs import ase_case_inputs
+    g = np.load(os.path.join(golden_dir, 'universe_reference.npz'))
+    for name in ('ase_nvt', 'ase_npt_triclinic'):
+        symbols, frac, latt, pp = ase_case_inputs(name)
+        cart = np.einsum('nfk,fkj->fnj', frac, latt)
+        fw = [i for i, sym in enumerate(symbols) if sym != 'Li']
+        for tag, dtype, atol in (('f64', np.float64, 1e-13), ('f32', np.float32, 2e-5)):
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                coords, cells = ko.universe_coords_latt(cart.astype(dtype), latt.astype(dtype))
+                assert coords.dtype == dtype
+                dc = ko.correct_drift(fw, ko.get_disp(coords, cells))
+            np.testing.assert_allclose(dc, g[f'{name}_{tag}_dc'], rtol=0, atol=atol)
