@@ -171,8 +171,10 @@ class ClockSampler:
     query, which stalled kernel launches inside a timed region that is only tens of milliseconds long."""
     BAD = {'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40, 'sw_power_cap': 0x4}
 
-    def __init__(self, index, period_s=0.004):
+    def __init__(self, index, period_s=None):
         import threading
+        if period_s is None:
+            period_s = float(os.environ.get('KB2_BENCH_CLOCK_PERIOD_MS', '4')) * 1e-3
         self.samples, self.max_clock, self.reasons = [], [], set()
         self._stop = threading.Event()
         self._thread = None
@@ -193,7 +195,8 @@ class ClockSampler:
         while not self._stop.is_set():
             try:
                 self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                self.max_clock.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                if not self.max_clock:  # a constant of the board: asked once
+                    self.max_clock.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
                 mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                 for name, bit in self.BAD.items():
                     if mask & bit:
@@ -504,13 +507,13 @@ def run_own(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--variant', type=int, default=None, help='self-moment kernel: 0 direct, 1 TMA ring, 2 arithmetic runs (default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--in-flight', type=int, default=2,
-                    help='analyses in flight: consecutive trajectories go to alternating CUDA streams (1 = one stream)')
+    ap.add_argument('--in-flight', type=int, default=4,
+                    help='analyses in flight: consecutive trajectories go round-robin to this many CUDA streams (1 = one stream)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

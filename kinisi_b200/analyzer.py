@@ -95,11 +95,12 @@ class Analyzer:
 
     @classmethod
     def _from_file(cls, trajectory, parser_params: dict, dtype: str = None, **kwargs):
-        """From one or a list of XDATCAR files (kinisi/analyzer.py:199-234); needs pymatgen like the reference."""
+        """From one or a list of XDATCAR files (kinisi/analyzer.py:199-234).  The reference reads them with
+        pymatgen.io.vasp.Xdatcar; where pymatgen is not installed the built-in reader (kinisi_b200/xdatcar.py) is used."""
         try:
             from pymatgen.io.vasp import Xdatcar
-        except ModuleNotFoundError:  # pragma: no cover
-            raise ModuleNotFoundError("To use the from_file method, pymatgen must be installed.")  # pragma: no cover
+        except ModuleNotFoundError:
+            from .xdatcar import Xdatcar
         if dtype is None:
             return cls._from_Xdatcar(Xdatcar(trajectory), parser_params, None, **kwargs)
         return cls._from_Xdatcar([Xdatcar(f) for f in trajectory], parser_params, dtype, **kwargs)

@@ -720,6 +720,50 @@ def test_universe_front_end(kb, golden_dir):
             kb.analyze.DiffusionAnalyzer.from_universe([u], parser_params=pp, dtype='consecutive')
 
 
+def test_from_file_reads_xdatcar(kb, tmp_path):
+    """`from_file` (kinisi/analyzer.py:199-234, diffusion_analyzer.py:148-175) through the built-in XDATCAR reader against
+    `from_pymatgen` on the same configurations; a list of files with dtype='identical' and 'consecutive'."""
+    from kinisi_b200.xdatcar import Xdatcar
+    from test_host_logic import _write_xdatcar
+    symbols, frac, latt, pp = ase_case_inputs('ase_npt_triclinic')
+    order = np.argsort([0 if sym == 'Li' else 1 for sym in symbols], kind='stable')  # XDATCAR groups the species
+    frac_f = np.round(np.transpose(frac[order], (1, 0, 2)), 9)
+    latt_r = np.round(latt, 9)
+    names = [symbols[i] for i in order]
+    species = sorted(set(names), key=names.index)
+    counts = [names.count(sp) for sp in species]
+    path = tmp_path / 'XDATCAR'
+    _write_xdatcar(path, species, counts, frac_f, latt_r, True)
+    pp = dict(pp, time_step=2.0)  # the pymatgen front-end takes femtoseconds
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        a = kb.analyze.DiffusionAnalyzer.from_file(str(path), parser_params=pp, uncertainty_params={'progress': False})
+        b = kb.analyze.DiffusionAnalyzer.from_pymatgen(Xdatcar(str(path)).structures, parser_params=pp,
+                                                       uncertainty_params={'progress': False})
+        c = kb.analyze.DiffusionAnalyzer.from_Xdatcar(Xdatcar(str(path)), parser_params=pp,
+                                                      uncertainty_params={'progress': False})
+        two = kb.analyze.DiffusionAnalyzer.from_file([str(path), str(path)], parser_params=pp, dtype='identical',
+                                                     uncertainty_params={'progress': False})
+        cons = kb.analyze.DiffusionAnalyzer.from_file([str(path), str(path)], parser_params=pp, dtype='consecutive',
+                                                      uncertainty_params={'progress': False})
+    for x in (b, c):
+        np.testing.assert_allclose(a.msd, x.msd, rtol=1e-12)  # the moment sums are accumulated with atomics
+        np.testing.assert_array_equal(a.dt, x.dt)
+    np.testing.assert_allclose(two.msd, a.msd, rtol=1e-12)
+    assert cons.dt.size >= a.dt.size and cons._diff._max_obs > a._diff._max_obs
+    # the same numbers as the oracle on the arrays that were written
+    coords = np.concatenate([frac_f[:1], frac_f], axis=0).transpose(1, 0, 2)
+    cells = np.concatenate([latt_r[:1], latt_r], axis=0)
+    li = [i for i, sym in enumerate(names) if sym == 'Li']
+    fw = [i for i, sym in enumerate(names) if sym != 'Li']
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        dc = ko.correct_drift(fw, ko.get_disp(coords, cells))
+    k = int(round(a.dt[0] / (pp['time_step'] * 1e-3 * pp['step_skip'])))
+    d = ko.displacements_for_lag(dc[li], k)
+    np.testing.assert_allclose(a.msd[0], np.mean(np.sum(d**2, axis=-1)), rtol=1e-9)
+
+
 def test_identical_trajectories_stack(kb):
     """dtype='identical' (kinisi/analyzer.py:111-116, 274-290): more atoms, n_o summed."""
     symbols = ['Li'] * 6 + ['O'] * 3

@@ -1,5 +1,7 @@
 """Host-side logic that needs no GPU: the Distribution container, shard bounds, the lag-grid / n_o
 bookkeeping of the parser mirror (checked against the oracle, which is pinned to the reference)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -132,3 +134,43 @@ def test_bootstrap_from_dict_needs_no_device():
     again = b.to_dict()
     np.testing.assert_array_equal(again['gradient']['samples'], grad.samples)
     assert again['start_dt'] == 3.0 and again['sigma'] is None
+
+
+def _write_xdatcar(path, species, counts, frac, latt, repeat_header):
+    """frac [F, N, 3], latt [F, 3, 3] -> XDATCAR text (one header, or one per configuration as NPT runs write)."""
+    import gzip
+    out = []
+    for f in range(frac.shape[0]):
+        if f == 0 or repeat_header:
+            out += ['synthetic', '   1.000000'] + ['  '.join(f'{x:.9f}' for x in row) for row in latt[f]]
+            out += ['  '.join(species), '  '.join(str(c) for c in counts)]
+        out.append(f'Direct configuration= {f + 1:5d}')
+        out += ['  '.join(f'{x:.9f}' for x in row) for row in frac[f]]
+    text = '\n'.join(out) + '\n'
+    opener = gzip.open if str(path).endswith('.gz') else open
+    with opener(path, 'wt') as fh:
+        fh.write(text)
+
+
+def test_xdatcar_reader(tmp_path):
+    """kinisi_b200/xdatcar.py: both XDATCAR layouts, gzip, and the surface PymatgenParser reads."""
+    from kinisi_b200.xdatcar import Xdatcar
+    rng = np.random.default_rng(0)
+    frac = np.round(rng.random((6, 5, 3)), 9)
+    latt = np.round(np.eye(3)[None] * 10.0 + 0.01 * rng.normal(size=(6, 3, 3)), 9)
+    fixed = np.repeat(latt[:1], 6, axis=0)
+    for name, cells, repeat in (('XDATCAR', fixed, False), ('XDATCAR_npt', latt, True), ('XDATCAR.gz', fixed, False)):
+        path = tmp_path / name
+        _write_xdatcar(path, ['Li', 'O'], [2, 3], frac, cells, repeat)
+        x = Xdatcar(str(path))
+        assert len(x.structures) == 6 and x.site_symbols == ['Li', 'Li', 'O', 'O', 'O']
+        np.testing.assert_allclose(x.frac_coords, frac, atol=1e-12)
+        np.testing.assert_allclose(x.lattices, cells, atol=1e-12)
+        s0 = x.structures[3]
+        assert [str(site.specie) for site in s0] == x.site_symbols and len(s0) == 5
+        np.testing.assert_allclose(s0.volume, abs(np.linalg.det(cells[3])), rtol=1e-12)
+        np.testing.assert_allclose(s0.lattice.matrix, cells[3], atol=1e-12)
+    ref = '/root/reference/kinisi/tests/inputs/example_XDATCAR.gz'
+    if os.path.exists(ref):  # the reference's own fixture (kinisi/tests/test_analyze.py:92-98), in the build container only
+        x = Xdatcar(ref)
+        assert x.frac_coords.shape == (140, 416, 3) and x.site_symbols.count('Li') == 192
