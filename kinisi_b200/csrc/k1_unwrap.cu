@@ -78,6 +78,21 @@ __global__ void invert_lattice_kernel(const double* __restrict__ latt, double* _
     o[8] = (a * e - b * d) * r;
 }
 
+constexpr int kFsBatch = 4;
+
+// a read-only global load the compiler keeps where it is written (volatile asm statements are not reordered among
+// themselves): used to issue a batch of independent loads back to back
+__device__ __forceinline__ float ld_nc_issue(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_nc_issue(const double* p) {
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // One thread per output frame, looping over a chunk of atoms: per-frame weighted sums of the
 // unwrapped displacement.  The sum over atoms commutes with the cumulative sum over time, so the
 // framework drift and the collective (MSTD/MSCD) sums need no per-atom scan and no per-atom atomics.
@@ -99,8 +114,35 @@ __global__ void __launch_bounds__(256) frame_sums_kernel(const T* __restrict__ c
         double L[9];
         load9(latt, L);
         double aw[3] = {0.0, 0.0, 0.0};
-#pragma unroll 8
-        for (int i = i0; i < i1; ++i) {
+        int i = i0;
+        if (!w) {
+            // kFsBatch atoms at a time with all their loads issued before the first use: the kernel is bound by the
+            // bytes it keeps in flight (one frame pair of one atom is 24 bytes per thread), not by issue or the pipes.
+            // (Taking the second frame from the neighbour lane instead of loading it -- half of these loads hit L1 --
+            // was slower: 98 us against 80 us; so were batches of 2, 6 and 8.)
+            for (; i + kFsBatch <= i1; i += kFsBatch) {
+                T v[kFsBatch][6];
+                int a[kFsBatch];
+#pragma unroll
+                for (int u = 0; u < kFsBatch; ++u) a[u] = idx[i + u];
+#pragma unroll
+                for (int u = 0; u < kFsBatch; ++u) {
+                    const T* base = coords + ((size_t)a[u] * F + t) * 3;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) v[u][k] = ld_nc_issue(base + k);
+                }
+#pragma unroll
+                for (int u = 0; u < kFsBatch; ++u) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        const double d = (double)v[u][3 + k] - (double)v[u][k];
+                        aw[k] += d - floor(d + 0.5);
+                    }
+                }
+            }
+        }
+#pragma unroll 4
+        for (; i < i1; ++i) {
             const T* base = coords + ((size_t)idx[i] * F + t) * 3;
             const double wi = w ? w[i] : 1.0;
 #pragma unroll
