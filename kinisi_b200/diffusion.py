@@ -278,7 +278,7 @@ class Bootstrap:
             else:
                 sums = torch.zeros((len(used), 2), dtype=torch.float64, device=self._device)
             if d.distributed:
-                dist.allreduce_sum_(sums)
+                dist.allreduce_sum_(sums, 'moments')
             if not np.array_equal(order, np.arange(len(order))):
                 inv = np.empty_like(order)
                 inv[order] = np.arange(len(order))
@@ -291,7 +291,7 @@ class Bootstrap:
             rows.append(engine.disp_moments(arr, mask)[:2])
         sums = torch.stack(rows)
         if self._lazy and d.distributed:
-            dist.allreduce_sum_(sums)
+            dist.allreduce_sum_(sums, 'moments')
         return sums
 
     def _collective_sums(self, used, weights, coll_mask):
@@ -304,7 +304,7 @@ class Bootstrap:
             else:
                 S = torch.zeros((3, d.dc.shape[2]), dtype=torch.float64, device=self._device)
             if d.distributed:
-                dist.allreduce_sum_(S)
+                dist.allreduce_sum_(S, 'frames')
             return engine.self_moments(S.unsqueeze(0), d.n_frames, d.lags[used], coll_mask)
         w = None if weights is None else self._dev(weights)
         rows = []

@@ -17,10 +17,28 @@ def rank():
     return td.get_rank() if active() else 0
 
 
-def allreduce_sum_(t):
-    """In-place sum all-reduce of a tensor (float64 moment sums / frame sums)."""
+_CHANNELS = {}
+
+
+def _channel(name):
+    """A process group of its own per kind of collective.  A communicator runs its collectives in issue order on one
+    internal stream: with several analyses in flight, the frame-sum all-reduce of the next trajectory would otherwise
+    queue behind the moment-sum all-reduce of the current one, which waits for its moment kernel -- stage 1 of the next
+    trajectory could not start before stage 2 of this one had finished.  Created on first use, in program order (the
+    same on every rank)."""
+    if name is None:
+        return None
+    key = (name, td.get_world_size(), td.get_rank())
+    if key not in _CHANNELS:
+        _CHANNELS[key] = td.new_group()
+    return _CHANNELS[key]
+
+
+def allreduce_sum_(t, channel=None):
+    """In-place sum all-reduce of a tensor (float64 moment sums / frame sums); `channel` names the communicator
+    (None: the default group)."""
     if active():
-        td.all_reduce(t, op=td.ReduceOp.SUM)
+        td.all_reduce(t, op=td.ReduceOp.SUM, group=_channel(channel))
     return t
 
 

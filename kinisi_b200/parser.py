@@ -487,7 +487,7 @@ class Parser:
                 if sums is None:
                     sums = torch.zeros((3, pitch), dtype=torch.float64, device=dev)
                 if self._distributed:
-                    dist.allreduce_sum_(sums)
+                    dist.allreduce_sum_(sums, 'frames')
             self._drift = None if n_fw == 0 else (sums, float(n_fw))
             step_sums, scale = (None, 0.0) if self._drift is None else (sums, 1.0 / n_fw)
             dc = torch.empty((len(sel), 3, pitch), dtype=torch.float64, device=dev)
@@ -537,7 +537,7 @@ class Parser:
         else:
             sums = torch.zeros((3, engine.pitch_for(traj.n_frames)), dtype=torch.float64, device=traj.device)
         if self._distributed:
-            dist.allreduce_sum_(sums)
+            dist.allreduce_sum_(sums, 'frames')
         return sums, float(n_fw)
 
     @property

@@ -42,16 +42,16 @@ def _worker(rank, world, port, out_dir):
         assert (n_sel, n_fwg) == (n_mobile, n_fw)
         # framework drift: per-frame sums of the local framework atoms, all-reduced, then scanned
         fw_sum = torch.from_numpy(u[n_mobile + f_lo:n_mobile + f_hi].sum(axis=0).T.copy())
-        dist.allreduce_sum_(fw_sum)
+        dist.allreduce_sum_(fw_sum, 'frames')
         drift = np.cumsum(fw_sum.numpy().T, axis=0) / n_fwg
         dc_local = np.cumsum(u[m_lo:m_hi], axis=1) - drift[None]
         lags = ko.time_intervals(n_frames, 0.001, 1, n_steps=25)
         S1, S2, _, _ = ko.raw_sums_streaming(dc_local, lags)
         sums = torch.from_numpy(np.stack([S1, S2], axis=1))
-        dist.allreduce_sum_(sums)
+        dist.allreduce_sum_(sums, 'moments')
         # collective sum for MSTD
         S = torch.from_numpy(dc_local.sum(axis=0).T.copy())
-        dist.allreduce_sum_(S)
+        dist.allreduce_sum_(S, 'frames')
         if rank == 0:
             np.savez(os.path.join(out_dir, 'out.npz'), sums=sums.numpy(), S=S.numpy(), lags=lags)
     finally:
