@@ -252,7 +252,7 @@ class ClockSampler:
 def run_own(args):
     import torch
     import torch.distributed as td
-    from kinisi_b200 import diffusion, dist, engine
+    from kinisi_b200 import diffusion, engine
     from kinisi_b200.parser import Parser
 
     world = int(os.environ.get('WORLD_SIZE', '1'))

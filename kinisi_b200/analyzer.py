@@ -4,7 +4,7 @@ path): routes a trajectory through a parser and keeps `(delta_t, disp_3d, n_o, v
 
 HDF5 save/load (kinisi/analyzer.py:33-67) is persistence, not part of this path: `save`/`load` raise.
 """
-from typing import List, Union
+from typing import Union
 
 import numpy as np
 

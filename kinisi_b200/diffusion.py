@@ -12,7 +12,7 @@ reference's seam, kinisi/diffusion.py:552-564; each entry is reduced by one kern
 device (csrc/k6_resample.cu).
 """
 import warnings
-from typing import List, Union
+from typing import Union
 
 import numpy as np
 import scipy.constants as const

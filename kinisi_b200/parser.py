@@ -13,7 +13,7 @@ What differs from the reference by design
     indexes it.  `memory_limit` therefore guards the device-resident displacement array instead.
 """
 import warnings
-from typing import List, Tuple, Union
+from typing import List, Tuple
 
 import numpy as np
 import torch
