@@ -5,8 +5,21 @@ import torch
 import torch.distributed as td
 
 
+_CHANNELS = {}
+_STATE = {'group': None, 'active': False}
+
+
 def active():
-    return td.is_available() and td.is_initialized() and td.get_world_size() > 1
+    """True inside an initialised process group of more than one rank (cached per default group: this is asked several
+    times per analysis)."""
+    if not (td.is_available() and td.is_initialized()):
+        _STATE['group'] = None
+        return False
+    g = td.group.WORLD
+    if _STATE['group'] is not g:
+        _STATE['group'], _STATE['active'] = g, td.get_world_size() > 1
+        _CHANNELS.clear()
+    return _STATE['active']
 
 
 def world_size():
@@ -17,8 +30,6 @@ def rank():
     return td.get_rank() if active() else 0
 
 
-_CHANNELS = {}
-
 
 def _channel(name):
     """A process group of its own per kind of collective.  A communicator runs its collectives in issue order on one
@@ -26,19 +37,25 @@ def _channel(name):
     queue behind the moment-sum all-reduce of the current one, which waits for its moment kernel -- stage 1 of the next
     trajectory could not start before stage 2 of this one had finished.  Created on first use, in program order (the
     same on every rank)."""
-    if name is None:
-        return None
-    key = (name, td.get_world_size(), td.get_rank())
-    if key not in _CHANNELS:
-        _CHANNELS[key] = td.new_group()
-    return _CHANNELS[key]
+    g = _CHANNELS.get(name)
+    if g is None:
+        g = _CHANNELS[name] = td.group.WORLD if name is None else td.new_group()
+    return g
+
+
+_SUM_OPTS = None
 
 
 def allreduce_sum_(t, channel=None):
     """In-place sum all-reduce of a tensor (float64 moment sums / frame sums); `channel` names the communicator
-    (None: the default group)."""
+    (None: the default group).  Goes to the process group's own entry point: the checks and logging of the
+    torch.distributed wrapper cost more host time than the collective takes on the device."""
+    global _SUM_OPTS
     if active():
-        td.all_reduce(t, op=td.ReduceOp.SUM, group=_channel(channel))
+        if _SUM_OPTS is None:
+            _SUM_OPTS = td.AllreduceOptions()
+            _SUM_OPTS.reduceOp = td.ReduceOp.SUM
+        _channel(channel).allreduce([t], _SUM_OPTS).wait()
     return t
 
 
