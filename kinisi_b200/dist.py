@@ -1,6 +1,9 @@
 """Multi-GPU plumbing: one process per GPU, atoms sharded across ranks, per-dt moment sums and the
 per-frame framework / collective sums joined by a sum all-reduce (NCCL over NVLink on the GPU box,
 gloo in the CPU tests).  Everything is a no-op when torch.distributed is not initialised."""
+import ctypes
+import os
+
 import torch
 import torch.distributed as td
 
@@ -19,6 +22,7 @@ def active():
     if _STATE['group'] is not g:
         _STATE['group'], _STATE['active'] = g, td.get_world_size() > 1
         _CHANNELS.clear()
+        _DIRECT.clear()
     return _STATE['active']
 
 
@@ -43,6 +47,89 @@ def _channel(name):
     return g
 
 
+class _NcclUniqueId(ctypes.Structure):
+    _fields_ = [('internal', ctypes.c_byte * 128)]
+
+
+class _DirectComm:
+    """One NCCL communicator driven through the library's C API, for the small float64 all-reduces of the path.
+
+    `ProcessGroupNCCL` runs every collective on a stream of its own (two event hand-overs per call) behind a good deal of
+    bookkeeping: 115-130 us of host time per call in the analysis loop, which made the host thread the bottleneck of a
+    sharded run.  Here `ncclAllReduce` is enqueued on the CALLER's stream, about 10 us.  Calls on
+    one communicator must run in the same order on every rank; they come from different streams (analyses in flight), so
+    each call waits for the event of the previous one on this communicator."""
+    _lib = None
+
+    @classmethod
+    def library(cls):
+        if cls._lib is None:
+            path = None
+            with open('/proc/self/maps') as f:  # the copy of libnccl torch has already loaded
+                for line in f:
+                    if 'libnccl.so' in line:
+                        path = line.split()[-1]
+                        break
+            if path is None:
+                raise OSError('libnccl is not loaded in this process')
+            lib = ctypes.CDLL(path)
+            lib.ncclGetUniqueId.argtypes = [ctypes.POINTER(_NcclUniqueId)]
+            lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _NcclUniqueId, ctypes.c_int]
+            lib.ncclAllReduce.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_void_p]
+            lib.ncclGetErrorString.restype = ctypes.c_char_p
+            lib.ncclGetErrorString.argtypes = [ctypes.c_int]
+            cls._lib = lib
+        return cls._lib
+
+    def __init__(self, device):
+        lib = self.library()
+        uid = _NcclUniqueId()
+        if td.get_rank() == 0:
+            self._check(lib.ncclGetUniqueId(ctypes.byref(uid)))
+        raw = torch.frombuffer(bytearray(bytes(uid)), dtype=torch.uint8).to(device)
+        td.broadcast(raw, 0)
+        ctypes.memmove(ctypes.byref(uid), bytes(raw.cpu().numpy().tobytes()), 128)
+        comm = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            self._check(lib.ncclCommInitRank(ctypes.byref(comm), td.get_world_size(), uid, td.get_rank()))
+        self._comm, self._last, self.device = comm, None, device
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError('NCCL: ' + self.library().ncclGetErrorString(rc).decode())
+
+    def allreduce_sum_f64(self, t):
+        stream = torch.cuda.current_stream(t.device)
+        if self._last is not None:
+            stream.wait_event(self._last)
+        self._check(self.library().ncclAllReduce(t.data_ptr(), t.data_ptr(), t.numel(), 8, 0, self._comm,
+                                                 stream.cuda_stream))  # 8 = ncclFloat64, 0 = ncclSum
+        self._last = torch.cuda.Event()
+        self._last.record(stream)
+
+
+_DIRECT = {}
+
+
+def _direct(name, t):
+    """The direct communicator for channel `name`, or None (CPU tensors, another backend, KB2_DIRECT_NCCL=0, or the
+    library could not be driven: the process group is used instead)."""
+    if not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous() or os.environ.get('KB2_DIRECT_NCCL', '1') == '0':
+        return None
+    key = (name, t.device.index)
+    if key not in _DIRECT:
+        comm = None
+        if td.get_backend() == 'nccl':
+            try:
+                comm = _DirectComm(t.device)
+            except Exception as exc:  # stay on the process group
+                import warnings
+                warnings.warn(f'kinisi_b200.dist: direct NCCL communicator unavailable ({exc}); using torch.distributed')
+        _DIRECT[key] = comm
+    return _DIRECT[key]
+
+
 _SUM_OPTS = None
 
 
@@ -52,6 +139,10 @@ def allreduce_sum_(t, channel=None):
     torch.distributed wrapper cost more host time than the collective takes on the device."""
     global _SUM_OPTS
     if active():
+        comm = _direct(channel, t)
+        if comm is not None:
+            comm.allreduce_sum_f64(t)
+            return t
         if _SUM_OPTS is None:
             _SUM_OPTS = td.AllreduceOptions()
             _SUM_OPTS.reduceOp = td.ReduceOp.SUM
