@@ -174,3 +174,17 @@ def test_xdatcar_reader(tmp_path):
     if os.path.exists(ref):  # the reference's own fixture (kinisi/tests/test_analyze.py:92-98), in the build container only
         x = Xdatcar(ref)
         assert x.frac_coords.shape == (140, 416, 3) and x.site_symbols.count('Li') == 192
+
+
+def test_direct_nccl_plumbing_is_inert_without_a_group():
+    """dist.allreduce_sum_ is a no-op outside a process group, and the direct NCCL communicator is only considered for
+    contiguous float64 CUDA tensors (everything else stays on torch.distributed)."""
+    import ctypes
+    import torch
+    from kinisi_b200 import dist
+    assert ctypes.sizeof(dist._NcclUniqueId) == 128  # ncclUniqueId is 128 bytes (nccl.h)
+    t = torch.arange(4, dtype=torch.float64)
+    assert not dist.active() and dist.allreduce_sum_(t, 'moments') is t and t.tolist() == [0.0, 1.0, 2.0, 3.0]
+    assert dist._direct('moments', t) is None  # a CPU tensor
+    assert dist.world_size() == 1 and dist.rank() == 0
+    assert dist.shard_bounds(10, 1, 3) == (4, 7)
