@@ -188,3 +188,54 @@ def test_direct_nccl_plumbing_is_inert_without_a_group():
     assert dist._direct('moments', t) is None  # a CPU tensor
     assert dist.world_size() == 1 and dist.rank() == 0
     assert dist.shard_bounds(10, 1, 3) == (4, 7)
+
+
+def test_xdatcar_reader_cartesian_and_volume_scale(tmp_path):
+    """Cartesian configurations are converted with the cell; a negative scale line is the cell volume (VASP convention)."""
+    from kinisi_b200.xdatcar import Xdatcar
+    cell = np.array([[4.0, 0.0, 0.0], [0.5, 5.0, 0.0], [0.0, 0.3, 6.0]])
+    frac = np.array([[0.1, 0.2, 0.3], [0.6, 0.7, 0.8]])
+    cart = frac @ cell
+    lines = ['cart', '  1.0'] + ['  '.join(f'{x:.10f}' for x in r) for r in cell] + ['Na Cl', '1 1', 'Cartesian configuration=     1']
+    lines += ['  '.join(f'{x:.10f}' for x in r) for r in cart]
+    (tmp_path / 'X1').write_text('\n'.join(lines) + '\n')
+    x = Xdatcar(str(tmp_path / 'X1'))
+    np.testing.assert_allclose(x.frac_coords[0], frac, atol=1e-9)
+    assert x.site_symbols == ['Na', 'Cl']
+    unit = np.eye(3)
+    lines = ['vol', '  -27.0'] + ['  '.join(f'{x:.10f}' for x in r) for r in unit] + ['Li', '1', 'Direct configuration=     1', '0.5 0.5 0.5']
+    (tmp_path / 'X2').write_text('\n'.join(lines) + '\n')
+    x = Xdatcar(str(tmp_path / 'X2'))
+    np.testing.assert_allclose(x.lattices[0], 3.0 * np.eye(3), rtol=1e-12)
+    np.testing.assert_allclose(x.structures[0].volume, 27.0, rtol=1e-12)
+    (tmp_path / 'X3').write_text('\n'.join(['empty', '1.0', '1 0 0', '0 1 0', '0 0 1', 'Li', '1']) + '\n')
+    with pytest.raises(ValueError, match='no configurations'):
+        Xdatcar(str(tmp_path / 'X3'))
+
+
+def test_universe_walk_matches_the_restatement():
+    """MDAnalysisParser.get_structure_coords_latt (host arithmetic of kinisi/parser.py:600-638) on a duck-typed universe
+    against the oracle's restatement; sub-sampling of atoms and frames; index selection by atom type."""
+    from duck_atoms import universe_from_arrays
+    from kinisi_b200.parser import MDAnalysisParser
+    from oracle import kinisi_oracle as ko
+    rng = np.random.default_rng(4)
+    frac = rng.random((6, 9, 3))
+    latt = np.eye(3)[None] * 8.0 + 0.05 * rng.normal(size=(9, 3, 3))
+    types = ['Li', 'O', 'Li', 'O', 'O', 'Li']
+    u = universe_from_arrays(types, frac, latt, np.float64)
+    structure, coords, cells, volume = MDAnalysisParser.get_structure_coords_latt(u, progress=False)
+    cart = np.einsum('nfk,fkj->fnj', frac, latt)
+    want, want_cells = ko.universe_coords_latt(cart, latt)
+    np.testing.assert_allclose(np.concatenate(coords, axis=1), want, rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(np.array(cells), want_cells, rtol=0, atol=0)
+    np.testing.assert_allclose(volume, abs(np.linalg.det(latt[0])), rtol=1e-12)
+    assert len(coords) == 10 and coords[0].shape == (6, 1, 3)
+    _, sub, sub_cells, _ = MDAnalysisParser.get_structure_coords_latt(u, sub_sample_atoms=2, sub_sample_traj=3, progress=False)
+    assert len(sub) == 4 and sub[0].shape == (3, 1, 3)
+    np.testing.assert_allclose(sub[1][:, 0], want[::2, 1 + 0], rtol=1e-13)
+    np.testing.assert_allclose(sub[2][:, 0], want[::2, 1 + 3], rtol=1e-13)
+    assert MDAnalysisParser.get_indices(structure, 'Li', None) == ([0, 2, 5], [1, 3, 4])
+    assert MDAnalysisParser.get_indices(structure, ['O'], [0])[1] == [0]
+    with pytest.raises(ValueError, match='no species'):
+        MDAnalysisParser.get_indices(structure, 'Xe', None)
