@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KB2_ABI_VERSION 4
+#define KB2_ABI_VERSION 5
 
 /* coordinate element types */
 #define KB2_F32 0
@@ -167,6 +167,31 @@ int kb2_self_moments_runs_planned(const double* dc, int n_atoms, int n_frames, i
  * stores the number of lags that became runs of one in *n_rest. */
 int kb2_self_moments_plan(const int32_t* lags_host, int n_lags, int n_frames, int32_t* run_k0, int32_t* run_delta,
                           int32_t* run_len, int32_t* run_n_chg, int max_runs, int* n_rest);
+
+/* The same sums through the lag-window kernel (variant 3, the default of the Python host side).  The grid
+ * (kinisi/parser.py:150-168) is cut into WINDOWS of up to 8 lags in arithmetic progression, kappa + w*D; a thread walks the
+ * origins j = t + a*D of one residue class downwards with the 8 most recent partner samples and the 16 accumulators of
+ * the window in registers: one origin and one partner sample per step serve 8 terms, the accumulators are folded across
+ * the warp once per work item, no step is predicated (csrc/k2_moments_win.cu).  Lags that fit no progression of >= 3
+ * become windows of one.  Same two-step protocol as the arithmetic-run kernel:
+ *   kb2_self_moments_win_workspace_bytes  size of a packed plan (host and device copy) for n_lags lags
+ *   kb2_self_moments_win_blocks           number of launches (blocks of 256 lags) = 256-byte counter slots needed
+ *   kb2_self_moments_win_plan_pack        plans on the host into plan_host; no device work; depends on (lags, n_frames) only
+ *   kb2_self_moments_win_planned          launches: plan_host = the host copy (headers are read by the call), plan_dev = the
+ *                                         same bytes in device memory (uploaded earlier in stream order; never written),
+ *                                         counters = kb2_self_moments_win_blocks(n_lags) * 256 bytes of device memory
+ *                                         (zeroed by the call; not shared between concurrent calls); sums[n_lags][2] is
+ *                                         zeroed by the call.
+ *   kb2_self_moments_win_plan             the windows of (the first 256 lags of) a grid, for tests and diagnostics: fills up
+ *                                         to max_wins entries of win_kappa / win_delta / win_len (host arrays, may be
+ *                                         NULL), returns the number of windows. */
+size_t kb2_self_moments_win_workspace_bytes(int n_lags);
+int kb2_self_moments_win_blocks(int n_lags);
+int kb2_self_moments_win_plan_pack(const int32_t* lags_host, int n_lags, int n_frames, void* plan_host);
+int kb2_self_moments_win_planned(const double* dc, int n_atoms, int n_frames, int64_t pitch, int n_lags, int dim_mask,
+                                 const void* plan_host, const void* plan_dev, void* counters, double* sums, void* stream);
+int kb2_self_moments_win_plan(const int32_t* lags_host, int n_lags, int n_frames, int32_t* win_kappa, int32_t* win_delta,
+                              int32_t* win_len, int max_wins);
 
 /* The same sums from ONE materialised displacement array disp[n_atoms][n_obs][3] (float64, the
  * reference seam: an entry of disp_3d as passed to the *Bootstrap constructors,

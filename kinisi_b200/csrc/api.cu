@@ -11,6 +11,18 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+// SM count of the CURRENT device (the launchers size persistent grids from it), cached per device ordinal.
+int device_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+    int sm = 148;
+    if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm <= 0) sm = 148;
+    if (dev >= 0 && dev < 64) cached[dev] = sm;
+    return sm;
+}
 }  // namespace kb2
 
 extern "C" int kb2_abi_version(void) { return KB2_ABI_VERSION; }
@@ -57,8 +69,7 @@ __global__ void __launch_bounds__(256) stream_copy_kernel(const double2* __restr
 
 extern "C" int kb2_stream_copy(const double* src, double* dst, size_t n, void* stream) {
     KB2_CHECK(n % 2 == 0, "kb2_stream_copy: n must be even");
-    int sm = 148;
-    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
+    const int sm = kb2::device_sm_count();
     stream_copy_kernel<<<sm * 8, 256, 0, (cudaStream_t)stream>>>((const double2*)src, (double2*)dst, n / 2);
     KB2_LAUNCH_CHECK();
     return 0;

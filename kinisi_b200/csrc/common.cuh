@@ -9,6 +9,7 @@
 namespace kb2 {
 
 void set_error(const char* fmt, ...);
+int device_sm_count();  // SM count of the current device (api.cu)
 
 #define KB2_CHECK(cond, ...)          \
     do {                              \

@@ -528,8 +528,7 @@ static int launch_unwrap(const void* coords, int n_atoms_total, int F, const dou
     // ticket counter = 0; totals = the "not ready" pattern
     KB2_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
     KB2_CUDA(cudaMemsetAsync((unsigned char*)workspace + 256, 0xFF, uw_workspace_bytes(n_idx, n_tiles) - 256, st));
-    int sm = 148;
-    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
+    const int sm = device_sm_count();
     const int grid = (int)std::min<int64_t>((int64_t)n_idx * n_tiles, (int64_t)sm * 3);
     unwrap_cumsum_kernel<T, MODE, CONSTL><<<grid, kUwThreads, smem, st>>>(
         c, (int64_t)n_atoms_total * F * 3, F, latt, inv, lstride, idx, n_idx, step_sums, step_scale, out, pitch, Tn, n_tiles,
@@ -579,8 +578,7 @@ extern "C" int kb2_frame_sums(const void* coords, int dtype, int mode, int n_ato
     KB2_CHECK(frame_sums, "kb2_frame_sums: null output");
     cudaStream_t st = (cudaStream_t)stream;
     KB2_CUDA(cudaMemsetAsync(frame_sums, 0, sizeof(double) * 3 * pitch, st));
-    int sm = 148;
-    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
+    const int sm = device_sm_count();
     const int tiles = ceil_div(Tn, 256);
     int chunks = ceil_div((int64_t)sm * 8, tiles);
     chunks = max(1, min(chunks, ceil_div(n_idx, 8)));
@@ -639,8 +637,7 @@ extern "C" int kb2_atom_sum(const double* dc, int n_atoms, int64_t pitch, const 
     KB2_CHECK(dc && out && n_atoms > 0 && pitch > 0, "kb2_atom_sum: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     KB2_CUDA(cudaMemsetAsync(out, 0, sizeof(double) * 3 * pitch, st));
-    int sm = 148;
-    cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
+    const int sm = device_sm_count();
     const int tiles = ceil_div(pitch, 256);
     int chunks = ceil_div((int64_t)sm * 8, (int64_t)tiles * 3);
     chunks = max(1, min(chunks, ceil_div(n_atoms, 8)));

@@ -257,8 +257,7 @@ extern "C" int kb2_self_moments(const double* dc, int n_atoms, int n_frames, int
     int comp[3] = {0, 0, 0}, ndim = 0;
     for (int c = 0; c < 3; ++c)
         if (dim_mask & (1 << c)) comp[ndim++] = c;
-    int sm_count = 148;
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, 0);
+    const int sm_count = device_sm_count();
 
     unsigned int* counter = (unsigned int*)workspace;
     double* partials = (double*)((char*)workspace + 256);
@@ -306,8 +305,7 @@ extern "C" int kb2_disp_moments(const double* disp, int n_atoms, int n_obs, int 
     KB2_CHECK(dim_mask >= 1 && dim_mask <= 7 && coll_mask >= 0 && coll_mask <= 7, "kb2_disp_moments: bad mask");
     cudaStream_t st = (cudaStream_t)stream;
     KB2_CUDA(cudaMemsetAsync(out, 0, 4 * sizeof(double), st));
-    int sm_count = 148;
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, 0);
+    const int sm_count = device_sm_count();
     const int64_t n_elem = (int64_t)n_atoms * n_obs;
     const int grid = (int)std::min<int64_t>(ceil_div(n_elem, 256), (int64_t)sm_count * 8);
     disp_self_kernel<<<grid, 256, 0, st>>>(disp, n_elem, dim_mask & 1, dim_mask & 2, dim_mask & 4, out);

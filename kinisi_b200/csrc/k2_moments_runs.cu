@@ -731,8 +731,7 @@ extern "C" int kb2_self_moments_runs_planned(const double* dc, int n_atoms, int 
     int comp[3] = {0, 0, 0}, ndim = 0;
     for (int c = 0; c < 3; ++c)
         if (dim_mask & (1 << c)) comp[ndim++] = c;
-    int sm_count = 148;
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, 0);
+    const int sm_count = device_sm_count();
     const int kcap = n_lags > kRunMaxLags ? kRunMaxLags : n_lags;
     const size_t stride = runs_plan_bytes(kcap, n_frames);
     const int blocks = (n_lags + kRunMaxLags - 1) / kRunMaxLags;

@@ -14,8 +14,9 @@ DIM_MASK = {'x': 1, 'y': 2, 'z': 4, 'xy': 3, 'xz': 5, 'yz': 6, 'xyz': 7}
 # self-moment kernel variants (kb2_self_moments `variant`)
 VARIANT_DIRECT = 0
 VARIANT_TMA = 1
-VARIANT_RUNS = 2  # arithmetic-run kernel (register window); plans on the host, needs the lags there
-DEFAULT_VARIANT = VARIANT_RUNS
+VARIANT_RUNS = 2  # arithmetic-run kernel (origin window in registers); plans on the host, needs the lags there
+VARIANT_WIN = 3   # lag-window kernel (partner window + accumulators in registers); plans on the host too
+DEFAULT_VARIANT = VARIANT_WIN
 
 # count of kernel launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = {'n': 0}
@@ -170,9 +171,20 @@ def self_moments(dc, n_frames, lags, mask=7, variant=None):
         variant = DEFAULT_VARIANT
     K = len(lags) if not isinstance(lags, torch.Tensor) else lags.numel()
     sums = torch.empty((K, 2), dtype=torch.float64, device=dc.device)
+    if (variant & 0xff) == VARIANT_WIN:
+        lags_host = np.ascontiguousarray(lags.cpu().numpy() if isinstance(lags, torch.Tensor) else lags, dtype=np.int32)
+        plan_host, plan_dev = _host_plan(lib, 'win', lags_host, n_frames, dc.device)
+        blocks = lib.kb2_self_moments_win_blocks(K)
+        counters = torch.empty(256 * blocks, dtype=torch.uint8, device=dc.device)
+        check(
+            lib.kb2_self_moments_win_planned(dc.data_ptr(), dc.shape[0], n_frames, dc.shape[2], K, mask,
+                                             plan_host.data_ptr(), plan_dev.data_ptr(), counters.data_ptr(),
+                                             sums.data_ptr(), _stream()), 'kb2_self_moments_win_planned')
+        _count(blocks)
+        return sums
     if (variant & 0xff) == VARIANT_RUNS:
         lags_host = np.ascontiguousarray(lags.cpu().numpy() if isinstance(lags, torch.Tensor) else lags, dtype=np.int32)
-        plan_host, plan_dev = _runs_plan(lib, lags_host, n_frames, dc.device)
+        plan_host, plan_dev = _host_plan(lib, 'runs', lags_host, n_frames, dc.device)
         blocks = (K + 191) // 192
         counters = torch.empty(256 * blocks, dtype=torch.uint8, device=dc.device)
         check(
@@ -191,30 +203,47 @@ def self_moments(dc, n_frames, lags, mask=7, variant=None):
     return sums
 
 
-_RUNS_PLANS = {}  # (lags, n_frames, device) -> (pinned host plan, device plan); the plan depends on nothing else
+_RUNS_PLANS = {}  # (kind, lags, n_frames, device) -> (pinned host plan, device plan, upload event)
 
 
-def _runs_plan(lib, lags_host, n_frames, device):
-    """The packed plan of the arithmetic-run kernel for a lag grid, planned once and kept on the device: repeated
-    analyses of trajectories of one shape (and the blocks of a staged ingest) only launch."""
-    key = (lags_host.tobytes(), int(n_frames), device.type, device.index)
+def _host_plan(lib, kind, lags_host, n_frames, device):
+    """The packed plan of a host-planned moment kernel ('win' or 'runs') for a lag grid, planned once and kept on the
+    device: repeated analyses of trajectories of one shape (and the blocks of a staged ingest) only launch.  The plan
+    depends on (lags, n_frames) only."""
+    key = (kind, lags_host.tobytes(), int(n_frames), device.type, device.index)
     hit = _RUNS_PLANS.get(key)
+    stream = torch.cuda.current_stream(device)
     if hit is not None:
         plan_host, plan_dev, uploaded = hit
         if not uploaded.query():  # uploaded on another stream and still in flight
-            torch.cuda.current_stream(device).wait_event(uploaded)
+            stream.wait_event(uploaded)
+        plan_dev.record_stream(stream)
         return plan_host, plan_dev
-    nbytes = lib.kb2_self_moments_runs_workspace_bytes(len(lags_host), int(n_frames))
+    if kind == 'win':
+        nbytes = lib.kb2_self_moments_win_workspace_bytes(len(lags_host))
+    else:
+        nbytes = lib.kb2_self_moments_runs_workspace_bytes(len(lags_host), int(n_frames))
     plan_host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-    check(lib.kb2_self_moments_runs_plan_pack(lags_host.ctypes.data, len(lags_host), int(n_frames), plan_host.data_ptr()),
-          'kb2_self_moments_runs_plan_pack')
+    pack = lib.kb2_self_moments_win_plan_pack if kind == 'win' else lib.kb2_self_moments_runs_plan_pack
+    check(pack(lags_host.ctypes.data, len(lags_host), int(n_frames), plan_host.data_ptr()), f'kb2_self_moments_{kind}_plan_pack')
     plan_dev = plan_host.to(device, non_blocking=True)
     uploaded = torch.cuda.Event()
-    uploaded.record(torch.cuda.current_stream(device))
+    uploaded.record(stream)
     if len(_RUNS_PLANS) >= 32:
         _RUNS_PLANS.pop(next(iter(_RUNS_PLANS)))
     _RUNS_PLANS[key] = (plan_host, plan_dev, uploaded)
     return plan_host, plan_dev
+
+
+def self_moments_windows(lags, n_frames):
+    """The windows kb2_self_moments_win would use: [(first lag, spacing, number of lags), ...]."""
+    lib = _lib.load()
+    lags_host = np.ascontiguousarray(lags, dtype=np.int32)
+    cap = max(1, len(lags_host))
+    arrs = [np.zeros(cap, dtype=np.int32) for _ in range(3)]
+    n = lib.kb2_self_moments_win_plan(lags_host.ctypes.data, len(lags_host), int(n_frames), arrs[0].ctypes.data,
+                                      arrs[1].ctypes.data, arrs[2].ctypes.data, cap)
+    return [tuple(int(a[i]) for a in arrs) for i in range(min(n, cap))]
 
 
 def self_moments_plan(lags, n_frames):
