@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KB2_ABI_VERSION 5
+#define KB2_ABI_VERSION 6
 
 /* coordinate element types */
 #define KB2_F32 0
@@ -192,6 +192,30 @@ int kb2_self_moments_win_planned(const double* dc, int n_atoms, int n_frames, in
                                  const void* plan_host, const void* plan_dev, void* counters, double* sums, void* stream);
 int kb2_self_moments_win_plan(const int32_t* lags_host, int n_lags, int n_frames, int32_t* win_kappa, int32_t* win_delta,
                               int32_t* win_len, int max_wins);
+
+/* The same sums through the tiled lag-window kernel (variant 4, the default of the Python host side; replaces the per-dt
+ * loop of kinisi/diffusion.py:571-602 over the list of kinisi/parser.py:208-216).  One component of a trajectory is read as
+ * a matrix with rows of D frames (D a multiple of the common difference of a progression of the grid,
+ * kinisi/parser.py:150-168); a lag is k = I*D + r, a WINDOW up to 8 lags with consecutive I and one r.  The rows a group
+ * of windows needs for a block of origin rows of a strip of 32 columns are copied into shared memory by the TMA engine
+ * (cp.async.bulk + mbarrier, three buffers in flight, one producer warp); consumer warps walk the windows out of shared
+ * memory with the partner window and the accumulators in registers: one origin and one partner sample per step serve 8
+ * terms (csrc/k2_moments_tile.cu).  dc must be 16-byte aligned and pitch a multiple of 16.  Same two-step protocol:
+ *   kb2_self_moments_tile_workspace_bytes  size of the packed plan (host and device copy); runs the planner (host only)
+ *   kb2_self_moments_tile_blocks           number of launches (blocks of 256 lags) = 256-byte counter slots needed
+ *   kb2_self_moments_tile_plan_pack        plans on the host into plan_host; depends on (lags, n_frames) only
+ *   kb2_self_moments_tile_planned          launches (plan_host: headers are read by the call; plan_dev: the same bytes on the
+ *                                          device, uploaded earlier in stream order; counters, sums: zeroed by the call)
+ *   kb2_self_moments_tile_plan             the windows of (the first 256 lags of) a grid, for tests and diagnostics: first
+ *                                          lag, lag spacing (= row length D) and number of lags per window; *n_tiles (may
+ *                                          be NULL) receives the number of tile templates. */
+size_t kb2_self_moments_tile_workspace_bytes(const int32_t* lags_host, int n_lags, int n_frames);
+int kb2_self_moments_tile_blocks(int n_lags);
+int kb2_self_moments_tile_plan_pack(const int32_t* lags_host, int n_lags, int n_frames, void* plan_host);
+int kb2_self_moments_tile_planned(const double* dc, int n_atoms, int n_frames, int64_t pitch, int n_lags, int dim_mask,
+                                  const void* plan_host, const void* plan_dev, void* counters, double* sums, void* stream);
+int kb2_self_moments_tile_plan(const int32_t* lags_host, int n_lags, int n_frames, int32_t* win_first, int32_t* win_delta,
+                               int32_t* win_len, int max_wins, int* n_tiles);
 
 /* The same sums from ONE materialised displacement array disp[n_atoms][n_obs][3] (float64, the
  * reference seam: an entry of disp_3d as passed to the *Bootstrap constructors,

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, 'libkinisi_b200.so')
 
 F32, F64 = 0, 1
 MODE_FRACTIONAL, MODE_DISPLACEMENT = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # name -> (restype, argtypes); mirrors include/kinisi_b200.h one to one
 SIGNATURES = {
@@ -44,6 +44,12 @@ SIGNATURES = {
     'kb2_self_moments_win_planned': (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                              c_void_p, c_void_p]),
     'kb2_self_moments_win_plan': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int]),
+    'kb2_self_moments_tile_workspace_bytes': (c_size_t, [c_void_p, c_int, c_int]),
+    'kb2_self_moments_tile_blocks': (c_int, [c_int]),
+    'kb2_self_moments_tile_plan_pack': (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    'kb2_self_moments_tile_planned': (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p]),
+    'kb2_self_moments_tile_plan': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_int)]),
     'kb2_self_moments_plan': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                       POINTER(c_int)]),
     'kb2_disp_moments': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),

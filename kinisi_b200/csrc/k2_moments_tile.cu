@@ -1,0 +1,932 @@
+// Stage 2, variant 4 (default): the tiled lag-window kernel.  Trajectory tiles are staged in shared memory by the TMA
+// engine (cp.async.bulk + mbarrier), the windows of a tile are walked by the consumer warps out of shared memory.
+//
+// Replaces the per-dt loop of MSDBootstrap.__init__ (kinisi/diffusion.py:571-602) over the list Parser.get_disps
+// builds (kinisi/parser.py:208-216): for every lag k, sum and sum of squares of |x[j+k] - x[j]|^2 over atoms and origins.
+//
+// Geometry.  Pick a row length D (even, >= 32) and read one component of one atom's trajectory as a matrix with rows of
+// D frames: frame f = a*D + t is (row a, column t).  Any lag is k = I*D + r (0 <= r < D): the partner of the origin
+// (a, t) is the frame (a + I)*D + (t + r), i.e. row a + I, column t + r, counted linearly (a column index >= D simply
+// runs into the next row).  A WINDOW is m <= 8 lags with consecutive I and one r -- kinisi's default grid
+// np.linspace(min_dt, max_dt, n_steps, dtype=int) (kinisi/parser.py:150-168) is a sequence of arithmetic progressions,
+// and D is a multiple of their common difference (the multiple splits one progression into interleaved ones; it is
+// chosen so that D fills whole strips of 32 columns).  A thread owns one column t, keeps the accumulators of the m lags
+// and the m most recent partner samples in registers and walks the origin rows DOWNWARDS: every step loads one origin
+// sample and one partner sample and forms m terms (8 FP64 instructions each).  Walking downwards the partner window
+// fills by itself at the top of a column (1, 2, ... m-1 terms, a static pattern): no tail, no per-lane predicate except
+// on the one partner sample of the top row that lies past the end of the trajectory for some columns.
+//
+// Tiles.  The lag-window kernel of the previous version (k2_moments_win.cu) loaded both samples of a step from global
+// memory into registers: 48 bytes per 8 terms from the L2, and the six scoreboards of a warp alias on the LDGs in flight,
+// so a step waited for the loads issued the step before (ncu: 4.3 long-scoreboard stall cycles per issue, FP64 pipe 49 %,
+// profiles/r02_k2_win_ncu_summary.txt).  Here a TILE is what a group of windows needs for a block of origin rows of one
+// strip of 32 columns of one atom: the origin rows (32 columns wide) and the partner rows (40 wide: the windows of a tile
+// may differ in r by up to 8).  One producer warp copies the rows of a tile into one of kTileBufs shared-memory buffers
+// with cp.async.bulk (global -> shared, completion on the buffer's `full` mbarrier); the consumer warps take the
+// (window, row block) UNITS of the tile from a counter in shared memory, walk them with LDS only, and arrive on the
+// buffer's `empty` mbarrier when they leave the tile.  Tiles are drawn from an atomic counter, the most expensive first,
+// atoms in L2-sized batches.  L2 -> SM traffic falls to ~2-3 bytes per term and is asynchronous, a whole tile ahead.
+//
+// Lags that fit no progression are windows of one (two samples per term: shared-memory bound, about the rate of the
+// direct kernel).  The extra first observation dc[a][k-1] of every lag (kinisi/parser.py:209) is added by a pre-pass.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <vector>
+
+#include "common.cuh"
+#include "k2_plan.h"
+
+namespace kb2 {
+
+constexpr int kTileM = 8;                    // lags per window
+constexpr int kTileWo = 32;                  // columns copied for an origin row
+constexpr int kTileWp = 40;                  // columns of a partner row = component stride within any row
+constexpr int kTileRowP = 3 * kTileWp;       // doubles per row (three components)
+constexpr int kTileRowO = kTileRowP;         // origin rows have the layout of partner rows (a SHARED tile has one row set)
+constexpr int kTileMaxBufs = 3;              // tile buffers in flight: 3 x 64 KB or 2 x 96 KB (chosen by the planner)
+constexpr int kTileSmemBufBytes = 192 * 1024;  // shared memory of all buffers
+constexpr int kTileGuardBytes = 4096;        // shared memory in front of the first buffer (look-ahead reads run below a tile)
+constexpr int kTileCW = 12;                  // consumer warps
+constexpr int kTileMaxLags = 256;            // lags per launch (CTA accumulators in shared memory)
+constexpr int kTileRA = 32;                  // most origin rows per unit
+constexpr int kTileMaxUnits = 96;            // units per tile
+constexpr int kTileMinLen = 3;               // shortest progression taken as such
+constexpr int kTileCandidates = 24;          // successors tried as the common difference
+constexpr int kTileSingleD = 64;             // D of a window of one lag (nothing is reused across its lags)
+constexpr long long kTileBatchBytes = 24ll << 20;  // trajectory bytes of one atom batch (L2 is 126 MB)
+
+// One (window, row block): lags (I0 + w)*D + r, w < m; origins a_top, a_top - 1, ... (nsteps of them).
+struct TileUnit {
+    int I0, r, m, acc_off;
+    int a_top, nsteps, top, pad;
+};
+static_assert(sizeof(TileUnit) == 32, "TileUnit is read as two int4");
+
+// One tile template (per strip and atom): origin rows [oLo, oLo + nO), partner rows [pLo, pLo + nP) starting at the
+// column offset cP0 (even), units [unit0, unit0 + nunits).
+struct TileTpl {
+    int D, oLo, nO, pLo;
+    int nP, cP0, unit0, nunits;
+    int nstrips, strip_prefix, spt, pad1;  // strips of 32 columns; spt of them side by side in one tile (nstrips here =
+                                           // number of strip GROUPS); strip_prefix = groups of the templates before this one
+};
+static_assert(sizeof(TileTpl) == 48, "TileTpl is read as three int4");
+
+struct TileDesc {  // what the producer publishes with a filled buffer
+    int stop, t0, D, oLo;
+    int pLo, cP0, unit0, nunits;
+    int nO, atom, ns, sub_doubles;  // ns strips in this tile, one every sub_doubles doubles of the buffer
+};
+
+namespace tile {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "KB2_TILE_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra KB2_TILE_DONE;\n\t"
+        "bra KB2_TILE_WAIT;\n\t"
+        "KB2_TILE_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk copy global -> shared through the TMA engine; completion (bytes) is signalled on `bar`.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only), and the arrival on an mbarrier that fires when all earlier
+// cp.async of the executing thread have landed (the pending count of the barrier is not incremented).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Register rings: the partner of step s lives in slot s mod RV, the origin of step s in slot s mod 2.  RV is even (so
+// that one unrolled block of RV steps keeps every register index static) and >= M + 1: a partner is loaded DV = RV - M
+// (1 or 2) steps before its first use, an origin one step before its use.  Shared-memory latency is ~30 cycles against
+// >= 16 m cycles of FP64 issue per step.
+template <int M>
+struct Cfg {
+    static constexpr int RV = ((M + 2) / 2) * 2;
+    static constexpr int DV = RV - M;
+    static constexpr int U = RV;
+};
+
+template <int NDIM, int M>
+struct Regs {
+    double vb[Cfg<M>::RV][3];
+    double ub[2][3];
+    double A1[M], A2[M];
+};
+
+// One step.  `po` / `pp` point at the origin / partner sample of step 0 of the column; S = the step's index relative
+// to them (compile time), PH = absolute step index mod U.  Loads the samples of the steps ahead, then forms NT terms
+// (lags 0 .. NT-1: lag w pairs the origin with the partner loaded w steps earlier).  DIAG: the last term uses the partner
+// of the top row, which lies past the end of the trajectory for the lanes with `kill` set.
+template <int NDIM, int M, int S, int PH, int NT, bool DIAG>
+__device__ __forceinline__ void step(const double* po, const double* pp, Regs<NDIM, M>& r, bool kill) {
+    constexpr int RV = Cfg<M>::RV, DV = Cfg<M>::DV;
+#pragma unroll
+    for (int c = 0; c < NDIM; ++c) r.vb[(PH + DV) % RV][c] = pp[-(S + DV) * kTileRowP + c * kTileWp];
+#pragma unroll
+    for (int c = 0; c < NDIM; ++c) r.ub[(PH + 1) % 2][c] = po[-(S + 1) * kTileRowO + c * kTileWp];
+#pragma unroll
+    for (int w = 0; w < NT; ++w) {
+        const int sl = (PH - w + RV) % RV;
+        double d2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < NDIM; ++c) {
+            const double d = r.vb[sl][c] - r.ub[PH % 2][c];
+            d2 = fma(d, d, d2);
+        }
+        if (DIAG && w == NT - 1) d2 = kill ? 0.0 : d2;
+        r.A1[w] += d2;
+        r.A2[w] = fma(d2, d2, r.A2[w]);
+    }
+}
+
+template <int NDIM, int M, int F>
+struct Prologue {  // partners of steps 0 .. DV-1, origin of step 0
+    __device__ __forceinline__ static void run(const double* po, const double* pp, Regs<NDIM, M>& r) {
+        if constexpr (F < Cfg<M>::DV) {
+#pragma unroll
+            for (int c = 0; c < NDIM; ++c) r.vb[F][c] = pp[-F * kTileRowP + c * kTileWp];
+            Prologue<NDIM, M, F + 1>::run(po, pp, r);
+        } else {
+#pragma unroll
+            for (int c = 0; c < NDIM; ++c) r.ub[0][c] = po[c * kTileWp];
+        }
+    }
+};
+
+// The fill: steps 0 .. M-1.  TOP columns form 1, 2, ... M terms, the last of each masked for the short lanes; lower
+// blocks only load during the first M-1 steps (the partners above their origin range) and form all M terms at step M-1.
+// Returns false when the column ended inside the fill.
+template <int NDIM, int M, int R>
+struct Fill {
+    __device__ __forceinline__ static bool run(const double* po, const double* pp, Regs<NDIM, M>& r, int total, bool top,
+                                               bool kill) {
+        if constexpr (R < M) {
+            if (R >= total) return false;
+            if (top)
+                step<NDIM, M, R, R % Cfg<M>::U, R + 1, true>(po, pp, r, kill);
+            else
+                step<NDIM, M, R, R % Cfg<M>::U, (R == M - 1 ? M : 0), false>(po, pp, r, false);
+            return Fill<NDIM, M, R + 1>::run(po, pp, r, total, top, kill);
+        } else {
+            return true;
+        }
+    }
+};
+
+template <int NDIM, int M, int UU>
+struct Main {
+    // steps of one unrolled block, the first at phase M mod U; returns true when the column is done
+    __device__ __forceinline__ static bool run(const double* po, const double* pp, Regs<NDIM, M>& r, int& left) {
+        constexpr int U = Cfg<M>::U;
+        if constexpr (UU < U) {
+            step<NDIM, M, UU, (M + UU) % U, M, false>(po, pp, r, false);
+            if (--left == 0) return true;
+            return Main<NDIM, M, UU + 1>::run(po, pp, r, left);
+        } else {
+            return false;
+        }
+    }
+};
+
+// Sums 2M values over the 32 lanes with a halving butterfly: after the exchange with lane ^ 16 a lane keeps half of its
+// values, after lane ^ 8 a quarter, ...; the lanes whose index has bit 0 clear end up with one complete sum each.
+template <int N>
+__device__ __forceinline__ void butterfly(double (&v)[16], int lane, int bit) {
+    if constexpr (N >= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double send = up ? v[i] : v[i + N];
+            const double keep = up ? v[i + N] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+        butterfly<N / 2>(v, lane, bit >> 1);
+    }
+}
+
+// Walks one column and adds the sums of the warp to the CTA's accumulators.
+template <int NDIM, int M>
+__device__ __forceinline__ void column(const double* po, const double* pp, int total, bool top, bool kill, bool active,
+                                       int acc_off, double* acc, int lane) {
+    Regs<NDIM, M> r;
+#pragma unroll
+    for (int w = 0; w < M; ++w) {
+        r.A1[w] = 0.0;
+        r.A2[w] = 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < Cfg<M>::RV; ++i)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) r.vb[i][c] = 0.0;
+    Prologue<NDIM, M, 0>::run(po, pp, r);
+    if (Fill<NDIM, M, 0>::run(po, pp, r, total, top, kill)) {
+        int left = total - M;
+        po -= M * kTileRowO;
+        pp -= M * kTileRowP;
+        if (left > 0) {
+#pragma unroll 1
+            while (!Main<NDIM, M, 0>::run(po, pp, r, left)) {
+                po -= Cfg<M>::U * kTileRowO;
+                pp -= Cfg<M>::U * kTileRowP;
+            }
+        }
+    }
+    // a lane without a column (ragged last strip) has read its neighbour's data: its sums are dropped
+    double v[16];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        v[w] = (w < M && active) ? r.A1[w] : 0.0;
+        v[8 + w] = (w < M && active) ? r.A2[w] : 0.0;
+    }
+    butterfly<8>(v, lane, 16);
+    const double s = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+    // value index held by this lane: bit 4 of the lane selects the upper half of 16, bit 3 of 8, bit 2 of 4, bit 1 of 2
+    const int idx = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    const int w = idx & 7, which = idx >> 3;
+    if ((lane & 1) == 0 && w < M) atomicAdd(acc + 2 * (acc_off + w) + which, s);
+}
+
+}  // namespace tile
+
+// NPW producer warps share the rows of a tile and copy them with 16-byte cp.async (LDGSTS, two warp instructions per row).
+// (cp.async.bulk, one TMA request per row and component, was measured first: a 1-D bulk copy of 256-320 bytes costs the
+// SM's TMA unit ~33 cycles, 260 of them per tile made the kernel 2.1-2.6 times slower, profiles/r02_k2_tile_copy_modes.txt.)  Tiles are dealt to the
+// CTAs round robin (tile c, c + grid, ...: the templates are sorted by cost, so every CTA gets the same mix): every
+// producer warp derives the sequence by itself, nothing is exchanged.
+template <int NDIM, int NPW>
+__global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
+    self_moments_tile_kernel(const double* __restrict__ dc, int n_atoms, int Tn, int64_t pitch, int c0, int c1, int c2,
+                             const TileTpl* __restrict__ tpls, int n_tpls, int strips_total,
+                             const TileUnit* __restrict__ units, int batch, const int32_t* __restrict__ acc_lag, int K,
+                             int nbuf, int buf_bytes, const int32_t* __restrict__ slot, double* __restrict__ out) {
+    using namespace tile;
+    constexpr int NT = 32 * (kTileCW + NPW);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // acc [2 * kTileMaxLags] | guard area: full[], empty[], next_unit[], desc[] | the tile buffers.  The look-ahead loads of
+    // a column run up to two rows below its tile: below the first buffer they land in the guard area (values unused).
+    constexpr int kAccBytes = 2 * kTileMaxLags * 8;
+    double* const acc = reinterpret_cast<double*>(smem_raw);
+    uint64_t* const full = reinterpret_cast<uint64_t*>(smem_raw + kAccBytes);
+    uint64_t* const empty = full + kTileMaxBufs;
+    int* const next_unit = reinterpret_cast<int*>(empty + kTileMaxBufs);
+    TileDesc* const desc = reinterpret_cast<TileDesc*>(reinterpret_cast<unsigned char*>(next_unit) + 16);
+    unsigned char* const bufs = smem_raw + kAccBytes + kTileGuardBytes;
+    static_assert(kTileMaxBufs <= 4 && 2 * kTileMaxBufs * 8 + 16 + kTileMaxBufs * sizeof(TileDesc) <= kTileGuardBytes, "guard area too small");
+    static_assert(kTileGuardBytes + kAccBytes >= 3 * kTileRowP * 8, "look-ahead reads below the first buffer must stay in shared memory");
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp >= kTileCW;
+    const int comp[3] = {c0, c1, c2};
+
+#pragma unroll 1
+    for (int i = tid; i < 2 * K; i += NT) acc[i] = 0.0;
+    if (tid == 0) {
+        for (int b = 0; b < kTileMaxBufs; ++b) {
+            mbar_init(&full[b], 32 * NPW + 1);
+            mbar_init(&empty[b], kTileCW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int n_batches = (n_atoms + batch - 1) / batch;
+    const int nb_last = n_atoms - (n_batches - 1) * batch;
+    const long long items_full = (long long)strips_total * batch, items_last = (long long)strips_total * nb_last;
+    const long long n_items = (long long)(n_batches - 1) * items_full + items_last;
+
+    if (producer) {
+        const int pw = warp - kTileCW;
+#pragma unroll 1
+        for (unsigned tau = 0;; ++tau) {
+            const int b = (int)(tau % (unsigned)nbuf);
+            const long long item = (long long)blockIdx.x + (long long)tau * gridDim.x;
+            if (item >= n_items) {
+                if (tau >= (unsigned)nbuf) mbar_wait(&empty[b], ((tau / (unsigned)nbuf) - 1) & 1);
+                if (pw == 0 && lane == 0) {
+                    desc[b].stop = 1;
+                    next_unit[b] = 0;
+                }
+                if (pw == 0 && lane == 0) mbar_arrive(&full[b]);
+                cp_async_arrive(&full[b]);
+                break;
+            }
+            // item -> (atom batch, strip slot, atom of the batch); strip slot -> (template, strip) by the prefix sums
+            int bi, nb;
+            long long x;
+            if (item < (long long)(n_batches - 1) * items_full) {
+                bi = (int)(item / items_full);
+                x = item - (long long)bi * items_full;
+                nb = batch;
+            } else {
+                bi = n_batches - 1;
+                x = item - (long long)(n_batches - 1) * items_full;
+                nb = nb_last;
+            }
+            const int y = (int)(x / nb);
+            const int al = (int)(x - (long long)y * nb);
+            int ti = 0;
+#pragma unroll 1
+            for (int base = 0; base < n_tpls; base += 32) {
+                const int idx = base + lane;
+                // strip_prefix of template idx + 1 <= y  <=>  the slot lies beyond template idx
+                const bool below = idx + 1 < n_tpls && __ldg(&tpls[idx + 1].strip_prefix) <= y;
+                const int cnt = __popc(__ballot_sync(0xffffffffu, below));
+                ti += cnt;
+                if (cnt < 32) break;
+            }
+            const int4 ta = __ldg(reinterpret_cast<const int4*>(tpls + ti));
+            const int4 tb = __ldg(reinterpret_cast<const int4*>(tpls + ti) + 1);
+            const int4 tc = __ldg(reinterpret_cast<const int4*>(tpls + ti) + 2);
+            const int D = ta.x, oLo = ta.y, nO = ta.z, pLo = ta.w, nP = tb.x, cP0 = tb.y, spt = tc.z;
+            const int t0 = (y - tc.y) * 32 * spt;
+            const int ns = min(spt, (D - t0 + 31) / 32);  // strips of this tile (the last group of a row may be short)
+            const int sub_bytes = (nO + nP) * (kTileRowP * 8);
+            const int atom = bi * batch + al;
+            const uint32_t buf_s = smem_u32(bufs + (size_t)b * buf_bytes);
+            const double* const src_atom = dc + (size_t)atom * 3 * pitch;
+            const int ipitch = (int)pitch;
+            // (the tile was decoded while the consumers were still busy with the buffer's previous occupant)
+            if (tau >= (unsigned)nbuf) mbar_wait(&empty[b], ((tau / (unsigned)nbuf) - 1) & 1);
+            if (pw == 0 && lane == 0) {
+                TileDesc d{0, t0, D, oLo, pLo, cP0, tb.z, tb.w, nO, atom, ns, sub_bytes / 8};
+                desc[b] = d;
+                next_unit[b] = 0;
+                mbar_arrive(&full[b]);  // (release: the descriptor is visible with the phase)
+            }
+            // Frames are 32-bit here (pitch < 2^30 is checked by the host call).  A chunk that starts at or beyond the pitch
+            // is not copied: what is missing is only ever read by masked lanes.  A row is NDIM * 16 (origin) or NDIM * 20
+            // (partner) chunks of two frames: chunk i of a row goes to lane i mod 32; rows alternate between the producer
+            // warps.
+#pragma unroll 1
+            for (int sidx = 0; sidx < ns; ++sidx) {
+                const int ts = t0 + 32 * sidx;
+                const uint32_t sub_s = buf_s + (uint32_t)(sidx * sub_bytes);
+                {
+                    const int c_lo = lane / 16, p_lo = lane - c_lo * 16;                // chunks 0..31
+                    const int c_hi = (lane + 32) / 16, p_hi = (lane + 32) - c_hi * 16;  // chunks 32..47
+                    const bool has_lo = c_lo < NDIM, has_hi = c_hi < NDIM;
+                    const int f_first = (oLo + pw) * D + ts;
+                    const double* s_lo = src_atom + (size_t)comp[has_lo ? c_lo : 0] * pitch + 2 * p_lo + f_first;
+                    const double* s_hi = src_atom + (size_t)comp[has_hi ? c_hi : 0] * pitch + 2 * p_hi + f_first;
+                    uint32_t d_lo = sub_s + (uint32_t)(c_lo * kTileWp + 2 * p_lo) * 8u + (uint32_t)pw * (kTileRowO * 8);
+                    uint32_t d_hi = sub_s + (uint32_t)(c_hi * kTileWp + 2 * p_hi) * 8u + (uint32_t)pw * (kTileRowO * 8);
+                    // rows whose 32 frames lie wholly below the pitch need no test
+                    const int room = ipitch - kTileWo - ts;  // f <= room  <=>  the row is whole
+                    int row = pw;
+                    const size_t sstep = (size_t)NPW * D;
+#pragma unroll 2
+                    for (; row < nO && (oLo + row) * D <= room; row += NPW) {
+                        if (has_lo) cp_async16(d_lo, s_lo);
+                        if (has_hi) cp_async16(d_hi, s_hi);
+                        s_lo += sstep, s_hi += sstep, d_lo += NPW * (kTileRowO * 8), d_hi += NPW * (kTileRowO * 8);
+                    }
+#pragma unroll 1
+                    for (; row < nO; row += NPW) {
+                        const int f = (oLo + row) * D + ts;
+                        if (has_lo && f + 2 * p_lo < ipitch) cp_async16(d_lo, s_lo);
+                        if (has_hi && f + 2 * p_hi < ipitch) cp_async16(d_hi, s_hi);
+                        s_lo += sstep, s_hi += sstep, d_lo += NPW * (kTileRowO * 8), d_hi += NPW * (kTileRowO * 8);
+                    }
+                }
+                {
+                    const int c_lo = lane / 20, p_lo = lane - c_lo * 20;
+                    const int c_hi = (lane + 32) / 20, p_hi = (lane + 32) - c_hi * 20;  // chunks 32..59
+                    const bool has_lo = c_lo < NDIM, has_hi = c_hi < NDIM && lane + 32 < NDIM * 20;
+                    const int f_first = (pLo + pw) * D + ts + cP0;
+                    const double* s_lo = src_atom + (size_t)comp[has_lo ? c_lo : 0] * pitch + 2 * p_lo + f_first;
+                    const double* s_hi = src_atom + (size_t)comp[has_hi ? c_hi : 0] * pitch + 2 * p_hi + f_first;
+                    const uint32_t base = sub_s + (uint32_t)nO * (kTileRowO * 8) + (uint32_t)pw * (kTileRowP * 8);
+                    uint32_t d_lo = base + (uint32_t)(c_lo * kTileWp + 2 * p_lo) * 8u;
+                    uint32_t d_hi = base + (uint32_t)(c_hi * kTileWp + 2 * p_hi) * 8u;
+                    const int room = ipitch - kTileWp - ts - cP0;
+                    int row = pw;
+                    const size_t sstep = (size_t)NPW * D;
+#pragma unroll 2
+                    for (; row < nP && (pLo + row) * D <= room; row += NPW) {
+                        if (has_lo) cp_async16(d_lo, s_lo);
+                        if (has_hi) cp_async16(d_hi, s_hi);
+                        s_lo += sstep, s_hi += sstep, d_lo += NPW * (kTileRowP * 8), d_hi += NPW * (kTileRowP * 8);
+                    }
+#pragma unroll 1
+                    for (; row < nP; row += NPW) {
+                        const int f = (pLo + row) * D + ts + cP0;
+                        if (has_lo && f + 2 * p_lo < ipitch) cp_async16(d_lo, s_lo);
+                        if (has_hi && f + 2 * p_hi < ipitch) cp_async16(d_hi, s_hi);
+                        s_lo += sstep, s_hi += sstep, d_lo += NPW * (kTileRowP * 8), d_hi += NPW * (kTileRowP * 8);
+                    }
+                }
+            }
+            cp_async_arrive(&full[b]);
+        }
+    } else {
+        // the extra first observation dc[a][k-1] of every lag (kinisi/parser.py:209): units of (lag, 32 atoms)
+        {
+            const int gw = blockIdx.x * kTileCW + warp, n_gw = gridDim.x * kTileCW;
+            const int ablocks = (n_atoms + 31) / 32;
+#pragma unroll 1
+            for (long long unit = gw; unit < (long long)K * ablocks; unit += n_gw) {
+                const int i = (int)(unit % K), ab = (int)(unit / K);
+                const int atom = ab * 32 + lane;
+                const int k = __ldg(acc_lag + i);
+                double d2 = 0.0;
+                if (atom < n_atoms) {
+#pragma unroll
+                    for (int c = 0; c < NDIM; ++c) {
+                        const double d = __ldg(dc + ((size_t)atom * 3 + comp[c]) * pitch + (k - 1));
+                        d2 = fma(d, d, d2);
+                    }
+                }
+                const double s1 = warp_sum(d2), s2 = warp_sum(d2 * d2);
+                if (lane == 0) {
+                    atomicAdd(acc + 2 * i, s1);
+                    atomicAdd(acc + 2 * i + 1, s2);
+                }
+            }
+        }
+#pragma unroll 1
+        for (unsigned tau = 0;; ++tau) {
+            const int b = (int)(tau % (unsigned)nbuf);
+            mbar_wait(&full[b], (tau / (unsigned)nbuf) & 1);
+            const TileDesc d = desc[b];
+            if (d.stop) break;
+            const double* const buf0 = reinterpret_cast<const double*>(bufs + (size_t)b * buf_bytes);
+            const int n_work = d.nunits * d.ns;
+#pragma unroll 1
+            while (true) {
+                int u = 0;
+                if (lane == 0) u = atomicAdd(&next_unit[b], 1);
+                u = __shfl_sync(0xffffffffu, u, 0);
+                if (u >= n_work) break;
+                // unit-major: the longest units of every strip of the tile go first
+                const int ui = u / d.ns, sidx = u - ui * d.ns;
+                const double* const bufO = buf0 + (size_t)sidx * d.sub_doubles;
+                const double* const bufP = bufO + (size_t)d.nO * kTileRowO;
+                const int t = d.t0 + 32 * sidx + lane;
+                const bool active = t < d.D;
+                const int4 ua = __ldg(reinterpret_cast<const int4*>(units + d.unit0 + ui));
+                const int4 ub = __ldg(reinterpret_cast<const int4*>(units + d.unit0 + ui) + 1);
+                const int I0 = ua.x, r = ua.y, m = ua.z, acc_off = ua.w, a_top = ub.x, nsteps = ub.y;
+                const bool top = ub.z != 0;
+                const int a_start = top ? a_top : a_top + (m - 1);
+                const int total = nsteps + (top ? 0 : m - 1);
+                // the partner of (a_top, first lag) lies past the end of the trajectory for the short lanes of a top unit
+                const bool kill = top && ((long long)(a_top + I0) * d.D + t + r > (long long)Tn - 1);
+                const double* po = bufO + (a_start - d.oLo) * kTileRowO + lane;
+                const double* pp = bufP + (a_start + I0 - d.pLo) * kTileRowP + (r - d.cP0) + lane;
+                switch (m) {
+                    case 8: column<NDIM, 8>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
+                    case 7: column<NDIM, 7>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
+                    case 6: column<NDIM, 6>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
+                    case 5: column<NDIM, 5>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
+                    case 4: column<NDIM, 4>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
+                    case 3: column<NDIM, 3>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
+                    case 2: column<NDIM, 2>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
+                    default: column<NDIM, 1>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[b]);
+        }
+    }
+    __syncthreads();
+    // one FP64 reduction per lag, moment and CTA straight into the caller's array (zeroed by the host call)
+#pragma unroll 1
+    for (int i = tid; i < 2 * K; i += NT) atomicAdd(out + 2 * slot[i >> 1] + (i & 1), acc[i]);
+}
+
+// ---- host-side planning -------------------------------------------------------------------------
+struct TileWinHost {
+    int D, I0, r, m, acc_off;
+};
+
+struct TilePlan {
+    std::vector<TileTpl> tpls;      // most expensive first
+    std::vector<TileUnit> units;
+    std::vector<int32_t> slot;      // accumulator index -> position in the caller's lag array
+    std::vector<int32_t> acc_lag;   // accumulator index -> lag
+    std::vector<TileWinHost> wins;  // for diagnostics
+    int strips_total = 0;
+    int nbuf = 2;                   // buffers in flight, kTileSmemBufBytes / nbuf bytes each
+    long long bytes_loaded = 0;     // per atom
+};
+
+// Row length for a progression of `len` lags with common difference d: a multiple of d, even, >= 32, that fills whole
+// strips of 32 columns and still leaves windows of several lags.
+static int choose_mult(int d, int len, int Tn) {
+    if (const char* e = getenv("KB2_TILE_MULT")) {  // experiments: force the multiple when it is admissible
+        const int mult = atoi(e);
+        if (mult >= 1 && ((long long)mult * d) % 2 == 0 && (long long)mult * d >= 32) return mult;
+    }
+    double best = 1e300;
+    int best_mult = 0;
+    for (int mult = 1; mult <= 64; ++mult) {
+        const long long D = (long long)mult * d;
+        if (D % 2 || D < 32) continue;
+        if (D > 2ll * Tn && best_mult) break;
+        const int ls = (len + mult - 1) / mult;            // lags of the longest interleaved progression
+        if (ls < 3 && best_mult) continue;
+        const int nw = (ls + kTileM - 1) / kTileM;
+        const double m_avg = (double)ls / nw;
+        const double waste = (double)(((D + 31) / 32) * 32) / (double)D;
+        const double rows = std::max(1.0, (double)Tn / (double)D);
+        // (the interleaved progressions beyond the first have a large r: their tiles need separate partner rows)
+        const double score = waste * (1.0 + 0.5 / m_avg) * (1.0 + 2.0 / rows) * (1.0 + 0.15 * (1.0 - 1.0 / mult));
+        if (score < best - 1e-12) {
+            best = score;
+            best_mult = mult;
+        }
+    }
+    if (!best_mult) {  // d odd and tiny: the first even multiple >= 32
+        best_mult = 1;
+        while (((long long)best_mult * d) % 2 || (long long)best_mult * d < 32) ++best_mult;
+    }
+    return best_mult;
+}
+
+static void plan_tiles_for(const int32_t* lags, int K, int Tn, int buf_bytes, TilePlan& plan) {
+    const std::vector<LagSegment> segs = cover_by_progressions(lags, K, Tn, kTileMinLen, kTileCandidates);
+    for (const LagSegment& sg : segs) {
+        if (sg.len == 1) {
+            const int k = sg.k0;
+            plan.wins.push_back({kTileSingleD, k / kTileSingleD, k % kTileSingleD, 1, (int)plan.slot.size()});
+            plan.slot.push_back(sg.slots[0]);
+            plan.acc_lag.push_back(k);
+            continue;
+        }
+        const int mult = choose_mult(sg.d, sg.len, Tn);
+        const int D = mult * sg.d;
+        for (int u = 0; u < mult && u < sg.len; ++u) {
+            const int ls = (sg.len - u + mult - 1) / mult;  // lags k0 + (u + i*mult)*d, i < ls
+            const int nw = (ls + kTileM - 1) / kTileM;
+            const int base = ls / nw, extra = ls % nw;
+            int at = 0;
+            for (int w = 0; w < nw; ++w) {
+                const int m = base + (w < extra ? 1 : 0);
+                const long long kfirst = (long long)sg.k0 + (long long)(u + (long long)at * mult) * sg.d;
+                plan.wins.push_back({D, (int)(kfirst / D), (int)(kfirst % D), m, (int)plan.slot.size()});
+                for (int i = 0; i < m; ++i) {
+                    plan.slot.push_back(sg.slots[u + (at + i) * mult]);
+                    plan.acc_lag.push_back(sg.k0 + (u + (at + i) * mult) * sg.d);
+                }
+                at += m;
+            }
+        }
+    }
+    // windows by family (D), then by r and I0
+    std::vector<int> order(plan.wins.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        const TileWinHost &x = plan.wins[a], &y = plan.wins[b];
+        if (x.D != y.D) return x.D < y.D;
+        if (x.r != y.r) return x.r < y.r;
+        return x.I0 < y.I0;
+    });
+    struct Tile {
+        TileTpl tp;
+        std::vector<TileUnit> units;
+        long long cost;
+    };
+    std::vector<Tile> tiles;
+    size_t g0 = 0;
+    while (g0 < order.size()) {
+        // an r-group: windows of one D whose r fits one partner strip (r - cP0 <= kTileWp - 32)
+        const TileWinHost& first = plan.wins[order[g0]];
+        const int cP0 = first.r & ~1;
+        size_t g1 = g0;
+        while (g1 < order.size() && plan.wins[order[g1]].D == first.D && plan.wins[order[g1]].r - cP0 <= kTileWp - 32) ++g1;
+        std::vector<int> grp(order.begin() + g0, order.begin() + g1);
+        g0 = g1;
+        std::stable_sort(grp.begin(), grp.end(), [&](int a, int b) { return plan.wins[a].I0 < plan.wins[b].I0; });
+        const int D = first.D;
+        // SHARED: the partner strip starts at the origin strip's first column, so a row of 40 columns can serve both roles
+        // (used for a tile when its origin and partner rows overlap enough that one row set is the smaller one)
+        const bool shared = cP0 == 0;
+        std::vector<int> rhat(grp.size());  // last origin row of every window (-1: only the first-observation term)
+        int rows = 0;
+        for (size_t i = 0; i < grp.size(); ++i) {
+            const TileWinHost& w = plan.wins[grp[i]];
+            const long long span = (long long)Tn - 1 - ((long long)w.I0 * D + w.r);
+            rhat[i] = span < 0 ? -1 : (int)(span / D);
+            rows = std::max(rows, rhat[i] + 1);
+        }
+        if (rows == 0) continue;
+        // A tile = (block of origin rows [aLo, aHi], run of consecutive windows).  Builds the tiles for blocks of H rows
+        // and returns the bytes they load; `out` == nullptr only counts.
+        auto build = [&](int H, std::vector<Tile>* out) -> long long {
+            long long total = 0;
+            for (int aLo = 0; aLo < rows; aLo += H) {
+                const int aHi = std::min(rows, aLo + H) - 1;
+                Tile cur;
+                int oHi = -1, pLo = 0, pHi = -1;
+                auto bytes_of = [&](int o_hi, int p_lo, int p_hi) -> long long {
+                    const long long sep = (long long)(o_hi - aLo + 1 + p_hi - p_lo + 1) * kTileRowP * 8;
+                    const long long one = (long long)(std::max(o_hi, p_hi) - std::min(aLo, p_lo) + 1) * kTileRowP * 8;
+                    return shared && one < sep ? one : sep;
+                };
+                auto flush = [&]() {
+                    if (cur.units.empty()) return;
+                    total += bytes_of(oHi, pLo, pHi) + 4096;  // (+ a charge per tile)
+                    if (out) {
+                        const long long sep = (long long)(oHi - aLo + 1 + pHi - pLo + 1), one = std::max(oHi, pHi) - std::min(aLo, pLo) + 1;
+                        if (shared && one < sep) {
+                            const int lo = std::min(aLo, pLo), hi = std::max(oHi, pHi);
+                            cur.tp = TileTpl{D, lo, 0, lo, hi - lo + 1, 0, 0, (int)cur.units.size(), 0, 0, 1, 0};
+                        } else {
+                            cur.tp = TileTpl{D, aLo, oHi - aLo + 1, pLo, pHi - pLo + 1, cP0, 0, (int)cur.units.size(), 0, 0, 1, 0};
+                        }
+                        // small tiles take several strips side by side: enough units for the consumer warps, one fill
+                        const int strips = (D + 31) / 32;
+                        const long long tb = (long long)(cur.tp.nO + cur.tp.nP) * kTileRowP * 8;
+                        int spt = (int)std::min<long long>(std::min(strips, 8), std::max<long long>(1, buf_bytes / tb));
+                        while (spt > 1 && (long long)spt * (long long)cur.units.size() > 4 * kTileMaxUnits) --spt;
+                        cur.tp.spt = spt;
+                        cur.tp.nstrips = (strips + spt - 1) / spt;
+                        std::stable_sort(cur.units.begin(), cur.units.end(), [](const TileUnit& x, const TileUnit& y) {
+                            return (long long)x.nsteps * x.m > (long long)y.nsteps * y.m;
+                        });
+                        cur.cost = 0;
+                        for (const TileUnit& u : cur.units) cur.cost += (long long)(u.nsteps + (u.top ? 0 : u.m - 1)) * (16 * u.m + 24);
+                        out->push_back(cur);
+                    }
+                    cur = Tile();
+                    oHi = pHi = -1;
+                };
+                for (size_t i = 0; i < grp.size(); ++i) {
+                    const TileWinHost& w = plan.wins[grp[i]];
+                    if (rhat[i] < aLo) continue;
+                    // The rows of a window are cut at the block boundaries, except that a top piece of fewer than m rows
+                    // goes to the block below it: a lower piece loads the m - 1 partner rows above its first origin, and
+                    // they must exist.
+                    const int top_lo = (rhat[i] / H) * H;
+                    const bool merged = rhat[i] - top_lo + 1 < w.m && top_lo >= H;
+                    if (merged && aLo == top_lo) continue;
+                    const bool top_w = rhat[i] <= aHi || (merged && aLo + H == top_lo);
+                    const int hi = top_w ? rhat[i] : aHi;
+                    const int plo = aLo + w.I0, phi = hi + w.I0 + (top_w ? 0 : w.m - 1);
+                    int n_ohi = hi, n_plo = plo, n_phi = phi;
+                    if (!cur.units.empty()) {
+                        n_ohi = std::max(oHi, hi);
+                        n_plo = std::min(pLo, plo);
+                        n_phi = std::max(pHi, phi);
+                        const int n_units = (int)cur.units.size() + (hi - aLo + kTileRA) / kTileRA;
+                        if (bytes_of(n_ohi, n_plo, n_phi) > buf_bytes || n_units > kTileMaxUnits) {
+                            flush();
+                            n_ohi = hi, n_plo = plo, n_phi = phi;
+                        }
+                    }
+                    if (bytes_of(n_ohi, n_plo, n_phi) > buf_bytes) return -1;  // one window does not fit: smaller blocks
+                    oHi = n_ohi, pLo = n_plo, pHi = n_phi;
+                    // units of this window: its range cut from the top into blocks of nearly equal height <= kTileRA
+                    const int n_rows = hi - aLo + 1, n_blk = (n_rows + kTileRA - 1) / kTileRA;
+                    int top_row = hi;
+                    for (int q = 0; q < n_blk; ++q) {
+                        const int h = n_rows / n_blk + (q < n_rows % n_blk ? 1 : 0);
+                        cur.units.push_back(TileUnit{w.I0, w.r, w.m, w.acc_off, top_row, h, (top_w && q == 0) ? 1 : 0, 0});
+                        top_row -= h;
+                    }
+                }
+                flush();
+            }
+            return total;
+        };
+        // block height: the one that loads the fewest bytes (whole columns when they fit)
+        int best_H = 0;
+        long long best_bytes = -1;
+        for (int nb = 1; nb <= rows; ++nb) {
+            const int H = (rows + nb - 1) / nb;
+            if (H < kTileM && nb > 1 && best_H) break;
+            const long long bytes = build(H, nullptr);
+            if (bytes >= 0 && (best_bytes < 0 || bytes < best_bytes)) {
+                best_bytes = bytes;
+                best_H = H;
+            }
+            if (H <= kTileM) break;
+            if (best_H && nb >= 8 && H < 4 * kTileRA) break;
+        }
+        if (!best_H) best_H = kTileM;
+        build(best_H, &tiles);
+    }
+    std::stable_sort(tiles.begin(), tiles.end(), [](const Tile& x, const Tile& y) { return x.cost > y.cost; });
+    int prefix = 0;
+    for (Tile& tl : tiles) {
+        tl.tp.unit0 = (int)plan.units.size();
+        tl.tp.strip_prefix = prefix;
+        prefix += tl.tp.nstrips;
+        plan.units.insert(plan.units.end(), tl.units.begin(), tl.units.end());
+        plan.tpls.push_back(tl.tp);
+    }
+    plan.strips_total = prefix;
+    plan.bytes_loaded = 0;
+    for (const TileTpl& tp : plan.tpls) plan.bytes_loaded += (long long)(tp.nO + tp.nP) * kTileRowP * 8 * ((tp.D + 31) / 32);
+}
+
+// Three buffers of 64 KB keep the producer a tile further ahead; two of 96 KB hold whole columns of ~100 rows.  The smaller
+// buffers are taken when they do not cost more than a tenth more traffic.
+static void plan_tiles(const int32_t* lags, int K, int Tn, TilePlan& plan) {
+    const char* e = getenv("KB2_TILE_BUFS");
+    const int force = e ? atoi(e) : 0;
+    TilePlan three, two;
+    if (force != 2) plan_tiles_for(lags, K, Tn, kTileSmemBufBytes / 3, three);
+    if (force != 3) plan_tiles_for(lags, K, Tn, kTileSmemBufBytes / 2, two);
+    const bool take3 = force == 3 || (force != 2 && three.bytes_loaded * 10 <= two.bytes_loaded * 11);
+    plan = take3 ? three : two;
+    plan.nbuf = take3 ? 3 : 2;
+}
+
+// Packed plan of one launch (<= kTileMaxLags lags): header (256 B) | templates | units | slots | lags by accumulator.
+struct TileHeader {
+    int K, n_tpls, n_units, strips_total;
+    int off_tpls, off_units, off_slot, off_lag;
+    int l0, bytes, nbuf, pad[5];
+};
+static_assert(sizeof(TileHeader) <= 256, "the header has 256 bytes");
+
+static size_t tile_plan_bytes(const TilePlan& p, int K) {
+    return 256 + align256(p.tpls.size() * sizeof(TileTpl)) + align256(p.units.size() * sizeof(TileUnit)) +
+           2 * align256((size_t)K * sizeof(int32_t));
+}
+
+static int tile_check_lags(const char* fn, const int32_t* lags_host, int n_lags, int n_frames) {
+    KB2_CHECK(lags_host && n_lags > 0 && n_frames > 0, "%s: empty problem", fn);
+    for (int i = 0; i < n_lags; ++i) {
+        KB2_CHECK(lags_host[i] >= 1 && lags_host[i] <= n_frames, "%s: lag %d out of range", fn, i);
+        KB2_CHECK(i == 0 || lags_host[i] >= lags_host[i - 1], "%s: lags must ascend", fn);
+    }
+    return 0;
+}
+
+static size_t tile_smem_bytes() { return (size_t)kTileGuardBytes + 2 * kTileMaxLags * 8 + (size_t)kTileSmemBufBytes; }
+
+}  // namespace kb2
+
+using namespace kb2;
+
+// Size of the packed plan for a lag grid (0 on invalid input): the planner runs to find out.
+extern "C" size_t kb2_self_moments_tile_workspace_bytes(const int32_t* lags_host, int n_lags, int n_frames) {
+    if (!lags_host || n_lags <= 0 || n_frames <= 0) return 0;
+    size_t total = 0;
+    for (int l0 = 0; l0 < n_lags; l0 += kTileMaxLags) {
+        const int K = std::min(kTileMaxLags, n_lags - l0);
+        TilePlan plan;
+        plan_tiles(lags_host + l0, K, n_frames, plan);
+        total += tile_plan_bytes(plan, K);
+    }
+    return total;
+}
+
+extern "C" int kb2_self_moments_tile_blocks(int n_lags) { return n_lags < 1 ? 1 : (n_lags + kTileMaxLags - 1) / kTileMaxLags; }
+
+// Plans the lag grid on the host into plan_host (kb2_self_moments_tile_workspace_bytes bytes).  Depends on (lags, n_frames) only.
+extern "C" int kb2_self_moments_tile_plan_pack(const int32_t* lags_host, int n_lags, int n_frames, void* plan_host) {
+    if (int rc = tile_check_lags("kb2_self_moments_tile_plan_pack", lags_host, n_lags, n_frames)) return rc;
+    KB2_CHECK(plan_host, "kb2_self_moments_tile_plan_pack: null pointer");
+    unsigned char* p = (unsigned char*)plan_host;
+    for (int l0 = 0; l0 < n_lags; l0 += kTileMaxLags) {
+        const int K = std::min(kTileMaxLags, n_lags - l0);
+        TilePlan plan;
+        plan_tiles(lags_host + l0, K, n_frames, plan);
+        KB2_CHECK((int)plan.slot.size() == K, "kb2_self_moments_tile_plan_pack: internal planning error");
+        for (const TileTpl& tp : plan.tpls)
+            KB2_CHECK((long long)tp.nO * kTileRowO * 8 + (long long)tp.nP * kTileRowP * 8 <= kTileSmemBufBytes / plan.nbuf && tp.nunits > 0,
+                      "kb2_self_moments_tile_plan_pack: a tile exceeds its buffer");
+        TileHeader h{};
+        h.K = K;
+        h.n_tpls = (int)plan.tpls.size();
+        h.n_units = (int)plan.units.size();
+        h.strips_total = plan.strips_total;
+        h.off_tpls = 256;
+        h.off_units = h.off_tpls + (int)align256(plan.tpls.size() * sizeof(TileTpl));
+        h.off_slot = h.off_units + (int)align256(plan.units.size() * sizeof(TileUnit));
+        h.off_lag = h.off_slot + (int)align256((size_t)K * sizeof(int32_t));
+        h.l0 = l0;
+        h.nbuf = plan.nbuf;
+        h.bytes = (int)tile_plan_bytes(plan, K);
+        memset(p, 0, (size_t)h.bytes);
+        memcpy(p, &h, sizeof(h));
+        if (!plan.tpls.empty()) memcpy(p + h.off_tpls, plan.tpls.data(), plan.tpls.size() * sizeof(TileTpl));
+        if (!plan.units.empty()) memcpy(p + h.off_units, plan.units.data(), plan.units.size() * sizeof(TileUnit));
+        memcpy(p + h.off_slot, plan.slot.data(), (size_t)K * sizeof(int32_t));
+        memcpy(p + h.off_lag, plan.acc_lag.data(), (size_t)K * sizeof(int32_t));
+        p += h.bytes;
+    }
+    return 0;
+}
+
+template <int NDIM>
+static int launch_tile(int sm_count, cudaStream_t st, const double* dc, int n_atoms, int Tn, int64_t pitch, const int comp[3],
+                       const TileTpl* tpls, int n_tpls, int strips_total, const TileUnit* units, int batch,
+                       const int32_t* acc_lag, int K, int nbuf, const int32_t* slot, double* out) {
+    const size_t smem = tile_smem_bytes();
+    constexpr int NPW = 2;
+    auto kern = self_moments_tile_kernel<NDIM, NPW>;
+    const int threads = 32 * (kTileCW + NPW);
+    KB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<sm_count, threads, smem, st>>>(dc, n_atoms, Tn, pitch, comp[0], comp[1], comp[2], tpls, n_tpls, strips_total, units,
+                                         batch, acc_lag, K, nbuf, kTileSmemBufBytes / nbuf, slot, out);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+// Launches the tile kernels of a packed plan: plan_host = the host copy (headers are read here), plan_dev = the same bytes
+// in device memory (uploaded before this call in stream order), counters = kb2_self_moments_tile_blocks(n_lags) * 256
+// bytes of device memory (zeroed by this call).  sums[n_lags][2] is zeroed first.
+extern "C" int kb2_self_moments_tile_planned(const double* dc, int n_atoms, int n_frames, int64_t pitch, int n_lags,
+                                             int dim_mask, const void* plan_host, const void* plan_dev, void* counters,
+                                             double* sums, void* stream) {
+    KB2_CHECK(dc && plan_host && plan_dev && sums, "kb2_self_moments_tile_planned: null pointer");
+    (void)counters;  // tiles are dealt round robin: no work counter (the argument keeps the protocol of the other planned kernels)
+    KB2_CHECK(n_atoms > 0 && n_frames > 0 && n_lags > 0, "kb2_self_moments_tile_planned: empty problem");
+    KB2_CHECK(pitch >= n_frames && pitch % 16 == 0 && pitch < (1ll << 30),
+              "kb2_self_moments_tile_planned: pitch must be a multiple of 16, >= n_frames and < 2^30");
+    KB2_CHECK(((uintptr_t)dc & 15) == 0, "kb2_self_moments_tile_planned: dc must be 16-byte aligned");
+    KB2_CHECK(dim_mask >= 1 && dim_mask <= 7, "kb2_self_moments_tile_planned: dim_mask must be in 1..7");
+    cudaStream_t st = (cudaStream_t)stream;
+    int comp[3] = {0, 0, 0}, ndim = 0;
+    for (int c = 0; c < 3; ++c)
+        if (dim_mask & (1 << c)) comp[ndim++] = c;
+    const int sm_count = device_sm_count();
+    KB2_CHECK(sm_count > 0, "kb2_self_moments_tile_planned: no CUDA device");
+    const int blocks = (n_lags + kTileMaxLags - 1) / kTileMaxLags;
+    KB2_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_lags * 2 * sizeof(double), st));
+    const int batch = (int)std::max<long long>(1, std::min<long long>(n_atoms, kTileBatchBytes / (3 * pitch * 8)));
+    const unsigned char* ph = (const unsigned char*)plan_host;
+    const char* pd = (const char*)plan_dev;
+    for (int b = 0; b < blocks; ++b) {
+        TileHeader h;
+        memcpy(&h, ph, sizeof(h));
+        KB2_CHECK(h.K > 0 && h.K <= kTileMaxLags && h.l0 == b * kTileMaxLags && h.l0 + h.K <= n_lags && h.bytes >= 256,
+                  "kb2_self_moments_tile_planned: the plan does not match the lag count");
+        KB2_CHECK((long long)h.strips_total * n_atoms < (1ll << 31) - (1 << 20), "kb2_self_moments_tile_planned: too many tiles");
+        const TileTpl* d_tpls = (const TileTpl*)(pd + h.off_tpls);
+        const TileUnit* d_units = (const TileUnit*)(pd + h.off_units);
+        const int32_t* d_slot = (const int32_t*)(pd + h.off_slot);
+        const int32_t* d_lag = (const int32_t*)(pd + h.off_lag);
+        KB2_CHECK(h.nbuf == 2 || h.nbuf == 3, "kb2_self_moments_tile_planned: corrupt plan");
+        int rc;
+        if (ndim == 3)
+            rc = launch_tile<3>(sm_count, st, dc, n_atoms, n_frames, pitch, comp, d_tpls, h.n_tpls, h.strips_total, d_units, batch,
+                                d_lag, h.K, h.nbuf, d_slot, sums + 2 * h.l0);
+        else if (ndim == 2)
+            rc = launch_tile<2>(sm_count, st, dc, n_atoms, n_frames, pitch, comp, d_tpls, h.n_tpls, h.strips_total, d_units, batch,
+                                d_lag, h.K, h.nbuf, d_slot, sums + 2 * h.l0);
+        else
+            rc = launch_tile<1>(sm_count, st, dc, n_atoms, n_frames, pitch, comp, d_tpls, h.n_tpls, h.strips_total, d_units, batch,
+                                d_lag, h.K, h.nbuf, d_slot, sums + 2 * h.l0);
+        if (rc) return rc;
+        ph += h.bytes;
+        pd += h.bytes;
+    }
+    return 0;
+}
+
+// The windows of the plan for (the first 256 lags of) a grid, for tests and diagnostics: fills up to max_wins entries of
+// win_first (first lag) / win_delta (row length D = lag spacing inside the window) / win_len and returns the number of
+// windows; *n_tiles receives the number of tile templates.
+extern "C" int kb2_self_moments_tile_plan(const int32_t* lags_host, int n_lags, int n_frames, int32_t* win_first,
+                                          int32_t* win_delta, int32_t* win_len, int max_wins, int* n_tiles) {
+    if (!lags_host || n_lags <= 0) return 0;
+    TilePlan plan;
+    plan_tiles(lags_host, std::min(n_lags, kTileMaxLags), n_frames, plan);
+    int n = 0;
+    for (const TileWinHost& w : plan.wins) {
+        if (n < max_wins) {
+            if (win_first) win_first[n] = w.I0 * w.D + w.r;
+            if (win_delta) win_delta[n] = w.D;
+            if (win_len) win_len[n] = w.m;
+        }
+        ++n;
+    }
+    if (n_tiles) *n_tiles = (int)plan.tpls.size();
+    return n;
+}

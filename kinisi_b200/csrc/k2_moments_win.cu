@@ -135,9 +135,10 @@ __device__ __forceinline__ void win_step(WinLane<NDIM>& ln, WinRegs<NDIM, M, RU>
 template <int NDIM, int M, int RU, int F>
 struct WinPrologue {  // partners of steps 0 .. DV-1, origins of steps 0 .. DU-1
     __device__ __forceinline__ static void run(WinLane<NDIM>& ln, WinRegs<NDIM, M, RU>& r) {
-        if constexpr (F < WinCfg<M, RU>::DV) {
-            ln.load_partner(r.vb[F]);
-            if constexpr (F < WinCfg<M, RU>::DU) ln.load_origin(r.ub[F]);
+        constexpr int DV = WinCfg<M, RU>::DV, DU = WinCfg<M, RU>::DU;
+        if constexpr (F < (DV > DU ? DV : DU)) {  // (DV < DU for windows of 2 and 6 lags)
+            if constexpr (F < DV) ln.load_partner(r.vb[F]);
+            if constexpr (F < DU) ln.load_origin(r.ub[F]);
             WinPrologue<NDIM, M, RU, F + 1>::run(ln, r);
         }
     }

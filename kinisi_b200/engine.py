@@ -16,7 +16,8 @@ VARIANT_DIRECT = 0
 VARIANT_TMA = 1
 VARIANT_RUNS = 2  # arithmetic-run kernel (origin window in registers); plans on the host, needs the lags there
 VARIANT_WIN = 3   # lag-window kernel (partner window + accumulators in registers); plans on the host too
-DEFAULT_VARIANT = VARIANT_WIN
+VARIANT_TILE = 4  # tiled lag-window kernel: tiles staged in shared memory by TMA bulk copies; plans on the host too
+DEFAULT_VARIANT = VARIANT_TILE
 
 # count of kernel launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = {'n': 0}
@@ -171,6 +172,17 @@ def self_moments(dc, n_frames, lags, mask=7, variant=None):
         variant = DEFAULT_VARIANT
     K = len(lags) if not isinstance(lags, torch.Tensor) else lags.numel()
     sums = torch.empty((K, 2), dtype=torch.float64, device=dc.device)
+    if (variant & 0xff) == VARIANT_TILE:
+        lags_host = np.ascontiguousarray(lags.cpu().numpy() if isinstance(lags, torch.Tensor) else lags, dtype=np.int32)
+        plan_host, plan_dev = _host_plan(lib, 'tile', lags_host, n_frames, dc.device)
+        blocks = lib.kb2_self_moments_tile_blocks(K)
+        counters = torch.empty(256 * blocks, dtype=torch.uint8, device=dc.device)
+        check(
+            lib.kb2_self_moments_tile_planned(dc.data_ptr(), dc.shape[0], n_frames, dc.shape[2], K, mask,
+                                              plan_host.data_ptr(), plan_dev.data_ptr(), counters.data_ptr(),
+                                              sums.data_ptr(), _stream()), 'kb2_self_moments_tile_planned')
+        _count(blocks)
+        return sums
     if (variant & 0xff) == VARIANT_WIN:
         lags_host = np.ascontiguousarray(lags.cpu().numpy() if isinstance(lags, torch.Tensor) else lags, dtype=np.int32)
         plan_host, plan_dev = _host_plan(lib, 'win', lags_host, n_frames, dc.device)
@@ -219,12 +231,17 @@ def _host_plan(lib, kind, lags_host, n_frames, device):
             stream.wait_event(uploaded)
         plan_dev.record_stream(stream)
         return plan_host, plan_dev
-    if kind == 'win':
+    if kind == 'tile':
+        nbytes = lib.kb2_self_moments_tile_workspace_bytes(lags_host.ctypes.data, len(lags_host), int(n_frames))
+        if nbytes == 0:
+            raise ValueError('kb2_self_moments_tile_workspace_bytes: invalid lag grid')
+    elif kind == 'win':
         nbytes = lib.kb2_self_moments_win_workspace_bytes(len(lags_host))
     else:
         nbytes = lib.kb2_self_moments_runs_workspace_bytes(len(lags_host), int(n_frames))
     plan_host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-    pack = lib.kb2_self_moments_win_plan_pack if kind == 'win' else lib.kb2_self_moments_runs_plan_pack
+    pack = {'tile': lib.kb2_self_moments_tile_plan_pack, 'win': lib.kb2_self_moments_win_plan_pack,
+            'runs': lib.kb2_self_moments_runs_plan_pack}[kind]
     check(pack(lags_host.ctypes.data, len(lags_host), int(n_frames), plan_host.data_ptr()), f'kb2_self_moments_{kind}_plan_pack')
     plan_dev = plan_host.to(device, non_blocking=True)
     uploaded = torch.cuda.Event()
@@ -244,6 +261,20 @@ def self_moments_windows(lags, n_frames):
     n = lib.kb2_self_moments_win_plan(lags_host.ctypes.data, len(lags_host), int(n_frames), arrs[0].ctypes.data,
                                       arrs[1].ctypes.data, arrs[2].ctypes.data, cap)
     return [tuple(int(a[i]) for a in arrs) for i in range(min(n, cap))]
+
+
+def self_moments_tiles(lags, n_frames):
+    """The windows kb2_self_moments_tile would use, [(first lag, row length = lag spacing, number of lags), ...], and
+    the number of tile templates."""
+    lib = _lib.load()
+    import ctypes
+    lags_host = np.ascontiguousarray(lags, dtype=np.int32)
+    cap = max(1, len(lags_host))
+    arrs = [np.zeros(cap, dtype=np.int32) for _ in range(3)]
+    n_tiles = ctypes.c_int(0)
+    n = lib.kb2_self_moments_tile_plan(lags_host.ctypes.data, len(lags_host), int(n_frames), arrs[0].ctypes.data,
+                                       arrs[1].ctypes.data, arrs[2].ctypes.data, cap, ctypes.byref(n_tiles))
+    return [tuple(int(a[i]) for a in arrs) for i in range(min(n, cap))], n_tiles.value
 
 
 def self_moments_plan(lags, n_frames):

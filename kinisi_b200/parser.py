@@ -674,6 +674,14 @@ class SingleOriginDisplacements(LazyDisplacements):
         f = int(self.frames[i])
         return self.dc[:, :, f:f + 1].permute(0, 2, 1).contiguous()
 
+    def stacked_with(self, others):
+        """`Analyzer._stack_trajectories` (kinisi/analyzer.py:274-290) stacks entry i = `dc[:, i:i+1]` of every
+        trajectory along the atom axis: the stacked sequence is again single-origin, over the same frames."""
+        dc = torch.cat([self.dc] + [o.dc for o in others], dim=0)
+        return SingleOriginDisplacements(dc, self.n_frames, self.frames,
+                                         self.n_atoms_global + sum(o.n_atoms_global for o in others),
+                                         distributed=self.distributed)
+
 
 def _frames_to_arrays(frames, get_frac, get_cell, sub_sample_traj, progress):
     """Walks a trajectory object frame by frame (kinisi/parser.py:309-325, 458-473) into one

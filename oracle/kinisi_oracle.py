@@ -581,6 +581,21 @@ def bootstrap_gls(stats,
     }
 
 
+def posterior_predictive(gradient, intercept, dt, cov, n_posterior_samples, n_predictive_samples, seed):
+    """kinisi/diffusion.py:509-521: for each of `n_posterior_samples` draws (with replacement) of (gradient,
+    intercept), `n_predictive_samples` draws of a multivariate normal about the straight line with the reconditioned
+    covariance (`allow_singular=True`).  Global numpy RNG as in the reference, seeded here.  Returns (ppd, drawn)."""
+    from scipy.stats import multivariate_normal
+    np.random.seed(seed)
+    ppd = np.zeros((n_posterior_samples, n_predictive_samples, dt.size))
+    drawn = np.random.randint(0, gradient.size, size=n_posterior_samples)
+    for i, n in enumerate(drawn):
+        mu = gradient[n] * dt + intercept[n]
+        mv = multivariate_normal(mean=mu, cov=cov, allow_singular=True)
+        ppd[i] = mv.rvs(n_predictive_samples)
+    return ppd.reshape(-1, dt.size), drawn
+
+
 def diffusion_coefficient(gradient, dims):
     """kinisi/diffusion.py:436: D [cm^2/s] from the MSD gradient [A^2/ps]."""
     return gradient / (2e4 * dims)

@@ -35,6 +35,19 @@ def kb():
     return ns
 
 
+@pytest.fixture(autouse=True)
+def _default_variant_is_restored():
+    """Every test starts on (and leaves behind) the shipped default moment kernel, the one bench.py times."""
+    from kinisi_b200 import engine
+    shipped = engine.DEFAULT_VARIANT
+    assert (shipped & 0xff) == engine.VARIANT_WIN
+    yield
+    engine.DEFAULT_VARIANT = shipped
+
+
+ALL_VARIANTS = [0, 1, 2, 3]
+
+
 def load(golden_dir, name):
     return np.load(os.path.join(golden_dir, name + '.npz'))
 
@@ -51,10 +64,10 @@ def check_boot(b, g, prefix, rtol=RTOL_MOMENT, ngp_atol=1e-10):
 # ---------------------------------------------------------------------------------------------
 # stage 1 + 2 against the reference's golden vectors
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('variant', [0, 1])
+@pytest.mark.parametrize('variant', ALL_VARIANTS)
 @pytest.mark.parametrize('name', list(ASE_CASES))
-def test_ase_parser_and_bootstraps(kb, golden_dir, name, variant):
-    kb.engine.DEFAULT_VARIANT = variant
+def test_ase_parser_and_bootstraps(kb, golden_dir, name, variant, monkeypatch):
+    monkeypatch.setattr(kb.engine, 'DEFAULT_VARIANT', variant)
     g = load(golden_dir, name)
     symbols, frac, latt, pp = ase_case_inputs(name)
     traj = trajectory_from_arrays(symbols, frac, latt)
@@ -160,7 +173,7 @@ def test_reference_kats(kb, golden_dir):
 # ---------------------------------------------------------------------------------------------
 # the moment kernels against the oracle's raw sums: tiles, partial tiles, both variants, f32 input
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('variant', [0, 0 | (16 << 8), 1, 2])
+@pytest.mark.parametrize('variant', [0, 0 | (16 << 8), 1, 2, 3])
 @pytest.mark.parametrize('dimension', ['xyz', 'xz', 'y'])
 def test_self_moment_kernels_raw_sums(kb, variant, dimension):
     n_atoms, n_frames = 5, 9300  # > 2 tiles of 4096 and > 4 tiles of 2048, last tile partial
@@ -180,7 +193,7 @@ def test_self_moment_kernels_raw_sums(kb, variant, dimension):
     np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
 
 
-@pytest.mark.parametrize('variant', [0, 1, 2])
+@pytest.mark.parametrize('variant', ALL_VARIANTS)
 def test_long_lag_grid_is_chunked(kb, variant):
     """More lags than one launch holds in shared memory (every lag of a 1500-frame trajectory)."""
     n_atoms, n_frames = 3, 1500
@@ -229,6 +242,31 @@ RUN_GRIDS = {
 
 @pytest.mark.parametrize('grid', sorted(RUN_GRIDS))
 @pytest.mark.parametrize('n_frames', [700, 5431])
+def test_lag_window_kernel_on_structured_and_irregular_grids(kb, grid, n_frames):
+    """kb2_self_moments_win (the default: partner window + accumulators in registers, progressions cut into windows of
+    <= 8 lags, leftovers as windows of one) against the oracle's raw sums on every kind of lag grid."""
+    n_atoms = 3
+    frac, latt = ko.synthetic_walk(n_atoms, n_frames, box=10.0, sigma=0.15, seed=77)
+    dc = ko.get_disp(frac, latt)
+    lags = RUN_GRIDS[grid](n_frames)
+    lags = lags[(lags >= 1) & (lags <= n_frames)]
+    if grid == 'all' and n_frames > 2000:
+        lags = lags[:1700]  # seven chunks of the 256-lag launch limit
+    S1, S2, _, _ = ko.raw_sums_streaming(dc, lags)
+    dct = _device_dc(kb, dc)
+    sums = kb.engine.self_moments(dct, n_frames, lags, 7, kb.engine.VARIANT_WIN).cpu().numpy()
+    np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
+    np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
+    S1, S2, _, _ = ko.raw_sums_streaming(dc, lags, 'xz')
+    sums = kb.engine.self_moments(dct, n_frames, lags, 5, kb.engine.VARIANT_WIN).cpu().numpy()
+    np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
+    np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
+    length = np.array([w[2] for w in kb.engine.self_moments_windows(lags[:256], n_frames)])
+    assert int(np.sum(length)) == min(len(lags), 256) and np.all(length <= 8) and np.all(length >= 1)
+
+
+@pytest.mark.parametrize('grid', sorted(RUN_GRIDS))
+@pytest.mark.parametrize('n_frames', [700, 5431])
 def test_arithmetic_run_kernel_on_structured_and_irregular_grids(kb, grid, n_frames):
     """kb2_self_moments_runs (register-window kernel + direct kernel for the leftover lags) against the
     oracle's raw sums on every kind of lag grid: bit-for-bit the same terms, reduction order aside."""
@@ -247,7 +285,8 @@ def test_arithmetic_run_kernel_on_structured_and_irregular_grids(kb, grid, n_fra
     assert sum(r[2] for r in runs) + rest == min(len(lags), 192)
 
 
-def test_arithmetic_run_kernel_many_atoms_and_tiles(kb):
+@pytest.mark.parametrize('variant', [2, 3])
+def test_structured_kernels_many_atoms_and_tiles(kb, variant):
     """Enough atoms and frames that every persistent CTA takes several work items, with a short trajectory
     tail (partial tiles, warps that straddle two origin tiles, inactive lanes)."""
     n_atoms, n_frames = 37, 12347
@@ -260,7 +299,7 @@ def test_arithmetic_run_kernel_many_atoms_and_tiles(kb):
     for mask, dim in ((7, 'xyz'), (5, 'xz'), (2, 'y')):
         if dim != 'xyz':
             S1, S2, _, _ = ko.raw_sums_streaming(dc, lags, dim)
-        sums = kb.engine.self_moments(dct, n_frames, lags, mask, kb.engine.VARIANT_RUNS).cpu().numpy()
+        sums = kb.engine.self_moments(dct, n_frames, lags, mask, variant).cpu().numpy()
         np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
         np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
 
@@ -1094,3 +1133,195 @@ def test_full_size_properties(kb):
     assert slope == pytest.approx(3 * 0.1**2, rel=0.05)
     ngp = 3 * (b[:, 1] / cnt) / (5 * msd**2) - 1
     assert np.all(np.abs(ngp[short][1:]) < 0.05)
+
+
+# ---------------------------------------------------------------------------------------------
+# the CUDA path against the oracle at BASELINE sizes ("What's weak" 2)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('variant', ALL_VARIANTS)
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+def test_baseline_length_slice_against_oracle(kb, variant, dtype, monkeypatch):
+    """BASELINE configs[1] in length and lag grid (20 000 frames, the real 100-lag grid, framework drift), on an atom
+    slice the streaming oracle does in seconds: MSD, MSTD and MSCD through the classes, every moment-kernel variant,
+    f32 and f64 wrapped coordinates.  The same terms as the reference (kinisi/diffusion.py:571-602, 655-688, 739-780)."""
+    monkeypatch.setattr(kb.engine, 'DEFAULT_VARIANT', variant)
+    n_mobile, n_fw, n_frames = 32, 64, 20000
+    frac, latt = ko.synthetic_walk(n_mobile, n_frames, box=26.0, sigma=0.1, seed=1001, n_framework=n_fw, dtype=dtype)
+    idx, fw = list(range(n_mobile)), list(range(n_mobile, n_mobile + n_fw))
+    parsed = ko.parse(ko.get_disp(frac.astype(np.float64), latt), idx, fw, 0.001, 1, n_steps=100)
+    p = kb.parser.Parser(kb.parser.Parser.get_disp(frac, latt[:1]), idx, fw, 0.001, 1, n_steps=100, memory_limit=64.,
+                         progress=False)
+    np.testing.assert_array_equal(p.time_intervals, parsed['lags'])
+    np.testing.assert_allclose(p._n_o, parsed['n_o'], rtol=1e-15)
+    q = np.where(np.arange(n_mobile) % 2 == 0, 1.0, -1.0)
+    for kind, cls, args in (('msd', kb.diffusion.MSDBootstrap, ()), ('mstd', kb.diffusion.MSTDBootstrap, ()),
+                            ('mscd', kb.diffusion.MSCDBootstrap, (q, ))):
+        b = cls(p.delta_t, p.disp_3d, *args, p._n_o, progress=False)
+        ref = ko.bootstrap_streaming(parsed, kind, q if kind == 'mscd' else None)
+        for key in ('dt', 'n', 'v', 's'):
+            np.testing.assert_allclose(getattr(b, key), ref[key], rtol=RTOL_MOMENT, err_msg=f'{kind} {key}')
+        np.testing.assert_allclose(b.ngp, ref['ngp'], rtol=1e-8, atol=1e-10, err_msg=kind)
+
+
+@pytest.mark.parametrize('variant', ALL_VARIANTS)
+@pytest.mark.parametrize('n_frames', [50000, 100000])
+def test_production_lag_grids_against_oracle(kb, variant, n_frames):
+    """`np.linspace(1, T, 100, dtype=int)` at T = 50 000 (four progressions of 25 lags) and T = 100 000 (one progression
+    with a one-sample carry every 11th lag): BASELINE configs[4] / configs[2] in length.  Raw per-lag sums of every
+    kernel variant against `raw_sums_streaming` (kinisi/parser.py:208-213 + diffusion.py:572-574), two dimensions."""
+    n_atoms = 3
+    rng = np.random.default_rng(n_frames)
+    dc = np.cumsum(rng.normal(0, 0.1, size=(n_atoms, n_frames, 3)), axis=1)
+    dc[:, 0] = 0.0
+    lags = np.linspace(1, n_frames, 100, dtype=int)
+    dct = _device_dc(kb, dc)
+    for mask, dim in ((7, 'xyz'), (3, 'xy')):
+        S1, S2, _, _ = ko.raw_sums_streaming(dc, lags, dim)
+        sums = kb.engine.self_moments(dct, n_frames, lags, mask, variant).cpu().numpy()
+        np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
+        np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
+
+
+def test_full_size_default_kernel_against_the_direct_kernel_and_an_oracle_slice(kb):
+    """BASELINE configs[1] at full size (448 atoms x 20 000 frames x 100 lags): the shipped default kernel against the
+    direct kernel on all atoms, and both against the oracle's sums of the first 16 atoms (additivity over atoms)."""
+    n_atoms, n_frames = 448, 20000
+    rng = np.random.default_rng(1002)
+    dc = np.cumsum(rng.normal(0, 0.1, size=(n_atoms, n_frames, 3)), axis=1)
+    dc[:, 0] = 0.0
+    lags = np.linspace(1, n_frames, 100, dtype=int)
+    dct = _device_dc(kb, dc)
+    default = kb.engine.self_moments(dct, n_frames, lags, 7).cpu().numpy()
+    direct = kb.engine.self_moments(dct, n_frames, lags, 7, kb.engine.VARIANT_DIRECT).cpu().numpy()
+    np.testing.assert_allclose(default, direct, rtol=1e-12)
+    S1, S2, _, _ = ko.raw_sums_streaming(dc[:16], lags)
+    head = kb.engine.self_moments(dct[:16].contiguous(), n_frames, lags, 7).cpu().numpy()
+    tail = kb.engine.self_moments(dct[16:].contiguous(), n_frames, lags, 7).cpu().numpy()
+    np.testing.assert_allclose(head[:, 0], S1, rtol=1e-12)
+    np.testing.assert_allclose(head[:, 1], S2, rtol=1e-12)
+    np.testing.assert_allclose(head + tail, default, rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# log-determinant (a10) and posterior predictive (f1)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n', [2, 5, 31, 64, 90, 128, 200])
+def test_log_determinant_and_absolute_log_likelihood(kb, n):
+    """`np.linalg.slogdet` of the reconditioned covariance (kinisi/diffusion.py:350-351).  Well-conditioned positive
+    definite input: the log-determinant to 1e-10 and ABSOLUTE log-likelihood values against the oracle's
+    slogdet + pinvh closure (:354-365).  Model covariance (indefinite): the clipped-spectrum sum
+    sum_r log max(lambda_r, lambda_max / cond_max) (:883-887).  n <= 128 takes the Jacobi kernel, above it the
+    library eigensolver + kb2_gls_prepare through the Bootstrap."""
+    rng = np.random.RandomState(100 + n)
+    dev = torch.device('cuda')
+    x = np.linspace(0.1, 9.0, n)
+    a = rng.randn(n, n)
+    cov = a @ a.T / n + np.diag(rng.uniform(0.5, 1.5, n))  # condition number ~ 10
+    y = 3.0 * x + 0.2 + rng.multivariate_normal(np.zeros(n), cov)
+    thetas = np.array([[3.0, 0.2], [2.5, 0.5], [3.4, -0.3], [0.1, 4.0]])
+    sign, logdet = np.linalg.slogdet(cov)
+    assert sign > 0
+    ll_fn, _, _ = ko.make_log_likelihood(x, y, cov)
+    ll_ref = np.array([ll_fn(t) for t in thetas])
+    if n <= kb.engine.spectral_prepare_max_n():
+        evals, proj, gls, logdet_term, info = kb.engine.spectral_prepare(torch.from_numpy(cov).to(dev),
+                                                                         torch.from_numpy(x).to(dev),
+                                                                         torch.from_numpy(y).to(dev), 1e16, True)
+    else:
+        lam, vec = torch.linalg.eigh(torch.from_numpy(cov).to(dev))
+        logdet_term = (torch.log(lam).sum() + float(np.log(2 * np.pi) * n)).reshape(1)
+        proj, gls = kb.engine.gls_prepare(lam, vec, torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), True)
+    np.testing.assert_allclose(float(logdet_term.item()) - n * np.log(2 * np.pi), logdet, rtol=1e-10, atol=1e-10)
+    ll = kb.engine.mvn_loglike(torch.from_numpy(thetas).to(dev), proj, logdet_term).cpu().numpy()
+    np.testing.assert_allclose(ll, ll_ref, rtol=1e-9, atol=1e-9)
+    if n <= kb.engine.spectral_prepare_max_n():
+        # an indefinite model covariance: the spectrum is clipped at lambda_max / cond_max before the logarithm
+        v = rng.uniform(0.5, 2.0, n) * np.linspace(1, 30, n)**2
+        n_o = 1000.0 / np.arange(1, n + 1)
+        cov = ko.populate_covariance_matrix(v, n_o)
+        w = np.linalg.eigvalsh(cov)
+        for cond_max in (1e16, 1e8):
+            _, _, _, logdet_term, _ = kb.engine.spectral_prepare(torch.from_numpy(cov).to(dev), torch.from_numpy(x).to(dev),
+                                                                 torch.from_numpy(y).to(dev), cond_max, True)
+            want = np.sum(np.log(np.maximum(w, w.max() / cond_max)))
+            # an eigenvalue within rounding of the clip level may fall on either side of it: |d log| <= eps * cond
+            np.testing.assert_allclose(float(logdet_term.item()) - n * np.log(2 * np.pi), want, rtol=1e-9, atol=1e-6)
+
+
+def test_log_likelihood_values_of_a_well_conditioned_analysis(kb):
+    """`Bootstrap.log_likelihood` is an API output: on a trajectory whose model covariance is positive definite and well
+    conditioned, its VALUES (not differences) against the oracle's closure over the oracle's own covariance."""
+    n_atoms, n_frames = 64, 4000
+    frac, latt = ko.synthetic_walk(n_atoms, n_frames, box=12.0, sigma=0.1, seed=77)
+    parsed = ko.parse(ko.get_disp(frac, latt), list(range(n_atoms)), [], 0.002, 1, n_steps=12)
+    ref = ko.bootstrap_streaming(parsed, 'msd')
+    p = kb.parser.Parser(kb.parser.Parser.get_disp(frac, latt), list(range(n_atoms)), [], 0.002, 1, n_steps=12,
+                         progress=False)
+    b = kb.diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False)
+    start = 2
+    b.diffusion(float(b.dt[start]), progress=False, n_samples=200, n_burn=100)
+    cov_ref = ko.generate_covariance_matrix(ref['v'], ref['n_o'], start)
+    w = np.linalg.eigvalsh(ko.populate_covariance_matrix(ref['v'][start:], ref['n_o'][start:]))
+    if w.min() <= 0 or w.max() / w.min() > 1e10:
+        pytest.skip('the model covariance of this walk is not well conditioned')
+    ll_fn, _, _ = ko.make_log_likelihood(ref['dt'][start:], ref['n'][start:], cov_ref)
+    thetas = np.array([[0.18, 0.0], [0.17, 0.05], [0.19, -0.04], [0.2, 0.1]])
+    np.testing.assert_allclose(b.log_likelihood(thetas), [ll_fn(t) for t in thetas], rtol=1e-7, atol=1e-7)
+
+
+def test_posterior_predictive_distribution(kb, golden_dir):
+    """`posterior_predictive` (kinisi/diffusion.py:492-521) against the oracle's restatement of the
+    reference loop (scipy multivariate_normal per posterior draw): the drawn posterior samples are the same (same
+    global-RNG call), per-draw means sit on the straight line, the pooled residual covariance is the reconditioned
+    covariance, and mean / variance per dt agree with the reference loop within Monte-Carlo error."""
+    g = load(golden_dir, 'regress_msd')
+    symbols, frac, latt, pp, start_idx, kind = regress_case_inputs('regress_msd')
+    an = kb.analyze.DiffusionAnalyzer.from_ase(trajectory_from_arrays(symbols, frac, latt), parser_params=pp,
+                                               uncertainty_params={'progress': False})
+    an.diffusion(float(g['start_dt']), {'progress': False, 'random_state': np.random.RandomState(11)})
+    b = an._diff
+    dr = int(np.argwhere(b.dt >= float(g['start_dt']))[0][0])
+    x = b.dt[dr:]
+    P, M = 48, 400
+    np.random.seed(5)
+    ppd = an.posterior_predictive({'n_posterior_samples': P, 'n_predictive_samples': M, 'progress': False})
+    assert ppd.shape == (P * M, x.size)
+    cov = b.covariance_matrix
+    ref, drawn = ko.posterior_predictive(b.gradient.samples, b.intercept.samples, x, cov, P, M, seed=5)
+    mu = b.gradient.samples[drawn][:, None] * x[None, :] + b.intercept.samples[drawn][:, None]
+    sd = np.sqrt(np.diag(cov))
+    got = ppd.reshape(P, M, -1)
+    # per-draw means: standard error sd / sqrt(M); 5 sigma over P * n values
+    assert np.all(np.abs(got.mean(axis=1) - mu) < 5.0 * sd / np.sqrt(M))
+    # pooled residual covariance against the reconditioned covariance: relative error ~ sqrt(2 / (P M)) = 1 %
+    res = (got - mu[:, None, :]).reshape(-1, x.size)
+    emp = res.T @ res / res.shape[0]
+    np.testing.assert_allclose(np.diag(emp), np.diag(cov), rtol=0.06)
+    np.testing.assert_allclose(emp, cov, rtol=0, atol=0.06 * np.outer(sd, sd).max())
+    # against the reference loop's samples: mean and variance per dt
+    ref = ref.reshape(P, M, -1)
+    se = np.sqrt(ppd.var(axis=0) / (P * M) + ref.reshape(-1, x.size).var(axis=0) / (P * M))
+    res_ref = (ref - mu[:, None, :]).reshape(-1, x.size)
+    assert np.all(np.abs(res.mean(axis=0) - res_ref.mean(axis=0)) < 5.0 * np.sqrt(2.0) * sd / np.sqrt(P * M))
+    np.testing.assert_allclose(res.var(axis=0), res_ref.var(axis=0), rtol=0.08)
+    assert np.all(se > 0)
+
+
+def test_identical_single_origin_trajectories_stack(kb):
+    """dtype='identical' with sampling='single-origin' (kinisi/analyzer.py:274-290 over parser.py:202-206): entry i of
+    the stacked sequence is frame i of every trajectory, not the lag-1 multi-origin displacement."""
+    symbols = ['Li'] * 5
+    trajs, dcs = [], []
+    for seed in (3, 4):
+        frac, latt = ko.synthetic_walk(5, 60, box=8.0, sigma=0.2, seed=seed)
+        trajs.append(trajectory_from_arrays(symbols, frac[:, 1:], latt[1:]))
+        dcs.append(ko.get_disp(frac, latt))
+    pp = dict(specie='Li', time_step=0.001, step_skip=1, n_steps=20, sampling='single-origin', progress=False)
+    an = kb.analyze.DiffusionAnalyzer.from_ase(trajs, parser_params=pp, dtype='identical')
+    one = kb.parser.ASEParser(trajs[0], **pp)
+    frames = one.disp_3d.frames
+    assert an._disp_3d.shape_of(0) == (10, 1, 3) and type(an._disp_3d).__name__ == 'SingleOriginDisplacements'
+    joint = np.concatenate(dcs, axis=0)
+    want = np.array([np.mean(np.sum(joint[:, f]**2, axis=-1)) for f in frames[:an.msd.size]])
+    np.testing.assert_allclose(an.msd, want, rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(an._disp_3d[3], joint[:, frames[3]:frames[3] + 1], rtol=1e-12, atol=1e-13)

@@ -1,5 +1,6 @@
-"""Lag-window kernel (variant 3) against the direct kernel (variant 0) and a torch float64 evaluation on a set of lag
-grids, then timings of variants 2 and 3 on the BASELINE shapes.  Run on a B200: python tools/k2win_probe.py [quick]"""
+"""A host-planned moment kernel (KB2_PROBE_VARIANT: 3 lag-window, 4 tiled lag-window (default)) against a torch float64
+evaluation on a set of lag grids, then timings of variants 2, 3 and 4 on the BASELINE shapes.
+Run on a B200: python tools/k2win_probe.py [quick]"""
 import json
 import os
 import sys
@@ -11,6 +12,7 @@ import torch
 from kinisi_b200 import engine
 
 dev = torch.device('cuda')
+VAR = int(os.environ.get('KB2_PROBE_VARIANT', '4'))
 gen = torch.Generator(device=dev)
 gen.manual_seed(1)
 
@@ -54,7 +56,7 @@ for name, T, lags in cases:
         ref = torch_sums(dc, T, lags)
         for mask, comps in ((7, (0, 1, 2)), (5, (0, 2)), (2, (1, ))):
             refm = ref if mask == 7 else torch_sums(dc, T, lags, comps)
-            out = engine.self_moments(dc, T, lags.astype(np.int32), mask, engine.VARIANT_WIN).cpu().numpy()
+            out = engine.self_moments(dc, T, lags.astype(np.int32), mask, VAR).cpu().numpy()
             err = np.max(np.abs(out - refm) / np.maximum(np.abs(refm), 1e-300))
             ok = err < 1e-11
             fails += not ok
@@ -75,7 +77,7 @@ for n_atoms, T in shapes:
     for gname, lags in grids.items():
         terms = n_atoms * float(np.sum(T - lags + 1))
         ref = None
-        for name, v in (('runs', 2), ('win', 3)):
+        for name, v in (('runs', 2), ('win', 3), ('tile', 4)):
             for _ in range(3):
                 out = engine.self_moments(dc, T, lags.astype(np.int32), 7, v)
             torch.cuda.synchronize()
@@ -92,5 +94,5 @@ for n_atoms, T in shapes:
             key = f'{name}_{gname}_{n_atoms}x{T}'
             res[key] = dict(ms=ms, terms_per_s=terms / ms * 1e3, fp64_tflops=16 * terms / ms * 1e3 / 1e12, relerr_vs_runs=err)
             print(key, res[key], flush=True)
-tag = os.environ.get('KB2_WIN_WARPS', 'def')
+tag = os.environ.get('KB2_PROBE_TAG', 'def')
 json.dump(res, open(f'/root/repo/gpurun_out/k2win_probe_{tag}.json', 'w'), indent=1)
