@@ -457,7 +457,7 @@ def run_own(args):
                 'sharding': 'atoms' if world > 1 else 'none',
                 'l2': f'inputs ({host.numel() * 4 / 1e6:.0f} MB f32 + {n_mob * 3 * T * 8 / 1e6:.0f} MB f64 per step) '
                       'exceed the 126 MB L2; no flush needed',
-                'self_moment_variant': {0: 'direct', 1: 'tma-ring', 2: 'arithmetic-runs', 3: 'lag-window'}[engine.DEFAULT_VARIANT & 0xff],
+                'self_moment_variant': {0: 'direct', 1: 'tma-ring', 2: 'arithmetic-runs', 3: 'lag-window', 4: 'tiled-lag-window'}[engine.DEFAULT_VARIANT & 0xff],
                 'wall_ms_per_step': wall_total / args.steps,
                 'analyses_in_flight': args.in_flight,
             },
@@ -510,7 +510,7 @@ def main():
     ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
-    ap.add_argument('--variant', type=int, default=None, help='self-moment kernel: 0 direct, 1 TMA ring, 2 arithmetic runs, 3 lag window (default)')
+    ap.add_argument('--variant', type=int, default=None, help='self-moment kernel: 0 direct, 1 TMA ring, 2 arithmetic runs, 3 lag window, 4 tiled lag window (default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--in-flight', type=int, default=4,
                     help='analyses in flight: consecutive trajectories go round-robin to this many CUDA streams (1 = one stream)')

@@ -4,7 +4,7 @@
 // Replaces the per-dt loop of MSDBootstrap.__init__ (kinisi/diffusion.py:571-602) over the list Parser.get_disps
 // builds (kinisi/parser.py:208-216): for every lag k, sum and sum of squares of |x[j+k] - x[j]|^2 over atoms and origins.
 //
-// Geometry.  Pick a row length D (even, >= 32) and read one component of one atom's trajectory as a matrix with rows of
+// Geometry.  Pick a row length D (>= 32) and read one component of one atom's trajectory as a matrix with rows of
 // D frames: frame f = a*D + t is (row a, column t).  Any lag is k = I*D + r (0 <= r < D): the partner of the origin
 // (a, t) is the frame (a + I)*D + (t + r), i.e. row a + I, column t + r, counted linearly (a column index >= D simply
 // runs into the next row).  A WINDOW is m <= 8 lags with consecutive I and one r -- kinisi's default grid
@@ -42,14 +42,13 @@
 namespace kb2 {
 
 constexpr int kTileM = 8;                    // lags per window
-constexpr int kTileWo = 32;                  // columns copied for an origin row
 constexpr int kTileWp = 40;                  // columns of a partner row = component stride within any row
 constexpr int kTileRowP = 3 * kTileWp;       // doubles per row (three components)
 constexpr int kTileRowO = kTileRowP;         // origin rows have the layout of partner rows (a SHARED tile has one row set)
 constexpr int kTileMaxBufs = 3;              // tile buffers in flight: 3 x 64 KB or 2 x 96 KB (chosen by the planner)
 constexpr int kTileSmemBufBytes = 192 * 1024;  // shared memory of all buffers
 constexpr int kTileGuardBytes = 4096;        // shared memory in front of the first buffer (look-ahead reads run below a tile)
-constexpr int kTileCW = 12;                  // consumer warps
+constexpr int kTileCW = 14;                  // consumer warps
 constexpr int kTileMaxLags = 256;            // lags per launch (CTA accumulators in shared memory)
 constexpr int kTileRA = 32;                  // most origin rows per unit
 constexpr int kTileMaxUnits = 96;            // units per tile
@@ -143,17 +142,37 @@ struct Regs {
     double A1[M], A2[M];
 };
 
-// One step.  `po` / `pp` point at the origin / partner sample of step 0 of the column; S = the step's index relative
-// to them (compile time), PH = absolute step index mod U.  Loads the samples of the steps ahead, then forms NT terms
-// (lags 0 .. NT-1: lag w pairs the origin with the partner loaded w steps earlier).  DIAG: the last term uses the partner
-// of the top row, which lies past the end of the trajectory for the lanes with `kill` set.
+// Sample pointers of a column walk.  With an odd row length D the rows of a tile start alternately at an even and an
+// odd frame, and a row is copied from the even frame at or below its start (16-byte copies): the samples of the rows of
+// one parity sit one column further right.  o[0] / p[0] serve the even steps counted from the step the pointers refer
+// to, o[1] / p[1] the odd ones (all equal for an even D).
+struct Ptrs {
+    const double* o[2];
+    const double* p[2];
+    __device__ __forceinline__ void advance(int steps) {  // `steps` rows down; an odd count swaps the parities
+        const double* const o0 = o[0] - steps * kTileRowO;
+        const double* const o1 = o[1] - steps * kTileRowO;
+        const double* const p0 = p[0] - steps * kTileRowP;
+        const double* const p1 = p[1] - steps * kTileRowP;
+        const bool swap = steps & 1;
+        o[0] = swap ? o1 : o0;
+        o[1] = swap ? o0 : o1;
+        p[0] = swap ? p1 : p0;
+        p[1] = swap ? p0 : p1;
+    }
+};
+
+// One step.  The pointers refer to step 0 of the current block; S = the step's index relative to them (compile time),
+// PH = absolute step index mod U.  Loads the samples of the steps ahead, then forms NT terms (lags 0 .. NT-1: lag w
+// pairs the origin with the partner loaded w steps earlier).  DIAG: the last term uses the partner of the top row, which
+// lies past the end of the trajectory for the lanes with `kill` set.
 template <int NDIM, int M, int S, int PH, int NT, bool DIAG>
-__device__ __forceinline__ void step(const double* po, const double* pp, Regs<NDIM, M>& r, bool kill) {
+__device__ __forceinline__ void step(const Ptrs& q, Regs<NDIM, M>& r, bool kill) {
     constexpr int RV = Cfg<M>::RV, DV = Cfg<M>::DV;
 #pragma unroll
-    for (int c = 0; c < NDIM; ++c) r.vb[(PH + DV) % RV][c] = pp[-(S + DV) * kTileRowP + c * kTileWp];
+    for (int c = 0; c < NDIM; ++c) r.vb[(PH + DV) % RV][c] = q.p[(S + DV) & 1][-(S + DV) * kTileRowP + c * kTileWp];
 #pragma unroll
-    for (int c = 0; c < NDIM; ++c) r.ub[(PH + 1) % 2][c] = po[-(S + 1) * kTileRowO + c * kTileWp];
+    for (int c = 0; c < NDIM; ++c) r.ub[(PH + 1) % 2][c] = q.o[(S + 1) & 1][-(S + 1) * kTileRowO + c * kTileWp];
 #pragma unroll
     for (int w = 0; w < NT; ++w) {
         const int sl = (PH - w + RV) % RV;
@@ -171,14 +190,14 @@ __device__ __forceinline__ void step(const double* po, const double* pp, Regs<ND
 
 template <int NDIM, int M, int F>
 struct Prologue {  // partners of steps 0 .. DV-1, origin of step 0
-    __device__ __forceinline__ static void run(const double* po, const double* pp, Regs<NDIM, M>& r) {
+    __device__ __forceinline__ static void run(const Ptrs& q, Regs<NDIM, M>& r) {
         if constexpr (F < Cfg<M>::DV) {
 #pragma unroll
-            for (int c = 0; c < NDIM; ++c) r.vb[F][c] = pp[-F * kTileRowP + c * kTileWp];
-            Prologue<NDIM, M, F + 1>::run(po, pp, r);
+            for (int c = 0; c < NDIM; ++c) r.vb[F][c] = q.p[F & 1][-F * kTileRowP + c * kTileWp];
+            Prologue<NDIM, M, F + 1>::run(q, r);
         } else {
 #pragma unroll
-            for (int c = 0; c < NDIM; ++c) r.ub[0][c] = po[c * kTileWp];
+            for (int c = 0; c < NDIM; ++c) r.ub[0][c] = q.o[0][c * kTileWp];
         }
     }
 };
@@ -188,15 +207,14 @@ struct Prologue {  // partners of steps 0 .. DV-1, origin of step 0
 // Returns false when the column ended inside the fill.
 template <int NDIM, int M, int R>
 struct Fill {
-    __device__ __forceinline__ static bool run(const double* po, const double* pp, Regs<NDIM, M>& r, int total, bool top,
-                                               bool kill) {
+    __device__ __forceinline__ static bool run(const Ptrs& q, Regs<NDIM, M>& r, int total, bool top, bool kill) {
         if constexpr (R < M) {
             if (R >= total) return false;
             if (top)
-                step<NDIM, M, R, R % Cfg<M>::U, R + 1, true>(po, pp, r, kill);
+                step<NDIM, M, R, R % Cfg<M>::U, R + 1, true>(q, r, kill);
             else
-                step<NDIM, M, R, R % Cfg<M>::U, (R == M - 1 ? M : 0), false>(po, pp, r, false);
-            return Fill<NDIM, M, R + 1>::run(po, pp, r, total, top, kill);
+                step<NDIM, M, R, R % Cfg<M>::U, (R == M - 1 ? M : 0), false>(q, r, false);
+            return Fill<NDIM, M, R + 1>::run(q, r, total, top, kill);
         } else {
             return true;
         }
@@ -206,12 +224,12 @@ struct Fill {
 template <int NDIM, int M, int UU>
 struct Main {
     // steps of one unrolled block, the first at phase M mod U; returns true when the column is done
-    __device__ __forceinline__ static bool run(const double* po, const double* pp, Regs<NDIM, M>& r, int& left) {
+    __device__ __forceinline__ static bool run(const Ptrs& q, Regs<NDIM, M>& r, int& left) {
         constexpr int U = Cfg<M>::U;
         if constexpr (UU < U) {
-            step<NDIM, M, UU, (M + UU) % U, M, false>(po, pp, r, false);
+            step<NDIM, M, UU, (M + UU) % U, M, false>(q, r, false);
             if (--left == 0) return true;
-            return Main<NDIM, M, UU + 1>::run(po, pp, r, left);
+            return Main<NDIM, M, UU + 1>::run(q, r, left);
         } else {
             return false;
         }
@@ -236,8 +254,9 @@ __device__ __forceinline__ void butterfly(double (&v)[16], int lane, int bit) {
 
 // Walks one column and adds the sums of the warp to the CTA's accumulators.
 template <int NDIM, int M>
-__device__ __forceinline__ void column(const double* po, const double* pp, int total, bool top, bool kill, bool active,
-                                       int acc_off, double* acc, int lane) {
+__device__ __forceinline__ void column(Ptrs q, int total, bool top, bool kill, bool active, int acc_off, double* acc,
+                                       int lane) {
+    static_assert(Cfg<M>::U % 2 == 0, "a block of the main loop keeps the row parities");
     Regs<NDIM, M> r;
 #pragma unroll
     for (int w = 0; w < M; ++w) {
@@ -248,17 +267,13 @@ __device__ __forceinline__ void column(const double* po, const double* pp, int t
     for (int i = 0; i < Cfg<M>::RV; ++i)
 #pragma unroll
         for (int c = 0; c < 3; ++c) r.vb[i][c] = 0.0;
-    Prologue<NDIM, M, 0>::run(po, pp, r);
-    if (Fill<NDIM, M, 0>::run(po, pp, r, total, top, kill)) {
+    Prologue<NDIM, M, 0>::run(q, r);
+    if (Fill<NDIM, M, 0>::run(q, r, total, top, kill)) {
         int left = total - M;
-        po -= M * kTileRowO;
-        pp -= M * kTileRowP;
+        q.advance(M);
         if (left > 0) {
 #pragma unroll 1
-            while (!Main<NDIM, M, 0>::run(po, pp, r, left)) {
-                po -= Cfg<M>::U * kTileRowO;
-                pp -= Cfg<M>::U * kTileRowP;
-            }
+            while (!Main<NDIM, M, 0>::run(q, r, left)) q.advance(Cfg<M>::U);
         }
     }
     // a lane without a column (ragged last strip) has read its neighbour's data: its sums are dropped
@@ -388,59 +403,39 @@ __global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
             // is not copied: what is missing is only ever read by masked lanes.  A row is NDIM * 16 (origin) or NDIM * 20
             // (partner) chunks of two frames: chunk i of a row goes to lane i mod 32; rows alternate between the producer
             // warps.
+            static_assert(NPW % 2 == 0, "a producer warp copies rows of one parity (odd D)");
+            const int c_lo = lane / 20, p_lo = lane - c_lo * 20;                // chunks 0..31 of a row of NDIM * 20
+            const int c_hi = (lane + 32) / 20, p_hi = (lane + 32) - c_hi * 20;  // chunks 32..59
+            const bool has_lo = c_lo < NDIM, has_hi = c_hi < NDIM && lane + 32 < NDIM * 20;
+            const double* const g_lo = src_atom + (size_t)comp[has_lo ? c_lo : 0] * pitch + 2 * p_lo;
+            const double* const g_hi = src_atom + (size_t)comp[has_hi ? c_hi : 0] * pitch + 2 * p_hi;
+            const uint32_t o_lo = (uint32_t)(c_lo * kTileWp + 2 * p_lo) * 8u + (uint32_t)pw * (kTileRowP * 8);
+            const uint32_t o_hi = (uint32_t)(c_hi * kTileWp + 2 * p_hi) * 8u + (uint32_t)pw * (kTileRowP * 8);
+            const size_t sstep = (size_t)NPW * D;
 #pragma unroll 1
             for (int sidx = 0; sidx < ns; ++sidx) {
                 const int ts = t0 + 32 * sidx;
                 const uint32_t sub_s = buf_s + (uint32_t)(sidx * sub_bytes);
-                {
-                    const int c_lo = lane / 16, p_lo = lane - c_lo * 16;                // chunks 0..31
-                    const int c_hi = (lane + 32) / 16, p_hi = (lane + 32) - c_hi * 16;  // chunks 32..47
-                    const bool has_lo = c_lo < NDIM, has_hi = c_hi < NDIM;
-                    const int f_first = (oLo + pw) * D + ts;
-                    const double* s_lo = src_atom + (size_t)comp[has_lo ? c_lo : 0] * pitch + 2 * p_lo + f_first;
-                    const double* s_hi = src_atom + (size_t)comp[has_hi ? c_hi : 0] * pitch + 2 * p_hi + f_first;
-                    uint32_t d_lo = sub_s + (uint32_t)(c_lo * kTileWp + 2 * p_lo) * 8u + (uint32_t)pw * (kTileRowO * 8);
-                    uint32_t d_hi = sub_s + (uint32_t)(c_hi * kTileWp + 2 * p_hi) * 8u + (uint32_t)pw * (kTileRowO * 8);
-                    // rows whose 32 frames lie wholly below the pitch need no test
-                    const int room = ipitch - kTileWo - ts;  // f <= room  <=>  the row is whole
-                    int row = pw;
-                    const size_t sstep = (size_t)NPW * D;
-#pragma unroll 2
-                    for (; row < nO && (oLo + row) * D <= room; row += NPW) {
-                        if (has_lo) cp_async16(d_lo, s_lo);
-                        if (has_hi) cp_async16(d_hi, s_hi);
-                        s_lo += sstep, s_hi += sstep, d_lo += NPW * (kTileRowO * 8), d_hi += NPW * (kTileRowO * 8);
-                    }
+                // the origin rows, then the partner rows (from column cP0); every row 40 columns from an even frame
 #pragma unroll 1
-                    for (; row < nO; row += NPW) {
-                        const int f = (oLo + row) * D + ts;
-                        if (has_lo && f + 2 * p_lo < ipitch) cp_async16(d_lo, s_lo);
-                        if (has_hi && f + 2 * p_hi < ipitch) cp_async16(d_hi, s_hi);
-                        s_lo += sstep, s_hi += sstep, d_lo += NPW * (kTileRowO * 8), d_hi += NPW * (kTileRowO * 8);
-                    }
-                }
-                {
-                    const int c_lo = lane / 20, p_lo = lane - c_lo * 20;
-                    const int c_hi = (lane + 32) / 20, p_hi = (lane + 32) - c_hi * 20;  // chunks 32..59
-                    const bool has_lo = c_lo < NDIM, has_hi = c_hi < NDIM && lane + 32 < NDIM * 20;
-                    const int f_first = (pLo + pw) * D + ts + cP0;
-                    const double* s_lo = src_atom + (size_t)comp[has_lo ? c_lo : 0] * pitch + 2 * p_lo + f_first;
-                    const double* s_hi = src_atom + (size_t)comp[has_hi ? c_hi : 0] * pitch + 2 * p_hi + f_first;
-                    const uint32_t base = sub_s + (uint32_t)nO * (kTileRowO * 8) + (uint32_t)pw * (kTileRowP * 8);
-                    uint32_t d_lo = base + (uint32_t)(c_lo * kTileWp + 2 * p_lo) * 8u;
-                    uint32_t d_hi = base + (uint32_t)(c_hi * kTileWp + 2 * p_hi) * 8u;
-                    const int room = ipitch - kTileWp - ts - cP0;
-                    int row = pw;
-                    const size_t sstep = (size_t)NPW * D;
+                for (int kind = 0; kind < 2; ++kind) {
+                    const int n_rows = kind ? nP : nO, rho0 = (kind ? pLo : oLo) + pw;
+                    const int f_first = rho0 * D + ts + (kind ? cP0 : 0) - (D & rho0 & 1);
+                    const double* s_lo = g_lo + f_first;
+                    const double* s_hi = g_hi + f_first;
+                    uint32_t d_lo = sub_s + o_lo + (kind ? (uint32_t)nO * (kTileRowP * 8) : 0u);
+                    uint32_t d_hi = sub_s + o_hi + (kind ? (uint32_t)nO * (kTileRowP * 8) : 0u);
+                    // rows whose 40 frames lie wholly below the pitch need no test
+                    int f = f_first, row = pw;
+                    const int whole = ipitch - kTileWp;
 #pragma unroll 2
-                    for (; row < nP && (pLo + row) * D <= room; row += NPW) {
+                    for (; row < n_rows && f <= whole; row += NPW, f += NPW * D) {
                         if (has_lo) cp_async16(d_lo, s_lo);
                         if (has_hi) cp_async16(d_hi, s_hi);
                         s_lo += sstep, s_hi += sstep, d_lo += NPW * (kTileRowP * 8), d_hi += NPW * (kTileRowP * 8);
                     }
 #pragma unroll 1
-                    for (; row < nP; row += NPW) {
-                        const int f = (pLo + row) * D + ts + cP0;
+                    for (; row < n_rows; row += NPW, f += NPW * D) {
                         if (has_lo && f + 2 * p_lo < ipitch) cp_async16(d_lo, s_lo);
                         if (has_hi && f + 2 * p_hi < ipitch) cp_async16(d_hi, s_hi);
                         s_lo += sstep, s_hi += sstep, d_lo += NPW * (kTileRowP * 8), d_hi += NPW * (kTileRowP * 8);
@@ -502,17 +497,25 @@ __global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
                 const int total = nsteps + (top ? 0 : m - 1);
                 // the partner of (a_top, first lag) lies past the end of the trajectory for the short lanes of a top unit
                 const bool kill = top && ((long long)(a_top + I0) * d.D + t + r > (long long)Tn - 1);
-                const double* po = bufO + (a_start - d.oLo) * kTileRowO + lane;
-                const double* pp = bufP + (a_start + I0 - d.pLo) * kTileRowP + (r - d.cP0) + lane;
+                // (odd D: the row with global index rho is stored from the even frame at or below its start, i.e. shifted
+                // right by rho & 1 columns)
+                const int odd = d.D & 1, p_start = a_start + I0;
+                const double* const po = bufO + (a_start - d.oLo) * kTileRowO + lane;
+                const double* const pp = bufP + (p_start - d.pLo) * kTileRowP + (r - d.cP0) + lane;
+                tile::Ptrs q;
+                q.o[0] = po + (odd & a_start);
+                q.o[1] = po + (odd & ~a_start);
+                q.p[0] = pp + (odd & p_start);
+                q.p[1] = pp + (odd & ~p_start);
                 switch (m) {
-                    case 8: column<NDIM, 8>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
-                    case 7: column<NDIM, 7>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
-                    case 6: column<NDIM, 6>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
-                    case 5: column<NDIM, 5>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
-                    case 4: column<NDIM, 4>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
-                    case 3: column<NDIM, 3>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
-                    case 2: column<NDIM, 2>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
-                    default: column<NDIM, 1>(po, pp, total, top, kill, active, acc_off, acc, lane); break;
+                    case 8: column<NDIM, 8>(q, total, top, kill, active, acc_off, acc, lane); break;
+                    case 7: column<NDIM, 7>(q, total, top, kill, active, acc_off, acc, lane); break;
+                    case 6: column<NDIM, 6>(q, total, top, kill, active, acc_off, acc, lane); break;
+                    case 5: column<NDIM, 5>(q, total, top, kill, active, acc_off, acc, lane); break;
+                    case 4: column<NDIM, 4>(q, total, top, kill, active, acc_off, acc, lane); break;
+                    case 3: column<NDIM, 3>(q, total, top, kill, active, acc_off, acc, lane); break;
+                    case 2: column<NDIM, 2>(q, total, top, kill, active, acc_off, acc, lane); break;
+                    default: column<NDIM, 1>(q, total, top, kill, active, acc_off, acc, lane); break;
                 }
             }
             __syncwarp();
@@ -541,18 +544,18 @@ struct TilePlan {
     long long bytes_loaded = 0;     // per atom
 };
 
-// Row length for a progression of `len` lags with common difference d: a multiple of d, even, >= 32, that fills whole
+// Row length for a progression of `len` lags with common difference d: a multiple of d, >= 32, that fills whole
 // strips of 32 columns and still leaves windows of several lags.
 static int choose_mult(int d, int len, int Tn) {
     if (const char* e = getenv("KB2_TILE_MULT")) {  // experiments: force the multiple when it is admissible
         const int mult = atoi(e);
-        if (mult >= 1 && ((long long)mult * d) % 2 == 0 && (long long)mult * d >= 32) return mult;
+        if (mult >= 1 && (long long)mult * d >= 32) return mult;
     }
     double best = 1e300;
     int best_mult = 0;
     for (int mult = 1; mult <= 64; ++mult) {
         const long long D = (long long)mult * d;
-        if (D % 2 || D < 32) continue;
+        if (D < 32) continue;
         if (D > 2ll * Tn && best_mult) break;
         const int ls = (len + mult - 1) / mult;            // lags of the longest interleaved progression
         if (ls < 3 && best_mult) continue;
@@ -567,9 +570,9 @@ static int choose_mult(int d, int len, int Tn) {
             best_mult = mult;
         }
     }
-    if (!best_mult) {  // d odd and tiny: the first even multiple >= 32
+    if (!best_mult) {
         best_mult = 1;
-        while (((long long)best_mult * d) % 2 || (long long)best_mult * d < 32) ++best_mult;
+        while ((long long)best_mult * d < 32) ++best_mult;
     }
     return best_mult;
 }
@@ -620,11 +623,13 @@ static void plan_tiles_for(const int32_t* lags, int K, int Tn, int buf_bytes, Ti
     std::vector<Tile> tiles;
     size_t g0 = 0;
     while (g0 < order.size()) {
-        // an r-group: windows of one D whose r fits one partner strip (r - cP0 <= kTileWp - 32)
+        // an r-group: windows of one D whose r fits one partner strip (r - cP0 <= kTileWp - 32; one column less for an
+        // odd D, whose rows may sit one column to the right)
         const TileWinHost& first = plan.wins[order[g0]];
         const int cP0 = first.r & ~1;
+        const int r_room = kTileWp - 32 - (first.D & 1);
         size_t g1 = g0;
-        while (g1 < order.size() && plan.wins[order[g1]].D == first.D && plan.wins[order[g1]].r - cP0 <= kTileWp - 32) ++g1;
+        while (g1 < order.size() && plan.wins[order[g1]].D == first.D && plan.wins[order[g1]].r - cP0 <= r_room) ++g1;
         std::vector<int> grp(order.begin() + g0, order.begin() + g1);
         g0 = g1;
         std::stable_sort(grp.begin(), grp.end(), [&](int a, int b) { return plan.wins[a].I0 < plan.wins[b].I0; });
@@ -754,14 +759,31 @@ static void plan_tiles_for(const int32_t* lags, int K, int Tn, int buf_bytes, Ti
 // Three buffers of 64 KB keep the producer a tile further ahead; two of 96 KB hold whole columns of ~100 rows.  The smaller
 // buffers are taken when they do not cost more than a tenth more traffic.
 static void plan_tiles(const int32_t* lags, int K, int Tn, TilePlan& plan) {
+    // (measured, tools/k2tile_sweep.sh: two buffers of 96 KB were never slower than three of 64 KB -- tiles of several strips
+    // and whole columns matter more than a third tile in flight -- so two is the default; KB2_TILE_BUFS=3 / 0 = by traffic)
     const char* e = getenv("KB2_TILE_BUFS");
-    const int force = e ? atoi(e) : 0;
+    const int force = e ? atoi(e) : 2;
     TilePlan three, two;
     if (force != 2) plan_tiles_for(lags, K, Tn, kTileSmemBufBytes / 3, three);
     if (force != 3) plan_tiles_for(lags, K, Tn, kTileSmemBufBytes / 2, two);
     const bool take3 = force == 3 || (force != 2 && three.bytes_loaded * 10 <= two.bytes_loaded * 11);
     plan = take3 ? three : two;
     plan.nbuf = take3 ? 3 : 2;
+    if (getenv("KB2_TILE_DEBUG")) {
+        fprintf(stderr, "tile plan: K %d T %d nbuf %d windows %zu templates %zu units %zu bytes/atom %lld\n", K, Tn, plan.nbuf,
+                plan.wins.size(), plan.tpls.size(), plan.units.size(), plan.bytes_loaded);
+        for (const TileTpl& tp : plan.tpls) {
+            long long steps = 0, terms = 0;
+            for (int u = 0; u < tp.nunits; ++u) {
+                const TileUnit& un = plan.units[tp.unit0 + u];
+                steps += un.nsteps + (un.top ? 0 : un.m - 1);
+                terms += (long long)un.nsteps * un.m - (un.top ? (long long)un.m * (un.m - 1) / 2 : 0);
+            }
+            fprintf(stderr, "  D %5d rows o[%d,+%d) p[%d,+%d) cP0 %d units %d spt %d groups %d steps %lld terms/col %lld KB %.1f\n", tp.D,
+                    tp.oLo, tp.nO, tp.pLo, tp.nP, tp.cP0, tp.nunits, tp.spt, tp.nstrips, steps, terms,
+                    (tp.nO + tp.nP) * kTileRowP * 8 * tp.spt / 1024.0);
+        }
+    }
 }
 
 // Packed plan of one launch (<= kTileMaxLags lags): header (256 B) | templates | units | slots | lags by accumulator.

@@ -162,15 +162,22 @@ def atom_sum(dc, weights=None):
 
 
 def self_moments(dc, n_frames, lags, mask=7, variant=None):
-    """sums [K, 2] = (sum d^2, sum d^4) per lag over atoms x observations; see kb2_self_moments /
-    kb2_self_moments_runs.
+    """sums [K, 2] = (sum d^2, sum d^4) per lag over atoms x observations; see kb2_self_moments_tile (the default),
+    kb2_self_moments_win, kb2_self_moments_runs, kb2_self_moments.
 
     dc: [n_atoms, 3, pitch] float64; lags: ascending, a host array (numpy / list) or an int32 device tensor.
-    The arithmetic-run variant plans on the host: with device-resident lags it costs a device->host copy."""
+    The tiled, window and run variants plan on the host: with device-resident lags that costs a device->host copy.
+    variant=None: the tiled kernel, or the register-window kernel for a grid without arithmetic structure."""
     lib = require_cuda()
+    K = len(lags) if not isinstance(lags, torch.Tensor) else lags.numel()
     if variant is None:
         variant = DEFAULT_VARIANT
-    K = len(lags) if not isinstance(lags, torch.Tensor) else lags.numel()
+        if variant == VARIANT_TILE:
+            lags_host = np.ascontiguousarray(lags.cpu().numpy() if isinstance(lags, torch.Tensor) else lags, dtype=np.int32)
+            if _mostly_single_lags(lags_host, n_frames):
+                # a grid without arithmetic structure (spacing='logarithmic', kinisi/parser.py:165): windows of one lag
+                # are shared-memory bound in the tiled kernel; the register-window kernel is 2-3 times faster there
+                variant = VARIANT_WIN
     sums = torch.empty((K, 2), dtype=torch.float64, device=dc.device)
     if (variant & 0xff) == VARIANT_TILE:
         lags_host = np.ascontiguousarray(lags.cpu().numpy() if isinstance(lags, torch.Tensor) else lags, dtype=np.int32)
@@ -213,6 +220,23 @@ def self_moments(dc, n_frames, lags, mask=7, variant=None):
                              ws.data_ptr(), sums.data_ptr(), _stream()), 'kb2_self_moments')
     _count(3 * ((K + 767) // 768))
     return sums
+
+
+_SINGLE_LAG_GRIDS = {}
+
+
+def _mostly_single_lags(lags_host, n_frames):
+    """True when more than half of the lags of a grid end up in windows of one lag in the tiled kernel's plan."""
+    key = (lags_host.tobytes(), int(n_frames))
+    hit = _SINGLE_LAG_GRIDS.get(key)
+    if hit is None:
+        wins, _ = self_moments_tiles(lags_host[:256], n_frames)
+        singles = sum(1 for w in wins if w[2] == 1)
+        hit = 2 * singles > min(len(lags_host), 256)
+        if len(_SINGLE_LAG_GRIDS) >= 64:
+            _SINGLE_LAG_GRIDS.pop(next(iter(_SINGLE_LAG_GRIDS)))
+        _SINGLE_LAG_GRIDS[key] = hit
+    return hit
 
 
 _RUNS_PLANS = {}  # (kind, lags, n_frames, device) -> (pinned host plan, device plan, upload event)

@@ -40,12 +40,12 @@ def _default_variant_is_restored():
     """Every test starts on (and leaves behind) the shipped default moment kernel, the one bench.py times."""
     from kinisi_b200 import engine
     shipped = engine.DEFAULT_VARIANT
-    assert (shipped & 0xff) == engine.VARIANT_WIN
+    assert (shipped & 0xff) == engine.VARIANT_TILE
     yield
     engine.DEFAULT_VARIANT = shipped
 
 
-ALL_VARIANTS = [0, 1, 2, 3]
+ALL_VARIANTS = [0, 1, 2, 3, 4]
 
 
 def load(golden_dir, name):
@@ -173,7 +173,7 @@ def test_reference_kats(kb, golden_dir):
 # ---------------------------------------------------------------------------------------------
 # the moment kernels against the oracle's raw sums: tiles, partial tiles, both variants, f32 input
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize('variant', [0, 0 | (16 << 8), 1, 2, 3])
+@pytest.mark.parametrize('variant', [0, 0 | (16 << 8), 1, 2, 3, 4])
 @pytest.mark.parametrize('dimension', ['xyz', 'xz', 'y'])
 def test_self_moment_kernels_raw_sums(kb, variant, dimension):
     n_atoms, n_frames = 5, 9300  # > 2 tiles of 4096 and > 4 tiles of 2048, last tile partial
@@ -242,6 +242,31 @@ RUN_GRIDS = {
 
 @pytest.mark.parametrize('grid', sorted(RUN_GRIDS))
 @pytest.mark.parametrize('n_frames', [700, 5431])
+def test_tiled_lag_window_kernel_on_structured_and_irregular_grids(kb, grid, n_frames):
+    """kb2_self_moments_tile (the default: tiles staged in shared memory, windows of <= 8 lags k = I*D + r with consecutive
+    I, leftovers as windows of one) against the oracle's raw sums on every kind of lag grid, 7 atoms (strips that end
+    inside a row, tiles of several strips, row blocks, shared and separate partner rows)."""
+    n_atoms = 7
+    frac, latt = ko.synthetic_walk(n_atoms, n_frames, box=10.0, sigma=0.15, seed=78)
+    dc = ko.get_disp(frac, latt)
+    lags = RUN_GRIDS[grid](n_frames)
+    lags = lags[(lags >= 1) & (lags <= n_frames)]
+    if grid == 'all' and n_frames > 2000:
+        lags = lags[:1700]  # seven chunks of the 256-lag launch limit
+    dct = _device_dc(kb, dc)
+    for mask, dim in ((7, 'xyz'), (6, 'yz'), (1, 'x')):
+        S1, S2, _, _ = ko.raw_sums_streaming(dc, lags, dim)
+        sums = kb.engine.self_moments(dct, n_frames, lags, mask, kb.engine.VARIANT_TILE).cpu().numpy()
+        np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
+        np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
+    wins, n_tiles = kb.engine.self_moments_tiles(lags[:256], n_frames)
+    length = np.array([w[2] for w in wins])
+    assert int(np.sum(length)) == min(len(lags), 256) and np.all(length <= 8) and np.all(length >= 1) and n_tiles >= 1
+    assert all(w[1] >= 32 for w in wins)  # row lengths: a strip of 32 columns at least
+
+
+@pytest.mark.parametrize('grid', sorted(RUN_GRIDS))
+@pytest.mark.parametrize('n_frames', [700, 5431])
 def test_lag_window_kernel_on_structured_and_irregular_grids(kb, grid, n_frames):
     """kb2_self_moments_win (the default: partner window + accumulators in registers, progressions cut into windows of
     <= 8 lags, leftovers as windows of one) against the oracle's raw sums on every kind of lag grid."""
@@ -285,7 +310,7 @@ def test_arithmetic_run_kernel_on_structured_and_irregular_grids(kb, grid, n_fra
     assert sum(r[2] for r in runs) + rest == min(len(lags), 192)
 
 
-@pytest.mark.parametrize('variant', [2, 3])
+@pytest.mark.parametrize('variant', [2, 3, 4])
 def test_structured_kernels_many_atoms_and_tiles(kb, variant):
     """Enough atoms and frames that every persistent CTA takes several work items, with a short trajectory
     tail (partial tiles, warps that straddle two origin tiles, inactive lanes)."""
