@@ -80,8 +80,12 @@ def make_inputs(seed, n_mobile, n_framework, n_frames, box, sigma, dtype=np.floa
 
 
 # ------------------------------------------------------------------------------------------------
-# the reference arm / CPU baseline: the oracle port (the reference is pure Python; it cannot travel)
+# the reference arm / CPU baseline: the UNMODIFIED reference (oracle/_ref, copied there by oracle/make_ref.py, with the
+# stand-ins of oracle/shims for the three packages this image lacks); the numpy oracle port only if oracle/_ref is missing
 # ------------------------------------------------------------------------------------------------
+REF_SAMPLE = dict(n_mobile=32, n_framework=64)  # atoms of one reference analysis (fixed: independent of the host)
+
+
 def _cpu_shard_sums(args):
     from oracle import kinisi_oracle as ko
     dc_sel, lags = args
@@ -116,30 +120,99 @@ def cpu_pass(frac, latt, n_mobile, n_framework, lags_cfg, pool=None, n_shards=1)
     return n_terms(n_mobile, dc.shape[1], parsed['lags']), dt
 
 
+def reference_modules():
+    """(kinisi.parser, kinisi.diffusion) of the unmodified reference under oracle/_ref, or None."""
+    try:
+        from oracle.make_ref import import_reference
+        return import_reference()
+    except Exception:
+        return None
+
+
+def reference_pass(mods, frac, latt, n_mobile, n_framework, n_steps=None, start_idx=None):
+    """One analysis by the UNMODIFIED reference: Parser.get_disp -> Parser -> MSDBootstrap -> .diffusion
+    (kinisi/parser.py:53-222, kinisi/diffusion.py:552-602, 305-436).  Returns (terms, seconds, D median)."""
+    import warnings
+    rp, rd = mods
+    n_steps = CFG['n_steps'] if n_steps is None else n_steps
+    start_idx = CFG['start_idx'] if start_idx is None else start_idx
+    t0 = time.perf_counter()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        cells = list(np.broadcast_to(latt, (frac.shape[1], 3, 3)))
+        disp = rp.Parser.get_disp([frac.astype(np.float64)], cells, progress=False)
+        p = rp.Parser(disp, np.arange(n_mobile), np.arange(n_mobile, n_mobile + n_framework), CFG['time_step'],
+                      CFG['step_skip'], n_steps=n_steps, memory_limit=64., progress=False)
+        b = rd.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False)
+        b.diffusion(float(p.delta_t[start_idx]), progress=False, random_state=np.random.RandomState(1))
+    dt = time.perf_counter() - t0
+    return n_terms(n_mobile, disp.shape[1], p.time_intervals), dt, float(b.D.n)
+
+
+_REF = {}
+
+
+def _ref_worker_init():
+    _REF['mods'] = reference_modules()
+    _REF['inputs'] = make_inputs(CFG['seed'] + os.getpid() % 1000, REF_SAMPLE['n_mobile'], REF_SAMPLE['n_framework'],
+                                 CFG['n_frames'], CFG['box'], CFG['sigma'])
+
+
+def _ref_worker_step(_):
+    frac, latt = _REF['inputs']
+    if _REF['mods'] is None:
+        t, dt = cpu_pass(frac, latt, REF_SAMPLE['n_mobile'], REF_SAMPLE['n_framework'], CFG['n_steps'])
+        return t, dt
+    t, dt, _d = reference_pass(_REF['mods'], frac, latt, REF_SAMPLE['n_mobile'], REF_SAMPLE['n_framework'])
+    return t, dt
+
+
+def _host_workers():
+    """One reference analysis per worker; the reference is single-threaded, so all host cores are used by running
+    independent analyses side by side (about 2.5 GB each at the sample size)."""
+    cores = os.cpu_count() or 1
+    try:
+        import psutil
+        cores = max(1, min(cores, int(psutil.virtual_memory().available // (3 << 30))))
+    except Exception:
+        pass
+    return cores
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm on all host cores, bounded sample per step."""
+    """--impl reference: the unmodified reference on the host cores.  One step = every worker analyses one bounded sample
+    of configs[1] (REF_SAMPLE atoms, the full 20 000 frames and 100 time intervals, covariance + sampler)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    n_mob = min(CFG['n_mobile'], 16 * cores)
-    n_fw = 64
-    frac, latt = make_inputs(CFG['seed'], n_mob, n_fw, CFG['n_frames'], CFG['box'], CFG['sigma'])
+    for v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ.setdefault(v, '1')  # one analysis per core
+    workers = _host_workers()
+    kind = 'reference' if reference_modules() is not None else 'port'
     ctx = mp.get_context('fork')
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(workers, initializer=_ref_worker_init) as pool:
         for _ in range(args.warmup):
-            cpu_pass(frac, latt, n_mob, n_fw, CFG['n_steps'], pool, cores)
+            pool.map(_ref_worker_step, range(workers), chunksize=1)
         t0 = time.perf_counter()
         terms = 0
         for _ in range(args.steps):
-            t, _dt = cpu_pass(frac, latt, n_mob, n_fw, CFG['n_steps'], pool, cores)
-            terms += t
+            terms += sum(t for t, _dt in pool.map(_ref_worker_step, range(workers), chunksize=1))
         total = time.perf_counter() - t0
     value = terms / total
-    sample = (f'{n_mob} of {CFG["n_mobile"]} mobile atoms + {n_fw} framework atoms x {CFG["n_frames"]} frames, '
-              f'{CFG["n_steps"]} dt, full covariance + 1500-step x 32-walker sampler; numpy oracle port of '
-              'kinisi/parser.py + kinisi/diffusion.py, moment sums atom-sharded over a fork pool')
+    sample = (f'{workers} independent analyses per step, each {REF_SAMPLE["n_mobile"]} of {CFG["n_mobile"]} mobile + '
+              f'{REF_SAMPLE["n_framework"]} framework atoms x {CFG["n_frames"]} frames, {CFG["n_steps"]} dt, covariance + '
+              f'1500-step x 32-walker sampler; ' +
+              ('unmodified kinisi 1.1.1 (oracle/_ref) with the oracle/shims stand-ins for uravu / emcee / statsmodels'
+               if kind == 'reference' else 'numpy oracle port (oracle/_ref missing)'))
+    # configs[0] whole, one process: 192 Li + 64 framework atoms x 5000 steps
+    cfg0 = None
+    mods = reference_modules()
+    if mods is not None:
+        f0, l0 = make_inputs(1001, 192, 64, 5000, 15.0, 0.1, dtype=np.float64)
+        t_0, s_0, d_0 = reference_pass(mods, f0, l0, 192, 64)
+        cfg0 = {'workload': 'configs[0]: 192 Li x 5000 steps, MSD + Bayesian D', 'terms_per_s': t_0 / s_0, 'seconds': s_0,
+                'cores': 1, 'D_median_cm2_s': d_0}
     line = {
         'impl': 'reference',
         'metric': METRIC,
@@ -155,9 +228,10 @@ def run_reference(args):
         'dtype': 'f64',
         'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'l2': 'n/a (host)'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': workers, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
+        'configs0': cfg0,
     }
     print(json.dumps(line))
 
@@ -247,6 +321,181 @@ class ClockSampler:
         return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': float(max(self.max_clock)),
                 'reasons': sorted(self.reasons), 'samples': len(self.samples),
                 'source': 'nvml' if self._thread is not None else 'nvidia-smi'}
+
+
+def synth_coords_device(torch, dev, n_atoms, n_frames, box, sigma, seed, chunk=256):
+    """Wrapped fractional coordinates [n_atoms, n_frames + 1, 3] float32 of a 3-D Gaussian random walk, generated on the
+    device in chunks of atoms (float64 cumulative sum, wrapped, then rounded to float32); frame 0 duplicated as the
+    reference's front-ends do (kinisi/parser.py:323-324)."""
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    out = torch.empty((n_atoms, n_frames + 1, 3), dtype=torch.float32, device=dev)
+    for a0 in range(0, n_atoms, chunk):
+        a1 = min(n_atoms, a0 + chunk)
+        steps = torch.randn((a1 - a0, n_frames, 3), dtype=torch.float64, device=dev, generator=gen) * (sigma / box)
+        steps[:, 0] = torch.rand((a1 - a0, 3), dtype=torch.float64, device=dev, generator=gen)
+        pos = torch.cumsum(steps, dim=1)
+        pos -= torch.floor(pos)
+        out[a0:a1, 1:] = pos.to(torch.float32)
+        del steps, pos
+    out[:, 0] = out[:, 1]
+    out.clamp_(0.0, 0.99999994)  # (a float32 rounding of 0.99999999 is 1.0: keep the coordinates inside [0, 1))
+    return out
+
+
+def named_shapes(args, torch, td, dev, world, rank, fp64_peak_tflops, hbm_peak_gbs):
+    """Timed sub-records for the other BASELINE.json configurations, after the headline: configs[2] (MSTD, 10 000 ions x
+    100 000 steps) and configs[4] (MSD, 100 000 atoms x 50 000 steps) STRONG-scaled over the ranks (atoms / N per rank,
+    device-resident float32 input generated on the device, the cumulative displacements streamed in 2 GB blocks);
+    configs[3] (MSCD, 1000 + 1000 ions, 1000 used time intervals -> 1000 x 1000 covariance) and configs[0] (192 Li x 5000
+    steps through ASEParser) on rank 0.  Every record: wall time per analysis from CUDA events (max over ranks),
+    stage times, terms/s, the FP64 fraction of the moment kernel and the HBM rate of the displacement kernel."""
+    from kinisi_b200 import diffusion, engine
+    from kinisi_b200 import parser as kparser
+    from kinisi_b200.parser import Parser
+    out = {}
+    k1 = {'ms': [], 'bytes': 0}
+    k2 = {'ms': []}
+    raw_k2, raw_k1 = engine.self_moments, engine.unwrap_cumsum
+
+    def t_k2(dc, n_frames, lg, mask=7, variant=None):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = raw_k2(dc, n_frames, lg, mask, variant)
+        e1.record()
+        k2['ms'].append((e0, e1))
+        return r
+
+    def t_k1(coords, mode, latt, latt_inv, latt_stride, idx, step_sums, step_scale, pitch, out=None):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = raw_k1(coords, mode, latt, latt_inv, latt_stride, idx, step_sums, step_scale, pitch, out=out)
+        e1.record()
+        k1['ms'].append((e0, e1))
+        k1['bytes'] += int(idx.numel()) * (coords.shape[1] * 3 * coords.element_size() + 3 * pitch * 8)
+        return r
+
+    def sync_max(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t[0])
+
+    def strong(name, kind, n_total, T, box, start_idx, passes=2):
+        n_local = n_total // world + (1 if rank < n_total % world else 0)
+        need = n_local * (T + 1) * 12 + kparser.STREAM_BLOCK_BYTES + (1 << 30)
+        free, _total = torch.cuda.mem_get_info(dev)
+        if need > free:
+            out[name] = {'skipped': f'{need / 1e9:.0f} GB needed per GPU at {world} GPU(s), {free / 1e9:.0f} GB free'}
+            return
+        coords = synth_coords_device(torch, dev, n_local, T, box, 0.1, 5000 + 17 * rank)
+        latt = (np.eye(3) * box)[None]
+        lags = lag_grid(T, CFG['n_steps'])
+        used = lags if kind == 'msd' else lags[:len(lags) // 2]
+        terms = n_terms(n_total, T, used)
+        start_dt = float(lags[start_idx] * CFG['time_step'])
+        pkw = dict(n_steps=CFG['n_steps'], memory_limit=64., progress=False, distributed=world > 1,
+                   global_counts=(n_total, 0) if world > 1 else None)
+        engine.self_moments, engine.unwrap_cumsum = t_k2, t_k1
+        try:
+            res = []
+            for it in range(passes + 1):
+                k1['ms'].clear(), k2['ms'].clear()
+                k1['bytes'] = 0
+                if world > 1:
+                    td.barrier()
+                torch.cuda.synchronize()
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
+                p = Parser(Parser.get_disp(coords, latt, progress=False, device=dev), np.arange(n_local), [], CFG['time_step'], 1, **pkw)
+                if kind == 'msd':
+                    b = diffusion.MSDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False)
+                else:
+                    b = diffusion.MSTDBootstrap(p.delta_t, p.disp_3d, p._n_o, progress=False)
+                ev[1].record()
+                if kind == 'msd':
+                    b.diffusion(start_dt, progress=False)
+                else:
+                    b.jump_diffusion(start_dt, progress=False)
+                _ = b.flatchain
+                ev[2].record()
+                torch.cuda.synchronize()
+                if it == 0:
+                    continue  # warm-up (plans, allocator)
+                rec = {'ms': sync_max(ev[0].elapsed_time(ev[2])), 'stage12_ms': sync_max(ev[0].elapsed_time(ev[1])),
+                       'stage3_ms': sync_max(ev[1].elapsed_time(ev[2])),
+                       'k1_ms': sync_max(sum(a.elapsed_time(z) for a, z in k1['ms'])),
+                       'k2_ms': sync_max(sum(a.elapsed_time(z) for a, z in k2['ms']))}
+                res.append(rec)
+            best = min(res, key=lambda r: r['ms'])
+            streamed = bool(getattr(p, '_streamed', False))
+            coef = b.D if kind == 'msd' else b.D_J
+            out[name] = {
+                'kind': kind, 'atoms': n_total, 'frames': T, 'atoms_per_gpu': n_local, 'scaling': 'strong',
+                'dc_streamed': streamed, 'ms_per_analysis': best['ms'], 'terms': terms,
+                'terms_per_s': terms / (best['ms'] * 1e-3), 'stage_ms': {'stage1+2': best['stage12_ms'], 'stage3': best['stage3_ms']},
+                'k2_ms': best['k2_ms'], 'k2_fp64_frac': 16.0 * terms / world / (best['k2_ms'] * 1e-3) / 1e12 / fp64_peak_tflops,
+                'k1_ms': best['k1_ms'], 'k1_hbm_gbs': k1['bytes'] / (best['k1_ms'] * 1e-3) / 1e9,
+                'k1_hbm_frac': k1['bytes'] / (best['k1_ms'] * 1e-3) / 1e9 / hbm_peak_gbs,
+                'coefficient_median_cm2_s': float(coef.n), 'true_cm2_s': 3 * 0.1**2 / CFG['time_step'] / (2e4 * 3),
+            }
+        finally:
+            engine.self_moments, engine.unwrap_cumsum = raw_k2, raw_k1
+        del coords, p, b
+        torch.cuda.empty_cache()
+
+    strong('configs[2]', 'mstd', 10000, 100000, 60.0, 5)
+    strong('configs[4]', 'msd', 100000, 50000, 120.0, 10)
+
+    if rank == 0:
+        # configs[3]: 1000 cations (+1) and 1000 anions (-1), 20 000 steps, n_steps = 2000 -> 1000 used time intervals
+        from kinisi_b200.analyze import ConductivityAnalyzer, DiffusionAnalyzer
+        n_ion, T, box = 2000, 20000, 40.0
+        coords = synth_coords_device(torch, dev, n_ion, T, box, 0.1, 7003)
+        latt = (np.eye(3) * box)[None]
+        q = np.where(np.arange(n_ion) < n_ion // 2, 1.0, -1.0)
+        recs = []
+        for it in range(3):
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
+            p = Parser(Parser.get_disp(coords, latt, progress=False, device=dev), np.arange(n_ion), [], CFG['time_step'], 1,
+                       n_steps=2000, memory_limit=64., progress=False)
+            b = diffusion.MSCDBootstrap(p.delta_t, p.disp_3d, q, p._n_o, progress=False)
+            ev[1].record()
+            b.conductivity(float(b.dt[100]), 500.0, box**3, progress=False)
+            _ = b.flatchain
+            ev[2].record()
+            torch.cuda.synchronize()
+            recs.append((ev[0].elapsed_time(ev[2]), ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
+        best = min(recs[1:])
+        lags = np.asarray(p.disp_3d.lags[:len(p.disp_3d.lags) // 2])
+        out['configs[3]'] = {'kind': 'mscd', 'atoms': n_ion, 'frames': T, 'time_intervals_used': int(b.dt.size),
+                             'covariance_n': int(b.dt.size - 100), 'ms_per_analysis': best[0],
+                             'stage_ms': {'stage1+2': best[1], 'stage3 (cov_build + eigh + gls_prepare + sampler)': best[2]},
+                             'self_terms_per_s': n_terms(n_ion, T, lags) / (best[1] * 1e-3), 'sigma_median_mS_cm': float(b.sigma.n)}
+        del coords, p, b
+        torch.cuda.empty_cache()
+        # configs[0]: 192 Li (+ 64 framework) x 5000 steps through ASEParser (host objects, float64) -> MSD -> D
+        sys.path.insert(0, os.path.join(ROOT, 'tests'))
+        from duck_atoms import trajectory_from_arrays
+        f0, l0 = make_inputs(1001, 192, 64, 5000, 15.0, 0.1, dtype=np.float64)
+        traj = trajectory_from_arrays(['Li'] * 192 + ['O'] * 64, f0[:, 1:], np.broadcast_to(l0, (5000, 3, 3)))
+        walls = []
+        for it in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            an = DiffusionAnalyzer.from_ase(traj, parser_params=dict(specie='Li', time_step=CFG['time_step'], step_skip=1,
+                                                                     progress=False), uncertainty_params={'progress': False})
+            an.diffusion(an.dt[10], {'progress': False})
+            d_med = an.D.n
+            torch.cuda.synchronize()
+            walls.append(time.perf_counter() - t0)
+        lags0 = lag_grid(5000, 100)
+        out['configs[0]'] = {'kind': 'msd via ASEParser (host walk of 5000 frame objects included)', 'atoms': 192, 'frames': 5000,
+                             'wall_ms_per_analysis': 1e3 * min(walls[1:]), 'terms_per_s': n_terms(192, 5000, lags0) / min(walls[1:]),
+                             'D_median_cm2_s': float(d_med)}
+    return out
 
 
 def run_own(args):
@@ -415,6 +664,16 @@ def run_own(args):
     del uw_out
     e2e_ms, _, b2 = timed(host, args.steps)
     clocks = sampler.stop() if sampler is not None else None
+    engine.self_moments = raw_self_moments
+    shapes = None
+    if not args.no_named_shapes:
+        try:
+            peaks0 = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            peaks0 = {}
+        del resident
+        torch.cuda.empty_cache()
+        shapes = named_shapes(args, torch, td, dev, world, rank, fp64_peak_tflops, peaks0.get('hbm_gbs', 6650.0))
 
     value = world * terms_rank * args.steps / (ms_total * 1e-3)
     e2e_value = world * terms_rank * args.steps / (e2e_ms * 1e-3)
@@ -434,10 +693,16 @@ def run_own(args):
         if world == 1 and not args.no_cpu_baseline:
             n_c, n_cf = 96, 64
             fc, lc = make_inputs(CFG['seed'], n_c, n_cf, T, CFG['box'], CFG['sigma'])
-            t_c, s_c = cpu_pass(fc, lc, n_c, n_cf, CFG['n_steps'])
-            cpu = {'value': t_c / s_c, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+            mods = reference_modules()
+            if mods is not None:
+                t_c, s_c, _d = reference_pass(mods, fc, lc, n_c, n_cf)
+                what, kind = 'unmodified kinisi 1.1.1 (oracle/_ref + oracle/shims)', 'reference'
+            else:
+                t_c, s_c = cpu_pass(fc, lc, n_c, n_cf, CFG['n_steps'])
+                what, kind = 'numpy oracle port', 'port'
+            cpu = {'value': t_c / s_c, 'unit': UNIT, 'cores': 1, 'kind': kind,
                    'sample': f'{n_c} of {n_mob} mobile + {n_cf} framework atoms x {T} frames, {CFG["n_steps"]} dt, '
-                             f'full covariance + sampler; numpy oracle port, {s_c:.1f} s'}
+                             f'full covariance + sampler; {what}, {s_c:.1f} s'}
         line = {
             'metric': METRIC,
             'value': value,
@@ -496,6 +761,7 @@ def run_own(args):
             'stage_ms': {'stage1_parser': float(stages[0]), 'stage2_moments': float(stages[1]),
                          'stage3_cov_mcmc': float(stages[2])},
             'cpu_baseline': cpu,
+            'named_shapes': shapes,
             'result': {'D_median_cm2_s': b.D.n, 'D_ci95': [float(x) for x in b.D.con_int()],
                        'D_true': 3 * CFG['sigma']**2 / CFG['time_step'] / (2e4 * 3)},
         }
@@ -512,6 +778,7 @@ def main():
     ap.add_argument('--impl', default='own', choices=['own', 'reference'])
     ap.add_argument('--variant', type=int, default=None, help='self-moment kernel: 0 direct, 1 TMA ring, 2 arithmetic runs, 3 lag window, 4 tiled lag window (default)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-named-shapes', action='store_true', help='skip the sub-records for configs[0], [2], [3], [4]')
     ap.add_argument('--in-flight', type=int, default=4,
                     help='analyses in flight: consecutive trajectories go round-robin to this many CUDA streams (1 = one stream)')
     args = ap.parse_args()

@@ -295,15 +295,14 @@ __device__ __forceinline__ void column(Ptrs q, int total, bool top, bool kill, b
 
 // NPW producer warps share the rows of a tile and copy them with 16-byte cp.async (LDGSTS, two warp instructions per row).
 // (cp.async.bulk, one TMA request per row and component, was measured first: a 1-D bulk copy of 256-320 bytes costs the
-// SM's TMA unit ~33 cycles, 260 of them per tile made the kernel 2.1-2.6 times slower, profiles/r02_k2_tile_copy_modes.txt.)  Tiles are dealt to the
-// CTAs round robin (tile c, c + grid, ...: the templates are sorted by cost, so every CTA gets the same mix): every
-// producer warp derives the sequence by itself, nothing is exchanged.
+// SM's TMA unit ~33 cycles, 260 of them per tile made the kernel 2.1-2.6 times slower, profiles/r02_k2_tile_copy_modes.txt.)
 template <int NDIM, int NPW>
 __global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
     self_moments_tile_kernel(const double* __restrict__ dc, int n_atoms, int Tn, int64_t pitch, int c0, int c1, int c2,
                              const TileTpl* __restrict__ tpls, int n_tpls, int strips_total,
                              const TileUnit* __restrict__ units, int batch, const int32_t* __restrict__ acc_lag, int K,
-                             int nbuf, int buf_bytes, const int32_t* __restrict__ slot, double* __restrict__ out) {
+                             int nbuf, int buf_bytes, unsigned int* work_counter, const int32_t* __restrict__ slot,
+                             double* __restrict__ out) {
     using namespace tile;
     constexpr int NT = 32 * (kTileCW + NPW);
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -319,6 +318,7 @@ __global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
     static_assert(kTileMaxBufs <= 4 && 2 * kTileMaxBufs * 8 + 16 + kTileMaxBufs * sizeof(TileDesc) <= kTileGuardBytes, "guard area too small");
     static_assert(kTileGuardBytes + kAccBytes >= 3 * kTileRowP * 8, "look-ahead reads below the first buffer must stay in shared memory");
 
+    __shared__ long long s_item[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool producer = warp >= kTileCW;
     const int comp[3] = {c0, c1, c2};
@@ -341,18 +341,25 @@ __global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
     const long long n_items = (long long)(n_batches - 1) * items_full + items_last;
 
     if (producer) {
+        // Tiles are drawn from an atomic counter (a CTA that starts late, e.g. behind another stream's kernel on its SM,
+        // simply takes fewer): producer warp 0 draws, one tile ahead so that the round trip hides behind the copies, and
+        // hands the number to the other producer warps through shared memory and a named barrier.
         const int pw = warp - kTileCW;
+        long long drawn = 0;
+        if (pw == 0 && lane == 0) s_item[0] = (long long)atomicAdd(work_counter, 1u);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW) : "memory");
 #pragma unroll 1
         for (unsigned tau = 0;; ++tau) {
             const int b = (int)(tau % (unsigned)nbuf);
-            const long long item = (long long)blockIdx.x + (long long)tau * gridDim.x;
+            const long long item = s_item[tau & 1];
+            if (pw == 0 && lane == 0 && item < n_items) drawn = (long long)atomicAdd(work_counter, 1u);
             if (item >= n_items) {
                 if (tau >= (unsigned)nbuf) mbar_wait(&empty[b], ((tau / (unsigned)nbuf) - 1) & 1);
                 if (pw == 0 && lane == 0) {
                     desc[b].stop = 1;
                     next_unit[b] = 0;
+                    mbar_arrive(&full[b]);
                 }
-                if (pw == 0 && lane == 0) mbar_arrive(&full[b]);
                 cp_async_arrive(&full[b]);
                 break;
             }
@@ -443,6 +450,8 @@ __global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
                 }
             }
             cp_async_arrive(&full[b]);
+            if (pw == 0 && lane == 0) s_item[(tau + 1) & 1] = drawn;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW) : "memory");
         }
     } else {
         // the extra first observation dc[a][k-1] of every lag (kinisi/parser.py:209): units of (lag, 32 atoms)
@@ -868,14 +877,14 @@ extern "C" int kb2_self_moments_tile_plan_pack(const int32_t* lags_host, int n_l
 template <int NDIM>
 static int launch_tile(int sm_count, cudaStream_t st, const double* dc, int n_atoms, int Tn, int64_t pitch, const int comp[3],
                        const TileTpl* tpls, int n_tpls, int strips_total, const TileUnit* units, int batch,
-                       const int32_t* acc_lag, int K, int nbuf, const int32_t* slot, double* out) {
+                       const int32_t* acc_lag, int K, int nbuf, unsigned int* counter, const int32_t* slot, double* out) {
     const size_t smem = tile_smem_bytes();
     constexpr int NPW = 2;
     auto kern = self_moments_tile_kernel<NDIM, NPW>;
     const int threads = 32 * (kTileCW + NPW);
     KB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<sm_count, threads, smem, st>>>(dc, n_atoms, Tn, pitch, comp[0], comp[1], comp[2], tpls, n_tpls, strips_total, units,
-                                         batch, acc_lag, K, nbuf, kTileSmemBufBytes / nbuf, slot, out);
+                                         batch, acc_lag, K, nbuf, kTileSmemBufBytes / nbuf, counter, slot, out);
     KB2_LAUNCH_CHECK();
     return 0;
 }
@@ -886,8 +895,7 @@ static int launch_tile(int sm_count, cudaStream_t st, const double* dc, int n_at
 extern "C" int kb2_self_moments_tile_planned(const double* dc, int n_atoms, int n_frames, int64_t pitch, int n_lags,
                                              int dim_mask, const void* plan_host, const void* plan_dev, void* counters,
                                              double* sums, void* stream) {
-    KB2_CHECK(dc && plan_host && plan_dev && sums, "kb2_self_moments_tile_planned: null pointer");
-    (void)counters;  // tiles are dealt round robin: no work counter (the argument keeps the protocol of the other planned kernels)
+    KB2_CHECK(dc && plan_host && plan_dev && counters && sums, "kb2_self_moments_tile_planned: null pointer");
     KB2_CHECK(n_atoms > 0 && n_frames > 0 && n_lags > 0, "kb2_self_moments_tile_planned: empty problem");
     KB2_CHECK(pitch >= n_frames && pitch % 16 == 0 && pitch < (1ll << 30),
               "kb2_self_moments_tile_planned: pitch must be a multiple of 16, >= n_frames and < 2^30");
@@ -901,6 +909,7 @@ extern "C" int kb2_self_moments_tile_planned(const double* dc, int n_atoms, int 
     KB2_CHECK(sm_count > 0, "kb2_self_moments_tile_planned: no CUDA device");
     const int blocks = (n_lags + kTileMaxLags - 1) / kTileMaxLags;
     KB2_CUDA(cudaMemsetAsync(sums, 0, (size_t)n_lags * 2 * sizeof(double), st));
+    KB2_CUDA(cudaMemsetAsync(counters, 0, (size_t)blocks * 256, st));
     const int batch = (int)std::max<long long>(1, std::min<long long>(n_atoms, kTileBatchBytes / (3 * pitch * 8)));
     const unsigned char* ph = (const unsigned char*)plan_host;
     const char* pd = (const char*)plan_dev;
@@ -915,16 +924,17 @@ extern "C" int kb2_self_moments_tile_planned(const double* dc, int n_atoms, int 
         const int32_t* d_slot = (const int32_t*)(pd + h.off_slot);
         const int32_t* d_lag = (const int32_t*)(pd + h.off_lag);
         KB2_CHECK(h.nbuf == 2 || h.nbuf == 3, "kb2_self_moments_tile_planned: corrupt plan");
+        unsigned int* counter = (unsigned int*)((char*)counters + (size_t)b * 256);
         int rc;
         if (ndim == 3)
             rc = launch_tile<3>(sm_count, st, dc, n_atoms, n_frames, pitch, comp, d_tpls, h.n_tpls, h.strips_total, d_units, batch,
-                                d_lag, h.K, h.nbuf, d_slot, sums + 2 * h.l0);
+                                d_lag, h.K, h.nbuf, counter, d_slot, sums + 2 * h.l0);
         else if (ndim == 2)
             rc = launch_tile<2>(sm_count, st, dc, n_atoms, n_frames, pitch, comp, d_tpls, h.n_tpls, h.strips_total, d_units, batch,
-                                d_lag, h.K, h.nbuf, d_slot, sums + 2 * h.l0);
+                                d_lag, h.K, h.nbuf, counter, d_slot, sums + 2 * h.l0);
         else
             rc = launch_tile<1>(sm_count, st, dc, n_atoms, n_frames, pitch, comp, d_tpls, h.n_tpls, h.strips_total, d_units, batch,
-                                d_lag, h.K, h.nbuf, d_slot, sums + 2 * h.l0);
+                                d_lag, h.K, h.nbuf, counter, d_slot, sums + 2 * h.l0);
         if (rc) return rc;
         ph += h.bytes;
         pd += h.bytes;

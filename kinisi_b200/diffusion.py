@@ -149,7 +149,7 @@ class Bootstrap:
         self._stats_dev = None  # [4, n] = n, v, s, ngp on the device
         self._stats_host = None
         self._dt = np.array([])
-        self._device = self._displacements.dc_unsynchronised.device if self._lazy else torch.device('cuda',
+        self._device = self._displacements.device if self._lazy else torch.device('cuda',
                                                                                      torch.cuda.current_device())
 
     # ---- helpers -----------------------------------------------------------------------------
@@ -268,13 +268,17 @@ class Bootstrap:
             lags = d.lags[used]
             order = np.argsort(lags, kind='stable')
             if d.n_atoms > 0:
-                # atoms are additive: with a staged ingest the kernel follows the transfer block by block
+                # atoms are additive: with a staged ingest the kernel follows the transfer block by block, and a
+                # streamed sequence rebuilds its displacements block by block (parser.LazyDisplacements.blocks)
                 sums = None
-                for r0, r1, ev in d.row_blocks():
-                    if ev is not None:
-                        torch.cuda.current_stream(self._device).wait_event(ev)
-                    part = engine.self_moments(d.dc_unsynchronised[r0:r1], d.n_frames, lags[order], mask)
+                want_coll = getattr(self, '_coll_request', None)
+                for r0, r1, rows in d.blocks():
+                    part = engine.self_moments(rows, d.n_frames, lags[order], mask)
                     sums = part if sums is None else sums.add_(part)
+                    if want_coll is not None:  # the collective sum of the same pass (one stage-1 run per block)
+                        w = want_coll['weights']
+                        S = engine.atom_sum(rows, None if w is None else w[r0:r1].contiguous())
+                        want_coll['S'] = S if want_coll['S'] is None else want_coll['S'].add_(S)
             else:
                 sums = torch.zeros((len(used), 2), dtype=torch.float64, device=self._device)
             if d.distributed:
@@ -299,10 +303,16 @@ class Bootstrap:
         d = self._displacements
         if self._lazy and not isinstance(d, SingleOriginDisplacements):
             w = None if weights is None else self._dev(weights)
-            if d.dc.shape[0] > 0:
-                S = engine.atom_sum(d.dc, w)
+            got = getattr(self, '_coll_request', None)
+            if got is not None and got['S'] is not None:
+                S = got['S']  # summed over the blocks of a streamed sequence by _self_sums
+            elif d.n_atoms > 0:
+                S = None
+                for r0, r1, rows in d.blocks():
+                    part = engine.atom_sum(rows, None if w is None else w[r0:r1].contiguous())
+                    S = part if S is None else S.add_(part)
             else:
-                S = torch.zeros((3, d.dc.shape[2]), dtype=torch.float64, device=self._device)
+                S = torch.zeros((3, engine.pitch_for(d.n_frames)), dtype=torch.float64, device=self._device)
             if d.distributed:
                 dist.allreduce_sum_(S, 'frames')
             return engine.self_moments(S.unsqueeze(0), d.n_frames, d.lags[used], coll_mask)
@@ -840,8 +850,14 @@ class _CollectiveBootstrap(Bootstrap):
             gcnt.append(float(n_local * shp[1]))
         if used:
             u = np.array(used)
+            # a streamed sequence rebuilds its displacements for every pass over the atoms: the per-atom moments and the
+            # (charge-weighted) atom sum are taken from one pass
+            self._coll_request = None
+            if self._lazy and getattr(self._displacements, 'streamed', False):
+                self._coll_request = {'weights': None if weights is None else self._dev(weights), 'S': None}
             self_sums = self._self_sums(u, self._mask)
             coll = self._collective_sums(u, weights, coll_mask)
+            self._coll_request = None
             self._finish(used, coll, m, div, self_sums, gcnt)
             if self._resample is not None or self._block:
                 pops = (self._population(i, coll_mask, weights, collective=True) for i in used)

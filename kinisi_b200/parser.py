@@ -25,6 +25,11 @@ from ._lib import MODE_DISPLACEMENT, MODE_FRACTIONAL
 _SIDE_STREAMS = {}
 _LATTICES = {}  # (lattice bytes, device) -> (lattices, inverses, upload event) on the device
 STAGE_BYTES = 32 << 20  # host->device copy granularity of the staged ingest (about 0.6 ms of PCIe time)
+# A cumulative-displacement array above STREAM_BYTES is not kept: stage 1 is re-run block by block (STREAM_BLOCK_BYTES of
+# float64 displacements at a time) in front of every consumer that reduces over atoms (BASELINE configs[4]: 100 000 atoms x
+# 50 000 frames would be 120 GB of float64 next to 60 GB of input).  Only for device-resident input.
+STREAM_BYTES = 8 << 30
+STREAM_BLOCK_BYTES = 2 << 30
 
 
 def _side_streams(device):
@@ -280,20 +285,56 @@ class LazyDisplacements:
     kernels never do that.
     """
 
-    def __init__(self, dc, n_frames, lags, n_atoms_global=None, stride=1, ready=None, distributed=False):
-        self._dc = dc  # [n_local_atoms, 3, pitch] float64 CUDA
+    def __init__(self, dc, n_frames, lags, n_atoms_global=None, stride=1, ready=None, distributed=False, source=None):
+        self._dc = dc  # [n_local_atoms, 3, pitch] float64 CUDA; None while the sequence is STREAMED from `source`
+        # streamed: (trajectory, int32 device indices of the selected atoms, drift or None): the displacements of a block
+        # of atoms are rebuilt from the coordinates whenever a consumer asks (`blocks()`), the whole array only for `dc`
+        self._source = source
         # True: dc holds this rank's shard of the atoms; sums over atoms are all-reduced (set by a distributed Parser)
         self.distributed = bool(distributed) and dist.active()
         # staged ingest: [(row0, row1, event)] -- rows [row0, row1) of dc are valid once the event has fired
         self._ready = list(ready) if ready else []
         self.n_frames = int(n_frames)
         self.lags = np.asarray(lags, dtype=np.int64)
-        self.n_atoms = dc.shape[0]
-        self.n_atoms_global = int(n_atoms_global if n_atoms_global is not None else dc.shape[0])
+        self.n_atoms = dc.shape[0] if dc is not None else int(source[1].numel())
+        self.n_atoms_global = int(n_atoms_global if n_atoms_global is not None else self.n_atoms)
+
+    @property
+    def streamed(self):
+        return self._dc is None
+
+    def blocks(self):
+        """Yields `(row0, row1, dc_rows)`: the displacement array in blocks of atoms, each valid on the current stream
+        when it is yielded.  Resident: the blocks of a staged ingest in the order they land (one block otherwise).
+        Streamed: stage 1 runs for one block at a time into ONE buffer -- a block must be consumed (in stream order)
+        before the next one is asked for."""
+        if self._dc is not None:
+            stream = torch.cuda.current_stream(self._dc.device)
+            for r0, r1, ev in self.row_blocks():
+                if ev is not None:
+                    stream.wait_event(ev)
+                yield r0, r1, self._dc[r0:r1]
+            return
+        traj, idx, drift = self._source
+        pitch = engine.pitch_for(self.n_frames)
+        per = max(1, min(self.n_atoms, int(STREAM_BLOCK_BYTES // (3 * pitch * 8))))
+        buf = torch.empty((per, 3, pitch), dtype=torch.float64, device=idx.device)
+        sums, scale = (None, 0.0) if drift is None else (drift[0], 1.0 / drift[1])
+        traj.make_resident()
+        for r0 in range(0, self.n_atoms, per):
+            r1 = min(self.n_atoms, r0 + per)
+            engine.unwrap_cumsum(traj.coords, traj.mode, traj.latt, traj.latt_inv, traj.latt_stride, idx[r0:r1], sums, scale,
+                                 pitch, out=buf[:r1 - r0])
+            yield r0, r1, buf[:r1 - r0]
 
     @property
     def dc(self):
-        """The whole array, valid on the current stream (waits for a staged ingest to finish)."""
+        """The whole array, valid on the current stream (waits for a staged ingest to finish; a streamed sequence
+        builds and keeps it: indexing, resampling and blocking need the array)."""
+        if self._dc is None:
+            traj, idx, drift = self._source
+            self._dc = traj.displacement(idx, drift)
+            self._source = None
         if self._ready:
             stream = torch.cuda.current_stream(self._dc.device)
             for _, _, ev in self._ready:
@@ -307,6 +348,10 @@ class LazyDisplacements:
         if not self._ready:
             return [(0, self.n_atoms, None)]
         return list(self._ready)
+
+    @property
+    def device(self):
+        return self._dc.device if self._dc is not None else self._source[1].device
 
     @property
     def dc_unsynchronised(self):
@@ -329,7 +374,7 @@ class LazyDisplacements:
     def __getitem__(self, i):
         if isinstance(i, slice):
             return LazyDisplacements(self._dc, self.n_frames, self.lags[i], self.n_atoms_global, ready=self._ready,
-                                     distributed=self.distributed)
+                                     distributed=self.distributed, source=self._source)
         k = int(self.lags[i])
         x = self.dc[:, :, :self.n_frames]
         first = x[:, :, k - 1:k]
@@ -418,8 +463,11 @@ class Parser:
             n_sel, self._n_fw_global = n_sel_local, len(drift_indices)
         self._n_atoms_global = n_sel
 
-        # memory guard (kinisi/parser.py:190-200), applied to what this build keeps resident
-        need_gb = n_sel_local * 3 * engine.pitch_for(n_frames) * 8 * 1e-9
+        # memory guard (kinisi/parser.py:190-200), applied to what this build keeps resident: the cumulative displacements
+        # of the selected atoms, or one block of them when they are streamed
+        dc_bytes = n_sel_local * 3 * engine.pitch_for(n_frames) * 8
+        self._streamed = bool(traj.resident and sampling == 'multi-origin' and dc_bytes > STREAM_BYTES)
+        need_gb = (min(dc_bytes, STREAM_BLOCK_BYTES) if self._streamed else dc_bytes) * 1e-9
         if need_gb > self.memory_limit:
             raise MemoryError(f"The memory limit of this job is {self.memory_limit:.1e} GB but the "
                               f"displacement values will use {need_gb:.1e} GB. Please either increase "
@@ -436,7 +484,10 @@ class Parser:
                                                           np.asarray(drift_indices, dtype=np.int64).reshape(-1)]), dev, np.int32)
             idx, fw_idx = both[:n_sel_local], both[n_sel_local:]
             self._drift = self._framework_mean(traj, drift_indices, fw_idx)
-            if n_sel_local > 0:
+            self._sel_idx_dev = idx
+            if self._streamed:
+                self._dc_sel = None
+            elif n_sel_local > 0:
                 self._dc_sel = traj.displacement(idx, self._drift)
             else:
                 self._dc_sel = torch.zeros((0, 3, engine.pitch_for(n_frames)), dtype=torch.float64, device=dev)
@@ -511,6 +562,8 @@ class Parser:
     @property
     def _dc_sel(self):
         """The drift-corrected displacement of the selected atoms, valid on the current stream."""
+        if self._dc_sel_staged is None and getattr(self, '_streamed', False):
+            return self.disp_3d.dc  # a streamed parser builds (and keeps) the array only on request
         if self._dc_ready:
             stream = torch.cuda.current_stream(self._dc_sel_staged.device)
             for _, _, ev in self._dc_ready:
@@ -644,8 +697,9 @@ class Parser:
             disp_3d = SingleOriginDisplacements(drift_corrected, n_frames, kept, n_atoms, ready=getattr(self, '_dc_ready', None),
                                                 distributed=getattr(self, '_distributed', False))
         else:
+            source = (self._traj, self._sel_idx_dev, self._drift) if getattr(self, '_streamed', False) else None
             disp_3d = LazyDisplacements(drift_corrected, n_frames, time_intervals[kept], n_atoms, ready=getattr(self, '_dc_ready', None),
-                                        distributed=getattr(self, '_distributed', False))
+                                        distributed=getattr(self, '_distributed', False), source=source)
         return delta_t, disp_3d, np.array(n_samples, dtype=float)
 
 

@@ -1350,3 +1350,38 @@ def test_identical_single_origin_trajectories_stack(kb):
     want = np.array([np.mean(np.sum(joint[:, f]**2, axis=-1)) for f in frames[:an.msd.size]])
     np.testing.assert_allclose(an.msd, want, rtol=1e-11, atol=1e-14)
     np.testing.assert_allclose(an._disp_3d[3], joint[:, frames[3]:frames[3] + 1], rtol=1e-12, atol=1e-13)
+
+
+def test_streamed_displacements(kb, monkeypatch):
+    """A displacement array above parser.STREAM_BYTES is never built (BASELINE configs[4] at one GPU: 120 GB of float64):
+    stage 1 is re-run block by block in front of the moment kernels and the atom sum.  Same statistics as the resident
+    path and the oracle (MSD, MSTD, MSCD with drift), several blocks with a partial last one; indexing the sequence
+    still gives the reference's array (kinisi/parser.py:208-213)."""
+    n_mobile, n_fw, n_frames = 45, 8, 2500
+    frac, latt = ko.synthetic_walk(n_mobile, n_frames, box=14.0, sigma=0.1, seed=91, n_framework=n_fw, dtype=np.float32)
+    idx, fw = list(range(n_mobile)), list(range(n_mobile, n_mobile + n_fw))
+    parsed = ko.parse(ko.get_disp(frac.astype(np.float64), latt), idx, fw, 0.002, 1, n_steps=50)
+    dev = torch.device('cuda')
+    coords = torch.from_numpy(frac).to(dev)
+    q = np.where(np.arange(n_mobile) % 3 == 0, -2.0, 1.0)
+    pitch = kb.engine.pitch_for(n_frames)
+    monkeypatch.setattr(kb.parser, 'STREAM_BYTES', 10 * 3 * pitch * 8)       # anything above 10 atoms streams
+    monkeypatch.setattr(kb.parser, 'STREAM_BLOCK_BYTES', 7 * 3 * pitch * 8)  # 7 atoms per block: 6 blocks + 3 atoms
+    p = kb.parser.Parser(kb.parser.Parser.get_disp(coords, latt[:1]), idx, fw, 0.002, 1, n_steps=50, progress=False)
+    assert p.disp_3d.streamed and p.disp_3d.n_atoms == n_mobile
+    for kind, cls, args in (('msd', kb.diffusion.MSDBootstrap, ()), ('mstd', kb.diffusion.MSTDBootstrap, ()),
+                            ('mscd', kb.diffusion.MSCDBootstrap, (q, ))):
+        b = cls(p.delta_t, p.disp_3d, *args, p._n_o, progress=False)
+        ref = ko.bootstrap_streaming(parsed, kind, q if kind == 'mscd' else None)
+        for key in ('dt', 'n', 'v', 's'):
+            np.testing.assert_allclose(getattr(b, key), ref[key], rtol=RTOL_MOMENT, err_msg=f'{kind} {key}')
+        np.testing.assert_allclose(b.ngp, ref['ngp'], rtol=1e-8, atol=1e-10)
+        assert p.disp_3d.streamed  # the reductions did not build the array
+    b.conductivity(float(b.dt[4]), 500.0, p.volume if p.volume else 1000.0, progress=False, n_samples=200, n_burn=100)
+    assert np.isfinite(b.sigma.n)
+    np.testing.assert_allclose(p.disp_3d[3], ko.displacements_for_lag(parsed['dc_sel'], int(parsed['lags'][3])), rtol=1e-10,
+                               atol=1e-11)
+    assert not p.disp_3d.streamed  # indexing built (and kept) it
+    with pytest.raises(MemoryError):
+        kb.parser.Parser(kb.parser.Parser.get_disp(coords, latt[:1]), idx, fw, 0.002, 1, n_steps=50, progress=False,
+                         memory_limit=1e-6)
