@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(1024) scan_frames_kernel(double* __restrict__ 
 // element-wise cp.async with padded strides spent 340 instructions per frame.
 constexpr int kUwE = 5;
 constexpr int kUwThreads = 256;
+constexpr int kUwCtasPerSm = 3;  // (128 threads x 6 CTAs, the same bytes in flight with twice the tiles per atom: 154 us against 119 us at configs[1])
 constexpr int kUwTile = kUwThreads * kUwE;
 constexpr unsigned long long kUwNotReady = 0xFFFFFFFFFFFFFFFFull;
 
@@ -273,7 +274,7 @@ __device__ __forceinline__ unsigned long long ld_l2_u64(const double* p) {  // L
 }
 
 template <typename T, int MODE, bool CONSTL>
-__global__ void __launch_bounds__(kUwThreads, 3) unwrap_cumsum_kernel(const T* __restrict__ coords, int64_t n_coords, int F,
+__global__ void __launch_bounds__(kUwThreads, kUwCtasPerSm) unwrap_cumsum_kernel(const T* __restrict__ coords, int64_t n_coords, int F,
                                                                      const double* __restrict__ latt,
                                                                      const double* __restrict__ inv, int lstride,
                                                                      const int32_t* __restrict__ idx, int n_idx,
@@ -529,7 +530,7 @@ static int launch_unwrap(const void* coords, int n_atoms_total, int F, const dou
     KB2_CUDA(cudaMemsetAsync(workspace, 0, 256, st));
     KB2_CUDA(cudaMemsetAsync((unsigned char*)workspace + 256, 0xFF, uw_workspace_bytes(n_idx, n_tiles) - 256, st));
     const int sm = device_sm_count();
-    const int grid = (int)std::min<int64_t>((int64_t)n_idx * n_tiles, (int64_t)sm * 3);
+    const int grid = (int)std::min<int64_t>((int64_t)n_idx * n_tiles, (int64_t)sm * kUwCtasPerSm);
     unwrap_cumsum_kernel<T, MODE, CONSTL><<<grid, kUwThreads, smem, st>>>(
         c, (int64_t)n_atoms_total * F * 3, F, latt, inv, lstride, idx, n_idx, step_sums, step_scale, out, pitch, Tn, n_tiles,
         (unsigned char*)workspace);
