@@ -50,7 +50,7 @@ constexpr int kTileSmemBufBytes = 192 * 1024;  // shared memory of all buffers
 constexpr int kTileGuardBytes = 4096;        // shared memory in front of the first buffer (look-ahead reads run below a tile)
 constexpr int kTileCW = 14;                  // consumer warps
 constexpr int kTileMaxLags = 256;            // lags per launch (CTA accumulators in shared memory)
-constexpr int kTileRA = 32;                  // most origin rows per unit
+constexpr int kTileRA = 64;                  // most origin rows per unit (sweep: tools/k2tile_sweep.sh, profiles/r02_k2_tile_sweeps.txt)
 constexpr int kTileMaxUnits = 96;            // units per tile
 constexpr int kTileMinLen = 3;               // shortest progression taken as such
 constexpr int kTileCandidates = 24;          // successors tried as the common difference
@@ -555,6 +555,17 @@ struct TilePlan {
 
 // Row length for a progression of `len` lags with common difference d: a multiple of d, >= 32, that fills whole
 // strips of 32 columns and still leaves windows of several lags.
+static bool tile_split_eights() {
+    const char* e = getenv("KB2_TILE_SPLIT");
+    return !(e && !strcmp(e, "even"));
+}
+
+static int tile_ra() {  // most origin rows per unit (KB2_TILE_RA: experiments)
+    const char* e = getenv("KB2_TILE_RA");
+    const int v = e ? atoi(e) : 0;
+    return v >= kTileM ? v : kTileRA;
+}
+
 static int choose_mult(int d, int len, int Tn) {
     if (const char* e = getenv("KB2_TILE_MULT")) {  // experiments: force the multiple when it is admissible
         const int mult = atoi(e);
@@ -600,11 +611,14 @@ static void plan_tiles_for(const int32_t* lags, int K, int Tn, int buf_bytes, Ti
         const int D = mult * sg.d;
         for (int u = 0; u < mult && u < sg.len; ++u) {
             const int ls = (sg.len - u + mult - 1) / mult;  // lags k0 + (u + i*mult)*d, i < ls
+            // windows of 8 and one remainder ("eights": one instantiation of the walk does nearly all the work, which
+            // matters for the instruction cache) or windows of nearly equal size ("even")
             const int nw = (ls + kTileM - 1) / kTileM;
             const int base = ls / nw, extra = ls % nw;
+            const bool eights = tile_split_eights();
             int at = 0;
             for (int w = 0; w < nw; ++w) {
-                const int m = base + (w < extra ? 1 : 0);
+                const int m = eights ? std::min(kTileM, ls - at) : base + (w < extra ? 1 : 0);
                 const long long kfirst = (long long)sg.k0 + (long long)(u + (long long)at * mult) * sg.d;
                 plan.wins.push_back({D, (int)(kfirst / D), (int)(kfirst % D), m, (int)plan.slot.size()});
                 for (int i = 0; i < m; ++i) {
@@ -657,6 +671,7 @@ static void plan_tiles_for(const int32_t* lags, int K, int Tn, int buf_bytes, Ti
         if (rows == 0) continue;
         // A tile = (block of origin rows [aLo, aHi], run of consecutive windows).  Builds the tiles for blocks of H rows
         // and returns the bytes they load; `out` == nullptr only counts.
+        const int RA = tile_ra();
         auto build = [&](int H, std::vector<Tile>* out) -> long long {
             long long total = 0;
             for (int aLo = 0; aLo < rows; aLo += H) {
@@ -713,7 +728,7 @@ static void plan_tiles_for(const int32_t* lags, int K, int Tn, int buf_bytes, Ti
                         n_ohi = std::max(oHi, hi);
                         n_plo = std::min(pLo, plo);
                         n_phi = std::max(pHi, phi);
-                        const int n_units = (int)cur.units.size() + (hi - aLo + kTileRA) / kTileRA;
+                        const int n_units = (int)cur.units.size() + (hi - aLo + RA) / RA;
                         if (bytes_of(n_ohi, n_plo, n_phi) > buf_bytes || n_units > kTileMaxUnits) {
                             flush();
                             n_ohi = hi, n_plo = plo, n_phi = phi;
@@ -722,7 +737,7 @@ static void plan_tiles_for(const int32_t* lags, int K, int Tn, int buf_bytes, Ti
                     if (bytes_of(n_ohi, n_plo, n_phi) > buf_bytes) return -1;  // one window does not fit: smaller blocks
                     oHi = n_ohi, pLo = n_plo, pHi = n_phi;
                     // units of this window: its range cut from the top into blocks of nearly equal height <= kTileRA
-                    const int n_rows = hi - aLo + 1, n_blk = (n_rows + kTileRA - 1) / kTileRA;
+                    const int n_rows = hi - aLo + 1, n_blk = (n_rows + RA - 1) / RA;
                     int top_row = hi;
                     for (int q = 0; q < n_blk; ++q) {
                         const int h = n_rows / n_blk + (q < n_rows % n_blk ? 1 : 0);
@@ -746,7 +761,7 @@ static void plan_tiles_for(const int32_t* lags, int K, int Tn, int buf_bytes, Ti
                 best_H = H;
             }
             if (H <= kTileM) break;
-            if (best_H && nb >= 8 && H < 4 * kTileRA) break;
+            if (best_H && nb >= 8 && H < 4 * RA) break;
         }
         if (!best_H) best_H = kTileM;
         build(best_H, &tiles);
