@@ -38,7 +38,7 @@ def k2_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the stage-2 kernel on this workload, from the
     ncu --set full capture summarised in profiles/ (None if the summary is missing)."""
     try:
-        d = json.load(open(os.path.join(ROOT, 'profiles', 'r01_k2_runs_traffic.json')))
+        d = json.load(open(os.path.join(ROOT, 'profiles', 'r02_k2_tile_traffic.json')))
         return float(d['dram_bytes_read'] + d['dram_bytes_write'])
     except Exception:
         return None
@@ -437,8 +437,10 @@ def named_shapes(args, torch, td, dev, world, rank, fp64_peak_tflops, hbm_peak_g
                 'k2_ms': best['k2_ms'], 'k2_fp64_frac': 16.0 * terms / world / (best['k2_ms'] * 1e-3) / 1e12 / fp64_peak_tflops,
                 'k1_ms': best['k1_ms'], 'k1_hbm_gbs': k1['bytes'] / (best['k1_ms'] * 1e-3) / 1e9,
                 'k1_hbm_frac': k1['bytes'] / (best['k1_ms'] * 1e-3) / 1e9 / hbm_peak_gbs,
-                'coefficient_median_cm2_s': float(coef.n), 'true_cm2_s': 3 * 0.1**2 / CFG['time_step'] / (2e4 * 3),
+                'coefficient_median_cm2_s': float(coef.n),
             }
+            if kind == 'msd':  # (the collective coefficient of one realisation of independent walkers is a noisy estimate)
+                out[name]['true_cm2_s'] = 3 * 0.1**2 / CFG['time_step'] / (2e4 * 3)
         finally:
             engine.self_moments, engine.unwrap_cumsum = raw_k2, raw_k1
         del coords, p, b
@@ -664,6 +666,20 @@ def run_own(args):
     del uw_out
     e2e_ms, _, b2 = timed(host, args.steps)
     clocks = sampler.stop() if sampler is not None else None
+    # the same bytes as a plain pinned host->device copy on every rank at once: the ceiling of `e2e` (one host feeds all GPUs)
+    if world > 1:
+        td.barrier()
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(5):
+        resident.copy_(host, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    tcopy = torch.tensor([c0.elapsed_time(c1) / 5], dtype=torch.float64, device=dev)
+    if world > 1:
+        td.all_reduce(tcopy, op=td.ReduceOp.MAX)
+    plain_h2d_ms = float(tcopy[0])
     engine.self_moments = raw_self_moments
     shapes = None
     if not args.no_named_shapes:
@@ -727,7 +743,9 @@ def run_own(args):
                 'analyses_in_flight': args.in_flight,
             },
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                    'ms_per_step': e2e_ms / args.steps},
+                    'ms_per_step': e2e_ms / args.steps, 'plain_pinned_h2d_ms_per_step': plain_h2d_ms,
+                    'plain_pinned_h2d_gbs_per_gpu': host.numel() * host.element_size() / (plain_h2d_ms * 1e-3) / 1e9,
+                    'fraction_of_plain_h2d': plain_h2d_ms / (e2e_ms / args.steps)},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {

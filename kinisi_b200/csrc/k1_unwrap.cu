@@ -9,6 +9,8 @@
 //
 // Algorithmic HBM bytes per (atom, frame): sizeof(coord)*3 read + 24 written for the scan kernel,
 // sizeof(coord)*3 read for the frame-sum kernel.  Both are HBM-bound.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <type_traits>
 
@@ -181,6 +183,178 @@ __global__ void __launch_bounds__(256) frame_sums_kernel(const T* __restrict__ c
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) atomicAdd(sums + c * pitch + t, acc[c]);
+}
+
+// ---- frame sums through a bulk-copy ring -------------------------------------------------------------------------
+// The kernel above keeps as many bytes in flight as its registers hold (24 bytes per thread and atom of a batch of four:
+// ncu showed 20 long-scoreboard stall cycles per issue at 3.2 TB/s).  Here a CTA owns a tile of kFbFrames frames and a chunk
+// of atoms; a producer thread copies the tile of one atom at a time -- one contiguous run of (kFbFrames + 1) * 3 elements
+// -- into a ring of kFbStages shared-memory stages with cp.async.bulk (the TMA engine; completion on the stage's `full`
+// mbarrier), so kFbStages * 12 KB per CTA are in flight whatever the register count; the consumer warps read the stage
+// (conflict-free: a lane's frame is 3 elements), accumulate w - floor(w + 1/2) per frame in registers over the atoms of
+// the chunk, and release the stage on its `empty` mbarrier.  Rows of the coordinate array are only element-aligned: a
+// copy starts at the 16-byte boundary at or below the tile (`mis` elements early) and is a multiple of 16 bytes; what
+// would run past the end of the array is fetched with plain loads.  Constant cell, unit weights (the framework drift of
+// every front-end; kinisi/parser.py:131-148); everything else takes the kernel above.
+constexpr int kFbFrames = 1024;
+constexpr int kFbStages = 4;
+constexpr int kFbConsumers = 256;
+constexpr int kFbPer = kFbFrames / kFbConsumers;
+
+template <typename T>
+__host__ __device__ constexpr int fb_stage_bytes() {
+    return (int)((((kFbFrames + 1) * 3 * sizeof(T) + 16 + 15) / 16) * 16 + 16);
+}
+
+namespace fb {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "KB2_FB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra KB2_FB_DONE;\n\t"
+        "bra KB2_FB_WAIT;\n\t"
+        "KB2_FB_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+}  // namespace fb
+
+template <typename T>
+__global__ void __launch_bounds__(kFbConsumers + 32) frame_sums_bulk_kernel(const T* __restrict__ coords, int64_t n_coords, int F,
+                                                                           const double* __restrict__ latt,
+                                                                           const int32_t* __restrict__ idx, int n_idx,
+                                                                           int per_chunk, double* __restrict__ sums,
+                                                                           int64_t pitch, int Tn) {
+    using namespace fb;
+    constexpr int SB = fb_stage_bytes<T>();
+    extern __shared__ __align__(128) unsigned char fb_smem[];
+    __shared__ uint64_t full[kFbStages], empty[kFbStages];
+    __shared__ int s_mis[kFbStages];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t0 = blockIdx.x * kFbFrames;
+    const int nf = min(kFbFrames, Tn - t0);
+    const int i0 = blockIdx.y * per_chunk, i1 = min(n_idx, i0 + per_chunk);
+    if (tid == 0) {
+        for (int s = 0; s < kFbStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kFbConsumers / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == kFbConsumers / 32) {
+        if (lane == 0) {
+            const char* const arr_end = reinterpret_cast<const char*>(coords + n_coords);
+#pragma unroll 1
+            for (int i = i0; i < i1; ++i) {
+                const int q = i - i0, s = q % kFbStages;
+                if (q >= kFbStages) mbar_wait(&empty[s], ((q / kFbStages) - 1) & 1);
+                const T* first = coords + ((size_t)__ldg(idx + i) * F + t0) * 3;
+                const int mis = (int)((reinterpret_cast<uintptr_t>(first) & 15) / sizeof(T));
+                const char* src = reinterpret_cast<const char*>(first - mis);
+                unsigned char* dst = fb_smem + (size_t)s * SB;
+                const int n_el = mis + 3 * (nf + 1);
+                int bytes = (int)(((size_t)n_el * sizeof(T) + 15) / 16) * 16;
+                const long long room = ((arr_end - src) / 16) * 16;  // whole 16-byte chunks before the end of the array
+                int bulk = bytes;
+                if ((long long)bulk > room) {
+                    bulk = (int)room;
+                    // the last elements of the whole array: plain loads (ordered before the arrival below)
+                    const T* g = reinterpret_cast<const T*>(src + bulk);
+                    T* d = reinterpret_cast<T*>(dst + bulk);
+                    for (int k = 0; g + k < coords + n_coords && (long long)bulk + (k + 1) * (long long)sizeof(T) <= bytes; ++k) d[k] = g[k];
+                }
+                s_mis[s] = mis;
+                if (bulk > 0) {
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)bulk);
+                    bulk_g2s(dst, src, (uint32_t)bulk, &full[s]);
+                } else {
+                    mbar_arrive(&full[s]);
+                }
+            }
+        }
+        return;
+    }
+    double aw[kFbPer][3];
+#pragma unroll
+    for (int j = 0; j < kFbPer; ++j) aw[j][0] = aw[j][1] = aw[j][2] = 0.0;
+#pragma unroll 1
+    for (int i = i0; i < i1; ++i) {
+        const int q = i - i0, s = q % kFbStages;
+        mbar_wait(&full[s], (q / kFbStages) & 1);
+        const T* raw = reinterpret_cast<const T*>(fb_smem + (size_t)s * SB) + s_mis[s];
+#pragma unroll
+        for (int j = 0; j < kFbPer; ++j) {
+            const int f = tid + j * kFbConsumers;
+            if (f < nf) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double d = (double)raw[(f + 1) * 3 + k] - (double)raw[f * 3 + k];
+                    aw[j][k] += d - floor(d + 0.5);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+    double L[9];
+    load9(latt, L);
+#pragma unroll
+    for (int j = 0; j < kFbPer; ++j) {
+        const int f = tid + j * kFbConsumers;
+        if (f < nf) {
+#pragma unroll
+            for (int l = 0; l < 3; ++l)
+                atomicAdd(sums + l * pitch + t0 + f, aw[j][0] * L[l] + aw[j][1] * L[3 + l] + aw[j][2] * L[6 + l]);
+        }
+    }
+}
+
+template <typename T>
+static int launch_frame_sums_bulk(const void* coords, int n_atoms_total, int F, const double* latt, const int32_t* idx, int n_idx,
+                                  double* sums, int64_t pitch, int Tn, cudaStream_t st) {
+    const int sm = device_sm_count();
+    const size_t smem = (size_t)kFbStages * fb_stage_bytes<T>();
+    const int tiles = ceil_div(Tn, kFbFrames);
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / smem));
+    int chunks = ceil_div((int64_t)sm * per_sm, tiles);
+    chunks = std::max(1, std::min(chunks, ceil_div(n_idx, 2 * kFbStages)));
+    chunks = std::min(chunks, 65535);
+    const int per = ceil_div(n_idx, chunks);
+    chunks = ceil_div(n_idx, per);
+    KB2_CUDA(cudaFuncSetAttribute(frame_sums_bulk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    frame_sums_bulk_kernel<T><<<dim3(tiles, chunks), kFbConsumers + 32, smem, st>>>((const T*)coords, (int64_t)n_atoms_total * F * 3, F,
+                                                                                  latt, idx, n_idx, per, sums, pitch, Tn);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+static bool frame_sums_bulk_enabled() {
+    static bool on = [] {
+        const char* e = getenv("KB2_FS_BULK");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 // One CTA per component: optional cumulative sum over time, then an affine map.
@@ -579,6 +753,11 @@ extern "C" int kb2_frame_sums(const void* coords, int dtype, int mode, int n_ato
     KB2_CHECK(frame_sums, "kb2_frame_sums: null output");
     cudaStream_t st = (cudaStream_t)stream;
     KB2_CUDA(cudaMemsetAsync(frame_sums, 0, sizeof(double) * 3 * pitch, st));
+    if (mode == KB2_MODE_FRACTIONAL && latt_stride == 0 && !w && frame_sums_bulk_enabled() && n_idx >= 2 * kFbStages) {
+        if (dtype == KB2_F32)
+            return launch_frame_sums_bulk<float>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, frame_sums, pitch, Tn, st);
+        return launch_frame_sums_bulk<double>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, frame_sums, pitch, Tn, st);
+    }
     const int sm = device_sm_count();
     const int tiles = ceil_div(Tn, 256);
     int chunks = ceil_div((int64_t)sm * 8, tiles);

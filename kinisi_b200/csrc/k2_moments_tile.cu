@@ -898,7 +898,14 @@ static int launch_tile(int sm_count, cudaStream_t st, const double* dc, int n_at
     auto kern = self_moments_tile_kernel<NDIM, NPW>;
     const int threads = 32 * (kTileCW + NPW);
     KB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<sm_count, threads, smem, st>>>(dc, n_atoms, Tn, pitch, comp[0], comp[1], comp[2], tpls, n_tpls, strips_total, units,
+    // The CTAs take every register of their SM: a few SMs are left to the one-CTA kernels of the regression (Jacobi, the
+    // one-warp sampler) of the analyses in flight on other streams, which would otherwise wait for this kernel to end.
+    static const int spare = [] {
+        const char* e = getenv("KB2_TILE_SPARE_SMS");
+        return e ? std::max(0, atoi(e)) : 2;
+    }();
+    const int grid = std::max(1, sm_count - spare);
+    kern<<<grid, threads, smem, st>>>(dc, n_atoms, Tn, pitch, comp[0], comp[1], comp[2], tpls, n_tpls, strips_total, units,
                                          batch, acc_lag, K, nbuf, kTileSmemBufBytes / nbuf, counter, slot, out);
     KB2_LAUNCH_CHECK();
     return 0;
