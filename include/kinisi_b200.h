@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KB2_ABI_VERSION 6
+#define KB2_ABI_VERSION 7
 
 /* coordinate element types */
 #define KB2_F32 0
@@ -319,6 +319,39 @@ int kb2_resample_means(const double* values, int64_t n_values, int64_t n_draws, 
 int kb2_reblock_levels(int64_t n_values);
 size_t kb2_reblock_workspace_bytes(int64_t n_values);
 int kb2_reblock(const double* values, int64_t n_values, double* workspace, double* stats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-GPU joins through peer memory (csrc/k7_peer.cu).  With the atoms of a trajectory sharded over
+ * ranks, the reference's sums over atoms -- np.mean(disp[:, framework], axis=1) in Parser.correct_drift
+ * (kinisi/parser.py:143-145), np.sum(disp, axis=0) in MSTDBootstrap / MSCDBootstrap (kinisi/diffusion.py:659, 751) and
+ * the per-lag sums behind np.mean / np.var in MSDBootstrap (:571-602) -- end with a sum over ranks of a [3][pitch] or
+ * [K][2] float64 array.  One launch per rank does it over NVLink: every rank stores its array into a window of every
+ * peer, raises a flag, and adds the W copies in rank order (bit-identical on all ranks).
+ *
+ *   kb2_peer_window_bytes    bytes of one rank's window for arrays of up to `capacity` doubles
+ *   kb2_peer_window_create   allocates and zeroes this rank's window (cudaMalloc, synchronises) and returns the 64-byte
+ *                            CUDA IPC handle its peers open; collective in spirit: every rank creates one, the caller
+ *                            exchanges the handles (the reference-side binding uses torch.distributed / MPI for that)
+ *   kb2_peer_window_open     maps a peer's window from its handle (enables peer access); _close unmaps it
+ *   kb2_peer_window_destroy  frees this rank's own window (after every peer has closed it)
+ *   kb2_peer_allreduce_f64   buf[0..n) <- sum over ranks, in place, enqueued on `stream`.  windows_host: HOST array of
+ *                            `world` device pointers, entry `rank` being this rank's own window; `seq` is the number of
+ *                            earlier calls on these windows -- every rank must issue the same calls (same n) in the same
+ *                            order, on any streams; at most kb2_peer_slots() calls are buffered, later ones wait on the
+ *                            device.  buf must be 16-byte aligned, n <= capacity.
+ *   kb2_peer_status          0, or the code of the last call whose wait for a peer ran out (KB2_PEER_TIMEOUT_S seconds,
+ *                            default 120): 1 a slot was never released, 2 a peer's copy never arrived.  Readable at any
+ *                            time (mapped host memory), no synchronisation.
+ * ------------------------------------------------------------------------------------------- */
+int kb2_peer_slots(void);
+size_t kb2_peer_window_bytes(int world, int64_t capacity);
+int kb2_peer_window_create(int world, int64_t capacity, void** window, unsigned char* handle64);
+int kb2_peer_window_open(const unsigned char* handle64, void** window);
+int kb2_peer_window_close(void* window);
+int kb2_peer_window_destroy(void* window);
+int kb2_peer_allreduce_f64(double* buf, int64_t n, void* const* windows_host, int world, int rank, int64_t capacity,
+                           uint64_t seq, void* stream);
+int kb2_peer_status(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py): a dependent-free DFMA loop and a streaming copy, to measure the

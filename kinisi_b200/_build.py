@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libkinisi_b200.so')
-SOURCES = ['api.cu', 'k0_ingest.cu', 'k1_unwrap.cu', 'k2_moments.cu', 'k2_moments_tma.cu', 'k2_moments_runs.cu', 'k2_moments_win.cu', 'k2_moments_tile.cu', 'k3_regress.cu', 'k4_eigen.cu', 'k6_resample.cu']
+SOURCES = ['api.cu', 'k0_ingest.cu', 'k1_unwrap.cu', 'k2_moments.cu', 'k2_moments_tma.cu', 'k2_moments_runs.cu', 'k2_moments_win.cu', 'k2_moments_tile.cu', 'k3_regress.cu', 'k4_eigen.cu', 'k6_resample.cu', 'k7_peer.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
     '-Wno-deprecated-gpu-targets'

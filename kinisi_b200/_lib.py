@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(HERE, 'libkinisi_b200.so')
 
 F32, F64 = 0, 1
 MODE_FRACTIONAL, MODE_DISPLACEMENT = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # name -> (restype, argtypes); mirrors include/kinisi_b200.h one to one
 SIGNATURES = {
@@ -69,6 +69,14 @@ SIGNATURES = {
     'kb2_reblock_levels': (c_int, [c_int64]),
     'kb2_reblock_workspace_bytes': (c_size_t, [c_int64]),
     'kb2_reblock': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    'kb2_peer_slots': (c_int, []),
+    'kb2_peer_window_bytes': (c_size_t, [c_int, c_int64]),
+    'kb2_peer_window_create': (c_int, [c_int, c_int64, POINTER(c_void_p), c_void_p]),
+    'kb2_peer_window_open': (c_int, [c_void_p, POINTER(c_void_p)]),
+    'kb2_peer_window_close': (c_int, [c_void_p]),
+    'kb2_peer_window_destroy': (c_int, [c_void_p]),
+    'kb2_peer_allreduce_f64': (c_int, [c_void_p, c_int64, POINTER(c_void_p), c_int, c_int, c_int64, c_uint64, c_void_p]),
+    'kb2_peer_status': (c_int, []),
     'kb2_fp64_peak': (c_int, [c_int, c_int, c_void_p, c_void_p]),
     'kb2_stream_copy': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
 }

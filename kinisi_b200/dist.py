@@ -1,6 +1,7 @@
 """Multi-GPU plumbing: one process per GPU, atoms sharded across ranks, per-dt moment sums and the
-per-frame framework / collective sums joined by a sum all-reduce (NCCL over NVLink on the GPU box,
-gloo in the CPU tests).  Everything is a no-op when torch.distributed is not initialised."""
+per-frame framework / collective sums joined by a sum over ranks -- one kernel of our own per join over
+peer memory (NVLink / NVSwitch, csrc/k7_peer.cu) on the GPU box, NCCL where the windows cannot be mapped,
+gloo in the CPU tests.  Everything is a no-op when torch.distributed is not initialised."""
 import ctypes
 import os
 
@@ -23,6 +24,10 @@ def active():
         _STATE['group'], _STATE['active'] = g, td.get_world_size() > 1
         _CHANNELS.clear()
         _DIRECT.clear()
+        for ch in _PEER.values():
+            if ch:
+                ch.close(collective=False)  # another process group: the old one cannot be asked to wait
+        _PEER.clear()
     return _STATE['active']
 
 
@@ -109,6 +114,125 @@ class _DirectComm:
         self._last.record(stream)
 
 
+class _PeerChannel:
+    """The joins of one channel through peer memory (csrc/k7_peer.cu): every rank owns a window of device memory that
+    its peers map through CUDA IPC, and one launch per rank stores the array into every window, raises a flag and adds
+    the copies in rank order.  No NCCL kernel, no communicator stream, no ordering events between the streams of the
+    analyses in flight (calls use the slots of the window round-robin and wait on the device for a slot to be released),
+    and the sums are bit-identical on all ranks.  Creation is collective: every rank reaches the first join of a
+    channel (and any join of a larger array than before) at the same point of the program."""
+
+    def __init__(self, device, capacity):
+        from . import _lib
+        self._libmod, self.device = _lib, device
+        lib = _lib.load()
+        self.world, self.rank = td.get_world_size(), td.get_rank()
+        self.capacity = int(capacity)
+        self.seq = 0
+        self._own, self._opened = None, []
+        handle = (ctypes.c_ubyte * 64)()
+        own = ctypes.c_void_p()
+        ok, err = 1, ''
+        with torch.cuda.device(device):
+            if lib.kb2_peer_window_create(self.world, self.capacity, ctypes.byref(own), handle) != 0:
+                ok, err = 0, lib.kb2_last_error().decode('utf-8', 'replace')
+        handles = [None] * self.world
+        td.all_gather_object(handles, (ok, bytes(handle), os.getpid()))
+        ptrs = (ctypes.c_void_p * self.world)()
+        if all(h[0] for h in handles):
+            self._own = own
+            with torch.cuda.device(device):
+                for q, (_, raw, _pid) in enumerate(handles):
+                    if q == self.rank:
+                        ptrs[q] = own.value
+                        continue
+                    p = ctypes.c_void_p()
+                    buf = (ctypes.c_ubyte * 64).from_buffer_copy(raw)
+                    if lib.kb2_peer_window_open(buf, ctypes.byref(p)) != 0:
+                        ok, err = 0, lib.kb2_last_error().decode('utf-8', 'replace')
+                        break
+                    self._opened.append(p)
+                    ptrs[q] = p.value
+        else:
+            ok = 0
+            err = err or 'a peer could not create its window'
+            if own.value:
+                self._own = own
+        # every rank must take the same road: one more exchange of the outcome
+        outcome = [None] * self.world
+        td.all_gather_object(outcome, ok)
+        self.ok = all(outcome)
+        self.error = err
+        self._ptrs = ptrs
+        if not self.ok:
+            self.close()
+
+    def close(self, collective=True):
+        """Unmaps the peers' windows, then frees this rank's own -- after every rank has unmapped it (`collective`)."""
+        lib = self._libmod.load()
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                lib.kb2_peer_window_close(p)
+            self._opened = []
+            if collective and td.is_initialized():
+                td.barrier()
+            if self._own is not None and self._own.value:
+                lib.kb2_peer_window_destroy(self._own)
+            self._own = None
+
+    def allreduce_sum_f64(self, t):
+        lib = self._libmod.load()
+        stream = torch.cuda.current_stream(t.device)
+        rc = lib.kb2_peer_allreduce_f64(t.data_ptr(), t.numel(), self._ptrs, self.world, self.rank, self.capacity, self.seq,
+                                        stream.cuda_stream)
+        self._libmod.check(rc, 'kb2_peer_allreduce_f64')
+        self.seq += 1
+        check_peer_status()
+
+
+def check_peer_status():
+    """Raises if a join through peer memory gave up waiting for a peer (the sums of that analysis are then meaningless)."""
+    from . import _lib
+    code = _lib.load().kb2_peer_status()
+    if code:
+        raise RuntimeError(f'kinisi_b200.dist: a join through peer memory timed out waiting for a peer (code {code}): '
+                           'the ranks did not issue the same analyses in the same order, or a rank died')
+
+
+_PEER = {}
+_PEER_MIN_CAPACITY = 1 << 15
+
+
+def _peer(name, t):
+    """The peer-memory channel `name` for tensors like `t`, or None (CPU tensors, not float64, another backend,
+    KB2_PEER_AR=0, or the windows could not be mapped: the NCCL road is taken instead)."""
+    if (name is None or not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous() or t.data_ptr() % 16
+            or os.environ.get('KB2_PEER_AR', '1') == '0' or td.get_backend() != 'nccl'
+            or td.get_world_size() > 16):
+        return None
+    key = (name, t.device.index)
+    ch = _PEER.get(key)
+    if ch is False:
+        return None
+    n = t.numel()
+    if ch is None or n > ch.capacity:
+        cap = _PEER_MIN_CAPACITY
+        while cap < n:
+            cap *= 2
+        if ch is not None:  # a longer trajectory than any before: every rank is here, nothing of this channel may be in flight
+            torch.cuda.synchronize(t.device)
+            td.barrier()
+            ch.close()
+        ch = _PeerChannel(t.device, cap)
+        if not ch.ok:
+            import warnings
+            warnings.warn(f'kinisi_b200.dist: peer-memory windows unavailable ({ch.error}); using NCCL all-reduces')
+            _PEER[key] = False
+            return None
+        _PEER[key] = ch
+    return ch
+
+
 _DIRECT = {}
 
 
@@ -138,7 +262,11 @@ def allreduce_sum_(t, channel=None):
     (None: the default group).  Goes to the process group's own entry point: the checks and logging of the
     torch.distributed wrapper cost more host time than the collective takes on the device."""
     global _SUM_OPTS
-    if active():
+    if active() and t.numel() > 0:
+        peer = _peer(channel, t)
+        if peer is not None:
+            peer.allreduce_sum_f64(t)
+            return t
         comm = _direct(channel, t)
         if comm is not None:
             comm.allreduce_sum_f64(t)
