@@ -14,7 +14,8 @@
 //     (4) waits until the W flags of its slice in its OWN window carry the token,
 //     (5) adds the W copies in rank order -- the same order on every rank, so all ranks hold bit-identical sums,
 //         which NCCL's ring does not promise -- and writes the result over the input slice,
-//     (6) tells every peer that its copy has been consumed (window[q].ack[slot][r][c] = token).
+//     (6) counts itself done; the last CTA of the launch tells every peer that this rank has consumed the slot
+//         (window[q].ack[slot][r] = token).
 //
 // Slices are independent: there is no barrier across the CTAs of a launch, and the exchange of one slice overlaps the
 // copies of the others.  Tokens are the call's sequence number + 1, the same on every rank because every rank issues
@@ -31,15 +32,16 @@
 namespace kb2 {
 
 constexpr int kPeerMaxWorld = 16;
-constexpr int kPeerMaxSlices = 32;
+constexpr int kPeerMaxSlices = 64;
 constexpr int kPeerThreads = 256;
-constexpr int kPeerSliceMin = 2048;  // doubles per slice before a second CTA is worth its launch
+constexpr int kPeerSliceMin = 1024;  // doubles per slice before a second CTA is worth its launch
 
 struct PeerWindows {
     unsigned char* base[kPeerMaxWorld];
 };
 
-// window layout: flags [slots][W][kPeerMaxSlices] u64 | acks (same) | data [slots][W][capacity] f64
+// window layout: flags [slots][W][kPeerMaxSlices] u64 | acks [slots][W] u64, done [slots] u64 (in a region of the size of
+// the flags) | data [slots][W][capacity] f64
 __host__ __device__ inline size_t peer_flag_words(int world, int slots) { return (size_t)slots * world * kPeerMaxSlices; }
 __host__ __device__ inline size_t peer_data_offset(int world, int slots) { return align256(2 * peer_flag_words(world, slots) * 8); }
 __host__ __device__ inline size_t peer_window_bytes(int world, int slots, int64_t capacity) {
@@ -83,9 +85,9 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(double* __
     __shared__ int s_bad;
     if (tid == 0) s_bad = 0;
     __syncthreads();
-    // (1) credit: the previous user of this slot (sequence seq - slots) has been consumed by every rank
+    // (1) credit: the previous user of this slot (sequence seq - slots, however it was sliced) has been consumed by every rank
     if (seq >= (unsigned long long)slots && tid < world) {
-        if (!wait_token(my_acks + cell + (size_t)tid * kPeerMaxSlices + c, token - slots, limit)) s_bad = 1;
+        if (!wait_token(my_acks + (size_t)slot * world + tid, token - slots, limit)) s_bad = 1;
     }
     __syncthreads();
     // (2) the slice goes to every window, the nearest "next" rank first so that the W ranks do not all write to rank 0 at once
@@ -136,11 +138,23 @@ __global__ void __launch_bounds__(kPeerThreads) peer_allreduce_kernel(double* __
             buf[i] = acc;
         }
     }
-    // (6) release the slot to its writers
+    // (6) the CTA that finishes last on this rank releases the slot to its writers
+    __shared__ int s_last;
     __syncthreads();
-    if (tid < world) {
+    if (tid == 0) {
+        __threadfence();
+        unsigned long long* done = my_acks + (size_t)slots * world + slot;
+        const unsigned long long before = atomicAdd(done, 1ull);
+        s_last = (before + 1 == (unsigned long long)gridDim.x);
+        if (s_last) {
+            atomicExch(done, 0ull);  // the next user of the slot cannot get here before the acknowledgements below
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    if (s_last && tid < world) {
         unsigned long long* acks_q = reinterpret_cast<unsigned long long*>(win.base[tid]) + words;
-        st_release_sys(acks_q + cell + (size_t)rank * kPeerMaxSlices + c, token);
+        st_release_sys(acks_q + (size_t)slot * world + rank, token);
     }
     if (tid == 0 && s_bad) atomicExch(status, s_bad);  // mapped host memory: visible without a synchronisation
 }
