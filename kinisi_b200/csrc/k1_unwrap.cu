@@ -672,6 +672,464 @@ __global__ void __launch_bounds__(kUwThreads, kUwCtasPerSm) unwrap_cumsum_kernel
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- unwrap + cumulative sum, one warp per atom ------------------------------------------------------------------
+// The kernel above cuts an atom into tiles handled by different CTAs and pays for it: three block barriers per tile (ncu:
+// 3.4 barrier-stall cycles per issue), a look-back through L2 flags, two memsets per call, 200 instructions per frame.
+// With at least a couple of atoms per SM there is enough parallelism ACROSS atoms, and the scan along time can stay inside
+// one warp: a warp owns an atom and walks its trajectory in sub-tiles of kWuE * 32 frames, carrying the running sum in
+// registers -- no barrier, no flag, no workspace.  What a warp cannot do with its own loads it gets from the TMA engine:
+//   stage s of the warp's ring (kWuStages stages)
+//     drift / out  [3][TW] f64    the per-frame framework sums of the sub-tile, bulk-copied from step_sums (L2-resident);
+//                                 the results overwrite them in place and leave with three bulk stores
+//     raw          (TW + 1) * 3   the sub-tile of the atom-major coordinate row, one contiguous bulk copy from the 16-byte
+//                                 boundary at or below its first element (`mis` elements early; the last bytes of the
+//                                 whole array, which a 16-byte copy would overrun, come with plain loads)
+//   lane 0 issues the copies of sub-tile i + kWuStages - 1 after the stores of sub-tile i - 1 have read their stage
+//   (cp.async.bulk.wait_group.read), every lane waits on the stage's mbarrier; a lane owns kWuE consecutive frames
+//   (kWuE odd: its walks through `raw`, stride 3 kWuE words, and through `out`, stride kWuE doubles, are conflict-free),
+//   unwraps them, scans them, adds the exclusive prefix of the lower lanes (five shuffle steps per component) and the
+//   running sum, and lane 31's last value is the new running sum.
+// So the bytes in flight no longer depend on registers or occupancy (6 warps per SM keep 18 stages = 146 KB in flight), a
+// frame costs ~60 instructions, and the sub-tiles of consecutive atoms follow each other without draining the ring.
+// Constant cell only (every front-end but an NPT run); the kernel above keeps the other modes and the calls with too few
+// atoms to fill the device this way.
+constexpr int kWuE = 7;
+constexpr int kWuTW = 32 * kWuE;  // frames per sub-tile (a multiple of 16: a sub-tile of the output row is 16-byte aligned)
+constexpr int kWuStages = 4;
+constexpr int kWuMaxWarps = 4;
+
+template <typename T>
+__host__ __device__ constexpr int wu_raw_bytes() {
+    return (int)((((kWuTW + 1) * 3 * sizeof(T) + 15 + 15) / 16) * 16);
+}
+template <typename T>
+__host__ __device__ constexpr int wu_stage_bytes() {
+    return 3 * kWuTW * 8 + wu_raw_bytes<T>();
+}
+template <typename T>
+__host__ __device__ constexpr int wu_warps_per_cta() {
+    return sizeof(T) == 4 ? 3 : 2;  // two CTAs per SM either way (97 KB / 105 KB of shared memory each)
+}
+
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(fb::smem_u32(ssrc)), "r"(bytes)
+                 : "memory");
+}
+
+template <typename T, bool DRIFT>
+__global__ void __launch_bounds__(kWuMaxWarps * 32) unwrap_cumsum_warp_kernel(const T* __restrict__ coords, int64_t n_coords, int F,
+                                                                         const double* __restrict__ latt,
+                                                                         const int32_t* __restrict__ idx, int n_idx,
+                                                                         const double* __restrict__ step_sums, double step_scale,
+                                                                         double* __restrict__ out, int64_t pitch, int Tn) {
+    using namespace fb;
+    constexpr int E = kWuE, TW = kWuTW, S = kWuStages, SB = wu_stage_bytes<T>();
+    extern __shared__ __align__(128) unsigned char wu_smem[];
+    __shared__ uint64_t full[kWuMaxWarps][S];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+    unsigned char* ring = wu_smem + (size_t)warp * S * SB;
+    if (lane == 0) {
+        for (int s = 0; s < S; ++s) mbar_init(&full[warp][s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    // atoms of this warp: i = blockIdx.x + gridDim.x * (warp + wpc * m), m = 0, 1, ... (consecutive atoms go to different SMs)
+    const int first_atom = blockIdx.x + gridDim.x * warp;
+    const int atom_step = gridDim.x * wpc;
+    if (first_atom >= n_idx) return;
+    const int n_my = (n_idx - first_atom + atom_step - 1) / atom_step;
+    const int n_sub = (int)((pitch + TW - 1) / TW);
+    const int64_t n_jobs = (int64_t)n_my * n_sub;
+    const char* const arr_end = reinterpret_cast<const char*>(coords + n_coords);
+
+    // lane 0: the copies of job j (atom m = j / n_sub, sub-tile j % n_sub) into stage j % S
+    auto issue = [&](int64_t j) {
+        const int m = (int)(j / n_sub), sub = (int)(j - (int64_t)m * n_sub), s = (int)(j % S);
+        const int a = first_atom + m * atom_step;
+        const int t0 = sub * TW;
+        const int nf = max(0, min(TW, Tn - t0));
+        unsigned char* st = ring + (size_t)s * SB;
+        if (nf == 0) {  // a sub-tile of the zero pad: nothing to fetch
+            mbar_arrive(&full[warp][s]);
+            return;
+        }
+        const T* first = coords + ((size_t)__ldg(idx + a) * F + t0) * 3;
+        const int mis = (int)((reinterpret_cast<uintptr_t>(first) & 15) / sizeof(T));
+        const char* src = reinterpret_cast<const char*>(first - mis);
+        unsigned char* dst = st + 3 * TW * 8;
+        const int bytes = (int)((((size_t)(mis + 3 * (nf + 1)) * sizeof(T)) + 15) / 16) * 16;
+        const long long room = ((arr_end - src) / 16) * 16;
+        int bulk = bytes;
+        if ((long long)bulk > room) {
+            bulk = (int)room;
+            const T* g = reinterpret_cast<const T*>(src + bulk);
+            T* d = reinterpret_cast<T*>(dst + bulk);
+            for (int k = 0; g + k < coords + n_coords && (long long)bulk + (k + 1) * (long long)sizeof(T) <= bytes; ++k) d[k] = g[k];
+        }
+        const int nd = (int)min((int64_t)TW, pitch - t0) * 8;  // bytes of one component of the drift (pitch is even: 16 | nd)
+        mbar_arrive_expect_tx(&full[warp][s], (uint32_t)(bulk + (DRIFT ? 3 * nd : 0)));
+        if (bulk > 0) bulk_g2s(dst, src, (uint32_t)bulk, &full[warp][s]);
+        if (DRIFT) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bulk_g2s(st + c * TW * 8, step_sums + c * pitch + t0, (uint32_t)nd, &full[warp][s]);
+        }
+    };
+
+    double L[9];
+    load9(latt, L);
+    if (lane == 0) {
+        for (int64_t j = 0; j < min((int64_t)(S - 1), n_jobs); ++j) issue(j);
+    }
+    double carry[3] = {0.0, 0.0, 0.0};
+    int sub = 0, m = 0, mis = 0;
+    int a = first_atom;
+#pragma unroll 1
+    for (int64_t j = 0; j < n_jobs; ++j) {
+        const int s = (int)(j % S);
+        if (sub == 0) {
+            const T* row = coords + (size_t)__ldg(idx + a) * F * 3;
+            mis = (int)((reinterpret_cast<uintptr_t>(row) & 15) / sizeof(T));  // TW * 3 elements are a multiple of 16 bytes:
+            carry[0] = carry[1] = carry[2] = 0.0;                             // the same for every sub-tile of the atom
+        }
+        const int t0 = sub * TW;
+        unsigned char* st = ring + (size_t)s * SB;
+        double* outs = reinterpret_cast<double*>(st);
+        mbar_wait(&full[warp][s], (uint32_t)((j / S) & 1));
+        const int f0 = lane * E;
+        double val[E][3];
+        if (t0 + f0 < Tn) {
+            const T* raw = reinterpret_cast<const T*>(st + 3 * TW * 8) + mis + f0 * 3;
+            T r[E + 1][3];
+#pragma unroll
+            for (int e = 0; e <= E; ++e)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) r[e][k] = raw[e * 3 + k];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                double u[3];
+                unwrapped_step_const<T>(r[e + 1], r[e], L, u);
+                const bool live = (t0 + f0 + e < Tn);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    double x = u[c];
+                    if (DRIFT) x -= step_scale * outs[c * TW + f0 + e];
+                    val[e][c] = live ? x : 0.0;
+                }
+            }
+#pragma unroll
+            for (int e = 1; e < E; ++e)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) val[e][c] += val[e - 1][c];
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) val[e][c] = 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double incl = warp_inclusive_scan(val[E - 1][c], lane);
+            const double off = carry[c] + (incl - val[E - 1][c]);
+#pragma unroll
+            for (int e = 0; e < E; ++e) val[e][c] += off;
+            carry[c] = __shfl_sync(0xffffffffu, val[E - 1][c], 31);
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) outs[c * TW + f0 + e] = (t0 + f0 + e < Tn) ? val[e][c] : 0.0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const uint32_t nd = (uint32_t)min((int64_t)TW, pitch - t0) * 8u;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bulk_s2g(out + ((size_t)a * 3 + c) * pitch + t0, outs + c * TW, nd);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (j + S - 1 < n_jobs) {
+                // stage (j - 1) % S is refilled once the stores of job j - 1 have read it (the group before the newest)
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                issue(j + S - 1);
+            }
+        }
+        __syncwarp();
+        if (++sub == n_sub) {
+            sub = 0;
+            ++m;
+            a += atom_step;
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+template <typename T>
+static int launch_unwrap_warp(const void* coords, int n_atoms_total, int F, const double* latt, const int32_t* idx, int n_idx,
+                              const double* step_sums, double step_scale, double* out, int64_t pitch, int Tn, cudaStream_t st) {
+    const int sm = device_sm_count();
+    const int wpc = wu_warps_per_cta<T>();
+    const size_t smem = (size_t)wpc * kWuStages * wu_stage_bytes<T>();
+    const int grid = std::min(2 * sm, ceil_div(n_idx, wpc));
+#define KB2_WU(D)                                                                                                            \
+    do {                                                                                                                     \
+        KB2_CUDA(cudaFuncSetAttribute(unwrap_cumsum_warp_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        unwrap_cumsum_warp_kernel<T, D><<<grid, wpc * 32, smem, st>>>((const T*)coords, (int64_t)n_atoms_total * F * 3, F, latt, idx, \
+                                                                      n_idx, step_sums, step_scale, out, pitch, Tn);        \
+    } while (0)
+    if (step_sums)
+        KB2_WU(true);
+    else
+        KB2_WU(false);
+#undef KB2_WU
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- unwrap + cumulative sum, tiles through bulk copies -------------------------------------------------------------
+// The (atom, 1280-frame tile) items, the ticket counter and the look-back over tile totals of unwrap_cumsum_kernel, with
+// the three things ncu charged it for taken out:
+//   * the 256-thread 16-byte cp.async loop with its bounds tests, and the 15 strided 8-byte drift loads per thread, are
+//     four bulk copies issued by ONE thread of a producer warp (TMA engine, completion on the stage's `full` mbarrier);
+//     the producer draws the tickets and runs up to two items ahead of the consumers;
+//   * the drift lands in the [3][TF] staging area, the results overwrite it in place and leave through bulk stores issued
+//     per warp (no output pass, no barrier in front of it); a stage goes back to the producer (`empty` mbarrier) once the
+//     stores have read it;
+//   * one named barrier per tile (the warp totals) instead of three block barriers: the look-back is done by every warp
+//     for itself (a tile has at most a few dozen predecessors), before the results are staged.
+// float32 coordinates, constant cell; everything else takes the kernels above.
+constexpr int kUbE = 5;
+constexpr int kUbThreads = 256;                // consumer threads; + one producer warp
+constexpr int kUbTile = kUbThreads * kUbE;     // = kUwTile: the workspace layout is shared
+static_assert(kUbTile == kUwTile, "the two tile kernels share kb2_unwrap_cumsum_workspace_bytes");
+
+template <typename T>
+__host__ __device__ constexpr int ub_raw_bytes() {
+    return (int)((((kUbTile + 1) * 3 * sizeof(T) + 15 + 15) / 16) * 16);
+}
+template <typename T>
+__host__ __device__ constexpr int ub_stage_bytes() {
+    return 3 * kUbTile * 8 + ub_raw_bytes<T>();
+}
+
+template <typename T, bool DRIFT>
+__global__ void __launch_bounds__(kUbThreads + 32, 2) unwrap_cumsum_bulk_kernel(const T* __restrict__ coords, int64_t n_coords, int F,
+                                                                              const double* __restrict__ latt,
+                                                                              const int32_t* __restrict__ idx, int n_idx,
+                                                                              const double* __restrict__ step_sums, double step_scale,
+                                                                              double* __restrict__ out, int64_t pitch, int Tn,
+                                                                              int n_tiles, unsigned char* __restrict__ workspace) {
+    using namespace fb;
+    constexpr int E = kUbE, TF = kUbTile, NT = kUbThreads, NW = NT / 32, SB = ub_stage_bytes<T>();
+    extern __shared__ __align__(128) unsigned char ub_smem[];
+    __shared__ uint64_t full[2], empty[2];
+    __shared__ unsigned int s_item[2];
+    __shared__ int s_mis[2];
+    __shared__ double s_tot[2][3][NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int n_work = (unsigned int)n_idx * (unsigned int)n_tiles;
+    unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);  // preset to 0xFFFFFFFF: the first ticket wraps to 0
+    double* totals = reinterpret_cast<double*>(workspace + 256);
+    if (tid == 0) {
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&full[b], 1);
+            mbar_init(&empty[b], NW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == NW) {
+        // ---- producer: tickets and bulk copies, up to two items ahead
+        if (lane == 0) {
+            const char* const arr_end = reinterpret_cast<const char*>(coords + n_coords);
+#pragma unroll 1
+            for (int it = 0;; ++it) {
+                const int b = it & 1;
+                if (it >= 2) mbar_wait(&empty[b], (uint32_t)(((it >> 1) - 1) & 1));
+                const unsigned int w = atomicAdd(counter, 1u) + 1u;
+                s_item[b] = w;
+                if (w >= n_work) {
+                    mbar_arrive(&full[b]);
+                    break;
+                }
+                const int atom = (int)(w % (unsigned)n_idx), tile = (int)(w / (unsigned)n_idx);  // tile-major order
+                const int t0 = tile * TF;
+                const int nf = max(0, min(TF, Tn - t0));
+                unsigned char* st = ub_smem + (size_t)b * SB;
+                if (nf == 0) {  // a tile of the zero pad
+                    s_mis[b] = 0;
+                    mbar_arrive(&full[b]);
+                    continue;
+                }
+                const T* first = coords + ((size_t)__ldg(idx + atom) * F + t0) * 3;
+                const int mis = (int)((reinterpret_cast<uintptr_t>(first) & 15) / sizeof(T));
+                const char* src = reinterpret_cast<const char*>(first - mis);
+                unsigned char* dst = st + 3 * TF * 8;
+                const int bytes = (int)((((size_t)(mis + 3 * (nf + 1)) * sizeof(T)) + 15) / 16) * 16;
+                const long long room = ((arr_end - src) / 16) * 16;
+                int bulk = bytes;
+                if ((long long)bulk > room) {  // the last bytes of the whole array: plain loads
+                    bulk = (int)room;
+                    const T* g = reinterpret_cast<const T*>(src + bulk);
+                    T* d = reinterpret_cast<T*>(dst + bulk);
+                    for (int k = 0; g + k < coords + n_coords && (long long)bulk + (k + 1) * (long long)sizeof(T) <= bytes; ++k) d[k] = g[k];
+                }
+                s_mis[b] = mis;
+                const int nd = (int)min((int64_t)TF, pitch - t0) * 8;
+                mbar_arrive_expect_tx(&full[b], (uint32_t)(bulk + (DRIFT ? 3 * nd : 0)));
+                if (bulk > 0) bulk_g2s(dst, src, (uint32_t)bulk, &full[b]);
+                if (DRIFT) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) bulk_g2s(st + c * TF * 8, step_sums + c * pitch + t0, (uint32_t)nd, &full[b]);
+                }
+            }
+        }
+        return;
+    }
+    // ---- consumers
+    double L[9];
+    load9(latt, L);
+    const int f0 = tid * E;
+#pragma unroll 1
+    for (int it = 0;; ++it) {
+        const int b = it & 1;
+        mbar_wait(&full[b], (uint32_t)((it >> 1) & 1));
+        const unsigned int w = s_item[b];
+        if (w >= n_work) break;
+        if (it >= 1 && lane == 0) {  // the stores of the previous item have read the other stage: back to the producer
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive(&empty[b ^ 1]);
+        }
+        const int atom = (int)(w % (unsigned)n_idx), tile = (int)(w / (unsigned)n_idx);
+        const int t0 = tile * TF;
+        double* tot_atom = totals + (size_t)atom * n_tiles * 3;
+        // look back early: lane j asks for the total of tile j of this atom now (an L2 round trip under the unwrapping)
+        unsigned long long early[3] = {kUwNotReady, kUwNotReady, kUwNotReady};
+        if (lane < tile) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) early[c] = ld_l2_u64(tot_atom + lane * 3 + c);
+        }
+        unsigned char* st = ub_smem + (size_t)b * SB;
+        double* outs = reinterpret_cast<double*>(st);
+        double val[E][3];
+        if (t0 + f0 < Tn) {
+            const T* raw = reinterpret_cast<const T*>(st + 3 * TF * 8) + s_mis[b] + f0 * 3;
+            T r[E + 1][3];
+#pragma unroll
+            for (int e = 0; e <= E; ++e)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) r[e][k] = raw[e * 3 + k];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                double u[3];
+                unwrapped_step_const<T>(r[e + 1], r[e], L, u);
+                const bool live = (t0 + f0 + e < Tn);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    double x = u[c];
+                    if (DRIFT) x -= step_scale * outs[c * TF + f0 + e];
+                    val[e][c] = live ? x : 0.0;
+                }
+            }
+#pragma unroll
+            for (int e = 1; e < E; ++e)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) val[e][c] += val[e - 1][c];
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) val[e][c] = 0.0;
+        }
+        double incl[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            incl[c] = warp_inclusive_scan(val[E - 1][c], lane);
+            if (lane == 31) s_tot[b][c][warp] = incl[c];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");  // the consumer warps only
+        // publish the tile total before collecting: no tile ever waits for another tile's wait
+        if (tid >= NT - 3 && n_tiles > 1) {
+            const int c = tid - (NT - 3);
+            double tot = 0.0;
+#pragma unroll
+            for (int wdx = 0; wdx < NW; ++wdx) tot += s_tot[b][c][wdx];
+            __stcg(tot_atom + tile * 3 + c, tot);
+        }
+        // the totals of the earlier tiles of this atom, collected by every warp for itself
+        double pc[3] = {0.0, 0.0, 0.0};
+        for (int j = lane; j < tile; j += 32) {
+            unsigned long long bits[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) bits[c] = (j == lane) ? early[c] : ld_l2_u64(tot_atom + j * 3 + c);
+            while (bits[0] == kUwNotReady || bits[1] == kUwNotReady || bits[2] == kUwNotReady) {
+                __nanosleep(32);
+#pragma unroll
+                for (int c = 0; c < 3; ++c) bits[c] = ld_l2_u64(tot_atom + j * 3 + c);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) pc[c] += __longlong_as_double((long long)bits[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double off = (tile > 0) ? warp_sum(pc[c]) : 0.0;
+#pragma unroll
+            for (int wdx = 0; wdx < NW; ++wdx) off += (wdx < warp) ? s_tot[b][c][wdx] : 0.0;
+            off += incl[c] - val[E - 1][c];
+#pragma unroll
+            for (int e = 0; e < E; ++e) outs[c * TF + f0 + e] = (t0 + f0 + e < Tn) ? val[e][c] + off : 0.0;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const int64_t w0 = (int64_t)t0 + warp * 32 * E;  // this warp's 160 frames of the three rows
+            const int64_t n_out = min((int64_t)(32 * E), pitch - w0);
+            if (n_out > 0) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    bulk_s2g(out + ((size_t)atom * 3 + c) * pitch + w0, outs + c * TF + warp * 32 * E, (uint32_t)(n_out * 8));
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+template <typename T>
+static int launch_unwrap_bulk(const void* coords, int n_atoms_total, int F, const double* latt, const int32_t* idx, int n_idx,
+                              const double* step_sums, double step_scale, double* out, int64_t pitch, int Tn, void* workspace,
+                              cudaStream_t st) {
+    const int sm = device_sm_count();
+    const size_t smem = 2 * (size_t)ub_stage_bytes<T>();
+    const int n_tiles = ceil_div(pitch, kUbTile);
+    KB2_CHECK((int64_t)n_idx * n_tiles < (1ll << 31), "kb2_unwrap_cumsum: too many (atom, tile) pairs for one call");
+    // ticket counter = 0xFFFFFFFF (the first atomicAdd + 1 wraps to ticket 0); totals = the "not ready" pattern: one memset
+    KB2_CUDA(cudaMemsetAsync(workspace, 0xFF, uw_workspace_bytes(n_idx, n_tiles), st));
+    const int grid = (int)std::min<int64_t>((int64_t)n_idx * n_tiles, (int64_t)sm * 2);
+#define KB2_UB(D)                                                                                                            \
+    do {                                                                                                                     \
+        KB2_CUDA(cudaFuncSetAttribute(unwrap_cumsum_bulk_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        unwrap_cumsum_bulk_kernel<T, D><<<grid, kUbThreads + 32, smem, st>>>((const T*)coords, (int64_t)n_atoms_total * F * 3, F,  \
+                                                                             latt, idx, n_idx, step_sums, step_scale, out, pitch, \
+                                                                             Tn, n_tiles, (unsigned char*)workspace);        \
+    } while (0)
+    if (step_sums)
+        KB2_UB(true);
+    else
+        KB2_UB(false);
+#undef KB2_UB
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+// which kernel kb2_unwrap_cumsum takes for float32 / float64 fractional coordinates in a constant cell.  KB2_UW_KERNEL:
+// 0 the cp.async tile kernel, 1 the warp-per-atom kernel, 2 the bulk-copy tile kernel (float32), unset: the default below
+static int unwrap_kernel_choice() {
+    const char* e = getenv("KB2_UW_KERNEL");  // (read per call: the tests switch it)
+    return e && e[0] ? atoi(e) : -1;
+}
+
+
 // Weighted sum over atoms of a component-major displacement array: out[c][t] += sum_a w[a] dc[a][c][t].
 // The collective displacement of MSTD (diffusion.py:659) and the charge-weighted one of MSCD (:751).
 __global__ void __launch_bounds__(256) atom_sum_kernel(const double* __restrict__ dc, int n_atoms, int64_t pitch,
@@ -803,6 +1261,18 @@ extern "C" int kb2_unwrap_cumsum(const void* coords, int dtype, int mode, int n_
         return rc;
     KB2_CHECK(dc_out && workspace, "kb2_unwrap_cumsum: null output or workspace");
     cudaStream_t st = (cudaStream_t)stream;
+    if (mode == KB2_MODE_FRACTIONAL && latt_stride == 0 && (reinterpret_cast<uintptr_t>(dc_out) & 15) == 0 &&
+        (!step_sums || (reinterpret_cast<uintptr_t>(step_sums) & 15) == 0)) {
+        int choice = unwrap_kernel_choice();
+        if (choice < 0) choice = (dtype == KB2_F32) ? 2 : 0;
+        if (choice == 2 && dtype == KB2_F32)
+            return launch_unwrap_bulk<float>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, step_sums, step_scale, dc_out, pitch, Tn, workspace, st);
+        if (choice == 1) {
+            if (dtype == KB2_F32)
+                return launch_unwrap_warp<float>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, step_sums, step_scale, dc_out, pitch, Tn, st);
+            return launch_unwrap_warp<double>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, step_sums, step_scale, dc_out, pitch, Tn, st);
+        }
+    }
 #define KB2_UC(T, M, C) \
     return launch_unwrap<T, M, C>(coords, n_atoms_total, n_frames_in, latt, latt_inv, latt_stride, idx, n_idx, step_sums, step_scale, dc_out, pitch, Tn, workspace, st)
     const bool constl = (mode == KB2_MODE_FRACTIONAL && latt_stride == 0);

@@ -1121,6 +1121,58 @@ def test_full_size_stage1_against_torch_fp64(kb):
         assert pad.numel() == 0 or float(pad.abs().max()) == 0.0  # the row padding stays zero
 
 
+@pytest.mark.parametrize('dtype', [np.float32, np.float64])
+@pytest.mark.parametrize('drift', [True, False])
+@pytest.mark.parametrize('shape', [(5, 3, 40), (37, 9, 223), (64, 8, 224), (70, 11, 225), (33, 7, 1571), (1000, 30, 301),
+                                   (2100, 12, 449), (311, 5, 1280), (40, 6, 1281), (9, 4, 6431)])
+def test_unwrap_kernels_agree(kb, monkeypatch, dtype, drift, shape):
+    """The three unwrap kernels -- the bulk-copy tile kernel (producer warp, TMA loads and stores; the default for
+    float32), the one-warp-per-atom kernel (bulk-copy ring, scan carried in registers) and the cp.async tile kernel --
+    against each other and against float64 torch: rows at every misalignment (odd frame counts), tiles and sub-tiles that
+    end inside the trajectory, one and several tiles per atom (look-back), more atoms than warps (a warp walks several
+    atoms without draining its ring), a scattered selection that includes the last row of the array (the bytes a 16-byte
+    copy would overrun), with and without the framework drift, and a zero row pad."""
+    from kinisi_b200._lib import MODE_FRACTIONAL
+    n_sel, n_fw, n_frames = shape
+    dev = torch.device('cuda')
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(11 + n_frames)
+    n_all = n_sel + n_fw + 3
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    steps = torch.randn((n_all, n_frames + 1, 3), dtype=torch.float64, device=dev, generator=gen) * 0.05
+    steps[:, 0] = torch.rand((n_all, 3), dtype=torch.float64, device=dev, generator=gen)
+    coords = (torch.cumsum(steps, dim=1) % 1.0).to(tdt).contiguous()
+    cell = np.array([[9.0, 0.3, 0.0], [0.0, 8.0, 0.2], [0.4, 0.0, 10.0]])
+    latt = torch.tensor(cell, dtype=torch.float64, device=dev).reshape(1, 3, 3)
+    inv = kb.engine.invert_lattice(latt)
+    perm = torch.randperm(n_all, device=dev, generator=gen)
+    sel = perm[:n_sel].to(torch.int32)
+    sel[0] = n_all - 1  # the last row of the coordinate array
+    fw = perm[n_sel:n_sel + n_fw].to(torch.int32).contiguous()
+    pitch = kb.engine.pitch_for(n_frames) + (32 if n_frames % 2 else 0)  # sometimes a pad longer than a 16-frame round-up
+    sums = kb.engine.frame_sums(coords, MODE_FRACTIONAL, latt, inv, 0, fw, None, pitch) if drift else None
+    scale = 1.0 / n_fw if drift else 0.0
+    got = {}
+    modes = ('2', '1', '0') if dtype == np.float32 else ('1', '0')
+    for mode in modes:
+        monkeypatch.setenv('KB2_UW_KERNEL', mode)
+        out = torch.full((n_sel, 3, pitch), float('nan'), dtype=torch.float64, device=dev)
+        got[mode] = kb.engine.unwrap_cumsum(coords, MODE_FRACTIONAL, latt, inv, 0, sel, sums, scale, pitch, out=out).clone()
+    monkeypatch.delenv('KB2_UW_KERNEL')
+    f64 = coords.to(torch.float64)[sel.long()]
+    d = f64[:, 1:] - f64[:, :-1]
+    u = (d - torch.floor(d + 0.5)) @ latt[0]
+    if drift:
+        u = u - sums[:, :n_frames].T[None] * scale
+    ref = torch.cumsum(u, dim=1).permute(0, 2, 1)
+    tol = 1e-12 * float(ref.abs().max()) * max(1.0, n_frames / 200)
+    for mode in modes:
+        assert not torch.isnan(got[mode]).any(), mode
+        assert float((got[mode][:, :, :n_frames] - ref).abs().max()) <= tol, mode
+        assert pitch == n_frames or float(got[mode][:, :, n_frames:].abs().max()) == 0.0, mode
+        assert float((got[mode] - got['0']).abs().max()) <= tol, mode
+
+
 def test_full_size_properties(kb):
     n_atoms, n_frames = 448, 20000
     dev = torch.device('cuda')

@@ -1,5 +1,5 @@
 """Times the stage-1 kernels (frame sums of the framework, unwrap + cumulative sum of the mobile atoms) on configs[1]."""
-import sys
+import os, sys
 sys.path.insert(0, '/root/repo')
 import numpy as np, torch
 from kinisi_b200 import engine
@@ -24,9 +24,19 @@ def timeit(fn, n=20):
     for _ in range(n): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-sums = engine.frame_sums(coords, MODE_FRACTIONAL, latt, inv, 0, fw, None, pitch)
-t_fs = timeit(lambda: engine.frame_sums(coords, MODE_FRACTIONAL, latt, inv, 0, fw, None, pitch))
-t_uw = timeit(lambda: engine.unwrap_cumsum(coords, MODE_FRACTIONAL, latt, inv, 0, idx, sums, 1.0 / n_fw, pitch))
+if n_fw:
+    sums = engine.frame_sums(coords, MODE_FRACTIONAL, latt, inv, 0, fw, None, pitch)
+    t_fs = timeit(lambda: engine.frame_sums(coords, MODE_FRACTIONAL, latt, inv, 0, fw, None, pitch))
+else:
+    sums, t_fs = None, float('nan')
+out = torch.empty((n_mob, 3, pitch), dtype=torch.float64, device=dev)
 b_fs = n_fw * (T + 1) * 12
 b_uw = n_mob * (T + 1) * 12 + n_mob * 3 * pitch * 8
-print('frame_sums %.1f us  %.0f GB/s   unwrap_cumsum %.1f us  %.0f GB/s' % (t_fs * 1e3, b_fs / t_fs / 1e6, t_uw * 1e3, b_uw / t_uw / 1e6))
+line = 'frame_sums %.1f us  %.0f GB/s' % (t_fs * 1e3, b_fs / t_fs / 1e6)
+for name, mode in (('cp.async tile kernel', '0'), ('warp-per-atom kernel', '1'), ('bulk-copy tile kernel', '2')):
+    if len(sys.argv) > 4 and sys.argv[4] != mode:
+        continue
+    os.environ['KB2_UW_KERNEL'] = mode
+    t_uw = timeit(lambda: engine.unwrap_cumsum(coords, MODE_FRACTIONAL, latt, inv, 0, idx, sums, 1.0 / max(n_fw, 1), pitch, out=out))
+    line += '   unwrap_cumsum (%s) %.1f us  %.0f GB/s' % (name, t_uw * 1e3, b_uw / t_uw / 1e6)
+print(line)
