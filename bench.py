@@ -666,6 +666,26 @@ def run_own(args):
                                                   1.0 / n_fw, pitch, out=uw_out))
     del uw_out
     e2e_ms, _, b2 = timed(host, args.steps)
+    # the other half of BASELINE.json's metric, "wall time per trajectory": one analysis at a time on one stream, each waited
+    # for before the next starts (device-resident input and pinned host input)
+    def latency(coords, n=8):
+        ms = []
+        for i in range(n + 2):
+            if world > 1:
+                td.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            b1 = step(coords)
+            _ = b1.flatchain
+            torch.cuda.synchronize()
+            if i >= 2:
+                ms.append(1e3 * (time.perf_counter() - t0))
+        t = torch.tensor([float(np.median(ms))], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t[0])
+
+    lat_resident_ms, lat_host_ms = latency(resident), latency(host)
     clocks = sampler.stop() if sampler is not None else None
     # the same bytes as a plain pinned host->device copy on every rank at once: the ceiling of `e2e` (one host feeds all GPUs)
     if world > 1:
@@ -749,6 +769,8 @@ def run_own(args):
                     'ms_per_step': e2e_ms / args.steps, 'plain_pinned_h2d_ms_per_step': plain_h2d_ms,
                     'plain_pinned_h2d_gbs_per_gpu': host.numel() * host.element_size() / (plain_h2d_ms * 1e-3) / 1e9,
                     'fraction_of_plain_h2d': plain_h2d_ms / (e2e_ms / args.steps)},
+            'latency': {'what': 'wall time of ONE analysis (stages 1-3, result read back), nothing else in flight; median of 8',
+                        'device_resident_input_ms': lat_resident_ms, 'pinned_host_input_ms': lat_host_ms},
             'gpu_launches': int(launches),
             'clocks': clocks,
             'roofline': {

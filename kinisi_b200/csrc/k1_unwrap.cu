@@ -916,13 +916,13 @@ __global__ void __launch_bounds__(kUbThreads + 32, 2) unwrap_cumsum_bulk_kernel(
                                                                               const int32_t* __restrict__ idx, int n_idx,
                                                                               const double* __restrict__ step_sums, double step_scale,
                                                                               double* __restrict__ out, int64_t pitch, int Tn,
-                                                                              int n_tiles, unsigned char* __restrict__ workspace) {
+                                                                              int n_tiles, unsigned char* __restrict__ workspace, int opts) {
     using namespace fb;
     constexpr int E = kUbE, TF = kUbTile, NT = kUbThreads, NW = NT / 32, SB = ub_stage_bytes<T>();
     extern __shared__ __align__(128) unsigned char ub_smem[];
     __shared__ uint64_t full[2], empty[2];
     __shared__ unsigned int s_item[2];
-    __shared__ int s_mis[2];
+    __shared__ int s_mis[2], s_atom[2], s_tile[2];
     __shared__ double s_tot[2][3][NW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned int n_work = (unsigned int)n_idx * (unsigned int)n_tiles;
@@ -955,6 +955,8 @@ __global__ void __launch_bounds__(kUbThreads + 32, 2) unwrap_cumsum_bulk_kernel(
                 const int t0 = tile * TF;
                 const int nf = max(0, min(TF, Tn - t0));
                 unsigned char* st = ub_smem + (size_t)b * SB;
+                s_atom[b] = atom;
+                s_tile[b] = tile;
                 if (nf == 0) {  // a tile of the zero pad
                     s_mis[b] = 0;
                     mbar_arrive(&full[b]);
@@ -995,23 +997,28 @@ __global__ void __launch_bounds__(kUbThreads + 32, 2) unwrap_cumsum_bulk_kernel(
         mbar_wait(&full[b], (uint32_t)((it >> 1) & 1));
         const unsigned int w = s_item[b];
         if (w >= n_work) break;
-        if (it >= 1 && lane == 0) {  // the stores of the previous item have read the other stage: back to the producer
+        if (it >= 1 && lane == 0) {  // the stores of the previous item have read the other stage: back to the producer at once
+            // (handing it back after the unwrapping instead, when the wait is free, costs the producer half an item of lead:
+            // 84 -> 91 us at configs[1])
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             mbar_arrive(&empty[b ^ 1]);
         }
-        const int atom = (int)(w % (unsigned)n_idx), tile = (int)(w / (unsigned)n_idx);
+        const int atom = s_atom[b], tile = s_tile[b];
         const int t0 = tile * TF;
         double* tot_atom = totals + (size_t)atom * n_tiles * 3;
+        unsigned char* st = ub_smem + (size_t)b * SB;
+        double* outs = reinterpret_cast<double*>(st);
+        // the body of an item, instantiated without the end-of-trajectory tests for tiles that lie inside it
+        auto body = [&](auto full_tag) __attribute__((always_inline)) {
+            constexpr bool FULL = decltype(full_tag)::value;
         // look back early: lane j asks for the total of tile j of this atom now (an L2 round trip under the unwrapping)
         unsigned long long early[3] = {kUwNotReady, kUwNotReady, kUwNotReady};
         if (lane < tile) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) early[c] = ld_l2_u64(tot_atom + lane * 3 + c);
         }
-        unsigned char* st = ub_smem + (size_t)b * SB;
-        double* outs = reinterpret_cast<double*>(st);
         double val[E][3];
-        if (t0 + f0 < Tn) {
+        if (FULL || t0 + f0 < Tn) {
             const T* raw = reinterpret_cast<const T*>(st + 3 * TF * 8) + s_mis[b] + f0 * 3;
             T r[E + 1][3];
 #pragma unroll
@@ -1022,7 +1029,7 @@ __global__ void __launch_bounds__(kUbThreads + 32, 2) unwrap_cumsum_bulk_kernel(
             for (int e = 0; e < E; ++e) {
                 double u[3];
                 unwrapped_step_const<T>(r[e + 1], r[e], L, u);
-                const bool live = (t0 + f0 + e < Tn);
+                const bool live = FULL || (t0 + f0 + e < Tn);
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     double x = u[c];
@@ -1072,12 +1079,17 @@ __global__ void __launch_bounds__(kUbThreads + 32, 2) unwrap_cumsum_bulk_kernel(
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             double off = (tile > 0) ? warp_sum(pc[c]) : 0.0;
-#pragma unroll
-            for (int wdx = 0; wdx < NW; ++wdx) off += (wdx < warp) ? s_tot[b][c][wdx] : 0.0;
+#pragma unroll 1
+            for (int wdx = 0; wdx < warp; ++wdx) off += s_tot[b][c][wdx];  // (a warp-uniform trip count)
             off += incl[c] - val[E - 1][c];
 #pragma unroll
-            for (int e = 0; e < E; ++e) outs[c * TF + f0 + e] = (t0 + f0 + e < Tn) ? val[e][c] + off : 0.0;
+            for (int e = 0; e < E; ++e) outs[c * TF + f0 + e] = (FULL || t0 + f0 + e < Tn) ? val[e][c] + off : 0.0;
         }
+        };
+        if (!(opts & 1) && t0 + TF <= Tn)
+            body(std::true_type{});
+        else
+            body(std::false_type{});
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
@@ -1106,12 +1118,14 @@ static int launch_unwrap_bulk(const void* coords, int n_atoms_total, int F, cons
     // ticket counter = 0xFFFFFFFF (the first atomicAdd + 1 wraps to ticket 0); totals = the "not ready" pattern: one memset
     KB2_CUDA(cudaMemsetAsync(workspace, 0xFF, uw_workspace_bytes(n_idx, n_tiles), st));
     const int grid = (int)std::min<int64_t>((int64_t)n_idx * n_tiles, (int64_t)sm * 2);
+    const char* eo = getenv("KB2_UB_OPTS");  // bit 0: no separate instantiation for full tiles (diagnostics)
+    const int opts = eo ? atoi(eo) : 0;
 #define KB2_UB(D)                                                                                                            \
     do {                                                                                                                     \
         KB2_CUDA(cudaFuncSetAttribute(unwrap_cumsum_bulk_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         unwrap_cumsum_bulk_kernel<T, D><<<grid, kUbThreads + 32, smem, st>>>((const T*)coords, (int64_t)n_atoms_total * F * 3, F,  \
                                                                              latt, idx, n_idx, step_sums, step_scale, out, pitch, \
-                                                                             Tn, n_tiles, (unsigned char*)workspace);        \
+                                                                             Tn, n_tiles, (unsigned char*)workspace, opts); \
     } while (0)
     if (step_sums)
         KB2_UB(true);

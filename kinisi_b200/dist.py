@@ -23,6 +23,9 @@ def active():
     if _STATE['group'] is not g:
         _STATE['group'], _STATE['active'] = g, td.get_world_size() > 1
         _CHANNELS.clear()
+        for comm in _DIRECT.values():
+            if comm is not None:
+                comm.close()
         _DIRECT.clear()
         for ch in _PEER.values():
             if ch:
@@ -63,7 +66,10 @@ class _DirectComm:
     bookkeeping: 115-130 us of host time per call in the analysis loop, which made the host thread the bottleneck of a
     sharded run.  Here `ncclAllReduce` is enqueued on the CALLER's stream, about 10 us.  Calls on
     one communicator must run in the same order on every rank; they come from different streams (analyses in flight), so
-    each call waits for the event of the previous one on this communicator."""
+    each call waits for the event of the previous one on this communicator.  Collectives on DIFFERENT communicators can run
+    at the same time on different streams; that is safe only because every rank issues them in the same host program order
+    (one analysis after the other, the same stages in each) -- a requirement of this module, as it is of NCCL itself.
+    Used only where the peer-memory windows of `_PeerChannel` cannot be mapped."""
     _lib = None
 
     @classmethod
@@ -84,6 +90,7 @@ class _DirectComm:
                                           ctypes.c_void_p, ctypes.c_void_p]
             lib.ncclGetErrorString.restype = ctypes.c_char_p
             lib.ncclGetErrorString.argtypes = [ctypes.c_int]
+            lib.ncclCommDestroy.argtypes = [ctypes.c_void_p]
             cls._lib = lib
         return cls._lib
 
@@ -103,6 +110,13 @@ class _DirectComm:
     def _check(self, rc):
         if rc != 0:
             raise RuntimeError('NCCL: ' + self.library().ncclGetErrorString(rc).decode())
+
+    def close(self):
+        """Destroys the communicator (after the work enqueued on it has finished)."""
+        if self._comm is not None and self._comm.value:
+            torch.cuda.synchronize(self.device)
+            self.library().ncclCommDestroy(self._comm)
+        self._comm = None
 
     def allreduce_sum_f64(self, t):
         stream = torch.cuda.current_stream(t.device)
