@@ -5,7 +5,7 @@ import os
 from ctypes import c_char_p, c_double, c_int, c_int64, c_size_t, c_uint64, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libkinisi_b200.so')
+LIB_PATH = os.environ.get('KB2_LIB_PATH') or os.path.join(HERE, 'libkinisi_b200.so')  # (the override: A/B probes of two builds)
 
 F32, F64 = 0, 1
 MODE_FRACTIONAL, MODE_DISPLACEMENT = 0, 1

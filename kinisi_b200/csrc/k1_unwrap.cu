@@ -196,6 +196,10 @@ __global__ void __launch_bounds__(256) frame_sums_kernel(const T* __restrict__ c
 // copy starts at the 16-byte boundary at or below the tile (`mis` elements early) and is a multiple of 16 bytes; what
 // would run past the end of the array is fetched with plain loads.  Constant cell, unit weights (the framework drift of
 // every front-end; kinisi/parser.py:131-148); everything else takes the kernel above.
+// ncu (profiles/r02_k1_frame_sums_bulk_ncu_summary.txt): 60 us, DRAM 54 %, first stall reason the shared-memory instruction
+// queue (4.8 mio_throttle cycles per issue: six 4-byte LDS per frame).  Three CONSECUTIVE frames per thread (12 LDS per 3
+// frames, odd lane stride) was measured on the same box: 4.46 -> 4.90 TB/s at 4000 atoms x 50 000 frames but 62.9 -> 66.8 us
+// at configs[1] (27 tiles of 768 frames: more, shorter CTAs) -- configs[1] is the only BASELINE shape with a framework.
 constexpr int kFbFrames = 1024;
 constexpr int kFbStages = 4;
 constexpr int kFbConsumers = 256;

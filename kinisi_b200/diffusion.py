@@ -616,7 +616,7 @@ class Bootstrap:
         pinned = engine.pinned_take(flat.numel() * 8)
         pinned[:flat.numel() * 8].view(torch.float64).reshape(flat.shape).copy_(flat, non_blocking=True)
         event = torch.cuda.Event()
-        event.record(torch.cuda.current_stream(self._device))
+        event.record(engine.current_stream(self._device))
         self._flatchain = self._gradient = self._intercept_dist = None
         self._flat_pending = (pinned, event, tuple(flat.shape), bool(fit_intercept))
 

@@ -196,9 +196,9 @@ class _PeerChannel:
 
     def allreduce_sum_f64(self, t):
         lib = self._libmod.load()
-        stream = torch.cuda.current_stream(t.device)
+        stream = torch._C._cuda_getCurrentRawStream(t.device.index)
         rc = lib.kb2_peer_allreduce_f64(t.data_ptr(), t.numel(), self._ptrs, self.world, self.rank, self.capacity, self.seq,
-                                        stream.cuda_stream)
+                                        stream)
         self._libmod.check(rc, 'kb2_peer_allreduce_f64')
         self.seq += 1
         check_peer_status()
@@ -219,9 +219,11 @@ _PEER_MIN_CAPACITY = 1 << 15
 
 def _peer(name, t):
     """The peer-memory channel `name` for tensors like `t`, or None (CPU tensors, not float64, another backend,
-    KB2_PEER_AR=0, or the windows could not be mapped: the NCCL road is taken instead)."""
+    KB2_PEER_AR=0, or the windows could not be mapped: the NCCL road is taken instead).  The process group is only the
+    rendezvous for the IPC handles: a gloo group with CUDA tensors works as well (ranks may even share one GPU, which is
+    how tests/test_gpu_peer.py runs two ranks on the driver's single-GPU box)."""
     if (name is None or not t.is_cuda or t.dtype != torch.float64 or not t.is_contiguous() or t.data_ptr() % 16
-            or os.environ.get('KB2_PEER_AR', '1') == '0' or td.get_backend() != 'nccl'
+            or os.environ.get('KB2_PEER_AR', '1') == '0' or td.get_backend() not in ('nccl', 'gloo')
             or td.get_world_size() > 16):
         return None
     key = (name, t.device.index)

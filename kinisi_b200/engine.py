@@ -44,6 +44,20 @@ def _stream():
     return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
 
 
+_STREAM_OBJECTS = {}
+
+
+def current_stream(device):
+    """torch.cuda.current_stream(device) without building a Stream object per call (~10 us each, a dozen per analysis):
+    the objects are kept by raw handle (torch's streams come from a pool and live as long as the process)."""
+    idx = device.index if device.index is not None else torch._C._cuda_getDevice()
+    raw = torch._C._cuda_getCurrentRawStream(idx)
+    s = _STREAM_OBJECTS.get((idx, raw))
+    if s is None:
+        s = _STREAM_OBJECTS[(idx, raw)] = torch.cuda.current_stream(device)
+    return s
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -248,7 +262,7 @@ def _host_plan(lib, kind, lags_host, n_frames, device):
     depends on (lags, n_frames) only."""
     key = (kind, lags_host.tobytes(), int(n_frames), device.type, device.index)
     hit = _RUNS_PLANS.get(key)
-    stream = torch.cuda.current_stream(device)
+    stream = current_stream(device)
     if hit is not None:
         plan_host, plan_dev, uploaded = hit
         if not uploaded.query():  # uploaded on another stream and still in flight
@@ -546,12 +560,14 @@ def const_to_device(a, device, np_dtype=np.float64):
     hit = _CONST_CACHE.get(key)
     if hit is not None:
         t, uploaded = hit
+        stream = current_stream(device)
         if not uploaded.query():  # uploaded on another stream and still in flight
-            torch.cuda.current_stream(device).wait_event(uploaded)
+            stream.wait_event(uploaded)
+        t.record_stream(stream)  # (an evicted entry must not be reused by its allocation stream under this reader)
         return t
     t = small_to_device(a, device, np_dtype)
     uploaded = torch.cuda.Event()
-    uploaded.record(torch.cuda.current_stream(device))
+    uploaded.record(current_stream(device))
     if len(_CONST_CACHE) >= 256:
         _CONST_CACHE.pop(next(iter(_CONST_CACHE)))
     _CONST_CACHE[key] = (t, uploaded)

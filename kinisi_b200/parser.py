@@ -77,7 +77,7 @@ class Trajectory:
             with torch.cuda.stream(self._side[0]):  # from the copy stream's pool: no cross-stream reuse hazard
                 self.coords = torch.empty(self._host.shape, dtype=self._host.dtype, device=device)
             self.coords.record_stream(self._side[1])
-            self.coords.record_stream(torch.cuda.current_stream(device))
+            self.coords.record_stream(engine.current_stream(device))
         else:
             self.coords = coords.to(device).contiguous()
         self.latt = self.latt_inv = None
@@ -86,7 +86,7 @@ class Trajectory:
         if mode == MODE_FRACTIONAL and latt is not None:
             latt_host = latt if isinstance(latt, np.ndarray) else None
             # with a staged ingest the lattices are prepared on the ingest stream, like everything else of stage 1
-            work = self._side[1] if self._host is not None else torch.cuda.current_stream(device)
+            work = self._side[1] if self._host is not None else engine.current_stream(device)
             with torch.cuda.stream(work):
                 cached = None
                 if latt_host is not None and latt_host.nbytes <= (64 << 10):
@@ -97,6 +97,8 @@ class Trajectory:
                     latt, inv, uploaded = cached
                     if not uploaded.query():
                         work.wait_event(uploaded)
+                    latt.record_stream(work)  # (an evicted entry must outlive its readers on other streams)
+                    inv.record_stream(work)
                 else:
                     latt = engine.to_device(latt, device, torch.float64).reshape(-1, 3, 3)
                     inv = None
@@ -118,8 +120,8 @@ class Trajectory:
                     self._latt_event = torch.cuda.Event()
                     self._latt_event.record(work)
             if self._host is not None:
-                self.latt.record_stream(torch.cuda.current_stream(device))
-                self.latt_inv.record_stream(torch.cuda.current_stream(device))
+                self.latt.record_stream(engine.current_stream(device))
+                self.latt_inv.record_stream(engine.current_stream(device))
 
     @property
     def device(self):
@@ -155,13 +157,13 @@ class Trajectory:
     def make_resident(self, rows=None):
         """Stage `rows` (default: every atom) and make the current stream wait for the copy."""
         if self._latt_event is not None:
-            torch.cuda.current_stream(self.device).wait_event(self._latt_event)
+            engine.current_stream(self.device).wait_event(self._latt_event)
             self._latt_event = None
         if self._host is None:
             return
         ev = self.stage(np.arange(self.coords.shape[0]) if rows is None else rows)
         if ev is not None:
-            torch.cuda.current_stream(self.device).wait_event(ev)
+            engine.current_stream(self.device).wait_event(ev)
 
     @property
     def n_atoms(self):
@@ -194,7 +196,7 @@ class Trajectory:
         n_f, n_a = int(frames.shape[0]), int(frames.shape[1])
         off = 1 if duplicate_first else 0
         copy, ingest = _side_streams(device)
-        main = torch.cuda.current_stream(device)
+        main = engine.current_stream(device)
         out_dtype = frames.dtype if cartesian_cells is None else torch.float64
         inv = None
         if cartesian_cells is not None:
@@ -309,7 +311,7 @@ class LazyDisplacements:
         Streamed: stage 1 runs for one block at a time into ONE buffer -- a block must be consumed (in stream order)
         before the next one is asked for."""
         if self._dc is not None:
-            stream = torch.cuda.current_stream(self._dc.device)
+            stream = engine.current_stream(self._dc.device)
             for r0, r1, ev in self.row_blocks():
                 if ev is not None:
                     stream.wait_event(ev)
@@ -336,7 +338,7 @@ class LazyDisplacements:
             self._dc = traj.displacement(idx, drift)
             self._source = None
         if self._ready:
-            stream = torch.cuda.current_stream(self._dc.device)
+            stream = engine.current_stream(self._dc.device)
             for _, _, ev in self._ready:
                 stream.wait_event(ev)
             self._ready = []
@@ -512,7 +514,7 @@ class Parser:
         per block of the displacement array, so a consumer on the caller's stream (the moment kernels) can follow
         block by block.  Atoms that are neither selected nor framework are never transferred."""
         dev = traj.device
-        main = torch.cuda.current_stream(dev)
+        main = engine.current_stream(dev)
         _, ingest = _side_streams(dev)
         n_frames, pitch = traj.n_frames, engine.pitch_for(traj.n_frames)
         row_bytes = traj.coords.shape[1] * 3 * traj.coords.element_size()
@@ -565,7 +567,7 @@ class Parser:
         if self._dc_sel_staged is None and getattr(self, '_streamed', False):
             return self.disp_3d.dc  # a streamed parser builds (and keeps) the array only on request
         if self._dc_ready:
-            stream = torch.cuda.current_stream(self._dc_sel_staged.device)
+            stream = engine.current_stream(self._dc_sel_staged.device)
             for _, _, ev in self._dc_ready:
                 stream.wait_event(ev)
             self._dc_ready = None

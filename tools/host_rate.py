@@ -37,7 +37,7 @@ t0 = time.perf_counter(); loop(200); wall = (time.perf_counter() - t0) / 200
 if rank == 0:
     print(f'world {world} T {T}: wall {wall * 1e3:.3f} ms per step')
     pr = cProfile.Profile(); pr.enable(); loop(100); pr.disable()
-    pstats.Stats(pr).sort_stats('tottime').print_stats(14)
+    pstats.Stats(pr).sort_stats('tottime').print_stats(60)
 else:
     loop(100)
 if world > 1:
