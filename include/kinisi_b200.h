@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KB2_ABI_VERSION 7
+#define KB2_ABI_VERSION 8
 
 /* coordinate element types */
 #define KB2_F32 0
@@ -148,6 +148,7 @@ int kb2_self_moments(const double* dc, int n_atoms, int n_frames, int64_t pitch,
  * (one partner sample per step serves up to 8 terms; lags that fit no progression become runs of one), and enqueues
  * one small plan copy on `stream`.  workspace: kb2_self_moments_runs_workspace_bytes(n_lags, n_frames) bytes. */
 size_t kb2_self_moments_runs_workspace_bytes(int n_lags, int n_frames);
+int kb2_self_moments_runs_blocks(int n_lags); /* launches (blocks of 192 lags) = 256-byte counter slots of the _planned form */
 int kb2_self_moments_runs(const double* dc, int n_atoms, int n_frames, int64_t pitch, const int32_t* lags_host,
                           int n_lags, int dim_mask, void* workspace, double* sums, void* stream);
 /* The same in two steps, for callers that keep the plan: it depends on (lags, n_frames) only.

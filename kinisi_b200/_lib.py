@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get('KB2_LIB_PATH') or os.path.join(HERE, 'libkinisi_b200.
 
 F32, F64 = 0, 1
 MODE_FRACTIONAL, MODE_DISPLACEMENT = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # name -> (restype, argtypes); mirrors include/kinisi_b200.h one to one
 SIGNATURES = {
@@ -36,6 +36,7 @@ SIGNATURES = {
     'kb2_self_moments_runs_planned': (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p]),
     'kb2_self_moments_runs_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'kb2_self_moments_runs_blocks': (c_int, [c_int]),
     'kb2_self_moments_runs': (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                       c_void_p]),
     'kb2_self_moments_win_workspace_bytes': (c_size_t, [c_int]),

@@ -671,6 +671,8 @@ static int check_lags(const char* fn, const int32_t* lags_host, int n_lags, int 
 
 using namespace kb2;
 
+extern "C" int kb2_self_moments_runs_blocks(int n_lags) { return n_lags < 1 ? 1 : (n_lags + kRunMaxLags - 1) / kRunMaxLags; }
+
 extern "C" size_t kb2_self_moments_runs_workspace_bytes(int n_lags, int n_frames) {
     const int t = n_frames < 1 ? 1 : n_frames;
     const int n = n_lags < 1 ? 1 : n_lags;

@@ -218,7 +218,7 @@ def self_moments(dc, n_frames, lags, mask=7, variant=None):
     if (variant & 0xff) == VARIANT_RUNS:
         lags_host = np.ascontiguousarray(lags.cpu().numpy() if isinstance(lags, torch.Tensor) else lags, dtype=np.int32)
         plan_host, plan_dev = _host_plan(lib, 'runs', lags_host, n_frames, dc.device)
-        blocks = (K + 191) // 192
+        blocks = lib.kb2_self_moments_runs_blocks(K)
         counters = torch.empty(256 * blocks, dtype=torch.uint8, device=dc.device)
         check(
             lib.kb2_self_moments_runs_planned(dc.data_ptr(), dc.shape[0], n_frames, dc.shape[2], K, mask,
