@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KB2_ABI_VERSION 8
+#define KB2_ABI_VERSION 9
 
 /* coordinate element types */
 #define KB2_F32 0
@@ -352,6 +352,23 @@ int kb2_peer_window_close(void* window);
 int kb2_peer_window_destroy(void* window);
 int kb2_peer_allreduce_f64(double* buf, int64_t n, void* const* windows_host, int world, int rank, int64_t capacity,
                            uint64_t seq, void* stream);
+/* The same join of a [rows][row_len] array cut by COLUMNS: slice c is columns [1024 c, 1024 (c + 1)) of every row.  This is
+ * how the [3][pitch] frame sums are joined, because it is how kb2_frame_sums_joined produces them: a rank may take either
+ * entry point for one and the same join (same windows, same seq).  kb2_peer_rows_slices(row_len): the number of slices, 0
+ * if row_len is odd or needs more than 128. */
+int kb2_peer_rows_slices(int64_t row_len);
+int kb2_peer_allreduce_rows_f64(double* buf, int rows, int64_t row_len, void* const* windows_host, int world, int rank,
+                                int64_t capacity, uint64_t seq, void* stream);
+/* kb2_frame_sums followed by the sum over ranks, in ONE kernel (np.mean(disp[:, framework], axis=1), kinisi/parser.py:143-145,
+ * with the framework atoms sharded over GPUs): the CTA that completes a tile of 1024 frames pushes it to the peers' windows,
+ * waits for their copies and writes the all-rank sums, while the CTAs of other tiles still compute.  On return of the
+ * kernel frame_sums holds the joined array.  tile_counters: 128 unsigned ints of device memory, zero on entry (the kernel
+ * leaves them zero), not shared with another call in flight.  Needs ceil(pitch / 1024) == ceil(n_out_frames / 1024) and
+ * kb2_peer_rows_slices(pitch) > 0; windows / world / rank / capacity / seq as for kb2_peer_allreduce_f64. */
+int kb2_frame_sums_joined(const void* coords, int dtype, int mode, int n_atoms_total, int n_frames_in, const double* latt,
+                          const double* latt_inv, int latt_stride, const int32_t* idx, const double* w, int n_idx,
+                          double* frame_sums, int64_t pitch, void* const* windows_host, int world, int rank, int64_t capacity,
+                          uint64_t seq, unsigned int* tile_counters, void* stream);
 int kb2_peer_status(void);
 
 /* ---------------------------------------------------------------------------------------------

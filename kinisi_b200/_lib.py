@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get('KB2_LIB_PATH') or os.path.join(HERE, 'libkinisi_b200.
 
 F32, F64 = 0, 1
 MODE_FRACTIONAL, MODE_DISPLACEMENT = 0, 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # name -> (restype, argtypes); mirrors include/kinisi_b200.h one to one
 SIGNATURES = {
@@ -77,6 +77,11 @@ SIGNATURES = {
     'kb2_peer_window_close': (c_int, [c_void_p]),
     'kb2_peer_window_destroy': (c_int, [c_void_p]),
     'kb2_peer_allreduce_f64': (c_int, [c_void_p, c_int64, POINTER(c_void_p), c_int, c_int, c_int64, c_uint64, c_void_p]),
+    'kb2_peer_rows_slices': (c_int, [c_int64]),
+    'kb2_peer_allreduce_rows_f64': (c_int, [c_void_p, c_int, c_int64, POINTER(c_void_p), c_int, c_int, c_int64, c_uint64,
+                                            c_void_p]),
+    'kb2_frame_sums_joined': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                      c_void_p, c_int64, POINTER(c_void_p), c_int, c_int, c_int64, c_uint64, c_void_p, c_void_p]),
     'kb2_peer_status': (c_int, []),
     'kb2_fp64_peak': (c_int, [c_int, c_int, c_void_p, c_void_p]),
     'kb2_stream_copy': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -10,11 +10,13 @@
 // Algorithmic HBM bytes per (atom, frame): sizeof(coord)*3 read + 24 written for the scan kernel,
 // sizeof(coord)*3 read for the frame-sum kernel.  Both are HBM-bound.
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <type_traits>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace kb2 {
 
@@ -95,6 +97,43 @@ __device__ __forceinline__ double ld_nc_issue(const double* p) {
     return v;
 }
 
+// ---- frame sums that end with the sum over ranks (atoms sharded over GPUs) -------------------------------------------
+// With `enabled`, the frame-sum kernels below finish the join themselves: the CTAs that add into a tile of kPeerFrameTile
+// frames count themselves on the tile's arrival counter, and the one that arrives last -- the tile's local sums are then
+// complete -- pushes the tile's three rows into the peers' windows, raises its flags, waits for the peers' copies of the
+// same tile, adds them in rank order and writes the all-rank sums over the tile (peer_join_slice, csrc/peer.cuh).  Tiles
+// are exchanged while the CTAs of later tiles still compute: compute and collective are one kernel, tile by tile, and what
+// the next kernel on the stream reads is the joined array.  The protocol is the one of kb2_peer_allreduce_rows_f64, so a
+// rank without local framework atoms (or a caller that summed several blocks first) joins the same call with that kernel.
+struct FrameJoin {
+    PeerJoin J;
+    unsigned int* counters;  // [kPeerMaxSlices] arrival counters of this call's tiles, zero on entry and on exit
+    int enabled;
+    int pad;
+};
+
+// called by all threads of a CTA after its additions into tile `tile` (columns [tile * kPeerFrameTile, ...) of the three
+// rows of sums): `expected` CTAs add into the tile
+__device__ __forceinline__ void frame_join_epilogue(const FrameJoin& fj, double* __restrict__ sums, int64_t pitch, int tile,
+                                                    unsigned int expected) {
+    __shared__ int s_join;
+    __threadfence();  // this thread's additions are performed before the arrival below
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int before = atomicAdd(fj.counters + tile, 1u);
+        s_join = (before + 1 == expected);
+        if (s_join) {
+            atomicExch(fj.counters + tile, 0u);
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    if (s_join) {
+        const long long c0 = (long long)tile * kPeerFrameTile;
+        peer_join_slice(fj.J, sums, 3, (long long)pitch, tile, c0, min((long long)pitch, c0 + kPeerFrameTile));
+    }
+}
+
 // One thread per output frame, looping over a chunk of atoms: per-frame weighted sums of the
 // unwrapped displacement.  The sum over atoms commutes with the cumulative sum over time, so the
 // framework drift and the collective (MSTD/MSCD) sums need no per-atom scan and no per-atom atomics.
@@ -104,9 +143,9 @@ __global__ void __launch_bounds__(256) frame_sums_kernel(const T* __restrict__ c
                                                          const double* __restrict__ inv, int lstride,
                                                          const int32_t* __restrict__ idx, const double* __restrict__ w,
                                                          int n_idx, int per_chunk, double* __restrict__ sums,
-                                                         int64_t pitch, int Tn) {
+                                                         int64_t pitch, int Tn, FrameJoin fj) {
     const int t = blockIdx.x * 256 + threadIdx.x;
-    if (t >= Tn) return;
+    if (t < Tn) {
     const int i0 = blockIdx.y * per_chunk;
     const int i1 = min(n_idx, i0 + per_chunk);
     double acc[3] = {0.0, 0.0, 0.0};
@@ -183,6 +222,14 @@ __global__ void __launch_bounds__(256) frame_sums_kernel(const T* __restrict__ c
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) atomicAdd(sums + c * pitch + t, acc[c]);
+    }
+    if (fj.enabled) {
+        // four 256-frame blocks (fewer at the end of the trajectory) times gridDim.y chunks add into one tile
+        constexpr int PER = kPeerFrameTile / 256;
+        const int tile = blockIdx.x / PER;
+        const unsigned int blocks = (unsigned int)min(PER, (int)gridDim.x - tile * PER);
+        frame_join_epilogue(fj, sums, pitch, tile, blocks * gridDim.y);
+    }
 }
 
 // ---- frame sums through a bulk-copy ring -------------------------------------------------------------------------
@@ -247,8 +294,9 @@ __global__ void __launch_bounds__(kFbConsumers + 32) frame_sums_bulk_kernel(cons
                                                                            const double* __restrict__ latt,
                                                                            const int32_t* __restrict__ idx, int n_idx,
                                                                            int per_chunk, double* __restrict__ sums,
-                                                                           int64_t pitch, int Tn) {
+                                                                           int64_t pitch, int Tn, FrameJoin fj) {
     using namespace fb;
+    static_assert(kFbFrames == kPeerFrameTile, "a CTA's tile is a slice of the join");
     constexpr int SB = fb_stage_bytes<T>();
     extern __shared__ __align__(128) unsigned char fb_smem[];
     __shared__ uint64_t full[kFbStages], empty[kFbStages];
@@ -297,8 +345,7 @@ __global__ void __launch_bounds__(kFbConsumers + 32) frame_sums_bulk_kernel(cons
                 }
             }
         }
-        return;
-    }
+    } else {
     double aw[kFbPer][3];
 #pragma unroll
     for (int j = 0; j < kFbPer; ++j) aw[j][0] = aw[j][1] = aw[j][2] = 0.0;
@@ -332,11 +379,14 @@ __global__ void __launch_bounds__(kFbConsumers + 32) frame_sums_bulk_kernel(cons
                 atomicAdd(sums + l * pitch + t0 + f, aw[j][0] * L[l] + aw[j][1] * L[3 + l] + aw[j][2] * L[6 + l]);
         }
     }
+    }
+    // (the producer warp comes here too: the join of a tile is the work of the whole CTA)
+    if (fj.enabled) frame_join_epilogue(fj, sums, pitch, blockIdx.x, gridDim.y);
 }
 
 template <typename T>
 static int launch_frame_sums_bulk(const void* coords, int n_atoms_total, int F, const double* latt, const int32_t* idx, int n_idx,
-                                  double* sums, int64_t pitch, int Tn, cudaStream_t st) {
+                                  double* sums, int64_t pitch, int Tn, const FrameJoin& fj, cudaStream_t st) {
     const int sm = device_sm_count();
     const size_t smem = (size_t)kFbStages * fb_stage_bytes<T>();
     const int tiles = ceil_div(Tn, kFbFrames);
@@ -348,7 +398,7 @@ static int launch_frame_sums_bulk(const void* coords, int n_atoms_total, int F, 
     chunks = ceil_div(n_idx, per);
     KB2_CUDA(cudaFuncSetAttribute(frame_sums_bulk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     frame_sums_bulk_kernel<T><<<dim3(tiles, chunks), kFbConsumers + 32, smem, st>>>((const T*)coords, (int64_t)n_atoms_total * F * 3, F,
-                                                                                  latt, idx, n_idx, per, sums, pitch, Tn);
+                                                                                  latt, idx, n_idx, per, sums, pitch, Tn, fj);
     KB2_LAUNCH_CHECK();
     return 0;
 }
@@ -1219,20 +1269,23 @@ extern "C" int kb2_invert_lattice(const double* latt, double* latt_inv, int n, v
     return 0;
 }
 
-extern "C" int kb2_frame_sums(const void* coords, int dtype, int mode, int n_atoms_total, int n_frames_in,
-                              const double* latt, const double* latt_inv, int latt_stride, const int32_t* idx,
-                              const double* w, int n_idx, double* frame_sums, int64_t pitch, void* stream) {
+static int frame_sums_impl(const char* fn, const void* coords, int dtype, int mode, int n_atoms_total, int n_frames_in,
+                           const double* latt, const double* latt_inv, int latt_stride, const int32_t* idx,
+                           const double* w, int n_idx, double* frame_sums, int64_t pitch, const FrameJoin& fj, void* stream) {
     int Tn = 0;
-    if (int rc = check_stage1("kb2_frame_sums", coords, dtype, mode, n_atoms_total, n_frames_in, latt, latt_inv,
+    if (int rc = check_stage1(fn, coords, dtype, mode, n_atoms_total, n_frames_in, latt, latt_inv,
                               latt_stride, idx, n_idx, pitch, &Tn))
         return rc;
-    KB2_CHECK(frame_sums, "kb2_frame_sums: null output");
+    KB2_CHECK(frame_sums, "%s: null output", fn);
+    if (fj.enabled)
+        KB2_CHECK(ceil_div(pitch, kPeerFrameTile) == ceil_div(Tn, kPeerFrameTile) && fj.J.n_slices == ceil_div(pitch, kPeerFrameTile),
+                  "%s: the row pad must not reach into a tile of %d frames of its own", fn, kPeerFrameTile);
     cudaStream_t st = (cudaStream_t)stream;
     KB2_CUDA(cudaMemsetAsync(frame_sums, 0, sizeof(double) * 3 * pitch, st));
     if (mode == KB2_MODE_FRACTIONAL && latt_stride == 0 && !w && frame_sums_bulk_enabled() && n_idx >= 2 * kFbStages) {
         if (dtype == KB2_F32)
-            return launch_frame_sums_bulk<float>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, frame_sums, pitch, Tn, st);
-        return launch_frame_sums_bulk<double>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, frame_sums, pitch, Tn, st);
+            return launch_frame_sums_bulk<float>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, frame_sums, pitch, Tn, fj, st);
+        return launch_frame_sums_bulk<double>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, frame_sums, pitch, Tn, fj, st);
     }
     const int sm = device_sm_count();
     const int tiles = ceil_div(Tn, 256);
@@ -1244,7 +1297,7 @@ extern "C" int kb2_frame_sums(const void* coords, int dtype, int mode, int n_ato
     dim3 grid(tiles, chunks);
 #define KB2_FS(T, M, C)                                                                                             \
     frame_sums_kernel<T, M, C><<<grid, 256, 0, st>>>((const T*)coords, n_frames_in, latt, latt_inv, latt_stride, idx, w, \
-                                                     n_idx, per, frame_sums, pitch, Tn)
+                                                     n_idx, per, frame_sums, pitch, Tn, fj)
     const bool constl = (mode == KB2_MODE_FRACTIONAL && latt_stride == 0);
     if (dtype == KB2_F32 && mode == KB2_MODE_FRACTIONAL) { if (constl) KB2_FS(float, KB2_MODE_FRACTIONAL, true); else KB2_FS(float, KB2_MODE_FRACTIONAL, false); }
     else if (dtype == KB2_F32) KB2_FS(float, KB2_MODE_DISPLACEMENT, false);
@@ -1253,6 +1306,34 @@ extern "C" int kb2_frame_sums(const void* coords, int dtype, int mode, int n_ato
 #undef KB2_FS
     KB2_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int kb2_frame_sums(const void* coords, int dtype, int mode, int n_atoms_total, int n_frames_in,
+                              const double* latt, const double* latt_inv, int latt_stride, const int32_t* idx,
+                              const double* w, int n_idx, double* frame_sums, int64_t pitch, void* stream) {
+    FrameJoin fj;
+    memset(&fj, 0, sizeof(fj));
+    return frame_sums_impl("kb2_frame_sums", coords, dtype, mode, n_atoms_total, n_frames_in, latt, latt_inv, latt_stride, idx, w,
+                           n_idx, frame_sums, pitch, fj, stream);
+}
+
+extern "C" int kb2_frame_sums_joined(const void* coords, int dtype, int mode, int n_atoms_total, int n_frames_in,
+                                     const double* latt, const double* latt_inv, int latt_stride, const int32_t* idx,
+                                     const double* w, int n_idx, double* frame_sums, int64_t pitch, void* const* windows_host,
+                                     int world, int rank, int64_t capacity, uint64_t seq, unsigned int* tile_counters,
+                                     void* stream) {
+    KB2_CHECK(tile_counters, "kb2_frame_sums_joined: null counters");
+    KB2_CHECK(3 * pitch <= capacity, "kb2_frame_sums_joined: 3 * pitch exceeds the capacity of the windows");
+    KB2_CHECK((reinterpret_cast<uintptr_t>(frame_sums) & 15) == 0 && pitch % 2 == 0, "kb2_frame_sums_joined: frame_sums must be 16-byte aligned, pitch even");
+    const int slices = kb2_peer_rows_slices(pitch);
+    KB2_CHECK(slices > 0, "kb2_frame_sums_joined: too many frames for one join (use kb2_frame_sums + kb2_peer_allreduce_f64)");
+    FrameJoin fj;
+    memset(&fj, 0, sizeof(fj));
+    if (int rc = peer_join_setup(&fj.J, windows_host, world, rank, capacity, seq, slices, "kb2_frame_sums_joined")) return rc;
+    fj.counters = tile_counters;
+    fj.enabled = 1;
+    return frame_sums_impl("kb2_frame_sums_joined", coords, dtype, mode, n_atoms_total, n_frames_in, latt, latt_inv, latt_stride,
+                           idx, w, n_idx, frame_sums, pitch, fj, stream);
 }
 
 extern "C" int kb2_scan_frames(double* buf, int n_frames, int64_t pitch, int cumulative, double divide,

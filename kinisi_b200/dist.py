@@ -143,7 +143,7 @@ class _PeerChannel:
         self.world, self.rank = td.get_world_size(), td.get_rank()
         self.capacity = int(capacity)
         self.seq = 0
-        self._own, self._opened = None, []
+        self._own, self._opened, self._counters = None, [], None
         handle = (ctypes.c_ubyte * 64)()
         own = ctypes.c_void_p()
         ok, err = 1, ''
@@ -195,13 +195,30 @@ class _PeerChannel:
             self._own = None
 
     def allreduce_sum_f64(self, t):
+        """In-place sum over ranks.  A [rows][even row length] array of up to 128 x 1024 columns is cut by columns, one
+        slice per 1024 columns of every row (the frame sums: the cut of the fused kernel, see `frame_sums_join`), anything
+        else as a flat array."""
         lib = self._libmod.load()
         stream = torch._C._cuda_getCurrentRawStream(t.device.index)
-        rc = lib.kb2_peer_allreduce_f64(t.data_ptr(), t.numel(), self._ptrs, self.world, self.rank, self.capacity, self.seq,
-                                        stream)
-        self._libmod.check(rc, 'kb2_peer_allreduce_f64')
+        if t.dim() == 2 and t.shape[0] > 1 and lib.kb2_peer_rows_slices(t.shape[1]) > 0:
+            rc = lib.kb2_peer_allreduce_rows_f64(t.data_ptr(), t.shape[0], t.shape[1], self._ptrs, self.world, self.rank,
+                                                 self.capacity, self.seq, stream)
+            self._libmod.check(rc, 'kb2_peer_allreduce_rows_f64')
+        else:
+            rc = lib.kb2_peer_allreduce_f64(t.data_ptr(), t.numel(), self._ptrs, self.world, self.rank, self.capacity,
+                                            self.seq, stream)
+            self._libmod.check(rc, 'kb2_peer_allreduce_f64')
         self.seq += 1
         check_peer_status()
+
+    def frame_sums_join(self):
+        """The arguments after `pitch` of kb2_frame_sums_joined for the next join of this channel (the call is counted):
+        (windows, world, rank, capacity, seq, tile counters)."""
+        if self._counters is None:  # 32 sets of 128 arrival counters, used round-robin: zero between calls
+            self._counters = torch.zeros(32 * 128, dtype=torch.int32, device=self.device)
+        seq = self.seq
+        self.seq += 1
+        return self._ptrs, self.world, self.rank, self.capacity, seq, self._counters.data_ptr() + 4 * 128 * (seq % 32)
 
 
 def check_peer_status():
@@ -268,6 +285,23 @@ def _direct(name, t):
                 warnings.warn(f'kinisi_b200.dist: direct NCCL communicator unavailable ({exc}); using torch.distributed')
         _DIRECT[key] = comm
     return _DIRECT[key]
+
+
+def frame_sums_channel(n_rows, pitch, device):
+    """The peer-memory channel through which a [n_rows][pitch] array of frame sums on `device` can be joined INSIDE the
+    kernel that produces it (kb2_frame_sums_joined), or None: the decision depends on the shape alone, so every rank takes
+    the same road."""
+    if not active() or os.environ.get('KB2_FUSED_JOIN', '1') == '0':
+        return None
+    from . import _lib
+    if _lib.load().kb2_peer_rows_slices(int(pitch)) <= 0 or n_rows != 3:
+        return None
+    device = torch.device(device)
+    ch = _PEER.get(('frames', device.index))
+    if ch and n_rows * int(pitch) <= ch.capacity:
+        return ch
+    probe = torch.empty((n_rows, int(pitch)), dtype=torch.float64, device=device)  # first use / a longer trajectory: the collective road
+    return _peer('frames', probe)
 
 
 _SUM_OPTS = None

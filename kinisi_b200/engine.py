@@ -128,10 +128,20 @@ def molecule_centres(coords, members, weights=None):
     return out
 
 
-def frame_sums(coords, mode, latt, latt_inv, latt_stride, idx, weights, pitch):
-    """[3, pitch] per-frame (weighted) sums over the atoms in idx; see kb2_frame_sums."""
+def frame_sums(coords, mode, latt, latt_inv, latt_stride, idx, weights, pitch, join=None):
+    """[3, pitch] per-frame (weighted) sums over the atoms in idx; see kb2_frame_sums.  `join`: a peer-memory channel
+    (dist.frame_sums_channel) -- the kernel then ends with the sum over ranks (kb2_frame_sums_joined)."""
     lib = require_cuda()
     out = torch.empty((3, pitch), dtype=torch.float64, device=coords.device)
+    if join is not None:
+        windows, world, rank, capacity, seq, counters = join.frame_sums_join()
+        check(
+            lib.kb2_frame_sums_joined(coords.data_ptr(), coords_dtype_code(coords), mode, coords.shape[0], coords.shape[1],
+                                      _ptr(latt), _ptr(latt_inv), latt_stride, idx.data_ptr(), _ptr(weights), idx.numel(),
+                                      out.data_ptr(), pitch, windows, world, rank, capacity, seq, counters, _stream()),
+            'kb2_frame_sums_joined')
+        _count(2)
+        return out
     check(
         lib.kb2_frame_sums(coords.data_ptr(), coords_dtype_code(coords), mode, coords.shape[0], coords.shape[1],
                            _ptr(latt), _ptr(latt_inv), latt_stride, idx.data_ptr(), _ptr(weights), idx.numel(),

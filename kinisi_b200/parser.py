@@ -248,11 +248,12 @@ class Trajectory:
         traj._frames_keepalive = keep
         return traj
 
-    def frame_sums(self, idx, weights=None):
-        """Per-frame (weighted) displacement sums over atoms idx (an int32 device tensor)."""
+    def frame_sums(self, idx, weights=None, join=None):
+        """Per-frame (weighted) displacement sums over atoms idx (an int32 device tensor); `join`: see engine.frame_sums."""
         self.make_resident()
         pitch = engine.pitch_for(self.n_frames)
-        return engine.frame_sums(self.coords, self.mode, self.latt, self.latt_inv, self.latt_stride, idx, weights, pitch)
+        return engine.frame_sums(self.coords, self.mode, self.latt, self.latt_inv, self.latt_stride, idx, weights, pitch,
+                                 join=join)
 
     def displacement(self, idx, drift=None):
         """dc [len(idx), 3, pitch] float64, component-major.  `drift` is None or (frame_sums, n_framework): the
@@ -585,10 +586,16 @@ class Parser:
         n_fw = self._n_fw_global
         if n_fw == 0:
             return None
+        # atoms sharded over ranks: the kernel that makes the local sums ends with the sum over ranks (one fused kernel over
+        # peer memory, csrc/k1_unwrap.cu frame_join_epilogue); a rank without local framework atoms joins with zeros
+        join = dist.frame_sums_channel(3, engine.pitch_for(traj.n_frames), traj.device) if self._distributed else None
         if n_fw_local > 0:
             if fw is None:
                 fw = engine.small_to_device(drift_indices, traj.device, np.int32)
-            sums = traj.frame_sums(fw)
+            sums = traj.frame_sums(fw, join=join)
+            if join is not None:
+                dist.check_peer_status()
+                return sums, float(n_fw)
         else:
             sums = torch.zeros((3, engine.pitch_for(traj.n_frames)), dtype=torch.float64, device=traj.device)
         if self._distributed:

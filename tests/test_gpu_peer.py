@@ -64,32 +64,47 @@ def _worker(rank, world, port, out_dir):
                     want = want + _local_array(n, seed, r)  # the kernel adds in rank order
                 assert torch.equal(x.cpu(), want), (n, seed)
         assert dist._PEER.get(('frames', 0)) and dist._PEER.get(('moments', 0)), 'the peer-memory road was not taken'
-        # (2) one trajectory on one rank and sharded by atom over the ranks
-        n_mob, n_fw, T = 48, 20, 3000
-        frac, latt = ko.synthetic_walk(n_mob, T, box=14.0, sigma=0.1, seed=17, n_framework=n_fw, dtype=np.float32)
-        q_all = np.where(np.arange(n_mob) % 3 == 0, -2.0, 1.0)
-        res = {}
-        for mode in ('single', 'sharded'):
-            if mode == 'single':
-                rows = np.arange(n_mob + n_fw)
-                idx, fw, q, kw = np.arange(n_mob), np.arange(n_mob, n_mob + n_fw), q_all, {}
-            else:
-                m_lo, m_hi = dist.shard_bounds(n_mob)
-                f_lo, f_hi = dist.shard_bounds(n_fw)
-                rows = np.concatenate([np.arange(m_lo, m_hi), n_mob + np.arange(f_lo, f_hi)])
-                idx, fw = np.arange(m_hi - m_lo), (m_hi - m_lo) + np.arange(f_hi - f_lo)
-                q, kw = q_all[m_lo:m_hi], dict(distributed=True, global_counts=(n_mob, n_fw))
-            coords = torch.from_numpy(np.ascontiguousarray(frac[rows])).to(dev)
-            p = Parser(Parser.get_disp(coords, latt), idx, fw, 0.001, 1, n_steps=40, progress=False, **kw)
-            out = {}
-            for kind, cls, args in (('msd', diffusion.MSDBootstrap, ()), ('mstd', diffusion.MSTDBootstrap, ()),
-                                    ('mscd', diffusion.MSCDBootstrap, (q, ))):
-                b = cls(p.delta_t, p.disp_3d, *args, p._n_o, progress=False)
-                out[kind] = np.stack([b.n, b.v])
-            res[mode] = out
-        dist.check_peer_status()
-        for kind in ('msd', 'mstd', 'mscd'):
-            np.testing.assert_allclose(res['sharded'][kind], res['single'][kind], rtol=1e-10, err_msg=kind)
+        # a [3][pitch] array is cut by columns (the cut of the fused frame-sum kernel)
+        for pitch in (16, 1024, 1040, 3008, 20000):
+            x = _local_array(3 * pitch, pitch, rank).reshape(3, pitch).to(dev)
+            dist.allreduce_sum_(x, 'frames')
+            want = _local_array(3 * pitch, pitch, 0)
+            for r in range(1, world):
+                want = want + _local_array(3 * pitch, pitch, r)
+            assert torch.equal(x.cpu().reshape(-1), want), pitch
+        # (2) one trajectory on one rank and sharded by atom over the ranks.  The framework frame sums are joined inside the
+        # kernel that makes them: 20 framework atoms -> the bulk-copy kernel on both ranks, 6 -> the register kernel,
+        # 1 -> rank 1 has none and joins the same call with the stand-alone kernel
+        for n_fw, T in ((20, 3000), (6, 1500), (1, 2100)):
+            n_mob = 48
+            frac, latt = ko.synthetic_walk(n_mob, T, box=14.0, sigma=0.1, seed=17 + n_fw, n_framework=n_fw, dtype=np.float32)
+            q_all = np.where(np.arange(n_mob) % 3 == 0, -2.0, 1.0)
+            res = {}
+            for mode in ('single', 'sharded'):
+                if mode == 'single':
+                    rows = np.arange(n_mob + n_fw)
+                    idx, fw, q, kw = np.arange(n_mob), np.arange(n_mob, n_mob + n_fw), q_all, {}
+                else:
+                    m_lo, m_hi = dist.shard_bounds(n_mob)
+                    f_lo, f_hi = dist.shard_bounds(n_fw)
+                    rows = np.concatenate([np.arange(m_lo, m_hi), n_mob + np.arange(f_lo, f_hi)]).astype(np.int64)
+                    idx, fw = np.arange(m_hi - m_lo), (m_hi - m_lo) + np.arange(f_hi - f_lo)
+                    q, kw = q_all[m_lo:m_hi], dict(distributed=True, global_counts=(n_mob, n_fw))
+                coords = torch.from_numpy(np.ascontiguousarray(frac[rows])).to(dev)
+                seq0 = dist._PEER[('frames', 0)].seq
+                p = Parser(Parser.get_disp(coords, latt), idx, fw, 0.001, 1, n_steps=40, progress=False, **kw)
+                if mode == 'sharded':
+                    assert dist._PEER[('frames', 0)].seq == seq0 + 1  # one join, fused into the frame-sum kernel where there are atoms
+                out = {}
+                for kind, cls, args in (('msd', diffusion.MSDBootstrap, ()), ('mstd', diffusion.MSTDBootstrap, ()),
+                                        ('mscd', diffusion.MSCDBootstrap, (q, ))):
+                    b = cls(p.delta_t, p.disp_3d, *args, p._n_o, progress=False)
+                    out[kind] = np.stack([b.n, b.v])
+                res[mode] = out
+            torch.cuda.synchronize()
+            dist.check_peer_status()
+            for kind in ('msd', 'mstd', 'mscd'):
+                np.testing.assert_allclose(res['sharded'][kind], res['single'][kind], rtol=1e-10, err_msg=f'{kind} n_fw={n_fw}')
         np.save(os.path.join(out_dir, f'ok{rank}.npy'), np.array([1]))
     finally:
         td.destroy_process_group()
