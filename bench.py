@@ -757,8 +757,11 @@ def run_own(args):
                 'workload': WORKLOAD,
                 'per_gpu': f'{n_mob + n_fw} atoms ({n_mob} mobile) x {T} frames, f32 wrapped fractional coordinates',
                 'sharding': 'atoms' if world > 1 else 'none',
-                'joins': ('none' if world == 1 else 'peer-memory kernel (kb2_peer_allreduce_f64), 2 per step'
-                          if any(kdist._PEER.values()) else 'NCCL all-reduce, 2 per step'),
+                'joins': ('none' if world == 1 else
+                          'peer memory: frame sums joined inside kb2_frame_sums_joined, moment sums by kb2_peer_allreduce_f64'
+                          if any(kdist._PEER.values()) and os.environ.get('KB2_FUSED_JOIN', '1') != '0' else
+                          'peer-memory kernel (kb2_peer_allreduce_f64), 2 per step' if any(kdist._PEER.values()) else
+                          'NCCL all-reduce, 2 per step'),
                 'l2': f'inputs ({host.numel() * 4 / 1e6:.0f} MB f32 + {n_mob * 3 * T * 8 / 1e6:.0f} MB f64 per step) '
                       'exceed the 126 MB L2; no flush needed',
                 'self_moment_variant': {0: 'direct', 1: 'tma-ring', 2: 'arithmetic-runs', 3: 'lag-window', 4: 'tiled-lag-window'}[engine.DEFAULT_VARIANT & 0xff],

@@ -275,8 +275,11 @@ def _host_plan(lib, kind, lags_host, n_frames, device):
     stream = current_stream(device)
     if hit is not None:
         plan_host, plan_dev, uploaded = hit
-        if not uploaded.query():  # uploaded on another stream and still in flight
-            stream.wait_event(uploaded)
+        if uploaded is not None:
+            if uploaded.query():
+                _RUNS_PLANS[key] = (plan_host, plan_dev, None)  # landed: later hits need not ask again
+            else:  # uploaded on another stream and still in flight
+                stream.wait_event(uploaded)
         plan_dev.record_stream(stream)
         return plan_host, plan_dev
     if kind == 'tile':
@@ -571,8 +574,11 @@ def const_to_device(a, device, np_dtype=np.float64):
     if hit is not None:
         t, uploaded = hit
         stream = current_stream(device)
-        if not uploaded.query():  # uploaded on another stream and still in flight
-            stream.wait_event(uploaded)
+        if uploaded is not None:
+            if uploaded.query():
+                _CONST_CACHE[key] = (t, None)  # landed: later hits need not ask again
+            else:  # uploaded on another stream and still in flight
+                stream.wait_event(uploaded)
         t.record_stream(stream)  # (an evicted entry must not be reused by its allocation stream under this reader)
         return t
     t = small_to_device(a, device, np_dtype)

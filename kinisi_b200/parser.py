@@ -15,6 +15,8 @@ What differs from the reference by design
 import warnings
 from typing import List, Tuple
 
+import contextlib
+
 import numpy as np
 import torch
 
@@ -23,6 +25,7 @@ from ._lib import MODE_DISPLACEMENT, MODE_FRACTIONAL
 
 
 _SIDE_STREAMS = {}
+_GRIDS = {}  # (min_dt, max_dt, n_steps, spacing) -> integer time-interval grid
 _LATTICES = {}  # (lattice bytes, device) -> (lattices, inverses, upload event) on the device
 STAGE_BYTES = 32 << 20  # host->device copy granularity of the staged ingest (about 0.6 ms of PCIe time)
 # A cumulative-displacement array above STREAM_BYTES is not kept: stage 1 is re-run block by block (STREAM_BLOCK_BYTES of
@@ -87,7 +90,8 @@ class Trajectory:
             latt_host = latt if isinstance(latt, np.ndarray) else None
             # with a staged ingest the lattices are prepared on the ingest stream, like everything else of stage 1
             work = self._side[1] if self._host is not None else engine.current_stream(device)
-            with torch.cuda.stream(work):
+            # (entering a stream context costs ~15 us of host time: not when the work stream is the current one)
+            with (torch.cuda.stream(work) if self._host is not None else contextlib.nullcontext()):
                 cached = None
                 if latt_host is not None and latt_host.nbytes <= (64 << 10):
                     # small lattices (the constant cell above all) and their inverses are kept on the device by content
@@ -95,8 +99,11 @@ class Trajectory:
                     cached = _LATTICES.get(key)
                 if cached is not None:
                     latt, inv, uploaded = cached
-                    if not uploaded.query():
-                        work.wait_event(uploaded)
+                    if uploaded is not None:
+                        if uploaded.query():
+                            _LATTICES[key] = (latt, inv, None)  # landed: later hits need not ask again
+                        else:
+                            work.wait_event(uploaded)
                     latt.record_stream(work)  # (an evicted entry must outlive its readers on other streams)
                     inv.record_stream(work)
                 else:
@@ -670,18 +677,27 @@ class Parser:
         return traj.numpy(drift=(traj.frame_sums(fw), float(len(drift_indices))))
 
     def get_time_intervals(self, n_steps: int, spacing: str) -> np.ndarray:
-        """The integer time-interval grid (kinisi/parser.py:150-168).  Integer work: stays on the host."""
+        """The integer time-interval grid (kinisi/parser.py:150-168).  Integer work: stays on the host (and is kept per
+        set of arguments: a loop over trajectories of one shape asks for the same grid every time)."""
         unit = self.step_skip * self.time_step
         min_dt = int(self.min_dt / unit)
         max_dt = int(self.max_dt / unit)
         if min_dt == 0:
             min_dt = 1
+        key = (min_dt, max_dt, int(n_steps), spacing)
+        hit = _GRIDS.get(key)
+        if hit is not None:
+            return hit.copy()
         if spacing == 'linear':
-            return np.linspace(min_dt, max_dt, n_steps, dtype=int)
+            grid = np.linspace(min_dt, max_dt, n_steps, dtype=int)
         elif spacing == 'logarithmic':
-            return np.unique(np.geomspace(min_dt, max_dt, n_steps, dtype=int))
+            grid = np.unique(np.geomspace(min_dt, max_dt, n_steps, dtype=int))
         else:
             raise ValueError("Only linear or logarithmic spacing is allowed.")
+        if len(_GRIDS) >= 64:
+            _GRIDS.pop(next(iter(_GRIDS)))
+        _GRIDS[key] = grid
+        return grid.copy()
 
     def get_disps(self, time_intervals: np.ndarray, drift_corrected, progress: bool = True):
         """
