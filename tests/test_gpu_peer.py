@@ -125,3 +125,53 @@ def test_two_ranks_join_through_peer_memory(tmp_path):
                 proc.kill()
     for r in range(world):
         assert os.path.exists(tmp_path / f'ok{r}.npy'), f'rank {r} failed'
+
+
+def _absent_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    os.environ['KB2_PEER_TIMEOUT_S'] = '2'
+    import torch.distributed as td
+    from kinisi_b200 import dist
+    torch.cuda.set_device(0)
+    dev = torch.device('cuda', 0)
+    td.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        x = torch.ones(300, dtype=torch.float64, device=dev)
+        dist.allreduce_sum_(x, 'moments')  # both ranks: the windows exist and work
+        torch.cuda.synchronize()
+        assert float(x[0]) == world
+        td.barrier()
+        if rank == 0:
+            y = torch.ones(300, dtype=torch.float64, device=dev)
+            dist.allreduce_sum_(y, 'moments')  # rank 1 never issues this one
+            torch.cuda.synchronize()  # returns after KB2_PEER_TIMEOUT_S, not never
+            raised = False
+            try:
+                dist.check_peer_status()
+            except RuntimeError as exc:
+                raised = 'timed out waiting for a peer' in str(exc)
+            assert raised, 'the missing peer went unnoticed'
+        np.save(os.path.join(out_dir, f'absent{rank}.npy'), np.array([1]))
+        td.barrier()
+    finally:
+        td.destroy_process_group()
+
+
+def test_a_peer_that_never_arrives_is_reported_not_waited_for(tmp_path):
+    """Every wait of the join kernels is bounded: a rank that does not issue its side of a join makes the others' kernel
+    give up after KB2_PEER_TIMEOUT_S and raise a status word, instead of hanging the device."""
+    import time
+    world = 2
+    ctx = mp.spawn(_absent_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=False)
+    deadline = time.time() + 120
+    try:
+        while not ctx.join(timeout=5):
+            assert time.time() < deadline, 'the ranks did not finish'
+    finally:
+        for proc in ctx.processes:
+            if proc.is_alive():
+                proc.kill()
+    for r in range(world):
+        assert os.path.exists(tmp_path / f'absent{r}.npy'), f'rank {r} failed'
