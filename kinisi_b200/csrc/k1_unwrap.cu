@@ -949,30 +949,34 @@ static int launch_unwrap_warp(const void* coords, int n_atoms_total, int F, cons
 //     stores have read it;
 //   * one named barrier per tile (the warp totals) instead of three block barriers: the look-back is done by every warp
 //     for itself (a tile has at most a few dozen predecessors), before the results are staged.
-// float32 coordinates, constant cell; everything else takes the kernels above.
+// Constant cell; NPT cells and displacement input take the kernels above.
 constexpr int kUbE = 5;
-constexpr int kUbThreads = 256;                // consumer threads; + one producer warp
-constexpr int kUbTile = kUbThreads * kUbE;     // = kUwTile: the workspace layout is shared
-static_assert(kUbTile == kUwTile, "the two tile kernels share kb2_unwrap_cumsum_workspace_bytes");
+// consumer threads NT (+ one producer warp); a tile is NT * kUbE frames.  float32 coordinates: 256 threads, 1280-frame tiles,
+// two 45 KB stages, two CTAs per SM.  float64 coordinates (what ASE and pymatgen hand over): the same stage would be 61 KB --
+// one CTA per SM -- so 128 threads, 640-frame tiles, two 31 KB stages, three CTAs per SM.
+template <typename T>
+__host__ __device__ constexpr int ub_threads() { return sizeof(T) == 4 ? 256 : 128; }
+constexpr int kUbMinTile = 128 * kUbE;  // the workspace is sized for the shorter tile (kb2_unwrap_cumsum_workspace_bytes)
+static_assert(256 * kUbE == kUwTile, "the float32 tile is the tile of unwrap_cumsum_kernel");
 
 template <typename T>
 __host__ __device__ constexpr int ub_raw_bytes() {
-    return (int)((((kUbTile + 1) * 3 * sizeof(T) + 15 + 15) / 16) * 16);
+    return (int)((((ub_threads<T>() * kUbE + 1) * 3 * sizeof(T) + 15 + 15) / 16) * 16);
 }
 template <typename T>
 __host__ __device__ constexpr int ub_stage_bytes() {
-    return 3 * kUbTile * 8 + ub_raw_bytes<T>();
+    return 3 * ub_threads<T>() * kUbE * 8 + ub_raw_bytes<T>();
 }
 
 template <typename T, bool DRIFT>
-__global__ void __launch_bounds__(kUbThreads + 32, 2) unwrap_cumsum_bulk_kernel(const T* __restrict__ coords, int64_t n_coords, int F,
+__global__ void __launch_bounds__(ub_threads<T>() + 32, sizeof(T) == 4 ? 2 : 3) unwrap_cumsum_bulk_kernel(const T* __restrict__ coords, int64_t n_coords, int F,
                                                                               const double* __restrict__ latt,
                                                                               const int32_t* __restrict__ idx, int n_idx,
                                                                               const double* __restrict__ step_sums, double step_scale,
                                                                               double* __restrict__ out, int64_t pitch, int Tn,
                                                                               int n_tiles, unsigned char* __restrict__ workspace, int opts) {
     using namespace fb;
-    constexpr int E = kUbE, TF = kUbTile, NT = kUbThreads, NW = NT / 32, SB = ub_stage_bytes<T>();
+    constexpr int E = kUbE, NT = ub_threads<T>(), TF = NT * E, NW = NT / 32, SB = ub_stage_bytes<T>();
     extern __shared__ __align__(128) unsigned char ub_smem[];
     __shared__ uint64_t full[2], empty[2];
     __shared__ unsigned int s_item[2];
@@ -1167,17 +1171,17 @@ static int launch_unwrap_bulk(const void* coords, int n_atoms_total, int F, cons
                               cudaStream_t st) {
     const int sm = device_sm_count();
     const size_t smem = 2 * (size_t)ub_stage_bytes<T>();
-    const int n_tiles = ceil_div(pitch, kUbTile);
+    const int n_tiles = ceil_div(pitch, ub_threads<T>() * kUbE);
     KB2_CHECK((int64_t)n_idx * n_tiles < (1ll << 31), "kb2_unwrap_cumsum: too many (atom, tile) pairs for one call");
     // ticket counter = 0xFFFFFFFF (the first atomicAdd + 1 wraps to ticket 0); totals = the "not ready" pattern: one memset
     KB2_CUDA(cudaMemsetAsync(workspace, 0xFF, uw_workspace_bytes(n_idx, n_tiles), st));
-    const int grid = (int)std::min<int64_t>((int64_t)n_idx * n_tiles, (int64_t)sm * 2);
+    const int grid = (int)std::min<int64_t>((int64_t)n_idx * n_tiles, (int64_t)sm * (sizeof(T) == 4 ? 2 : 3));
     const char* eo = getenv("KB2_UB_OPTS");  // bit 0: no separate instantiation for full tiles (diagnostics)
     const int opts = eo ? atoi(eo) : 0;
 #define KB2_UB(D)                                                                                                            \
     do {                                                                                                                     \
         KB2_CUDA(cudaFuncSetAttribute(unwrap_cumsum_bulk_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        unwrap_cumsum_bulk_kernel<T, D><<<grid, kUbThreads + 32, smem, st>>>((const T*)coords, (int64_t)n_atoms_total * F * 3, F,  \
+        unwrap_cumsum_bulk_kernel<T, D><<<grid, ub_threads<T>() + 32, smem, st>>>((const T*)coords, (int64_t)n_atoms_total * F * 3, F,  \
                                                                              latt, idx, n_idx, step_sums, step_scale, out, pitch, \
                                                                              Tn, n_tiles, (unsigned char*)workspace, opts); \
     } while (0)
@@ -1191,7 +1195,7 @@ static int launch_unwrap_bulk(const void* coords, int n_atoms_total, int F, cons
 }
 
 // which kernel kb2_unwrap_cumsum takes for float32 / float64 fractional coordinates in a constant cell.  KB2_UW_KERNEL:
-// 0 the cp.async tile kernel, 1 the warp-per-atom kernel, 2 the bulk-copy tile kernel (float32), unset: the default below
+// 0 the cp.async tile kernel, 1 the warp-per-atom kernel, 2 the bulk-copy tile kernel, unset: by atom count (see the caller)
 static int unwrap_kernel_choice() {
     const char* e = getenv("KB2_UW_KERNEL");  // (read per call: the tests switch it)
     return e && e[0] ? atoi(e) : -1;
@@ -1347,7 +1351,7 @@ extern "C" int kb2_scan_frames(double* buf, int n_frames, int64_t pitch, int cum
 
 extern "C" size_t kb2_unwrap_cumsum_workspace_bytes(int n_idx, int64_t pitch) {
     if (n_idx < 1 || pitch < 1) return 256;
-    return uw_workspace_bytes(n_idx, ceil_div(pitch, kUwTile));
+    return uw_workspace_bytes(n_idx, ceil_div(pitch, kUbMinTile));  // (the kernel with the shortest tile: float64 bulk copies)
 }
 
 extern "C" int kb2_unwrap_cumsum(const void* coords, int dtype, int mode, int n_atoms_total, int n_frames_in,
@@ -1363,9 +1367,21 @@ extern "C" int kb2_unwrap_cumsum(const void* coords, int dtype, int mode, int n_
     if (mode == KB2_MODE_FRACTIONAL && latt_stride == 0 && (reinterpret_cast<uintptr_t>(dc_out) & 15) == 0 &&
         (!step_sums || (reinterpret_cast<uintptr_t>(step_sums) & 15) == 0)) {
         int choice = unwrap_kernel_choice();
-        if (choice < 0) choice = (dtype == KB2_F32) ? 2 : 0;
-        if (choice == 2 && dtype == KB2_F32)
-            return launch_unwrap_bulk<float>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, step_sums, step_scale, dc_out, pitch, Tn, workspace, st);
+        if (choice < 0) {
+            // The tickets of an atom's consecutive tiles are n_idx apart: with fewer atoms than about 4/3 of the persistent grid
+            // a tile runs at the same time as its predecessor and waits for its total in the middle of the item, before its
+            // results can be staged -- the cp.async kernel looks back AFTER staging and loses less.  Measured at 20 000 frames
+            // (tools/k1probe.py, profiles/r02_k1_probe.txt): float32 133 atoms 95 against 83 us, 300 atoms equal, 448 atoms 91
+            // against 118 us, 2000 atoms 4.4 against 3.5 TB/s; float64 448 atoms 215 against 135 us, 700 atoms 5.1 against
+            // 3.4 TB/s.
+            const int64_t grid = (int64_t)device_sm_count() * (dtype == KB2_F32 ? 2 : 3);
+            choice = ((int64_t)n_idx * 3 >= grid * 4) ? 2 : 0;
+        }
+        if (choice == 2) {
+            if (dtype == KB2_F32)
+                return launch_unwrap_bulk<float>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, step_sums, step_scale, dc_out, pitch, Tn, workspace, st);
+            return launch_unwrap_bulk<double>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, step_sums, step_scale, dc_out, pitch, Tn, workspace, st);
+        }
         if (choice == 1) {
             if (dtype == KB2_F32)
                 return launch_unwrap_warp<float>(coords, n_atoms_total, n_frames_in, latt, idx, n_idx, step_sums, step_scale, dc_out, pitch, Tn, st);

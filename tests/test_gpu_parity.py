@@ -1126,8 +1126,8 @@ def test_full_size_stage1_against_torch_fp64(kb):
 @pytest.mark.parametrize('shape', [(5, 3, 40), (37, 9, 223), (64, 8, 224), (70, 11, 225), (33, 7, 1571), (1000, 30, 301),
                                    (2100, 12, 449), (311, 5, 1280), (40, 6, 1281), (9, 4, 6431)])
 def test_unwrap_kernels_agree(kb, monkeypatch, dtype, drift, shape):
-    """The three unwrap kernels -- the bulk-copy tile kernel (producer warp, TMA loads and stores; the default for
-    float32), the one-warp-per-atom kernel (bulk-copy ring, scan carried in registers) and the cp.async tile kernel --
+    """The three unwrap kernels -- the bulk-copy tile kernel (producer warp, TMA loads and stores; the default: 1280-frame
+    tiles for float32, 640-frame tiles for float64), the one-warp-per-atom kernel (bulk-copy ring, scan carried in registers) and the cp.async tile kernel --
     against each other and against float64 torch: rows at every misalignment (odd frame counts), tiles and sub-tiles that
     end inside the trajectory, one and several tiles per atom (look-back), more atoms than warps (a warp walks several
     atoms without draining its ring), a scattered selection that includes the last row of the array (the bytes a 16-byte
@@ -1153,7 +1153,7 @@ def test_unwrap_kernels_agree(kb, monkeypatch, dtype, drift, shape):
     sums = kb.engine.frame_sums(coords, MODE_FRACTIONAL, latt, inv, 0, fw, None, pitch) if drift else None
     scale = 1.0 / n_fw if drift else 0.0
     got = {}
-    modes = ('2', '1', '0') if dtype == np.float32 else ('1', '0')
+    modes = ('2', '1', '0')
     for mode in modes:
         monkeypatch.setenv('KB2_UW_KERNEL', mode)
         out = torch.full((n_sel, 3, pitch), float('nan'), dtype=torch.float64, device=dev)

@@ -9,8 +9,10 @@ n_mob, n_fw, T = 448, 1088, 20000
 if len(sys.argv) > 3:
     n_mob, n_fw, T = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 gen = torch.Generator(device=dev); gen.manual_seed(1)
-steps = torch.randn((n_mob + n_fw, T + 1, 3), dtype=torch.float32, device=dev, generator=gen) * 0.004
+tdt = torch.float64 if os.environ.get('K1_DTYPE') == 'f64' else torch.float32
+steps = torch.randn((n_mob + n_fw, T + 1, 3), dtype=tdt, device=dev, generator=gen) * 0.004
 coords = (torch.cumsum(steps, dim=1) % 1.0).contiguous()
+esz = coords.element_size()
 latt = (torch.eye(3, dtype=torch.float64, device=dev) * 26.0).reshape(1, 3, 3)
 inv = engine.invert_lattice(latt)
 pitch = engine.pitch_for(T)
@@ -30,8 +32,8 @@ if n_fw:
 else:
     sums, t_fs = None, float('nan')
 out = torch.empty((n_mob, 3, pitch), dtype=torch.float64, device=dev)
-b_fs = n_fw * (T + 1) * 12
-b_uw = n_mob * (T + 1) * 12 + n_mob * 3 * pitch * 8
+b_fs = n_fw * (T + 1) * 3 * esz
+b_uw = n_mob * (T + 1) * 3 * esz + n_mob * 3 * pitch * 8
 line = 'frame_sums %.1f us  %.0f GB/s' % (t_fs * 1e3, b_fs / t_fs / 1e6)
 for name, mode in (('cp.async tile kernel', '0'), ('warp-per-atom kernel', '1'), ('bulk-copy tile kernel', '2')):
     if len(sys.argv) > 4 and sys.argv[4] != mode:
