@@ -1136,9 +1136,9 @@ __global__ void __launch_bounds__(ub_threads<T>() + 32, sizeof(T) == 4 ? 2 : 3) 
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            double off = (tile > 0) ? warp_sum(pc[c]) : 0.0;
-#pragma unroll 1
-            for (int wdx = 0; wdx < warp; ++wdx) off += s_tot[b][c][wdx];  // (a warp-uniform trip count)
+            // the totals of the earlier tiles (one per lane) and of the lower warps of this tile (lanes 0 .. warp - 1) in ONE
+            // butterfly: a loop over the lower warps cost the last warp 80 instructions behind the barrier
+            double off = warp_sum(pc[c] + ((lane < warp) ? s_tot[b][c][lane] : 0.0));
             off += incl[c] - val[E - 1][c];
 #pragma unroll
             for (int e = 0; e < E; ++e) outs[c * TF + f0 + e] = (FULL || t0 + f0 + e < Tn) ? val[e][c] + off : 0.0;
