@@ -999,11 +999,40 @@ __global__ void __launch_bounds__(ub_threads<T>() + 32, sizeof(T) == 4 ? 2 : 3) 
         // ---- producer: tickets and bulk copies, up to two items ahead
         if (lane == 0) {
             const char* const arr_end = reinterpret_cast<const char*>(coords + n_coords);
+            // The ticket of an item is drawn one item early and its coordinate run is prefetched into L2 then
+            // (cp.async.bulk.prefetch.L2): the copy into the stage, issued one item later, finds it there -- the consumers
+            // spent 16 % of their stall samples waiting for `full` with the HBM latency inside the one item of lead that
+            // two stages give.
+            // (Only with many atoms, opts bit 1: the extra ticket in flight per CTA brings the tiles of one atom closer together
+            // in time, and at configs[1] -- 448 atoms, 296 CTAs -- the look-back waits cost more than the prefetch gains:
+            // 76 -> 81-93 us, against 4.39 -> 4.59 TB/s at 4000 atoms.  Without it the ticket is drawn when the stage is free.)
+            const bool ahead = (opts & 2) != 0;
+            unsigned int w_ahead = ahead ? atomicAdd(counter, 1u) + 1u : 0u;
 #pragma unroll 1
             for (int it = 0;; ++it) {
                 const int b = it & 1;
-                if (it >= 2) mbar_wait(&empty[b], (uint32_t)(((it >> 1) - 1) & 1));
-                const unsigned int w = atomicAdd(counter, 1u) + 1u;
+                if (!ahead) {
+                    if (it >= 2) mbar_wait(&empty[b], (uint32_t)(((it >> 1) - 1) & 1));
+                    w_ahead = atomicAdd(counter, 1u) + 1u;
+                }
+                const unsigned int w = w_ahead;
+                if (ahead && w < n_work) {
+                    w_ahead = atomicAdd(counter, 1u) + 1u;
+                    if (w_ahead < n_work) {
+                        const int atom_a = (int)(w_ahead % (unsigned)n_idx), tile_a = (int)(w_ahead / (unsigned)n_idx);
+                        const int t0_a = tile_a * TF;
+                        const int nf_a = min(TF, Tn - t0_a);
+                        if (nf_a > 0) {
+                            const T* first_a = coords + ((size_t)__ldg(idx + atom_a) * F + t0_a) * 3;
+                            const char* src_a = reinterpret_cast<const char*>(first_a) - (reinterpret_cast<uintptr_t>(first_a) & 15);
+                            long long bytes_a = (((reinterpret_cast<const char*>(first_a + 3 * (nf_a + 1)) - src_a) + 15) / 16) * 16;
+                            bytes_a = min(bytes_a, (long long)(((arr_end - src_a) / 16) * 16));
+                            if (bytes_a > 0)
+                                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_a), "r"((uint32_t)bytes_a) : "memory");
+                        }
+                    }
+                }
+                if (ahead && it >= 2) mbar_wait(&empty[b], (uint32_t)(((it >> 1) - 1) & 1));
                 s_item[b] = w;
                 if (w >= n_work) {
                     mbar_arrive(&full[b]);
@@ -1176,8 +1205,8 @@ static int launch_unwrap_bulk(const void* coords, int n_atoms_total, int F, cons
     // ticket counter = 0xFFFFFFFF (the first atomicAdd + 1 wraps to ticket 0); totals = the "not ready" pattern: one memset
     KB2_CUDA(cudaMemsetAsync(workspace, 0xFF, uw_workspace_bytes(n_idx, n_tiles), st));
     const int grid = (int)std::min<int64_t>((int64_t)n_idx * n_tiles, (int64_t)sm * (sizeof(T) == 4 ? 2 : 3));
-    const char* eo = getenv("KB2_UB_OPTS");  // bit 0: no separate instantiation for full tiles (diagnostics)
-    const int opts = eo ? atoi(eo) : 0;
+    const char* eo = getenv("KB2_UB_OPTS");  // bit 0: no separate instantiation for full tiles (diagnostics); bit 1: L2 prefetch
+    const int opts = eo ? atoi(eo) : ((int64_t)n_idx >= 4ll * grid ? 2 : 0);
 #define KB2_UB(D)                                                                                                            \
     do {                                                                                                                     \
         KB2_CUDA(cudaFuncSetAttribute(unwrap_cumsum_bulk_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -39,7 +39,8 @@ for name, mode in (('cp.async tile kernel', '0'), ('warp-per-atom kernel', '1'),
     if len(sys.argv) > 4 and sys.argv[4] != mode:
         continue
     os.environ['KB2_UW_KERNEL'] = mode.split(':')[0]
-    os.environ['KB2_UB_OPTS'] = mode.split(':')[1] if ':' in mode else '0'
+    if ':' in mode:
+        os.environ['KB2_UB_OPTS'] = mode.split(':')[1]
     t_uw = timeit(lambda: engine.unwrap_cumsum(coords, MODE_FRACTIONAL, latt, inv, 0, idx, sums, 1.0 / max(n_fw, 1), pitch, out=out))
     line += '   unwrap_cumsum (%s) %.1f us  %.0f GB/s' % (name, t_uw * 1e3, b_uw / t_uw / 1e6)
 print(line)
