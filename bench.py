@@ -765,7 +765,7 @@ def run_own(args):
                 'per_gpu': f'{n_mob + n_fw} atoms ({n_mob} mobile) x {T} frames, f32 wrapped fractional coordinates',
                 'sharding': 'atoms' if world > 1 else 'none',
                 'joins': ('none' if world == 1 else
-                          'peer memory: frame sums joined inside kb2_frame_sums_joined, moment sums by kb2_peer_allreduce_f64'
+                          'peer memory, no launch of their own: frame sums joined inside kb2_frame_sums_joined, moment sums inside kb2_moment_stats_joined'
                           if any(kdist._PEER.values()) and os.environ.get('KB2_FUSED_JOIN', '1') != '0' else
                           'peer-memory kernel (kb2_peer_allreduce_f64), 2 per step' if any(kdist._PEER.values()) else
                           'NCCL all-reduce, 2 per step'),

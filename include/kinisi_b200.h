@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KB2_ABI_VERSION 9
+#define KB2_ABI_VERSION 10
 
 /* coordinate element types */
 #define KB2_F32 0
@@ -369,6 +369,13 @@ int kb2_frame_sums_joined(const void* coords, int dtype, int mode, int n_atoms_t
                           const double* latt_inv, int latt_stride, const int32_t* idx, const double* w, int n_idx,
                           double* frame_sums, int64_t pitch, void* const* windows_host, int world, int rank, int64_t capacity,
                           uint64_t seq, unsigned int* tile_counters, void* stream);
+/* kb2_moment_stats with the sum over ranks of ngp_sums [n][2] (the per-lag sums of the atoms' own displacements, local to
+ * this rank on entry: np.mean / np.var over atoms x origins, kinisi/diffusion.py:571-602) done first, in place, by the same
+ * kernel: n <= 512.  main_sums may be ngp_sums itself (MSD) or an array that is already equal on all ranks (MSTD / MSCD).  The
+ * join is the one kb2_peer_allreduce_f64(ngp_sums, 2 n, ...) would do (same windows, same seq). */
+int kb2_moment_stats_joined(const double* main_sums, const double* cnt, const double* divisor, double* ngp_sums,
+                            const double* gcnt, int n, double* out_n, double* out_v, double* out_s, double* out_ngp,
+                            void* const* windows_host, int world, int rank, int64_t capacity, uint64_t seq, void* stream);
 int kb2_peer_status(void);
 
 /* ---------------------------------------------------------------------------------------------

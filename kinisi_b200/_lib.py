@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get('KB2_LIB_PATH') or os.path.join(HERE, 'libkinisi_b200.
 
 F32, F64 = 0, 1
 MODE_FRACTIONAL, MODE_DISPLACEMENT = 0, 1
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # name -> (restype, argtypes); mirrors include/kinisi_b200.h one to one
 SIGNATURES = {
@@ -82,6 +82,8 @@ SIGNATURES = {
                                             c_void_p]),
     'kb2_frame_sums_joined': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                       c_void_p, c_int64, POINTER(c_void_p), c_int, c_int, c_int64, c_uint64, c_void_p, c_void_p]),
+    'kb2_moment_stats_joined': (c_int, [c_void_p] * 5 + [c_int] + [c_void_p] * 4 + [POINTER(c_void_p), c_int, c_int, c_int64, c_uint64,
+                                                                               c_void_p]),
     'kb2_peer_status': (c_int, []),
     'kb2_fp64_peak': (c_int, [c_int, c_int, c_void_p, c_void_p]),
     'kb2_stream_copy': (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),

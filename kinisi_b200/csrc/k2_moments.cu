@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "peer.cuh"
 #include "k2_common.cuh"
 
 namespace kb2 {
@@ -123,6 +124,31 @@ __global__ void moment_stats_kernel(const double* __restrict__ ms, const double*
     const double g = gcnt[i];
     const double gm = gs[2 * i] / g;
     out_ngp[i] = (gs[2 * i + 1] / g * 3.0) / (gm * gm * 5.0) - 1.0;
+}
+
+// The same with the per-lag sums of the atoms' own displacements still local to this rank (atoms sharded over GPUs): ONE CTA
+// first joins gs [n][2] over the ranks through peer memory (peer_join_slice: the protocol of kb2_peer_allreduce_f64 for an
+// array of one slice, so 2 n <= 1024), in place, then finishes the statistics from the joined sums -- the join and its
+// consumer are one kernel.  ms may be gs (MSD) or an array that is already the same on every rank (the collective sums).
+__global__ void __launch_bounds__(256) moment_stats_joined_kernel(const double* __restrict__ ms, const double* __restrict__ cnt,
+                                                                  const double* __restrict__ divisor, double* gs,
+                                                                  const double* __restrict__ gcnt, int n, double* __restrict__ out_n,
+                                                                  double* __restrict__ out_v, double* __restrict__ out_s,
+                                                                  double* __restrict__ out_ngp, PeerJoin J) {
+    peer_join_slice(J, gs, 1, 2ll * n, 0, 0, 2ll * n);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double m1 = __ldcg(ms + 2 * i), m2 = __ldcg(ms + 2 * i + 1), c = cnt[i];
+        const double mean = m1 / c;
+        const double var = (m2 - m1 * mean) / (c - 1.0);
+        const double v = var / divisor[i];
+        out_n[i] = mean;
+        out_v[i] = v;
+        out_s[i] = sqrt(v);
+        const double g = gcnt[i];
+        const double gm = __ldcg(gs + 2 * i) / g;
+        out_ngp[i] = (__ldcg(gs + 2 * i + 1) / g * 3.0) / (gm * gm * 5.0) - 1.0;
+    }
 }
 
 // ---- moments of one materialised displacement array (the reference seam) ----------------------
@@ -294,6 +320,23 @@ extern "C" int kb2_moment_stats(const double* main_sums, const double* cnt, cons
     KB2_CHECK(n > 0, "kb2_moment_stats: n must be positive");
     moment_stats_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(main_sums, cnt, divisor, ngp_sums, gcnt, n,
                                                                             out_n, out_v, out_s, out_ngp);
+    KB2_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int kb2_moment_stats_joined(const double* main_sums, const double* cnt, const double* divisor, double* ngp_sums,
+                                       const double* gcnt, int n, double* out_n, double* out_v, double* out_s, double* out_ngp,
+                                       void* const* windows_host, int world, int rank, int64_t capacity, uint64_t seq,
+                                       void* stream) {
+    KB2_CHECK(main_sums && cnt && divisor && ngp_sums && gcnt && out_n && out_v && out_s && out_ngp,
+              "kb2_moment_stats_joined: null pointer");
+    KB2_CHECK(n > 0 && 2 * n <= 1024, "kb2_moment_stats_joined: 1 <= n <= 512 (longer grids: kb2_peer_allreduce_f64 + kb2_moment_stats)");
+    KB2_CHECK(2ll * n <= capacity, "kb2_moment_stats_joined: 2 n exceeds the capacity of the windows");
+    KB2_CHECK((reinterpret_cast<uintptr_t>(ngp_sums) & 15) == 0, "kb2_moment_stats_joined: ngp_sums must be 16-byte aligned");
+    PeerJoin J;
+    if (int rc = peer_join_setup(&J, windows_host, world, rank, capacity, seq, 1, "kb2_moment_stats_joined")) return rc;
+    moment_stats_joined_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(main_sums, cnt, divisor, ngp_sums, gcnt, n, out_n, out_v, out_s,
+                                                                    out_ngp, J);
     KB2_LAUNCH_CHECK();
     return 0;
 }

@@ -282,7 +282,11 @@ class Bootstrap:
             else:
                 sums = torch.zeros((len(used), 2), dtype=torch.float64, device=self._device)
             if d.distributed:
-                dist.allreduce_sum_(sums, 'moments')
+                # the sum over ranks is done by the kernel that consumes the sums (_finish -> kb2_moment_stats_joined) where
+                # the grid is short enough for one slice; by a kernel of its own otherwise
+                self._moments_join = dist.moments_channel(sums.numel(), sums.device)
+                if self._moments_join is None:
+                    dist.allreduce_sum_(sums, 'moments')
             if not np.array_equal(order, np.arange(len(order))):
                 inv = np.empty_like(order)
                 inv[order] = np.arange(len(order))
@@ -331,7 +335,10 @@ class Bootstrap:
         else:
             packed = self._const(np.stack([np.asarray(cnt, dtype=np.float64), np.asarray(divisor, dtype=np.float64),
                                            np.asarray(gcnt, dtype=np.float64)]))  # one upload: counts, divisors, NGP counts
-            self._stats_dev = engine.moment_stats(main_sums, packed[0], packed[1], ngp_sums, packed[2])
+            join, self._moments_join = getattr(self, '_moments_join', None), None
+            self._stats_dev = engine.moment_stats(main_sums, packed[0], packed[1], ngp_sums, packed[2], join=join)
+            if join is not None:
+                dist.check_peer_status()
         self._dt = np.asarray(self._delta_t, dtype=float)[np.asarray(used, dtype=np.int64)] if len(used) else np.array([])
         self._n_o = self._n_o[:len(used)]  # diffusion.py:602
         self._euclidian_displacements = _LazyEuclidian(self._displacements, used, self._slice, self.dims)

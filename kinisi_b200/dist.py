@@ -213,6 +213,13 @@ class _PeerChannel:
         engine.LAUNCHES['n'] += 1
         check_peer_status()
 
+    def next_join(self):
+        """(windows, world, rank, capacity, seq) of the next join of this channel, for a kernel that does the join itself
+        (kb2_moment_stats_joined); the call is counted."""
+        seq = self.seq
+        self.seq += 1
+        return self._ptrs, self.world, self.rank, self.capacity, seq
+
     def frame_sums_join(self):
         """The arguments after `pitch` of kb2_frame_sums_joined for the next join of this channel (the call is counted):
         (windows, world, rank, capacity, seq, tile counters)."""
@@ -287,6 +294,20 @@ def _direct(name, t):
                 warnings.warn(f'kinisi_b200.dist: direct NCCL communicator unavailable ({exc}); using torch.distributed')
         _DIRECT[key] = comm
     return _DIRECT[key]
+
+
+def moments_channel(n, device):
+    """The peer-memory channel through which n per-lag sums (a flat array of one slice: n <= 1024) can be joined inside the
+    kernel that consumes them (kb2_moment_stats_joined), or None.  Depends on n alone: every rank takes the same road."""
+    if not active() or n > 1024 or n < 2 or os.environ.get('KB2_FUSED_JOIN', '1') == '0':
+        return None
+    device = torch.device(device)
+    if device.type != 'cuda':
+        return None
+    ch = _PEER.get(('moments', device.index))
+    if ch:
+        return ch
+    return _peer('moments', torch.empty(int(n), dtype=torch.float64, device=device))
 
 
 def frame_sums_channel(n_rows, pitch, device):

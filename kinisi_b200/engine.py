@@ -398,10 +398,22 @@ def reblock(values):
     return stats[:levels]
 
 
-def moment_stats(main_sums, cnt, divisor, ngp_sums, gcnt):
+def moment_stats(main_sums, cnt, divisor, ngp_sums, gcnt, join=None):
+    """[4, n] = n, v, s, ngp from the per-lag sums; see kb2_moment_stats.  `join`: a peer-memory channel
+    (dist.moments_channel) -- ngp_sums is then still local to this rank and the kernel sums it over the ranks first, in
+    place (kb2_moment_stats_joined)."""
     lib = require_cuda()
     n = cnt.numel()
     out = torch.empty((4, n), dtype=torch.float64, device=cnt.device)
+    if join is not None:
+        windows, world, rank, capacity, seq = join.next_join()
+        check(
+            lib.kb2_moment_stats_joined(main_sums.data_ptr(), cnt.data_ptr(), divisor.data_ptr(), ngp_sums.data_ptr(),
+                                        gcnt.data_ptr(), n, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                                        out[3].data_ptr(), windows, world, rank, capacity, seq, _stream()),
+            'kb2_moment_stats_joined')
+        _count()
+        return out
     check(
         lib.kb2_moment_stats(main_sums.data_ptr(), cnt.data_ptr(), divisor.data_ptr(), ngp_sums.data_ptr(),
                              gcnt.data_ptr(), n, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
