@@ -83,6 +83,32 @@ def test_argument_errors_are_reported_without_a_gpu(lib_path):
     assert lib.kb2_reblock_workspace_bytes(7) >= 8 * (4 + 2)
 
 
+def test_peer_entry_points_reject_bad_arguments_without_a_device(lib_path):
+    """The joins over ranks (csrc/k7_peer.cu, peer.cuh): the sizing helpers are host arithmetic, and the argument checks come
+    before any CUDA call."""
+    import ctypes
+    from kinisi_b200 import _lib
+    lib = _lib.load()
+    assert lib.kb2_peer_slots() == 8
+    assert lib.kb2_peer_rows_slices(1024) == 1 and lib.kb2_peer_rows_slices(1026) == 2 and lib.kb2_peer_rows_slices(131072) == 128
+    assert lib.kb2_peer_rows_slices(131074) == 0 and lib.kb2_peer_rows_slices(1023) == 0  # too long for one join; odd
+    assert lib.kb2_peer_window_bytes(0, 1024) == 0 and lib.kb2_peer_window_bytes(17, 1024) == 0
+    two, eight = lib.kb2_peer_window_bytes(2, 1 << 15), lib.kb2_peer_window_bytes(8, 1 << 15)
+    assert two >= 8 * 2 * (1 << 15) * 8 and eight >= 4 * two - (1 << 20)  # slots x ranks x capacity doubles, plus the flags
+    windows = (ctypes.c_void_p * 2)(16, 32)
+    rc = lib.kb2_peer_allreduce_f64(16, 100, windows, 2, 0, 64, 0, None)
+    assert rc != 0 and b'capacity' in lib.kb2_last_error()
+    rc = lib.kb2_peer_allreduce_f64(24, 10, windows, 2, 0, 64, 0, None)
+    assert rc != 0 and b'aligned' in lib.kb2_last_error()
+    rc = lib.kb2_peer_allreduce_rows_f64(16, 3, 1023, windows, 2, 0, 1 << 20, 0, None)
+    assert rc != 0 and b'even' in lib.kb2_last_error()
+    rc = lib.kb2_moment_stats_joined(16, 16, 16, 16, 16, 600, 16, 16, 16, 16, windows, 2, 0, 1 << 15, 0, None)
+    assert rc != 0 and b'512' in lib.kb2_last_error()
+    rc = lib.kb2_frame_sums_joined(16, 0, 0, 4, 10, 16, 16, 0, 16, None, 2, 16, 16, windows, 2, 0, 32, 0, 16, None)
+    assert rc != 0 and b'capacity' in lib.kb2_last_error()
+    assert lib.kb2_peer_status() == 0
+
+
 def test_run_plan_is_host_only(lib_path):
     """kb2_self_moments_runs_plan_pack needs no device: the packed plan of BASELINE configs[1]'s grid has one block with
     one 99-lag progression and one single lag."""
@@ -106,6 +132,7 @@ def test_sass_has_tma_and_fp64(lib_path):
     sass = subprocess.run([cuobjdump, '-sass', lib_path], capture_output=True, text=True).stdout
     assert 'sm_100a' in sass
     assert 'UBLKCP' in sass and 'SYNCS' in sass
+    assert 'UBLKPF' in sass  # cp.async.bulk.prefetch.L2 (the unwrap kernel's look-ahead)
     assert 'DFMA' in sass
 
 
