@@ -289,8 +289,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 }  // namespace fb
 
-template <typename T>
-__global__ void __launch_bounds__(kFbConsumers + 32) frame_sums_bulk_kernel(const T* __restrict__ coords, int64_t n_coords, int F,
+template <typename T, bool JOIN>
+__global__ void __launch_bounds__(kFbConsumers + 32, sizeof(T) == 4 ? 4 : 2) frame_sums_bulk_kernel(const T* __restrict__ coords, int64_t n_coords, int F,
                                                                            const double* __restrict__ latt,
                                                                            const int32_t* __restrict__ idx, int n_idx,
                                                                            int per_chunk, double* __restrict__ sums,
@@ -380,8 +380,9 @@ __global__ void __launch_bounds__(kFbConsumers + 32) frame_sums_bulk_kernel(cons
         }
     }
     }
-    // (the producer warp comes here too: the join of a tile is the work of the whole CTA)
-    if (fj.enabled) frame_join_epilogue(fj, sums, pitch, blockIdx.x, gridDim.y);
+    // (the producer warp comes here too: the join of a tile is the work of the whole CTA; an instantiation of its own, so that
+    // the single-GPU kernel does not carry the join's registers: 66 against 56)
+    if (JOIN) frame_join_epilogue(fj, sums, pitch, blockIdx.x, gridDim.y);
 }
 
 template <typename T>
@@ -396,9 +397,15 @@ static int launch_frame_sums_bulk(const void* coords, int n_atoms_total, int F, 
     chunks = std::min(chunks, 65535);
     const int per = ceil_div(n_idx, chunks);
     chunks = ceil_div(n_idx, per);
-    KB2_CUDA(cudaFuncSetAttribute(frame_sums_bulk_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    frame_sums_bulk_kernel<T><<<dim3(tiles, chunks), kFbConsumers + 32, smem, st>>>((const T*)coords, (int64_t)n_atoms_total * F * 3, F,
-                                                                                  latt, idx, n_idx, per, sums, pitch, Tn, fj);
+    if (fj.enabled) {
+        KB2_CUDA(cudaFuncSetAttribute(frame_sums_bulk_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        frame_sums_bulk_kernel<T, true><<<dim3(tiles, chunks), kFbConsumers + 32, smem, st>>>((const T*)coords, (int64_t)n_atoms_total * F * 3,
+                                                                                            F, latt, idx, n_idx, per, sums, pitch, Tn, fj);
+    } else {
+        KB2_CUDA(cudaFuncSetAttribute(frame_sums_bulk_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        frame_sums_bulk_kernel<T, false><<<dim3(tiles, chunks), kFbConsumers + 32, smem, st>>>((const T*)coords, (int64_t)n_atoms_total * F * 3,
+                                                                                             F, latt, idx, n_idx, per, sums, pitch, Tn, fj);
+    }
     KB2_LAUNCH_CHECK();
     return 0;
 }
