@@ -176,6 +176,32 @@ def test_xdatcar_reader(tmp_path):
         assert x.frac_coords.shape == (140, 416, 3) and x.site_symbols.count('Li') == 192
 
 
+def test_time_interval_grid_is_kept_by_value():
+    """get_time_intervals keeps the grid of a set of arguments (a loop over trajectories of one shape asks for the same one
+    every time): the caller gets a copy, and writing to it does not reach the next caller."""
+    from kinisi_b200.parser import Parser
+    p = Parser.__new__(Parser)
+    p.time_step, p.step_skip = 0.5, 4
+    p.min_dt, p.max_dt = 2.0, 5000 * 2.0
+    first = p.get_time_intervals(100, 'linear')
+    np.testing.assert_array_equal(first, np.linspace(1, 5000, 100, dtype=int))
+    first[:] = -1
+    again = p.get_time_intervals(100, 'linear')
+    np.testing.assert_array_equal(again, np.linspace(1, 5000, 100, dtype=int))
+    with pytest.raises(ValueError, match='Only linear or logarithmic'):
+        p.get_time_intervals(100, 'cubic')
+
+
+def test_peer_plumbing_is_inert_without_a_group():
+    """Outside a process group nothing asks for peer-memory windows: no channel, no fused join."""
+    import torch
+    from kinisi_b200 import dist
+    assert dist.frame_sums_channel(3, 20000, torch.device('cpu')) is None
+    assert dist.moments_channel(200, torch.device('cpu')) is None
+    assert not dist._PEER
+    dist.check_peer_status()  # no status word has been raised
+
+
 def test_direct_nccl_plumbing_is_inert_without_a_group():
     """dist.allreduce_sum_ is a no-op outside a process group, and the direct NCCL communicator is only considered for
     contiguous float64 CUDA tensors (everything else stays on torch.distributed)."""
