@@ -771,7 +771,9 @@ def run_own(args):
                           'NCCL all-reduce, 2 per step'),
                 'l2': f'inputs ({host.numel() * 4 / 1e6:.0f} MB f32 + {n_mob * 3 * T * 8 / 1e6:.0f} MB f64 per step) '
                       'exceed the 126 MB L2; no flush needed',
-                'self_moment_variant': {0: 'direct', 1: 'tma-ring', 2: 'arithmetic-runs', 3: 'lag-window', 4: 'tiled-lag-window'}[engine.DEFAULT_VARIANT & 0xff],
+                'self_moment_variant': {0: 'direct', 1: 'tma-ring', 2: 'arithmetic-runs', 3: 'lag-window', 4: 'tiled-lag-window'}[
+                    (engine.choose_variant(lags, T) if engine.DEFAULT_VARIANT == engine.VARIANT_AUTO else engine.DEFAULT_VARIANT) & 0xff]
+                + (' (chosen by the lag grid)' if engine.DEFAULT_VARIANT == engine.VARIANT_AUTO else ' (forced)'),
                 'wall_ms_per_step': wall_total / args.steps,
                 'analyses_in_flight': args.in_flight,
             },

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KB2_ABI_VERSION 10
+#define KB2_ABI_VERSION 11
 
 /* coordinate element types */
 #define KB2_F32 0
@@ -209,7 +209,11 @@ int kb2_self_moments_win_plan(const int32_t* lags_host, int n_lags, int n_frames
  *                                          device, uploaded earlier in stream order; counters, sums: zeroed by the call)
  *   kb2_self_moments_tile_plan             the windows of (the first 256 lags of) a grid, for tests and diagnostics: first
  *                                          lag, lag spacing (= row length D) and number of lags per window; *n_tiles (may
- *                                          be NULL) receives the number of tile templates. */
+ *                                          be NULL) receives the number of tile templates
+ *   kb2_self_moments_tile_plan_cost        what the plan costs per atom (host only): out[0] = bytes copied into shared
+ *                                          memory, out[1] = consumer issue cycles (steps x (16 m + 24) over all strips),
+ *                                          out[2] = terms of the column walks.  The host side compares out[0] with the
+ *                                          24 n_frames bytes of an atom to choose the kernel for a grid. */
 size_t kb2_self_moments_tile_workspace_bytes(const int32_t* lags_host, int n_lags, int n_frames);
 int kb2_self_moments_tile_blocks(int n_lags);
 int kb2_self_moments_tile_plan_pack(const int32_t* lags_host, int n_lags, int n_frames, void* plan_host);
@@ -217,6 +221,17 @@ int kb2_self_moments_tile_planned(const double* dc, int n_atoms, int n_frames, i
                                   const void* plan_host, const void* plan_dev, void* counters, double* sums, void* stream);
 int kb2_self_moments_tile_plan(const int32_t* lags_host, int n_lags, int n_frames, int32_t* win_first, int32_t* win_delta,
                                int32_t* win_len, int max_wins, int* n_tiles);
+int kb2_self_moments_tile_plan_cost(const int32_t* lags_host, int n_lags, int n_frames, double* out);
+
+/* Which of the kernels above for a lag grid (host only; what the Python host side does when no variant is forced).  The
+ * reference has one code path for every grid (kinisi/diffusion.py:571-602); here the tiled kernel is taken while its
+ * producers copy <= 2 bytes per term (kinisi's default 100-point grid on trajectories of >= 20 000 frames), the run kernel
+ * for long runs of one spacing, the window kernel while the windows stay long, the direct kernel otherwise -- thresholds
+ * from a measured survey of 68 grids (csrc/k2_moments_tile.cu, profiles/r02_k2_grid_survey.txt).  Returns the variant
+ * number (0 direct, 2 runs, 3 windows, 4 tiles) or -1 on invalid input; features[4] (may be NULL) receives the bytes
+ * per term of the tile plan, the run model's fraction, the share of terms in windows of <= 3 lags and the mean window
+ * length. */
+int kb2_self_moments_choose(const int32_t* lags_host, int n_lags, int n_frames, double* features);
 
 /* The same sums from ONE materialised displacement array disp[n_atoms][n_obs][3] (float64, the
  * reference seam: an entry of disp_3d as passed to the *Bootstrap constructors,

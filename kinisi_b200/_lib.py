@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get('KB2_LIB_PATH') or os.path.join(HERE, 'libkinisi_b200.
 
 F32, F64 = 0, 1
 MODE_FRACTIONAL, MODE_DISPLACEMENT = 0, 1
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # name -> (restype, argtypes); mirrors include/kinisi_b200.h one to one
 SIGNATURES = {
@@ -51,6 +51,8 @@ SIGNATURES = {
     'kb2_self_moments_tile_planned': (c_int, [c_void_p, c_int, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                               c_void_p, c_void_p]),
     'kb2_self_moments_tile_plan': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_int)]),
+    'kb2_self_moments_tile_plan_cost': (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    'kb2_self_moments_choose': (c_int, [c_void_p, c_int, c_int, c_void_p]),
     'kb2_self_moments_plan': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                       POINTER(c_int)]),
     'kb2_disp_moments': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),

@@ -964,6 +964,106 @@ extern "C" int kb2_self_moments_tile_planned(const double* dc, int n_atoms, int 
     return 0;
 }
 
+// What the plan of a grid costs per atom (host only; the variant choice of the host side reads it): out[0] = bytes the
+// producers copy into shared memory (all launches, all strips), out[1] = consumer issue cycles (the planner's own unit
+// cost, steps x (16 m + 24), over all strips), out[2] = terms formed in the column walks.
+extern "C" int kb2_self_moments_tile_plan_cost(const int32_t* lags_host, int n_lags, int n_frames, double* out) {
+    if (int rc = tile_check_lags("kb2_self_moments_tile_plan_cost", lags_host, n_lags, n_frames)) return rc;
+    KB2_CHECK(out, "kb2_self_moments_tile_plan_cost: null pointer");
+    out[0] = out[1] = out[2] = 0.0;
+    for (int l0 = 0; l0 < n_lags; l0 += kTileMaxLags) {
+        const int K = std::min(kTileMaxLags, n_lags - l0);
+        TilePlan plan;
+        plan_tiles(lags_host + l0, K, n_frames, plan);
+        out[0] += (double)plan.bytes_loaded;
+        for (const TileTpl& tp : plan.tpls) {
+            double cyc = 0.0, terms = 0.0;
+            for (int u = 0; u < tp.nunits; ++u) {
+                const TileUnit& un = plan.units[tp.unit0 + u];
+                cyc += (double)(un.nsteps + (un.top ? 0 : un.m - 1)) * (16 * un.m + 24);
+                terms += (double)un.nsteps * un.m - (un.top ? (double)un.m * (un.m - 1) / 2 : 0.0);
+            }
+            const int strips = (tp.D + 31) / 32;
+            out[1] += cyc * strips;
+            out[2] += terms * tp.D;
+        }
+    }
+    return 0;
+}
+
+extern "C" int kb2_self_moments_win_plan(const int32_t* lags_host, int n_lags, int n_frames, int32_t* win_kappa,
+                                         int32_t* win_delta, int32_t* win_len, int max_wins);
+extern "C" int kb2_self_moments_plan(const int32_t* lags_host, int n_lags, int n_frames, int32_t* run_k0,
+                                     int32_t* run_delta, int32_t* run_len, int32_t* run_n_chg, int max_runs, int* n_rest);
+
+// Which moment kernel for a lag grid (host only).  The tiled kernel reaches 0.6-0.75 of the FP64 peak while its producers
+// copy less than ~2 bytes per term; beyond that it is bound by the L2 -> shared-memory traffic (fraction ~ 1 / (1.2 + 0.5 b),
+// b = bytes per term), which is what happens when the lags of a grid spread over many residues r of the row length (dense
+// grids, short trajectories, grids whose spacing drifts every few lags).  The other kernels do not depend on r:
+//   * arithmetic runs: long runs of one spacing; model 0.67 * terms / sum_runs origins * (len + 20 + 10 changes), 32 per
+//     term of a lag outside the runs;
+//   * register windows: as long as the windows stay long (terms in windows of <= 3 lags <= 10 %, mean length >= 5);
+//   * direct: everything else (no structure needed).
+// Thresholds from a survey of 68 grids np.linspace(1, T, n, dtype=int), T = 1000 ... 100 000, n = 50 ... 2000
+// (tools/k2grid_survey.py, profiles/r02_k2_grid_survey.txt): the choice is within 10 % of the best kernel on 65 of them,
+// the geometric mean of chosen / best time is 1.014 (always tiled: 1.75).  features (may be NULL) receives b, the run
+// model, the share of short windows and the mean window length.  Returns 0 (direct), 2 (runs), 3 (windows), 4 (tiles),
+// or -1 on invalid input.
+extern "C" int kb2_self_moments_choose(const int32_t* lags_host, int n_lags, int n_frames, double* features) {
+    if (tile_check_lags("kb2_self_moments_choose", lags_host, n_lags, n_frames)) return -1;
+    const double T = (double)n_frames;
+    double cost[3];
+    if (kb2_self_moments_tile_plan_cost(lags_host, n_lags, n_frames, cost)) return -1;
+    double terms = 0.0;
+    for (int i = 0; i < n_lags; ++i) terms += T - lags_host[i] + 1;
+    const double b = cost[0] / std::max(terms, 1.0);
+    // runs: the plan of the first launch (192 lags)
+    double runs_eff = 0.0;
+    {
+        const int K = std::min(n_lags, 192);
+        std::vector<int32_t> k0(K), dl(K), ln(K), ch(K);
+        int rest = 0;
+        const int n = kb2_self_moments_plan(lags_host, K, n_frames, k0.data(), dl.data(), ln.data(), ch.data(), K, &rest);
+        double t2 = 0.0, run_terms = 0.0, c = 0.0;
+        for (int i = 0; i < K; ++i) t2 += T - lags_host[i];
+        for (int i = 0; i < n && i < K; ++i) {
+            const double origins = T - k0[i] - 0.5 * (ln[i] - 1) * dl[i];
+            run_terms += origins * ln[i];
+            c += origins * (ln[i] + 20.0 + 10.0 * abs(ch[i]));
+        }
+        c += 32.0 * std::max(t2 - run_terms, 0.0);
+        runs_eff = c > 0.0 ? 0.67 * t2 / c : 0.0;
+    }
+    // windows: the plan of the first launch (256 lags)
+    double small = 1.0, mbar = 0.0;
+    {
+        const int K = std::min(n_lags, 256);
+        std::vector<int32_t> kp(K), dl(K), ln(K);
+        const int n = std::min(K, kb2_self_moments_win_plan(lags_host, K, n_frames, kp.data(), dl.data(), ln.data(), K));
+        double w_all = 0.0, w_small = 0.0, o_all = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const double origins = T - kp[i] - 0.5 * (ln[i] - 1) * dl[i];
+            w_all += origins * ln[i];
+            o_all += origins;
+            if (ln[i] <= 3) w_small += origins * ln[i];
+        }
+        if (w_all > 0.0 && o_all > 0.0) {
+            small = w_small / w_all;
+            mbar = w_all / o_all;
+        }
+    }
+    if (features) {
+        features[0] = b;
+        features[1] = runs_eff;
+        features[2] = small;
+        features[3] = mbar;
+    }
+    if (b <= 2.0) return 4;
+    if (runs_eff >= 0.55) return 2;
+    if (small <= 0.1 && mbar >= 5.0) return 3;
+    return 0;
+}
+
 // The windows of the plan for (the first 256 lags of) a grid, for tests and diagnostics: fills up to max_wins entries of
 // win_first (first lag) / win_delta (row length D = lag spacing inside the window) / win_len and returns the number of
 // windows; *n_tiles receives the number of tile templates.

@@ -17,7 +17,8 @@ VARIANT_TMA = 1
 VARIANT_RUNS = 2  # arithmetic-run kernel (origin window in registers); plans on the host, needs the lags there
 VARIANT_WIN = 3   # lag-window kernel (partner window + accumulators in registers); plans on the host too
 VARIANT_TILE = 4  # tiled lag-window kernel: tiles staged in shared memory by TMA bulk copies; plans on the host too
-DEFAULT_VARIANT = VARIANT_TILE
+VARIANT_AUTO = -1  # chosen per lag grid by kb2_self_moments_choose (tiles for kinisi's default grid on long trajectories)
+DEFAULT_VARIANT = VARIANT_AUTO
 
 # count of kernel launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = {'n': 0}
@@ -191,17 +192,14 @@ def self_moments(dc, n_frames, lags, mask=7, variant=None):
 
     dc: [n_atoms, 3, pitch] float64; lags: ascending, a host array (numpy / list) or an int32 device tensor.
     The tiled, window and run variants plan on the host: with device-resident lags that costs a device->host copy.
-    variant=None: the tiled kernel, or the register-window kernel for a grid without arithmetic structure."""
+    variant=None: DEFAULT_VARIANT; VARIANT_AUTO (the shipped default) chooses by the lag grid (choose_variant)."""
     lib = require_cuda()
     K = len(lags) if not isinstance(lags, torch.Tensor) else lags.numel()
     if variant is None:
         variant = DEFAULT_VARIANT
-        if variant == VARIANT_TILE:
-            lags_host = np.ascontiguousarray(lags.cpu().numpy() if isinstance(lags, torch.Tensor) else lags, dtype=np.int32)
-            if _mostly_single_lags(lags_host, n_frames):
-                # a grid without arithmetic structure (spacing='logarithmic', kinisi/parser.py:165): windows of one lag
-                # are shared-memory bound in the tiled kernel; the register-window kernel is 2-3 times faster there
-                variant = VARIANT_WIN
+    if variant == VARIANT_AUTO:
+        lags_host = np.ascontiguousarray(lags.cpu().numpy() if isinstance(lags, torch.Tensor) else lags, dtype=np.int32)
+        variant = choose_variant(lags_host, n_frames)
     sums = torch.empty((K, 2), dtype=torch.float64, device=dc.device)
     if (variant & 0xff) == VARIANT_TILE:
         lags_host = np.ascontiguousarray(lags.cpu().numpy() if isinstance(lags, torch.Tensor) else lags, dtype=np.int32)
@@ -246,21 +244,27 @@ def self_moments(dc, n_frames, lags, mask=7, variant=None):
     return sums
 
 
-_SINGLE_LAG_GRIDS = {}
+_CHOSEN = {}  # (lags, n_frames) -> (variant, features)
 
 
-def _mostly_single_lags(lags_host, n_frames):
-    """True when more than half of the lags of a grid end up in windows of one lag in the tiled kernel's plan."""
+def choose_variant(lags_host, n_frames, with_features=False):
+    """The moment kernel for a lag grid (kb2_self_moments_choose): the tiled kernel while its plan copies <= 2 bytes per
+    term (kinisi's default grid, kinisi/parser.py:150-168, on long trajectories), else the run kernel (long runs of one
+    spacing), the window kernel (long windows) or the direct kernel (no structure: spacing='logarithmic',
+    kinisi/parser.py:165).  Host only; cached per (grid, n_frames)."""
+    lags_host = np.ascontiguousarray(lags_host, dtype=np.int32)
     key = (lags_host.tobytes(), int(n_frames))
-    hit = _SINGLE_LAG_GRIDS.get(key)
+    hit = _CHOSEN.get(key)
     if hit is None:
-        wins, _ = self_moments_tiles(lags_host[:256], n_frames)
-        singles = sum(1 for w in wins if w[2] == 1)
-        hit = 2 * singles > min(len(lags_host), 256)
-        if len(_SINGLE_LAG_GRIDS) >= 64:
-            _SINGLE_LAG_GRIDS.pop(next(iter(_SINGLE_LAG_GRIDS)))
-        _SINGLE_LAG_GRIDS[key] = hit
-    return hit
+        feats = np.zeros(4)
+        v = _lib.load().kb2_self_moments_choose(lags_host.ctypes.data, len(lags_host), int(n_frames), feats.ctypes.data)
+        if v < 0:
+            raise ValueError('kb2_self_moments_choose: ' + _lib.load().kb2_last_error().decode('utf-8', 'replace'))
+        hit = (v, dict(zip(('tile_bytes_per_term', 'runs_model', 'short_window_share', 'mean_window'), feats.tolist())))
+        if len(_CHOSEN) >= 64:
+            _CHOSEN.pop(next(iter(_CHOSEN)))
+        _CHOSEN[key] = hit
+    return hit if with_features else hit[0]
 
 
 _RUNS_PLANS = {}  # (kind, lags, n_frames, device) -> (pinned host plan, device plan, upload event)

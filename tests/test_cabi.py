@@ -124,6 +124,42 @@ def test_run_plan_is_host_only(lib_path):
     assert header[2] > 80  # (run, strip) pairs
 
 
+def test_kernel_choice_is_host_only(lib_path):
+    """kb2_self_moments_choose needs no device.  BASELINE configs[1] / [2] / [4] (kinisi's default 100-point grid,
+    kinisi/parser.py:150-168, on >= 20 000 frames) keep the tiled kernel; configs[3]'s dense grid (2000 points on 20 000
+    frames) is one long run of spacing 10 -> the run kernel; the default grid on configs[0]'s 5000 frames (spacing
+    alternating 50 / 51) spreads over too many residues for the tiles -> the window kernel; a logarithmic grid
+    (kinisi/parser.py:165) has no structure -> the direct kernel.  tile_plan_cost agrees with the terms of the grid."""
+    import numpy as np
+    from kinisi_b200 import _lib, engine
+    lib = _lib.load()
+
+    def grid(T, n, used=None):
+        return np.unique(np.linspace(1, T, n, dtype=int))[:used].astype(np.int32)
+
+    assert engine.choose_variant(grid(20000, 100), 20000) == engine.VARIANT_TILE
+    assert engine.choose_variant(grid(100000, 100, 50), 100000) == engine.VARIANT_TILE
+    assert engine.choose_variant(grid(50000, 100), 50000) == engine.VARIANT_TILE
+    assert engine.choose_variant(grid(20000, 2000, 1000), 20000) == engine.VARIANT_RUNS
+    assert engine.choose_variant(grid(5000, 100), 5000) == engine.VARIANT_WIN
+    log = np.unique(np.geomspace(1, 20000, 100).astype(int)).astype(np.int32)
+    v, feats = engine.choose_variant(log, 20000, with_features=True)
+    assert v == engine.VARIANT_DIRECT and feats['short_window_share'] > 0.5 and feats['tile_bytes_per_term'] > 2.0
+    assert engine.choose_variant(np.array([3], dtype=np.int32), 50) in (0, 2, 3, 4)
+    # errors: unsorted lags, a lag beyond the trajectory
+    bad = np.array([5, 3], dtype=np.int32)
+    assert lib.kb2_self_moments_choose(bad.ctypes.data, 2, 100, None) == -1 and b'ascend' in lib.kb2_last_error()
+    with pytest.raises(ValueError, match='out of range'):
+        engine.choose_variant(np.array([1, 200], dtype=np.int32), 100)
+    # the plan walks every term of the grid once (ragged strips count whole: a few per cent above)
+    lags = grid(20000, 100)
+    out = np.zeros(3)
+    assert lib.kb2_self_moments_tile_plan_cost(lags.ctypes.data, len(lags), 20000, out.ctypes.data) == 0
+    terms = float(np.sum(20000 - lags))
+    assert terms <= out[2] <= 1.05 * terms
+    assert out[0] < 2.0 * terms and out[1] > 0
+
+
 def test_sass_has_tma_and_fp64(lib_path):
     """The TMA variant really uses the bulk-copy engine (UBLKCP) and the moment kernels are FP64."""
     cuobjdump = '/usr/local/cuda/bin/cuobjdump'

@@ -40,7 +40,7 @@ def _default_variant_is_restored():
     """Every test starts on (and leaves behind) the shipped default moment kernel, the one bench.py times."""
     from kinisi_b200 import engine
     shipped = engine.DEFAULT_VARIANT
-    assert (shipped & 0xff) == engine.VARIANT_TILE
+    assert shipped == engine.VARIANT_AUTO
     yield
     engine.DEFAULT_VARIANT = shipped
 
@@ -1257,6 +1257,40 @@ def test_production_lag_grids_against_oracle(kb, variant, n_frames):
         sums = kb.engine.self_moments(dct, n_frames, lags, mask, variant).cpu().numpy()
         np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
         np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
+
+
+AUTO_GRIDS = {  # name -> (n_frames, lags, the kernel kb2_self_moments_choose takes)
+    'default grid, 20 000 frames': (20000, np.linspace(1, 20000, 100, dtype=int), 4),
+    'default grid, 5000 frames': (5000, np.linspace(1, 5000, 100, dtype=int), 3),
+    'dense grid (configs[3])': (20000, np.linspace(1, 20000, 2000, dtype=int)[:1000], 2),
+    '400 points, spacing drifting every 8th lag': (20000, np.linspace(1, 20000, 400, dtype=int), 0),
+    'logarithmic': (20000, np.unique(np.geomspace(1, 20000, 100).astype(int)), 0),
+}
+
+
+@pytest.mark.parametrize('grid', sorted(AUTO_GRIDS))
+def test_kernel_chosen_by_the_grid_against_oracle(kb, grid):
+    """variant=None (VARIANT_AUTO, what the classes and bench.py run): the kernel kb2_self_moments_choose takes for the
+    grid gives the oracle's raw sums (kinisi/parser.py:208-213 + diffusion.py:572-574), and so does every other kernel
+    on the same grid -- the choice changes the speed, never the terms."""
+    n_frames, lags, want = AUTO_GRIDS[grid]
+    assert kb.engine.DEFAULT_VARIANT == kb.engine.VARIANT_AUTO
+    assert kb.engine.choose_variant(lags, n_frames) == want
+    n_atoms = 2
+    rng = np.random.default_rng(len(lags) + n_frames)
+    dc = np.cumsum(rng.normal(0, 0.1, size=(n_atoms, n_frames, 3)), axis=1)
+    dc[:, 0] = 0.0
+    S1, S2, _, _ = ko.raw_sums_streaming(dc, lags)
+    dct = _device_dc(kb, dc)
+    before = kb.engine.LAUNCHES['n']
+    sums = kb.engine.self_moments(dct, n_frames, lags, 7).cpu().numpy()
+    assert kb.engine.LAUNCHES['n'] > before
+    np.testing.assert_allclose(sums[:, 0], S1, rtol=1e-12)
+    np.testing.assert_allclose(sums[:, 1], S2, rtol=1e-12)
+    for variant in (0, 2, 3, 4):
+        if variant != want:
+            other = kb.engine.self_moments(dct, n_frames, lags, 7, variant).cpu().numpy()
+            np.testing.assert_allclose(other, sums, rtol=1e-12)
 
 
 def test_full_size_default_kernel_against_the_direct_kernel_and_an_oracle_slice(kb):
