@@ -34,6 +34,21 @@ UNIT = 'terms/s'
 WORKLOAD = 'configs[1]: LLZO-like 1536 atoms (448 Li) x 20000 steps, 100 dt, MSD+covariance+emcee D'
 
 
+def bench_config(args):
+    """`config` of the JSON line: the workload, the same dictionary in both arms (what differs between the arms -- the
+    bounded sample of the reference arm, the joins and the kernel of the GPU arm -- is in `cpu_baseline.sample` / `run`)."""
+    n_all, n_mob, T = CFG['n_mobile'] + CFG['n_framework'], CFG['n_mobile'], CFG['n_frames']
+    return {
+        'workload': WORKLOAD,
+        'per_gpu': f'{n_all} atoms ({n_mob} mobile) x {T} frames, f32 wrapped fractional coordinates',
+        'sharding': 'atoms' if args.gpus > 1 else 'none',
+        'l2': f'inputs ({n_all * (T + 1) * 12 / 1e6:.0f} MB f32 + {n_mob * 3 * T * 8 / 1e6:.0f} MB f64 per step) '
+              'exceed the 126 MB L2; no flush needed',
+        'analyses_in_flight': f'GPU arm: {args.in_flight} analyses on {args.in_flight} streams (`value` is their throughput, '
+                              '`latency` one analysis alone); reference arm: one analysis per host core',
+    }
+
+
 def k2_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the stage-2 kernel on this workload, from the
     ncu --set full capture summarised in profiles/ (None if the summary is missing)."""
@@ -227,7 +242,7 @@ def run_reference(args):
         'vs_baseline': None,
         'dtype': 'f64',
         'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'l2': 'n/a (host)'},
+        'config': bench_config(args),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': workers, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -343,6 +358,9 @@ def synth_coords_device(torch, dev, n_atoms, n_frames, box, sigma, seed, chunk=2
     return out
 
 
+K2_NAMES = {0: 'direct', 1: 'tma-ring', 2: 'arithmetic-runs', 3: 'lag-window', 4: 'tiled-lag-window'}
+
+
 def named_shapes(args, torch, td, dev, world, rank, fp64_peak_tflops, hbm_peak_gbs):
     """Timed sub-records for the other BASELINE.json configurations, after the headline: configs[2] (MSTD, 10 000 ions x
     100 000 steps) and configs[4] (MSD, 100 000 atoms x 50 000 steps) STRONG-scaled over the ranks (atoms / N per rank,
@@ -432,7 +450,8 @@ def named_shapes(args, torch, td, dev, world, rank, fp64_peak_tflops, hbm_peak_g
             coef = b.D if kind == 'msd' else b.D_J
             out[name] = {
                 'kind': kind, 'atoms': n_total, 'frames': T, 'atoms_per_gpu': n_local, 'scaling': 'strong',
-                'dc_streamed': streamed, 'ms_per_analysis': best['ms'], 'terms': terms,
+                'dc_streamed': streamed, 'k2_kernel': K2_NAMES[engine.choose_variant(np.asarray(used, dtype=np.int32), T)],
+                'ms_per_analysis': best['ms'], 'terms': terms,
                 'terms_per_s': terms / (best['ms'] * 1e-3), 'stage_ms': {'stage1+2': best['stage12_ms'], 'stage3': best['stage3_ms']},
                 'k2_ms': best['k2_ms'], 'k2_fp64_frac': 16.0 * terms / world / (best['k2_ms'] * 1e-3) / 1e12 / fp64_peak_tflops,
                 'k1_ms': best['k1_ms'], 'k1_hbm_gbs': k1['bytes'] / (best['k1_ms'] * 1e-3) / 1e9,
@@ -473,7 +492,8 @@ def named_shapes(args, torch, td, dev, world, rank, fp64_peak_tflops, hbm_peak_g
         best = min(recs[1:])
         lags = np.asarray(p.disp_3d.lags[:len(p.disp_3d.lags) // 2])
         out['configs[3]'] = {'kind': 'mscd', 'atoms': n_ion, 'frames': T, 'time_intervals_used': int(b.dt.size),
-                             'covariance_n': int(b.dt.size - 100), 'ms_per_analysis': best[0],
+                             'covariance_n': int(b.dt.size - 100),
+                             'k2_kernel': K2_NAMES[engine.choose_variant(lags.astype(np.int32), T)], 'ms_per_analysis': best[0],
                              'stage_ms': {'stage1+2': best[1], 'stage3 (cov_build + eigh + gls_prepare + sampler)': best[2]},
                              'self_terms_per_s': n_terms(n_ion, T, lags) / (best[1] * 1e-3), 'sigma_median_mS_cm': float(b.sigma.n)}
         del coords, p, b
@@ -760,17 +780,13 @@ def run_own(args):
             'vs_baseline': None,
             'dtype': 'f64',
             'data': 'synthetic',
-            'config': {
-                'workload': WORKLOAD,
-                'per_gpu': f'{n_mob + n_fw} atoms ({n_mob} mobile) x {T} frames, f32 wrapped fractional coordinates',
-                'sharding': 'atoms' if world > 1 else 'none',
+            'config': bench_config(args),
+            'run': {
                 'joins': ('none' if world == 1 else
                           'peer memory, no launch of their own: frame sums joined inside kb2_frame_sums_joined, moment sums inside kb2_moment_stats_joined'
                           if any(kdist._PEER.values()) and os.environ.get('KB2_FUSED_JOIN', '1') != '0' else
                           'peer-memory kernel (kb2_peer_allreduce_f64), 2 per step' if any(kdist._PEER.values()) else
                           'NCCL all-reduce, 2 per step'),
-                'l2': f'inputs ({host.numel() * 4 / 1e6:.0f} MB f32 + {n_mob * 3 * T * 8 / 1e6:.0f} MB f64 per step) '
-                      'exceed the 126 MB L2; no flush needed',
                 'self_moment_variant': {0: 'direct', 1: 'tma-ring', 2: 'arithmetic-runs', 3: 'lag-window', 4: 'tiled-lag-window'}[
                     (engine.choose_variant(lags, T) if engine.DEFAULT_VARIANT == engine.VARIANT_AUTO else engine.DEFAULT_VARIANT) & 0xff]
                 + (' (chosen by the lag grid)' if engine.DEFAULT_VARIANT == engine.VARIANT_AUTO else ' (forced)'),
