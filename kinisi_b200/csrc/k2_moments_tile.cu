@@ -69,8 +69,10 @@ static_assert(sizeof(TileUnit) == 32, "TileUnit is read as two int4");
 struct TileTpl {
     int D, oLo, nO, pLo;
     int nP, cP0, unit0, nunits;
-    int nstrips, strip_prefix, spt, pad1;  // strips of 32 columns; spt of them side by side in one tile (nstrips here =
-                                           // number of strip GROUPS); strip_prefix = groups of the templates before this one
+    int nstrips, strip_prefix, spt, pack_w;  // strips of 32 columns; spt of them side by side in one tile (nstrips here =
+                                             // number of strip GROUPS); strip_prefix = groups of the templates before this one;
+                                             // pack_w > 0: the last strip has pack_w columns and its tile takes that strip of
+                                             // SEVERAL atoms side by side (see tile_pack)
 };
 static_assert(sizeof(TileTpl) == 48, "TileTpl is read as three int4");
 
@@ -78,7 +80,16 @@ struct TileDesc {  // what the producer publishes with a filled buffer
     int stop, t0, D, oLo;
     int pLo, cP0, unit0, nunits;
     int nO, atom, ns, sub_doubles;  // ns strips in this tile, one every sub_doubles doubles of the buffer
+    int pack_w, pack_n, pack_wp, pad;  // pack_w > 0: pack_n atoms' pieces of pack_w columns, one every pack_wp columns of a row
 };
+
+// A ragged last strip (D mod 32 = w columns) leaves 32 - w lanes of every warp that walks it idle: 22 of 32 at kinisi's
+// default grid on 20 000 frames (D = 202 = 6 * 32 + 10, a tenth of all lane-steps).  A piece of such a strip needs
+// w + 8 columns of a 40-column row (8: the room for the residues r of its windows), so the tile of the last strip holds
+// that strip of P = 40 / wp consecutive ATOMS side by side, wp = w + 8 rounded up to even (16-byte copies); lane l walks
+// column l mod w of atom l / w.  All atoms share the template, so the units and their control flow are those of one atom.
+__host__ __device__ inline int tile_pack_wp(int w) { return (w + 8 + 1) & ~1; }
+__host__ __device__ inline int tile_pack_atoms(int w) { return w > 0 && w < 32 ? kTileWp / tile_pack_wp(w) : 1; }
 
 namespace tile {
 
@@ -351,8 +362,50 @@ __global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
 #pragma unroll 1
         for (unsigned tau = 0;; ++tau) {
             const int b = (int)(tau % (unsigned)nbuf);
-            const long long item = s_item[tau & 1];
+            long long item = s_item[tau & 1];
             if (pw == 0 && lane == 0 && item < n_items) drawn = (long long)atomicAdd(work_counter, 1u);
+            int bi = 0, nb = 1, y = 0, al = 0, pack_w = 0, pack_n = 1;
+            int4 ta = make_int4(0, 0, 0, 0), tb = ta, tc = ta;
+#pragma unroll 1
+            while (item < n_items) {
+                // item -> (atom batch, strip slot, atom of the batch); strip slot -> (template, strip) by the prefix sums
+                long long x;
+                if (item < (long long)(n_batches - 1) * items_full) {
+                    bi = (int)(item / items_full);
+                    x = item - (long long)bi * items_full;
+                    nb = batch;
+                } else {
+                    bi = n_batches - 1;
+                    x = item - (long long)(n_batches - 1) * items_full;
+                    nb = nb_last;
+                }
+                y = (int)(x / nb);
+                al = (int)(x - (long long)y * nb);
+                int ti = 0;
+#pragma unroll 1
+                for (int base = 0; base < n_tpls; base += 32) {
+                    const int idx = base + lane;
+                    // strip_prefix of template idx + 1 <= y  <=>  the slot lies beyond template idx
+                    const bool below = idx + 1 < n_tpls && __ldg(&tpls[idx + 1].strip_prefix) <= y;
+                    const int cnt = __popc(__ballot_sync(0xffffffffu, below));
+                    ti += cnt;
+                    if (cnt < 32) break;
+                }
+                ta = __ldg(reinterpret_cast<const int4*>(tpls + ti));
+                tb = __ldg(reinterpret_cast<const int4*>(tpls + ti) + 1);
+                tc = __ldg(reinterpret_cast<const int4*>(tpls + ti) + 2);
+                // the packed last strip of a template: the tile of atom al (a multiple of P) serves atoms al .. al + P - 1,
+                // the items of the others are empty -- the item drawn ahead is taken at once and another one drawn
+                pack_w = (tc.w > 0 && y - tc.y == tc.x - 1) ? tc.w : 0;
+                const int P = tile_pack_atoms(pack_w);
+                pack_n = min(P, nb - al);
+                if (pack_w == 0 || al % P == 0) break;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW) : "memory");  // (every producer thread has read the slot)
+                if (pw == 0 && lane == 0) s_item[tau & 1] = drawn;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW) : "memory");
+                item = s_item[tau & 1];
+                if (pw == 0 && lane == 0 && item < n_items) drawn = (long long)atomicAdd(work_counter, 1u);
+            }
             if (item >= n_items) {
                 if (tau >= (unsigned)nbuf) mbar_wait(&empty[b], ((tau / (unsigned)nbuf) - 1) & 1);
                 if (pw == 0 && lane == 0) {
@@ -363,45 +416,19 @@ __global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
                 cp_async_arrive(&full[b]);
                 break;
             }
-            // item -> (atom batch, strip slot, atom of the batch); strip slot -> (template, strip) by the prefix sums
-            int bi, nb;
-            long long x;
-            if (item < (long long)(n_batches - 1) * items_full) {
-                bi = (int)(item / items_full);
-                x = item - (long long)bi * items_full;
-                nb = batch;
-            } else {
-                bi = n_batches - 1;
-                x = item - (long long)(n_batches - 1) * items_full;
-                nb = nb_last;
-            }
-            const int y = (int)(x / nb);
-            const int al = (int)(x - (long long)y * nb);
-            int ti = 0;
-#pragma unroll 1
-            for (int base = 0; base < n_tpls; base += 32) {
-                const int idx = base + lane;
-                // strip_prefix of template idx + 1 <= y  <=>  the slot lies beyond template idx
-                const bool below = idx + 1 < n_tpls && __ldg(&tpls[idx + 1].strip_prefix) <= y;
-                const int cnt = __popc(__ballot_sync(0xffffffffu, below));
-                ti += cnt;
-                if (cnt < 32) break;
-            }
-            const int4 ta = __ldg(reinterpret_cast<const int4*>(tpls + ti));
-            const int4 tb = __ldg(reinterpret_cast<const int4*>(tpls + ti) + 1);
-            const int4 tc = __ldg(reinterpret_cast<const int4*>(tpls + ti) + 2);
             const int D = ta.x, oLo = ta.y, nO = ta.z, pLo = ta.w, nP = tb.x, cP0 = tb.y, spt = tc.z;
             const int t0 = (y - tc.y) * 32 * spt;
             const int ns = min(spt, (D - t0 + 31) / 32);  // strips of this tile (the last group of a row may be short)
             const int sub_bytes = (nO + nP) * (kTileRowP * 8);
             const int atom = bi * batch + al;
+            const int pack_wp = tile_pack_wp(pack_w);
             const uint32_t buf_s = smem_u32(bufs + (size_t)b * buf_bytes);
             const double* const src_atom = dc + (size_t)atom * 3 * pitch;
             const int ipitch = (int)pitch;
             // (the tile was decoded while the consumers were still busy with the buffer's previous occupant)
             if (tau >= (unsigned)nbuf) mbar_wait(&empty[b], ((tau / (unsigned)nbuf) - 1) & 1);
             if (pw == 0 && lane == 0) {
-                TileDesc d{0, t0, D, oLo, pLo, cP0, tb.z, tb.w, nO, atom, ns, sub_bytes / 8};
+                TileDesc d{0, t0, D, oLo, pLo, cP0, tb.z, tb.w, nO, atom, ns, sub_bytes / 8, pack_w, pack_n, pack_wp, 0};
                 desc[b] = d;
                 next_unit[b] = 0;
                 mbar_arrive(&full[b]);  // (release: the descriptor is visible with the phase)
@@ -413,9 +440,13 @@ __global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
             static_assert(NPW % 2 == 0, "a producer warp copies rows of one parity (odd D)");
             const int c_lo = lane / 20, p_lo = lane - c_lo * 20;                // chunks 0..31 of a row of NDIM * 20
             const int c_hi = (lane + 32) / 20, p_hi = (lane + 32) - c_hi * 20;  // chunks 32..59
-            const bool has_lo = c_lo < NDIM, has_hi = c_hi < NDIM && lane + 32 < NDIM * 20;
-            const double* const g_lo = src_atom + (size_t)comp[has_lo ? c_lo : 0] * pitch + 2 * p_lo;
-            const double* const g_hi = src_atom + (size_t)comp[has_hi ? c_hi : 0] * pitch + 2 * p_hi;
+            // a packed tile: chunk p of a row belongs to the piece of atom + p / (wp / 2), columns 2 (p mod wp / 2) of it
+            const int half_wp = pack_w ? pack_wp / 2 : 20;
+            const int j_lo = p_lo / half_wp, j_hi = p_hi / half_wp;
+            const int q_lo = 2 * (p_lo - j_lo * half_wp), q_hi = 2 * (p_hi - j_hi * half_wp);  // first column within the piece
+            const bool has_lo = c_lo < NDIM && j_lo < pack_n, has_hi = c_hi < NDIM && lane + 32 < NDIM * 20 && j_hi < pack_n;
+            const double* const g_lo = src_atom + ((size_t)(has_lo ? j_lo : 0) * 3 + comp[has_lo ? c_lo : 0]) * pitch + q_lo;
+            const double* const g_hi = src_atom + ((size_t)(has_hi ? j_hi : 0) * 3 + comp[has_hi ? c_hi : 0]) * pitch + q_hi;
             const uint32_t o_lo = (uint32_t)(c_lo * kTileWp + 2 * p_lo) * 8u + (uint32_t)pw * (kTileRowP * 8);
             const uint32_t o_hi = (uint32_t)(c_hi * kTileWp + 2 * p_hi) * 8u + (uint32_t)pw * (kTileRowP * 8);
             const size_t sstep = (size_t)NPW * D;
@@ -443,8 +474,8 @@ __global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
                     }
 #pragma unroll 1
                     for (; row < n_rows; row += NPW, f += NPW * D) {
-                        if (has_lo && f + 2 * p_lo < ipitch) cp_async16(d_lo, s_lo);
-                        if (has_hi && f + 2 * p_hi < ipitch) cp_async16(d_hi, s_hi);
+                        if (has_lo && f + q_lo < ipitch) cp_async16(d_lo, s_lo);
+                        if (has_hi && f + q_hi < ipitch) cp_async16(d_hi, s_hi);
                         s_lo += sstep, s_hi += sstep, d_lo += NPW * (kTileRowP * 8), d_hi += NPW * (kTileRowP * 8);
                     }
                 }
@@ -496,8 +527,13 @@ __global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
                 const int ui = u / d.ns, sidx = u - ui * d.ns;
                 const double* const bufO = buf0 + (size_t)sidx * d.sub_doubles;
                 const double* const bufP = bufO + (size_t)d.nO * kTileRowO;
-                const int t = d.t0 + 32 * sidx + lane;
-                const bool active = t < d.D;
+                // (a packed tile: lane -> column lane mod w of the piece of atom lane / w; the lanes beyond the pieces read
+                // piece 0 and their sums are dropped)
+                const int pj = d.pack_w ? lane / d.pack_w : 0;
+                const int pcl = d.pack_w ? lane - pj * d.pack_w : lane;
+                const int lane_off = d.pack_w ? (pj < d.pack_n ? pj * d.pack_wp : 0) + pcl : lane;
+                const int t = d.t0 + 32 * sidx + pcl;
+                const bool active = t < d.D && pj < d.pack_n;
                 const int4 ua = __ldg(reinterpret_cast<const int4*>(units + d.unit0 + ui));
                 const int4 ub = __ldg(reinterpret_cast<const int4*>(units + d.unit0 + ui) + 1);
                 const int I0 = ua.x, r = ua.y, m = ua.z, acc_off = ua.w, a_top = ub.x, nsteps = ub.y;
@@ -509,8 +545,8 @@ __global__ void __launch_bounds__(32 * (kTileCW + NPW), 1)
                 // (odd D: the row with global index rho is stored from the even frame at or below its start, i.e. shifted
                 // right by rho & 1 columns)
                 const int odd = d.D & 1, p_start = a_start + I0;
-                const double* const po = bufO + (a_start - d.oLo) * kTileRowO + lane;
-                const double* const pp = bufP + (p_start - d.pLo) * kTileRowP + (r - d.cP0) + lane;
+                const double* const po = bufO + (a_start - d.oLo) * kTileRowO + lane_off;
+                const double* const pp = bufP + (p_start - d.pLo) * kTileRowP + (r - d.cP0) + lane_off;
                 tile::Ptrs q;
                 q.o[0] = po + (odd & a_start);
                 q.o[1] = po + (odd & ~a_start);
@@ -558,6 +594,11 @@ struct TilePlan {
 static bool tile_split_eights() {
     const char* e = getenv("KB2_TILE_SPLIT");
     return !(e && !strcmp(e, "even"));
+}
+
+static bool tile_packing() {  // KB2_TILE_PACK=0: ragged strips one atom at a time (experiments)
+    const char* e = getenv("KB2_TILE_PACK");
+    return !(e && !strcmp(e, "0"));
 }
 
 static int tile_ra() {  // most origin rows per unit (KB2_TILE_RA: experiments)
@@ -701,6 +742,9 @@ static void plan_tiles_for(const int32_t* lags, int K, int Tn, int buf_bytes, Ti
                         while (spt > 1 && (long long)spt * (long long)cur.units.size() > 4 * kTileMaxUnits) --spt;
                         cur.tp.spt = spt;
                         cur.tp.nstrips = (strips + spt - 1) / spt;
+                        // a ragged last strip that is a tile of its own takes several atoms side by side (tile_pack_atoms)
+                        const int w_last = D - 32 * (strips - 1);
+                        cur.tp.pack_w = (spt == 1 && tile_packing() && tile_pack_atoms(w_last) >= 2) ? w_last : 0;
                         std::stable_sort(cur.units.begin(), cur.units.end(), [](const TileUnit& x, const TileUnit& y) {
                             return (long long)x.nsteps * x.m > (long long)y.nsteps * y.m;
                         });
@@ -984,7 +1028,7 @@ extern "C" int kb2_self_moments_tile_plan_cost(const int32_t* lags_host, int n_l
                 terms += (double)un.nsteps * un.m - (un.top ? (double)un.m * (un.m - 1) / 2 : 0.0);
             }
             const int strips = (tp.D + 31) / 32;
-            out[1] += cyc * strips;
+            out[1] += cyc * (tp.pack_w ? strips - 1 + 1.0 / tile_pack_atoms(tp.pack_w) : (double)strips);
             out[2] += terms * tp.D;
         }
     }
