@@ -589,13 +589,6 @@ struct TilePlan {
     long long bytes_loaded = 0;     // per atom
 };
 
-// Row length for a progression of `len` lags with common difference d: a multiple of d, >= 32, that fills whole
-// strips of 32 columns and still leaves windows of several lags.
-static bool tile_split_eights() {
-    const char* e = getenv("KB2_TILE_SPLIT");
-    return !(e && !strcmp(e, "even"));
-}
-
 static bool tile_packing() {  // KB2_TILE_PACK=0: ragged strips one atom at a time (experiments)
     const char* e = getenv("KB2_TILE_PACK");
     return !(e && !strcmp(e, "0"));
@@ -607,6 +600,8 @@ static int tile_ra() {  // most origin rows per unit (KB2_TILE_RA: experiments)
     return v >= kTileM ? v : kTileRA;
 }
 
+// Row length for a progression of `len` lags with common difference d: a multiple of d, >= 32, that fills whole
+// strips of 32 columns and still leaves windows of several lags.
 static int choose_mult(int d, int len, int Tn) {
     if (const char* e = getenv("KB2_TILE_MULT")) {  // experiments: force the multiple when it is admissible
         const int mult = atoi(e);
@@ -638,7 +633,7 @@ static int choose_mult(int d, int len, int Tn) {
     return best_mult;
 }
 
-static void plan_tiles_for(const int32_t* lags, int K, int Tn, int buf_bytes, TilePlan& plan) {
+static void plan_tiles_for(const int32_t* lags, int K, int Tn, int buf_bytes, int cap, bool eights, TilePlan& plan) {
     const std::vector<LagSegment> segs = cover_by_progressions(lags, K, Tn, kTileMinLen, kTileCandidates);
     for (const LagSegment& sg : segs) {
         if (sg.len == 1) {
@@ -654,12 +649,11 @@ static void plan_tiles_for(const int32_t* lags, int K, int Tn, int buf_bytes, Ti
             const int ls = (sg.len - u + mult - 1) / mult;  // lags k0 + (u + i*mult)*d, i < ls
             // windows of 8 and one remainder ("eights": one instantiation of the walk does nearly all the work, which
             // matters for the instruction cache) or windows of nearly equal size ("even")
-            const int nw = (ls + kTileM - 1) / kTileM;
+            const int nw = (ls + cap - 1) / cap;
             const int base = ls / nw, extra = ls % nw;
-            const bool eights = tile_split_eights();
             int at = 0;
             for (int w = 0; w < nw; ++w) {
-                const int m = eights ? std::min(kTileM, ls - at) : base + (w < extra ? 1 : 0);
+                const int m = eights ? std::min(cap, ls - at) : base + (w < extra ? 1 : 0);
                 const long long kfirst = (long long)sg.k0 + (long long)(u + (long long)at * mult) * sg.d;
                 plan.wins.push_back({D, (int)(kfirst / D), (int)(kfirst % D), m, (int)plan.slot.size()});
                 for (int i = 0; i < m; ++i) {
@@ -831,12 +825,50 @@ static void plan_tiles(const int32_t* lags, int K, int Tn, TilePlan& plan) {
     // and whole columns matter more than a third tile in flight -- so two is the default; KB2_TILE_BUFS=3 / 0 = by traffic)
     const char* e = getenv("KB2_TILE_BUFS");
     const int force = e ? atoi(e) : 2;
-    TilePlan three, two;
-    if (force != 2) plan_tiles_for(lags, K, Tn, kTileSmemBufBytes / 3, three);
-    if (force != 3) plan_tiles_for(lags, K, Tn, kTileSmemBufBytes / 2, two);
-    const bool take3 = force == 3 || (force != 2 && three.bytes_loaded * 10 <= two.bytes_loaded * 11);
-    plan = take3 ? three : two;
-    plan.nbuf = take3 ? 3 : 2;
+    // How the progressions are cut into windows.  The column walk is instantiated per window length M, its main loop
+    // unrolled over the register ring (~0.29 KB x RV(M) x M of code: 23 KB for M = 8, 16 for 7, 14 for 6, 8.6 for 5), and the
+    // walks that run side by side on an SM have to share its 32 KB instruction cache: windows of 8 + 3 + 6 (the first 50
+    // points of the default grid on 100 000 frames, groups of 11 lags between carries) ran at 0.61 of the FP64 peak with
+    // 2.5 no-instruction stall cycles per issue, the same lags cut 6 + 5 at 0.79; windows of 7 + 6 on four progressions of 25
+    // at 0.58 against 0.77 for 8 + 8 + 8 + 1 (profiles/r02_k2_tile_split.txt).  So: the cheapest cut by the unit cost model
+    // among those whose walks (each with >= 5 % of the work) fit 28 KB; the smallest footprint when none does.
+    struct Cut { int cap; bool eights; };
+    std::vector<Cut> cuts = {{8, true}, {8, false}, {7, true}, {6, true}, {6, false}, {5, true}};
+    if (const char* sp = getenv("KB2_TILE_SPLIT")) cuts = {{kTileM, strcmp(sp, "even") != 0}};
+    TilePlan best_plan;
+    double best_cost = 0.0, best_foot = 0.0;
+    bool have = false, best_fits = false;
+    int best_nbuf = 2;
+    for (const Cut& cut : cuts) {
+        TilePlan three, two;
+        if (force != 2) plan_tiles_for(lags, K, Tn, kTileSmemBufBytes / 3, cut.cap, cut.eights, three);
+        if (force != 3) plan_tiles_for(lags, K, Tn, kTileSmemBufBytes / 2, cut.cap, cut.eights, two);
+        const bool take3 = force == 3 || (force != 2 && three.bytes_loaded * 10 <= two.bytes_loaded * 11);
+        TilePlan& cand = take3 ? three : two;
+        double by_m[kTileM + 1] = {0}, total = 0.0;
+        for (const TileTpl& tp : cand.tpls) {
+            const int strips = (tp.D + 31) / 32;
+            const double w = tp.pack_w ? strips - 1 + 1.0 / tile_pack_atoms(tp.pack_w) : (double)strips;
+            for (int u = 0; u < tp.nunits; ++u) {
+                const TileUnit& un = cand.units[tp.unit0 + u];
+                const double c = w * (double)(un.nsteps + (un.top ? 0 : un.m - 1)) * (16 * un.m + 24);
+                by_m[un.m] += c;
+                total += c;
+            }
+        }
+        double foot = 0.0;
+        for (int m = 1; m <= kTileM; ++m)
+            if (by_m[m] >= 0.05 * total) foot += 0.29 * (((m + 2) / 2) * 2) * m;
+        const bool fits = foot <= 28.0;
+        const bool better = !have || (fits && !best_fits) || (fits == best_fits && (fits ? total < 0.97 * best_cost : foot < best_foot - 0.01));
+        if (better) {
+            best_plan = cand;
+            best_cost = total, best_foot = foot, best_fits = fits, best_nbuf = take3 ? 3 : 2;
+            have = true;
+        }
+    }
+    plan = best_plan;
+    plan.nbuf = best_nbuf;
     if (getenv("KB2_TILE_DEBUG")) {
         fprintf(stderr, "tile plan: K %d T %d nbuf %d windows %zu templates %zu units %zu bytes/atom %lld\n", K, Tn, plan.nbuf,
                 plan.wins.size(), plan.tpls.size(), plan.units.size(), plan.bytes_loaded);
