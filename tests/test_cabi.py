@@ -160,6 +160,26 @@ def test_kernel_choice_is_host_only(lib_path):
     assert out[0] < 2.0 * terms and out[1] > 0
 
 
+def test_window_cut_follows_the_instruction_cache(lib_path):
+    """The tile planner cuts a progression into windows so that the column walks running side by side fit the instruction
+    cache (csrc/k2_moments_tile.cu, plan_tiles): groups of 11 lags between carries (first half of kinisi's default grid,
+    kinisi/parser.py:150-168, on 100 000 frames: what MSTD / MSCD keep) become 6 + 5, not 8 + 3 next to a 6; one long
+    progression (20 000 frames) and four of 25 (50 000 frames) stay windows of 8 and a remainder.  Host only."""
+    import numpy as np
+    from collections import Counter
+    from kinisi_b200 import engine
+
+    def cut(T, used):
+        lags = np.linspace(1, T, 100, dtype=int)[:used].astype(np.int32)
+        wins, n_tiles = engine.self_moments_tiles(lags, T)
+        assert sum(w[2] for w in wins) == used and n_tiles >= 1
+        return Counter(w[2] for w in wins)
+
+    assert cut(100000, 50) == Counter({6: 5, 5: 4})
+    assert cut(20000, 100) == Counter({8: 12, 3: 1, 1: 1})
+    assert cut(50000, 100) == Counter({8: 12, 1: 4})
+
+
 def test_sass_has_tma_and_fp64(lib_path):
     """The TMA variant really uses the bulk-copy engine (UBLKCP) and the moment kernels are FP64."""
     cuobjdump = '/usr/local/cuda/bin/cuobjdump'
