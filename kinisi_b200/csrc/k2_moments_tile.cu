@@ -834,7 +834,11 @@ static void plan_tiles(const int32_t* lags, int K, int Tn, TilePlan& plan) {
     // among those whose walks (each with >= 5 % of the work) fit 28 KB; the smallest footprint when none does.
     struct Cut { int cap; bool eights; };
     std::vector<Cut> cuts = {{8, true}, {8, false}, {7, true}, {6, true}, {6, false}, {5, true}};
-    if (const char* sp = getenv("KB2_TILE_SPLIT")) cuts = {{kTileM, strcmp(sp, "even") != 0}};
+    if (const char* sp = getenv("KB2_TILE_SPLIT")) {  // experiments: KB2_TILE_SPLIT=even|eights, KB2_TILE_CAP=5..8
+        const char* cp = getenv("KB2_TILE_CAP");
+        const int cap = cp ? std::min(kTileM, std::max(2, atoi(cp))) : kTileM;
+        cuts = {{cap, strcmp(sp, "even") != 0}};
+    }
     TilePlan best_plan;
     double best_cost = 0.0, best_foot = 0.0;
     bool have = false, best_fits = false;
