@@ -1293,6 +1293,30 @@ def test_kernel_chosen_by_the_grid_against_oracle(kb, grid):
             np.testing.assert_allclose(other, sums, rtol=1e-12)
 
 
+@pytest.mark.parametrize('n_frames,n_steps', [(20000, 100), (3333, 100), (8000, 250), (707, 20)])
+def test_tile_kernel_packs_ragged_strips(kb, n_frames, n_steps):
+    """Row lengths with a short last strip (D mod 32 <= 12: 202 at BASELINE configs[1], 101 / 202 / 808, 257, 74 here) put
+    that strip of 2-4 consecutive atoms into one tile (csrc/k2_moments_tile.cu, tile_pack_atoms).  Atom counts around the
+    pair and the L2-batch boundaries (one atom, an odd count, 50 + 1 at 20 000 frames), three dimension masks: the sums are
+    the oracle's (kinisi/parser.py:208-213 + diffusion.py:572-574) for the small counts and the direct kernel's for all."""
+    lags = np.unique(np.linspace(1, n_frames, n_steps, dtype=int))
+    wins, _ = kb.engine.self_moments_tiles(lags, n_frames)
+    assert any(w[2] > 1 and 0 < w[1] % 32 <= 12 for w in wins), 'no ragged row length in this grid'
+    rng = np.random.default_rng(n_frames + n_steps)
+    for n_atoms in (1, 2, 3, 51):
+        dc = np.cumsum(rng.normal(0, 0.1, size=(n_atoms, n_frames, 3)), axis=1)
+        dc[:, 0] = 0.0
+        dct = _device_dc(kb, dc)
+        for mask, dim in ((7, 'xyz'), (5, 'xz'), (2, 'y')):
+            tiled = kb.engine.self_moments(dct, n_frames, lags, mask, kb.engine.VARIANT_TILE).cpu().numpy()
+            direct = kb.engine.self_moments(dct, n_frames, lags, mask, kb.engine.VARIANT_DIRECT).cpu().numpy()
+            np.testing.assert_allclose(tiled, direct, rtol=1e-12, err_msg=f'{n_atoms} atoms, {dim}')
+            if n_atoms <= 3 and mask == 7:
+                S1, S2, _, _ = ko.raw_sums_streaming(dc, lags, dim)
+                np.testing.assert_allclose(tiled[:, 0], S1, rtol=1e-12)
+                np.testing.assert_allclose(tiled[:, 1], S2, rtol=1e-12)
+
+
 def test_full_size_default_kernel_against_the_direct_kernel_and_an_oracle_slice(kb):
     """BASELINE configs[1] at full size (448 atoms x 20 000 frames x 100 lags): the shipped default kernel against the
     direct kernel on all atoms, and both against the oracle's sums of the first 16 atoms (additivity over atoms)."""
